@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/*.npz from the LIVE reference.
+
+Run in the build container only:   python tests/golden/gen_golden.py
+It imports the unmodified reference classes (see refload.py), drives them with seeded
+inputs and records every observable of the step/observation path.  The fixtures are
+committed; the tests never import the reference.
+
+Recorded per family (all citations relative to /root/reference):
+  GRID   mapf_gridworld.py:70-224   reset/step/get_obs/get_state/get_avail_actions
+  PRIMAL mapf_primal.py:103-135, 343-386, 407-499, 549-667
+  PDIST  MARL-curve-main/src/envs/marl_partial.py:931-955 (per-goal hop-distance maps)
+"""
+import contextlib
+import io
+import os
+import random
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from refload import REF_SRC, load_reference  # noqa: E402
+
+GRID, PRIMAL, PARTIAL = load_reference()
+
+
+# --------------------------------------------------------------------------- helpers
+def write_movingai(tmpdir, grid_rows, n_lines):
+    """grid_rows: list[str] of '.'/'@'.  Writes <tmp>/m.map and <tmp>/s-{1..25}.scen."""
+    h, w = len(grid_rows), len(grid_rows[0])
+    mp = os.path.join(tmpdir, "m.map")
+    with open(mp, "w") as f:
+        f.write("type octile\nheight %d\nwidth %d\nmap\n" % (h, w))
+        for r in grid_rows:
+            f.write(r + "\n")
+    free = [(i, j) for i in range(h) for j in range(w) if grid_rows[i][j] == "."]
+    for k in range(1, 26):
+        with open(os.path.join(tmpdir, "s-%d.scen" % k), "w") as f:
+            f.write("version 1\n")
+            for n in range(n_lines):
+                a = free[(n * 7 + k) % len(free)]
+                b = free[(n * 13 + 3 * k + 1) % len(free)]
+                f.write("0\tm.map\t%d\t%d\t%d\t%d\t%d\t%d\t1.0\n" % (w, h, a[0], a[1], b[0], b[1]))
+    return mp, os.path.join(tmpdir, "s-")
+
+
+def rows_from_map(m):
+    return ["".join("@" if v else "." for v in row) for row in m]
+
+
+def free_cells(obst):
+    return [(i, j) for i in range(obst.shape[0]) for j in range(obst.shape[1]) if not obst[i, j]]
+
+
+# --------------------------------------------------------------------------- GRID
+def run_grid(name, obst, starts, goals, actions, step_reward=-0.01, collide_reward=-10,
+             episode_limit=10000):
+    """obst: bool[H,W]; starts/goals: list of (p0,p1) indexing _full_obs[p0][p1]."""
+    n = len(starts)
+    T = actions.shape[0]
+    with tempfile.TemporaryDirectory() as td:
+        mp, sp = write_movingai(td, rows_from_map(obst), max(n + 2, 30))
+        env = GRID.MAPF_GRID(mp, sp, n_agents=n, episode_limit=episode_limit, seed=1,
+                             render="none", step_reward=step_reward,
+                             collide_reward=collide_reward, debug=False)
+    # pin starts / goals (the reference samples them from a random .scen)
+    for i in range(n):
+        env._agent_init_pos[i] = tuple(int(v) for v in starts[i])
+        env._agent_goal_pos[i] = tuple(int(v) for v in goals[i])
+    env.agent_starts = [env._agent_init_pos[i] for i in range(n)]
+    env.agent_goals = [env._agent_goal_pos[i] for i in range(n)]
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        obs0 = env.reset()
+        avail0 = np.array(env.get_avail_actions(), dtype=np.uint8)
+        H, W = obst.shape
+        rec = dict(pos=[], node=[], edge=[], dones=[], reward=[], state=[], avail=[], step_count=[])
+        for t in range(T):
+            r, dones, info = env.step(actions[t])
+            obs = env.get_obs()
+            st = env.get_state()
+            assert obs.shape == (n, H * W) and all((obs[k] == st).all() for k in range(n))
+            rec["pos"].append(np.array(env.agent_positions, dtype=np.int16))
+            rec["node"].append(np.array(env._node_collision_agents, dtype=np.int32))
+            rec["edge"].append(np.array(env._edge_collision_agents, dtype=np.int32))
+            rec["dones"].append(np.array(dones, dtype=np.uint8))
+            rec["reward"].append(float(r))
+            rec["state"].append(st.astype(np.int8))
+            rec["avail"].append(np.array(env.get_avail_actions(), dtype=np.uint8))
+            rec["step_count"].append(info["_step_count"])
+    out = dict(
+        family="GRID", obst=obst.astype(np.uint8), starts=np.array(starts, dtype=np.int16),
+        goals=np.array(goals, dtype=np.int16), actions=actions.astype(np.uint8),
+        step_reward=np.float64(step_reward), collide_reward=np.float64(collide_reward),
+        episode_limit=np.int64(episode_limit), obs0=np.asarray(obs0)[0].astype(np.int8),
+        avail0=avail0,
+        pos=np.array(rec["pos"]), node=np.array(rec["node"]), edge=np.array(rec["edge"]),
+        dones=np.array(rec["dones"]), reward=np.array(rec["reward"], dtype=np.float64),
+        state=np.array(rec["state"]), avail=np.array(rec["avail"]),
+        step_count=np.array(rec["step_count"], dtype=np.int32))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "T=%d N=%d HxW=%dx%d sum_reward=%.6f" % (T, n, obst.shape[0], obst.shape[1],
+                                                                 float(np.sum(out["reward"]))))
+
+
+def gen_grid():
+    # KAT B.1
+    obst = np.zeros((10, 10), bool)
+    obst[5, 5] = True
+    run_grid("grid_kat_b1", obst, [(2, 2), (3, 2), (5, 4), (0, 0)], [(9, 9), (2, 2), (9, 0), (0, 1)],
+             np.array([[1, 0, 3, 0], [4, 4, 4, 3], [0, 4, 4, 1], [4, 4, 4, 4]]))
+    # c1: BASELINE config 1 -- 10x10 empty, 4 agents, seeded random actions
+    perm = np.random.RandomState(0).permutation(100)
+    cells = [(int(p) // 10, int(p) % 10) for p in perm]
+    run_grid("grid_c1", np.zeros((10, 10), bool), cells[:4], cells[4:8],
+             np.random.RandomState(1).randint(0, 5, [200, 4]))
+    # helloworld_v1 fixture (8x8, 2x2 block, corner starts, diagonal goals), episode limit hit
+    obst = np.zeros((8, 8), bool)
+    obst[3:5, 3:5] = True
+    run_grid("grid_hello8", obst, [(7, 7), (0, 0), (7, 0), (0, 7)], [(0, 0), (7, 7), (0, 7), (7, 0)],
+             np.random.RandomState(2).randint(0, 5, [60, 4]), episode_limit=40)
+    # random 16x16, float rewards (exercises the f64 add order), 12 agents
+    rs = np.random.RandomState(3)
+    obst = rs.rand(16, 16) < 0.2
+    fc = free_cells(obst)
+    idx = rs.permutation(len(fc))
+    starts = [fc[i] for i in idx[:12]]
+    goals = [fc[i] for i in idx[6:18]]  # some goals are other agents' starts
+    run_grid("grid_rand16", obst, starts, goals, rs.randint(0, 5, [80, 12]),
+             step_reward=-0.013, collide_reward=-0.7)
+    # crowded 6x6, overlapping starts allowed (edge counts > 1, node groups > 2)
+    rs = np.random.RandomState(4)
+    obst = np.zeros((6, 6), bool)
+    obst[2, 2] = obst[3, 4] = True
+    fc = free_cells(obst)
+    starts = [fc[i] for i in rs.randint(0, len(fc), 10)]
+    goals = [fc[i] for i in rs.randint(0, len(fc), 10)]
+    run_grid("grid_crowd6", obst, starts, goals, rs.randint(0, 5, [60, 10]))
+    # real MovingAI map + scen through the reference's own parser (x/y quirk included)
+    random.seed(11)
+    mp = os.path.join(REF_SRC, "mapf_baseline", "mapf-map", "random-32-32-20.map")
+    sp = os.path.join(REF_SRC, "mapf_baseline", "scen-random", "random-32-32-20-random-")
+    env = GRID.MAPF_GRID(mp, sp, n_agents=32, seed=1, render="none")
+    obst = np.array([[c != "." for c in row] for row in env._original_grid])
+    run_grid("grid_real32", obst, list(env.agent_starts), list(env.agent_goals),
+             np.random.RandomState(5).randint(0, 5, [40, 32]))
+
+
+# --------------------------------------------------------------------------- PRIMAL
+def primal_world(obst, starts, goals):
+    world = -obst.astype(int)
+    g = np.zeros_like(world)
+    for k, (s, gg) in enumerate(zip(starts, goals)):
+        world[s] = k + 1
+        g[gg] = k + 1
+    return world, g
+
+
+def mask5(lst):
+    m = np.zeros(5, np.uint8)
+    for a in lst:
+        m[a] = 1
+    return m
+
+
+def run_primal(name, obst, starts, goals, fov, actions, n_costs=3):
+    n = len(starts)
+    T = actions.shape[0]
+    world0, goals0 = primal_world(obst, starts, goals)
+    env = PRIMAL.MAPFEnv(num_agents=n, observation_size=fov, world0=world0.copy(), goals0=goals0.copy())
+    statuses = []
+    orig_act = env.world.act
+
+    def act_spy(action, agent_id):
+        s = orig_act(action, agent_id)
+        statuses.append(s)
+        return s
+
+    env.world.act = act_spy
+
+    def observe_all():
+        o = np.zeros((n, 4, fov, fov), np.uint8)
+        v = np.zeros((n, 3), np.float64)
+        for i in range(1, n + 1):
+            maps, vec = env._observe(i)
+            for c in range(4):
+                assert set(np.unique(maps[c])) <= {0.0, 1.0}
+                o[i - 1, c] = maps[c].astype(np.uint8)
+            v[i - 1] = vec
+        return o, v
+
+    obs0, vec0 = observe_all()
+    avail0 = np.array([mask5(env._listNextValidActions(i)) for i in range(1, n + 1)])
+    costs0 = np.array([env.getAstarCosts(env.world.getPos(i), env.world.getGoal(i))
+                       for i in range(1, min(n, n_costs) + 1)], dtype=np.int32)
+    rec = {k: [] for k in ("status", "reward", "done_mid", "next_mid", "on_goal", "valid",
+                           "pos", "obs", "vec", "avail", "done")}
+    for t in range(T):
+        row = {k: [] for k in ("reward", "done_mid", "next_mid", "on_goal", "valid")}
+        statuses.clear()
+        for i in range(1, n + 1):
+            state, reward, done, nxt, on_goal, blocking, valid = env._step((i, int(actions[t, i - 1])))
+            assert blocking is False
+            row["reward"].append(float(reward))
+            row["done_mid"].append(bool(done))
+            row["next_mid"].append(mask5(nxt))
+            row["on_goal"].append(bool(on_goal))
+            row["valid"].append(bool(valid))
+        rec["status"].append(np.array(statuses, dtype=np.int8))
+        rec["reward"].append(np.array(row["reward"], dtype=np.float64))
+        rec["done_mid"].append(np.array(row["done_mid"], dtype=np.uint8))
+        rec["next_mid"].append(np.array(row["next_mid"], dtype=np.uint8))
+        rec["on_goal"].append(np.array(row["on_goal"], dtype=np.uint8))
+        rec["valid"].append(np.array(row["valid"], dtype=np.uint8))
+        rec["pos"].append(np.array(env.getPositions(), dtype=np.int16))
+        o, v = observe_all()
+        rec["obs"].append(o)
+        rec["vec"].append(v)
+        rec["avail"].append(np.array([mask5(env._listNextValidActions(i, int(actions[t, i - 1])))
+                                      for i in range(1, n + 1)]))
+        rec["done"].append(bool(env.world.done()))
+    costsT = np.array([env.getAstarCosts(env.world.getPos(i), env.world.getGoal(i))
+                       for i in range(1, min(n, n_costs) + 1)], dtype=np.int32)
+    out = dict(family="PRIMAL", obst=obst.astype(np.uint8), starts=np.array(starts, dtype=np.int16),
+               goals=np.array(goals, dtype=np.int16), fov=np.int64(fov), actions=actions.astype(np.uint8),
+               obs0=obs0, vec0=vec0, avail0=avail0, costs0=costs0, costsT=costsT,
+               **{k: np.array(v) for k, v in rec.items()})
+    out["done"] = out["done"].astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "T=%d N=%d HxW=%dx%d F=%d moved_frac=%.2f collisions=%d" % (
+        T, n, obst.shape[0], obst.shape[1], fov, float(np.mean(out["status"] >= 0)),
+        int(np.sum(out["status"] == -3))))
+
+
+def rand_primal_case(seed, h, w, density, n):
+    rs = np.random.RandomState(seed)
+    obst = rs.rand(h, w) < density
+    fc = free_cells(obst)
+    idx = rs.permutation(len(fc))
+    starts = [fc[i] for i in idx[:n]]
+    idg = rs.permutation(len(fc))
+    goals = [fc[i] for i in idg[:n]]
+    return rs, obst, starts, goals
+
+
+def gen_primal():
+    # KAT B.2
+    obst = np.zeros((7, 7), bool)
+    obst[3, 3] = True
+    run_primal("primal_kat_b2", obst, [(1, 1), (1, 2), (5, 5)], [(1, 3), (1, 1), (5, 5)], 5,
+               np.array([[1, 3, 0], [2, 3, 1], [0, 1, 4]]))
+    rs, obst, s, g = rand_primal_case(1000, 20, 20, 0.2, 8)        # c2 shape
+    run_primal("primal_c2", obst, s, g, 11, rs.randint(0, 5, [60, 8]))
+    rs, obst, s, g = rand_primal_case(2000, 32, 32, 0.3, 32)       # c3 shape
+    run_primal("primal_c3", obst, s, g, 11, rs.randint(0, 5, [24, 32]))
+    rs, obst, s, g = rand_primal_case(3000, 7, 7, 0.1, 12)         # crowded: many robot collisions
+    run_primal("primal_crowd", obst, s, g, 5, rs.randint(0, 5, [60, 12]))
+    rs, obst, s, g = rand_primal_case(4000, 12, 12, 0.15, 5)       # even FOV (the ctor default is 10)
+    run_primal("primal_f10", obst, s, g, 10, rs.randint(0, 5, [30, 5]))
+    rs, obst, s, g = rand_primal_case(5000, 9, 9, 0.1, 6)          # tiny FOV
+    run_primal("primal_f3", obst, s, g, 3, rs.randint(0, 5, [30, 6]))
+    rs, obst, s, g = rand_primal_case(6000, 10, 14, 0.2, 6)        # rectangular world
+    run_primal("primal_rect", obst, s, g, 7, rs.randint(0, 5, [30, 6]))
+    rs, obst, s, g = rand_primal_case(7000, 40, 40, 0.25, 7)       # N not a multiple of 4, W > 32
+    run_primal("primal_n7w40", obst, s, g, 11, rs.randint(0, 5, [20, 7]))
+
+
+# --------------------------------------------------------------------------- PARTIAL distance maps
+def run_pdist(name, map_file, scen_prefix, n, seed):
+    random.seed(seed)
+    mp = os.path.join(REF_SRC, "mapf_baseline", "mapf-map", map_file)
+    sp = os.path.join(REF_SRC, "mapf_baseline", "scen-random", scen_prefix)
+    env = PARTIAL.MARL_PARTIAL_ENV(mp, sp, n_agents=n, obs_window=5, obs_knn_agents=min(5, n), render="none")
+    grid = env._original_grid
+    H, W = len(grid), len(grid[0])
+    obst = np.array([[c != "." for c in row] for row in grid])
+    dist = np.full((n, H, W), -1, np.int32)
+    for a in range(n):
+        for num, d in env._goal_dist[a].items():
+            dist[a, num // W, num % W] = d
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), family="PDIST", obst=obst.astype(np.uint8),
+                        goals=np.array(env._agent_goal_pos, dtype=np.int16),
+                        starts=np.array(env._agent_init_pos, dtype=np.int16), dist=dist)
+    print("wrote", name, "N=%d HxW=%dx%d maxdist=%d" % (n, H, W, dist.max()))
+
+
+def gen_pdist():
+    run_pdist("pdist_empty8", "empty-8-8.map", "empty-8-8-random-", 10, 21)
+    run_pdist("pdist_rand32", "random-32-32-20.map", "random-32-32-20-random-", 4, 22)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["grid", "primal", "pdist"]
+    if "grid" in which:
+        gen_grid()
+    if "primal" in which:
+        gen_primal()
+    if "pdist" in which:
+        gen_pdist()

@@ -1,0 +1,110 @@
+"""Load the UNMODIFIED reference env classes from /root/reference for fixture generation.
+
+Only usable in the build container (the GPU box has no /root/reference). Nothing in
+tests/, bench.py or smoke() imports this module at run time; it exists so that the
+committed fixtures under tests/golden/ can be regenerated and audited.
+
+The reference imports a few packages that are absent here (gym, smac, matplotlib,
+od_mstar3). They are replaced by the thinnest possible stand-ins:
+  gym.Env = object, gym.spaces.{Discrete,Tuple}  -- only used to declare action_space
+  smac.env.multiagentenv.MultiAgentEnv           -- the reference's OWN
+        MARL-curve-main/src/envs/multiagentenv.py class
+  matplotlib.colors.hsv_to_rgb                   -- render-only
+  od_mstar3.cpp_mstar.find_path                  -- always raises NoSolutionError, which
+        makes MAPFEnv.get_blocking_reward() return 0 * BLOCKING_COST: the blocking
+        reward (un-vendored third-party arithmetic) is fenced off.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REF = os.environ.get("MAPF_REFERENCE_ROOT", "/root/reference")
+REF_SRC = os.path.join(REF, "MARL-curve-main", "src")
+
+
+def _install_stubs():
+    if "gym" not in sys.modules:
+        gym = types.ModuleType("gym")
+        gym.Env = object
+        spaces = types.ModuleType("gym.spaces")
+
+        class Discrete:
+            def __init__(self, n):
+                self.n = n
+
+        class Tuple(tuple):
+            def __new__(cls, items):
+                return super().__new__(cls, items)
+
+        spaces.Discrete = Discrete
+        spaces.Tuple = Tuple
+        gym.spaces = spaces
+        sys.modules["gym"] = gym
+        sys.modules["gym.spaces"] = spaces
+    if "smac" not in sys.modules:
+        spec = importlib.util.spec_from_file_location(
+            "_ref_multiagentenv", os.path.join(REF_SRC, "envs", "multiagentenv.py"))
+        mae = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mae)
+        smac = types.ModuleType("smac")
+        smac_env = types.ModuleType("smac.env")
+        smac_mae = types.ModuleType("smac.env.multiagentenv")
+        smac_mae.MultiAgentEnv = mae.MultiAgentEnv
+        smac.env = smac_env
+        smac_env.multiagentenv = smac_mae
+        sys.modules["smac"] = smac
+        sys.modules["smac.env"] = smac_env
+        sys.modules["smac.env.multiagentenv"] = smac_mae
+    try:
+        import matplotlib.colors  # noqa: F401
+    except Exception:
+        mpl = types.ModuleType("matplotlib")
+        colors = types.ModuleType("matplotlib.colors")
+        colors.hsv_to_rgb = lambda x: x
+        mpl.colors = colors
+        sys.modules["matplotlib"] = mpl
+        sys.modules["matplotlib.colors"] = colors
+    if "od_mstar3" not in sys.modules:
+        od = types.ModuleType("od_mstar3")
+        cpp = types.ModuleType("od_mstar3.cpp_mstar")
+        csa = types.ModuleType("od_mstar3.col_set_addition")
+
+        class NoSolutionError(Exception):
+            pass
+
+        class OutOfTimeError(Exception):
+            pass
+
+        def find_path(world, starts, goals, inflation, time_limit):
+            raise NoSolutionError()
+
+        csa.NoSolutionError = NoSolutionError
+        csa.OutOfTimeError = OutOfTimeError
+        cpp.find_path = find_path
+        od.cpp_mstar = cpp
+        od.col_set_addition = csa
+        sys.modules["od_mstar3"] = od
+        sys.modules["od_mstar3.cpp_mstar"] = cpp
+        sys.modules["od_mstar3.col_set_addition"] = csa
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)  # for `utils.draw`
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_reference():
+    """Returns (mapf_gridworld, mapf_primal, marl_partial) reference modules."""
+    if not os.path.isdir(REF):
+        raise RuntimeError("reference tree not present at %s" % REF)
+    _install_stubs()
+    grid = _load("_ref_mapf_gridworld", os.path.join(REF, "mapf_gridworld.py"))
+    primal = _load("_ref_mapf_primal", os.path.join(REF, "mapf_primal.py"))
+    partial = _load("_ref_marl_partial", os.path.join(REF_SRC, "envs", "marl_partial.py"))
+    return grid, primal, partial
