@@ -1,0 +1,245 @@
+/*
+ * mapf_b200.h -- C ABI of libmapf_b200.so: the batched MAPF grid-world step/observation
+ * engine for NVIDIA B200 (sm_100a).
+ *
+ * The reference (DongmingShen/MAPF-MARL) has NO foreign-function interface for this path:
+ * its environments are pure-Python classes.  Each entry point below therefore cites the
+ * reference *method* it replaces (paths relative to the reference root; GRID =
+ * mapf_gridworld.py, PRIMAL = mapf_primal.py, PARTIAL = MARL-curve-main/src/envs/marl_partial.py).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ / torch types, no exceptions.
+ *   - Every function returns 0 (MAPF_OK) or a negative mapf_status; the message is
+ *     available from mapf_last_error().
+ *   - Pointers named *_dev are DEVICE pointers owned by the caller (e.g. torch tensors),
+ *     pointers named *_host are HOST pointers.  The handle owns the environment state
+ *     (positions, goals, done flags, bitmaps, distance maps) in device memory.
+ *   - Calls are stream-ordered on `stream` (a cudaStream_t passed as void*, NULL = the
+ *     legacy default stream) and never synchronise, except the *_host entry points and
+ *     mapf_error_flags / mapf_stats which return host data and therefore wait for the stream.
+ *   - Not thread-safe per handle; one handle per (process, device); the caller has made
+ *     the device current (cudaSetDevice / torch.cuda.set_device) before mapf_create.
+ *   - Arrays are row-major and dense.  E = n_envs, N = n_agents, H = height, W = width,
+ *     F = fov.  A position is (p0, p1): p0 indexes the FIRST axis of the map, exactly as
+ *     `_full_obs[pos[0]][pos[1]]` (GRID:299) and `state[x, y]` (PRIMAL:117) do.
+ */
+#ifndef MAPF_B200_H
+#define MAPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAPF_ABI_VERSION 1
+
+typedef enum mapf_status {
+  MAPF_OK = 0,
+  MAPF_ERR_INVALID_ARG = -1,
+  MAPF_ERR_CUDA = -2,
+  MAPF_ERR_UNSUPPORTED = -3,
+  MAPF_ERR_ALLOC = -4
+} mapf_status;
+
+/* Collision / reward semantics (SURVEY.md section 8 preamble). */
+typedef enum mapf_mode {
+  /* mode A "detect": MAPF_GRID.step, GRID:85-141.  Actions {0:(-1,0) 1:(+1,0) 2:(0,-1)
+   * 3:(0,+1) 4:stay} (GRID:319-342); agents may overlap; node/edge collisions are
+   * counted and penalised, never resolved (GRID:344-383). */
+  MAPF_MODE_GRID = 0,
+  /* mode B "sequential claim": State.moveAgent swept over ids 1..N, PRIMAL:103-135 and
+   * MAPFEnv._step, PRIMAL:549-637.  Actions {0:stay 1:(0,+1) 2:(+1,0) 3:(0,-1) 4:(-1,0)}
+   * (dirDict, PRIMAL:28). */
+  MAPF_MODE_PRIMAL = 1
+} mapf_mode;
+
+typedef enum mapf_obs_mode {
+  MAPF_OBS_FULLMAP = 0,   /* GRID get_obs/get_state, GRID:143-196: int8[E, H*W], -1 wall else agent count */
+  MAPF_OBS_PRIMAL_FOV = 1 /* PRIMAL _observe, PRIMAL:343-386: [E, N, 4, F, F] + double[E, N, 3] */
+} mapf_obs_mode;
+
+typedef enum mapf_dtype {
+  MAPF_U8 = 0,
+  MAPF_I64 = 1,
+  MAPF_F32 = 2,
+  MAPF_I8 = 3
+} mapf_dtype;
+
+/* Device-side error flag bits (mapf_error_flags). */
+#define MAPF_FLAG_BAD_ACTION 1u   /* action outside {0..4}: GRID:92 / PRIMAL:556 assert */
+#define MAPF_FLAG_BAD_POSITION 2u /* start/goal out of bounds at reset */
+#define MAPF_FLAG_START_ON_WALL 4u
+#define MAPF_FLAG_START_OVERLAP 8u /* PRIMAL only: two agents on one cell (State.scanForAgents, PRIMAL:53-66) */
+
+/* Indices into the int64[MAPF_N_STATS] vector returned by mapf_stats. */
+enum {
+  MAPF_STAT_ENV_STEPS = 0,    /* environment steps executed */
+  MAPF_STAT_AGENT_STEPS = 1,  /* agent-steps executed (= env steps * N, or swept agents) */
+  MAPF_STAT_ENV_COLLISIONS = 2,   /* GRID: wall/border bumps (GRID:105-107); PRIMAL: status -1/-2 */
+  MAPF_STAT_NODE_COLLISIONS = 3,  /* GRID: sum of node flags (GRID:344-362); PRIMAL: status -3 */
+  MAPF_STAT_EDGE_COLLISIONS = 4,  /* GRID: sum of edge counts (GRID:364-383) */
+  MAPF_STAT_GOAL_ARRIVALS = 5,    /* agents that newly reached their goal */
+  MAPF_STAT_EPISODES_DONE = 6,    /* env steps that ended with terminated == 1 */
+  MAPF_STAT_RESERVED = 7,
+  MAPF_N_STATS = 8
+};
+
+/* Constructor arguments.  Mirrors the keyword arguments of MAPF_GRID.__init__ (GRID:21-32)
+ * and MAPFEnv.__init__ (PRIMAL:175-176) plus the batch dimensions. */
+typedef struct mapf_cfg {
+  int32_t abi_version;   /* MAPF_ABI_VERSION */
+  int32_t n_envs;        /* E >= 1 */
+  int32_t n_agents;      /* N in [1, 255] */
+  int32_t height;        /* H in [1, 255] */
+  int32_t width;         /* W in [1, 255] */
+  int32_t mode;          /* mapf_mode */
+  int32_t obs_mode;      /* mapf_obs_mode */
+  int32_t fov;           /* F = observation_size (PRIMAL:188); ignored for MAPF_OBS_FULLMAP */
+  int32_t shared_map;    /* 1: one map [H, W] shared by all envs; 0: int8[E, H, W] */
+  int32_t episode_limit; /* GRID:26, 116 */
+  int32_t goal_dist;     /* 1: keep int16[E, N, H, W] BFS distance maps in the handle */
+  int32_t collect_stats; /* 1: accumulate the mapf_stats counters */
+  double step_reward;    /* GRID:29 */
+  double collide_reward; /* GRID:30 */
+  /* PRIMAL reward table, PRIMAL:25 (ACTION_COST, IDLE_COST, GOAL_REWARD, COLLISION_REWARD) */
+  double action_cost;
+  double idle_cost;
+  double goal_reward;
+  double collision_reward;
+  /* mag_lut_host[s] = |(dx,dy)| for s = dx*dx + dy*dy, s in [0, mag_lut_len).  Built by the
+   * host with the reference's own expression so that the goal vector is bit-identical:
+   * `(dx**2 + dy**2) ** .5` (PRIMAL:382).  Must cover s <= (H-1)^2 + (W-1)^2. */
+  const double* mag_lut_host;
+  int32_t mag_lut_len;
+  int32_t reserved;
+} mapf_cfg;
+
+/* Outputs of one step.  Every pointer is a device pointer and may be NULL (not written). */
+typedef struct mapf_step_out {
+  /* [E] team reward.  GRID: `sum(rewards)` folded left to right (GRID:141).
+   * PRIMAL: the same fold over the per-agent rewards (convenience, no reference counterpart). */
+  double* reward_dev;
+  /* [E].  GRID: episode_done(), GRID:267.  PRIMAL: world.done() after the sweep, PRIMAL:159-165. */
+  uint8_t* terminated_dev;
+  /* [E, N] per-agent reward.  GRID: `rewards[i]` before the sum (GRID:94-130).  PRIMAL: `reward`
+   * returned by _step (PRIMAL:579-597), blocking reward excluded. */
+  double* agent_reward_dev;
+  /* [E, N].  GRID: `_agent_dones` after the step (GRID:112-117).  PRIMAL: `on_goal` (PRIMAL:633). */
+  uint8_t* dones_dev;
+  /* [E, N].  PRIMAL: moveAgent status {2,1,0,-1,-2,-3} (PRIMAL:138-144).  GRID: env-collision flag. */
+  int8_t* status_dev;
+  /* [E, N] GRID `_node_collision_agents` (GRID:344-362); PRIMAL: 0. */
+  int16_t* node_dev;
+  /* [E, N] GRID `_edge_collision_agents` (GRID:364-383); PRIMAL: 0. */
+  int16_t* edge_dev;
+  /* [E, N] PRIMAL `valid_action` (PRIMAL:571); GRID: 1. */
+  uint8_t* valid_dev;
+  /* [E, N] PRIMAL `done` as returned by the i-th _step call of the sweep (mid-sweep, PRIMAL:626). */
+  uint8_t* done_mid_dev;
+  /* [E, N, 5] PRIMAL `nextActions` as returned by the i-th _step call (mid-sweep, PRIMAL:630). */
+  uint8_t* next_mid_dev;
+  /* [E, N, 5] available-action mask after the step.  GRID: get_avail_actions (GRID:198-224).
+   * PRIMAL: _listNextValidActions(i, action_i) evaluated after the whole sweep (PRIMAL:639-667). */
+  uint8_t* avail_dev;
+} mapf_step_out;
+
+/* Host-buffer mirror of the outputs used by mapf_step_observe_host (pinned memory recommended). */
+typedef struct mapf_host_io {
+  const uint8_t* actions_host; /* [E, N] */
+  double* reward_host;         /* [E] or NULL */
+  uint8_t* terminated_host;    /* [E] or NULL */
+  uint8_t* dones_host;         /* [E, N] or NULL */
+  uint8_t* avail_host;         /* [E, N, 5] or NULL */
+  void* obs_host;              /* obs in obs_dtype or NULL */
+  double* vec_host;            /* [E, N, 3] or NULL */
+  int32_t obs_dtype;           /* mapf_dtype */
+  int32_t reserved;
+} mapf_host_io;
+
+typedef struct mapf_handle mapf_handle;
+
+/* Error text of the last failing call on `h` (h == NULL: last failing mapf_create of this thread). */
+const char* mapf_last_error(const mapf_handle* h);
+
+/* Fills *cfg with the reference's defaults (GRID:25-31, PRIMAL:25, 175-176). */
+void mapf_default_cfg(mapf_cfg* cfg);
+
+/* Replaces MAPF_GRID.__init__ (GRID:21-68) / MAPFEnv.__init__ + State.__init__ (PRIMAL:175-203, 44-51):
+ * allocates the device-resident state for E environments.  No map is loaded yet. */
+int mapf_create(const mapf_cfg* cfg, mapf_handle** out);
+int mapf_destroy(mapf_handle* h);
+
+/* Replaces MAPF_GRID.reset (GRID:70-83) / MAPFEnv._reset + _setWorld with world0/goals0
+ * (PRIMAL:389-402, 278-309).
+ *   map_dev    int8 [E,H,W] (or [H,W] when shared_map): non-zero = obstacle.  NULL keeps the maps.
+ *   starts_dev int16[E,N,2], goals_dev int16[E,N,2].  NULL keeps the stored starts / goals
+ *              (GRID re-uses the positions sampled in __init__, GRID:79).
+ *   env_mask_dev uint8[E] or NULL: only environments with a non-zero mask are reset. */
+int mapf_reset(mapf_handle* h, const int8_t* map_dev, const int16_t* starts_dev, const int16_t* goals_dev,
+               const uint8_t* env_mask_dev, void* stream);
+
+/* Replaces the goal re-assignment of the lifelong variant (MAPF-490-main/Global.cpp:85-94 informs the
+ * rule): overwrite the goals of agents whose dirty flag is set.  goals_dev int16[E,N,2], dirty_dev uint8[E,N]. */
+int mapf_set_goals(mapf_handle* h, const int16_t* goals_dev, const uint8_t* dirty_dev, void* stream);
+
+/* Replaces MAPF_GRID.step (GRID:85-141) or one full sweep `for id in 1..N: MAPFEnv._step((id, a[id]))`
+ * (PRIMAL:549-637).  actions_dev: [E,N] of act_dtype (MAPF_U8 or MAPF_I64). */
+int mapf_step(mapf_handle* h, const void* actions_dev, int act_dtype, const mapf_step_out* out, void* stream);
+
+/* PRIMAL only: sweep agents agent_lo <= i < agent_hi (0-based).  [i, i+1) is exactly one
+ * MAPFEnv._step((i+1, a)) call (PRIMAL:549). */
+int mapf_step_agents(mapf_handle* h, const void* actions_dev, int act_dtype, int agent_lo, int agent_hi,
+                     const mapf_step_out* out, void* stream);
+
+/* Replaces get_obs/get_state (GRID:143-196) or `_observe(id)` for every id (PRIMAL:343-386).
+ *   MAPF_OBS_FULLMAP:    obs_dev int8[E, H*W] (MAPF_I8); vec_dev ignored.
+ *   MAPF_OBS_PRIMAL_FOV: obs_dev [E,N,4,F,F] of obs_dtype (MAPF_U8 or MAPF_F32), channel order
+ *                        [poss_map, goal_map, goals_map, obs_map] (PRIMAL:386);
+ *                        vec_dev double[E,N,3] = [dx/mag, dy/mag, mag] or NULL. */
+int mapf_observe(mapf_handle* h, void* obs_dev, int obs_dtype, double* vec_dev, void* stream);
+
+/* mapf_step followed by mapf_observe in ONE kernel launch (state is staged in shared memory once). */
+int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, const mapf_step_out* out,
+                      void* obs_dev, int obs_dtype, double* vec_dev, void* stream);
+
+/* Host-buffer form of mapf_step_observe: copies io->actions_host to the device, runs the fused
+ * kernel, copies the requested outputs back and waits for them.  This is the call the e2e
+ * benchmark times. */
+int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream);
+
+/* Replaces get_avail_actions (GRID:198-224) / _listNextValidActions(id, prev_action) (PRIMAL:639-667)
+ * for the current state.  avail_dev uint8[E,N,5]. */
+int mapf_avail(mapf_handle* h, uint8_t* avail_dev, void* stream);
+
+/* Replaces MARL_PARTIAL_ENV.__setup_agent_goal_dist (PARTIAL:931-955) and MAPFEnv.getAstarCosts
+ * (PRIMAL:407-499): 4-connected hop distance from every cell to each agent's goal.
+ *   dirty_dev uint8[E,N] or NULL (all).  dist_dev int16[E,N,H,W] or NULL (= the handle's own maps,
+ *   requires cfg.goal_dist).  Walls = -1, unreachable free cells = -2.
+ *   primal_costs != 0 reproduces getAstarCosts' quirk: unreachable cells keep `state` (0 or the id
+ *   of the agent standing there, PRIMAL:496-498). */
+int mapf_bfs(mapf_handle* h, const uint8_t* dirty_dev, int16_t* dist_dev, int primal_costs, void* stream);
+
+/* State read-back (getPositions/getGoals, PRIMAL:236-246; agent_positions, GRID:61). int16[E,N,2]. */
+int mapf_get_positions(mapf_handle* h, int16_t* pos_dev, void* stream);
+int mapf_get_goals(mapf_handle* h, int16_t* goals_dev, void* stream);
+/* uint8[E,N] `_agent_dones` (GRID) / on_goal (PRIMAL); int32[E] `_step_count` (GRID:93). */
+int mapf_get_dones(mapf_handle* h, uint8_t* dones_dev, void* stream);
+int mapf_get_step_count(mapf_handle* h, int32_t* step_count_dev, void* stream);
+
+/* Copies the int64[MAPF_N_STATS] counters to stats_host (waits for the stream). */
+int mapf_stats(mapf_handle* h, int64_t* stats_host, void* stream);
+/* Reads and clears the device error-flag word (waits for the stream). */
+int mapf_error_flags(mapf_handle* h, uint32_t* flags_host, void* stream);
+
+/* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
+int64_t mapf_launch_count(const mapf_handle* h);
+/* Library identification: ABI version and the -gencode it was built for ("sm_100a"). */
+int mapf_abi_version(void);
+const char* mapf_build_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPF_B200_H */

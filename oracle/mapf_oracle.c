@@ -1,0 +1,541 @@
+/*
+ * mapf_oracle.c -- CPU restatement of the reference's step/observation path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (mapf_marl_b200/) never calls into this file and has no CPU fallback.
+ *
+ * Parity status: PINNED.  Every function below is checked bit-for-bit against traces
+ * recorded from the live, unmodified reference classes (the .npz files under tests/golden/, produced by
+ * tests/golden/gen_golden.py) in tests/test_oracle_golden.py.
+ *
+ * The reference is pure Python (no compilable sources), so this file restates its
+ * algorithms in plain C, one environment at a time, parallelised over environments with
+ * OpenMP exactly like the reference's ParallelRunner runs one env per worker process
+ * (MARL-curve-main/src/runners/parallel_runner.py:23-31).  Citations: GRID =
+ * mapf_gridworld.py, PRIMAL = mapf_primal.py, PARTIAL = MARL-curve-main/src/envs/marl_partial.py.
+ *
+ * Floating point: compiled with -ffp-contract=off so `r += c * k` is a rounded multiply
+ * followed by a rounded add, as in CPython.  The goal-vector magnitude uses libm pow(s, .5),
+ * the same call CPython makes for `(dx**2 + dy**2) ** .5` (PRIMAL:382).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct oracle_env {
+  int E, N, H, W, F;
+  int shared_map;
+  int episode_limit;
+  double step_reward, collide_reward;                              /* GRID:29-30 */
+  int sum_mode;          /* 0: left fold (CPython <= 3.11 sum); 1: CPython >= 3.12 sum (Neumaier) */
+  int step_is_int;       /* the step_reward kwarg was a Python int */
+  int collide_is_int;    /* the collide_reward kwarg was a Python int (the GRID default -10 is) */
+  double action_cost, idle_cost, goal_reward, collision_reward;    /* PRIMAL:25 */
+  int8_t* map;       /* [Emap,H,W] non-zero = obstacle */
+  int16_t* state;    /* [E,H,W] GRID: _full_obs (-1 wall, else agent count) GRID:57,132-135
+                               PRIMAL: State.state (-1 wall, 0 free, id) PRIMAL:32-47 */
+  int16_t* goals;    /* [E,H,W] PRIMAL State.goals (id at goal cell) */
+  int16_t* pos;      /* [E,N,2] */
+  int16_t* goal;     /* [E,N,2] */
+  int16_t* start;    /* [E,N,2] */
+  uint8_t* done;     /* [E,N]  GRID _agent_dones */
+  int32_t* step_count; /* [E] */
+  int threads;
+} oracle_env;
+
+static const int8_t* env_map(const oracle_env* o, int e) {
+  return o->map + (size_t)(o->shared_map ? 0 : e) * o->H * o->W;
+}
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+oracle_env* oracle_create(int E, int N, int H, int W, int F, int shared_map, int episode_limit,
+                          double step_reward, double collide_reward, double action_cost, double idle_cost,
+                          double goal_reward, double collision_reward, int threads, int sum_mode,
+                          int step_is_int, int collide_is_int) {
+  oracle_env* o = (oracle_env*)calloc(1, sizeof(oracle_env));
+  o->E = E; o->N = N; o->H = H; o->W = W; o->F = F;
+  o->shared_map = shared_map;
+  o->episode_limit = episode_limit;
+  o->step_reward = step_reward; o->collide_reward = collide_reward;
+  o->action_cost = action_cost; o->idle_cost = idle_cost;
+  o->goal_reward = goal_reward; o->collision_reward = collision_reward;
+  o->sum_mode = sum_mode; o->step_is_int = step_is_int; o->collide_is_int = collide_is_int;
+  size_t cells = (size_t)H * W;
+  o->map = (int8_t*)calloc((shared_map ? 1 : (size_t)E) * cells, 1);
+  o->state = (int16_t*)calloc((size_t)E * cells, sizeof(int16_t));
+  o->goals = (int16_t*)calloc((size_t)E * cells, sizeof(int16_t));
+  o->pos = (int16_t*)calloc((size_t)E * N * 2, sizeof(int16_t));
+  o->goal = (int16_t*)calloc((size_t)E * N * 2, sizeof(int16_t));
+  o->start = (int16_t*)calloc((size_t)E * N * 2, sizeof(int16_t));
+  o->done = (uint8_t*)calloc((size_t)E * N, 1);
+  o->step_count = (int32_t*)calloc((size_t)E, sizeof(int32_t));
+  o->threads = threads > 0 ? threads : oracle_max_threads();
+  return o;
+}
+
+void oracle_destroy(oracle_env* o) {
+  if (!o) return;
+  free(o->map); free(o->state); free(o->goals); free(o->pos); free(o->goal); free(o->start);
+  free(o->done); free(o->step_count); free(o);
+}
+
+void oracle_get_positions(const oracle_env* o, int16_t* out) { memcpy(out, o->pos, (size_t)o->E * o->N * 4); }
+void oracle_get_dones(const oracle_env* o, uint8_t* out) { memcpy(out, o->done, (size_t)o->E * o->N); }
+void oracle_get_step_count(const oracle_env* o, int32_t* out) { memcpy(out, o->step_count, (size_t)o->E * 4); }
+
+/* ------------------------------------------------------------------------------------------
+ * GRID   (mapf_gridworld.py)
+ * ---------------------------------------------------------------------------------------- */
+
+/* __create_grid + __init_full_obs + __update_agent_view, GRID:282-299: grid = -1 on obstacles,
+ * else the number of agents standing on the cell. */
+static void grid_rebuild_full_obs(oracle_env* o, int e) {
+  const int8_t* m = env_map(o, e);
+  int16_t* st = o->state + (size_t)e * o->H * o->W;
+  for (int c = 0; c < o->H * o->W; ++c) st[c] = m[c] ? -1 : 0;
+  const int16_t* p = o->pos + (size_t)e * o->N * 2;
+  for (int i = 0; i < o->N; ++i) st[p[2 * i] * o->W + p[2 * i + 1]] += 1;
+}
+
+/* reset, GRID:70-83 (positions restored from _agent_init_pos; counters zeroed). */
+void oracle_grid_reset(oracle_env* o, const int8_t* map, const int16_t* starts, const int16_t* goals) {
+  size_t cells = (size_t)o->H * o->W;
+  if (map) memcpy(o->map, map, (o->shared_map ? 1 : (size_t)o->E) * cells);
+  if (starts) memcpy(o->start, starts, (size_t)o->E * o->N * 4);
+  if (goals) memcpy(o->goal, goals, (size_t)o->E * o->N * 4);
+  memcpy(o->pos, o->start, (size_t)o->E * o->N * 4);
+  memset(o->done, 0, (size_t)o->E * o->N);
+  memset(o->step_count, 0, (size_t)o->E * 4);
+#pragma omp parallel for schedule(static) num_threads(o->threads)
+  for (int e = 0; e < o->E; ++e) grid_rebuild_full_obs(o, e);
+}
+
+/* __is_valid GRID:270 and __is_cell_obstacle GRID:278 (obstacle == grid value -1). */
+static int grid_free(const oracle_env* o, const int8_t* m, int p0, int p1) {
+  if (!(0 <= p0 && p0 < o->H && 0 <= p1 && p1 < o->W)) return 0;
+  return m[p0 * o->W + p1] == 0;
+}
+
+/* get_avail_agent_actions, GRID:203-224. */
+static void grid_avail_agent(const oracle_env* o, const int8_t* m, int p0, int p1, uint8_t* out5) {
+  out5[0] = (uint8_t)grid_free(o, m, p0 - 1, p1);
+  out5[1] = (uint8_t)grid_free(o, m, p0 + 1, p1);
+  out5[2] = (uint8_t)grid_free(o, m, p0, p1 - 1);
+  out5[3] = (uint8_t)grid_free(o, m, p0, p1 + 1);
+  out5[4] = 1;
+}
+
+void oracle_grid_avail(const oracle_env* o, uint8_t* avail) {
+#pragma omp parallel for schedule(static) num_threads(o->threads)
+  for (int e = 0; e < o->E; ++e) {
+    const int8_t* m = env_map(o, e);
+    for (int i = 0; i < o->N; ++i) {
+      const int16_t* p = o->pos + ((size_t)e * o->N + i) * 2;
+      grid_avail_agent(o, m, p[0], p[1], avail + ((size_t)e * o->N + i) * 5);
+    }
+  }
+}
+
+/* get_obs / get_state, GRID:143-196: the flattened _full_obs (every agent sees the same row). */
+void oracle_grid_state(const oracle_env* o, int8_t* out) {
+  size_t n = (size_t)o->E * o->H * o->W;
+  for (size_t k = 0; k < n; ++k) out[k] = (int8_t)o->state[k];
+}
+
+/* `sum(rewards)`, GRID:141, as the interpreter running the reference computes it.
+ *   sum_mode 0: plain left fold (builtin sum of CPython <= 3.11).
+ *   sum_mode 1: CPython >= 3.12 builtin sum (Python/bltinmodule.c): exact integer accumulation while the
+ *     items are ints; at the first float the partial sum becomes float(i) + x; afterwards floats are
+ *     added with Neumaier compensation, ints with a plain add; the compensation is folded in at the end.
+ * is_int[i] tells whether rewards[i] is a Python int (no float constant was ever added to it). */
+static double py_sum(const double* x, const uint8_t* is_int, int n, int sum_mode) {
+  if (sum_mode == 0) {
+    double total = 0.0;
+    for (int i = 0; i < n; ++i) total += x[i];
+    return total;
+  }
+  double acc = 0.0, c = 0.0;
+  int in_float = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!in_float) {
+      acc = acc + x[i];                 /* exact while ints; the first float item: float(i_result) + x */
+      if (!is_int[i]) { in_float = 1; c = 0.0; }
+    } else if (is_int[i]) {
+      acc += x[i];
+    } else {
+      double t = acc + x[i];
+      if (fabs(acc) >= fabs(x[i])) c += (acc - t) + x[i];
+      else c += (x[i] - t) + acc;
+      acc = t;
+    }
+  }
+  if (in_float && c != 0.0 && isfinite(c)) acc += c;
+  return acc;
+}
+
+/* step, GRID:85-141 for one environment. Returns the number of invalid actions seen. */
+static int grid_step_env(oracle_env* o, int e, const uint8_t* act, double* reward, uint8_t* terminated,
+                         double* agent_reward, int8_t* envflag, int16_t* node_out, int16_t* edge_out,
+                         uint8_t* avail, int16_t* scratch /* [2N + H*W] */) {
+  const int N = o->N, W = o->W;
+  const int8_t* m = env_map(o, e);
+  int16_t* pos = o->pos + (size_t)e * N * 2;
+  const int16_t* goal = o->goal + (size_t)e * N * 2;
+  uint8_t* done = o->done + (size_t)e * N;
+  int16_t* newp = scratch;            /* new_agent_position, GRID:95 */
+  int16_t* cnt = scratch + 2 * N;     /* agent_at_grid, GRID:348 */
+  double rew_local[256];
+  uint8_t rew_is_int[256];
+  int bad = 0;
+  o->step_count[e] += 1;                                            /* GRID:93 */
+  for (int i = 0; i < N; ++i) {                                     /* GRID:99-118 */
+    int n0 = pos[2 * i], n1 = pos[2 * i + 1];
+    double r = 0.0;
+    int flag = 0;
+    rew_is_int[i] = (uint8_t)(done[i] ? o->collide_is_int : (o->collide_is_int && o->step_is_int));
+    if (!done[i]) {
+      int a = act[i];
+      int t0 = n0, t1 = n1;                                         /* __agent_step, GRID:319-342 */
+      if (a == 0) t0 -= 1; else if (a == 1) t0 += 1; else if (a == 2) t1 -= 1; else if (a == 3) t1 += 1;
+      else if (a != 4) bad++;
+      if (a >= 0 && a <= 3) {
+        if (grid_free(o, m, t0, t1)) { n0 = t0; n1 = t1; } else flag = 1;
+      }
+      if (flag) r += o->collide_reward;                             /* GRID:105-106 */
+      r += o->step_reward;                                          /* GRID:110 */
+    }
+    newp[2 * i] = (int16_t)n0; newp[2 * i + 1] = (int16_t)n1;
+    if (n0 == goal[2 * i] && n1 == goal[2 * i + 1]) done[i] = 1;    /* GRID:112-113 */
+    if (o->step_count[e] >= o->episode_limit) done[i] = 1;          /* GRID:116-117 */
+    rew_local[i] = r;
+    if (envflag) envflag[i] = (int8_t)flag;
+  }
+  /* __count_node_collision, GRID:344-362 */
+  memset(cnt, 0, sizeof(int16_t) * (size_t)o->H * W);
+  for (int i = 0; i < N; ++i) cnt[newp[2 * i] * W + newp[2 * i + 1]] += 1;
+  /* __count_edge_collision, GRID:364-383 */
+  for (int i = 0; i < N; ++i) {
+    int node = cnt[newp[2 * i] * W + newp[2 * i + 1]] > 1 ? 1 : 0;
+    int edge = 0;
+    int io0 = pos[2 * i], io1 = pos[2 * i + 1], in0 = newp[2 * i], in1 = newp[2 * i + 1];
+    if (!(io0 == in0 && io1 == in1)) {
+      for (int j = 0; j < N; ++j) {
+        if (j == i) continue;
+        if (pos[2 * j] == in0 && pos[2 * j + 1] == in1) {           /* j_old == i_new */
+          int jn0 = newp[2 * j], jn1 = newp[2 * j + 1];
+          if (jn0 == io0 && jn1 == io1 && !(jn0 == in0 && jn1 == in1)) edge++;
+        }
+      }
+    }
+    rew_local[i] += o->collide_reward * node;                       /* GRID:128 */
+    rew_local[i] += o->collide_reward * edge;                       /* GRID:129 */
+    if (node_out) node_out[i] = (int16_t)node;
+    if (edge_out) edge_out[i] = (int16_t)edge;
+  }
+  /* GRID:132-135 */
+  for (int i = 0; i < 2 * N; ++i) pos[i] = newp[i];
+  grid_rebuild_full_obs(o, e);
+  double total = py_sum(rew_local, rew_is_int, N, o->sum_mode);     /* sum(rewards), GRID:141 */
+  int all_done = 1;
+  for (int i = 0; i < N; ++i) {
+    if (agent_reward) agent_reward[i] = rew_local[i];
+    all_done &= done[i];
+  }
+  if (reward) *reward = total;
+  if (terminated) *terminated = (uint8_t)all_done;                  /* episode_done, GRID:267 */
+  if (avail)                                                        /* GRID:140 */
+    for (int i = 0; i < N; ++i) grid_avail_agent(o, m, pos[2 * i], pos[2 * i + 1], avail + 5 * i);
+  return bad;
+}
+
+int oracle_grid_step(oracle_env* o, const uint8_t* actions, double* reward, uint8_t* terminated,
+                     double* agent_reward, int8_t* envflag, int16_t* node, int16_t* edge, uint8_t* avail) {
+  int bad = 0;
+  const int N = o->N;
+#pragma omp parallel num_threads(o->threads) reduction(+ : bad)
+  {
+    int16_t* scratch = (int16_t*)malloc(sizeof(int16_t) * (2 * (size_t)N + (size_t)o->H * o->W));
+#pragma omp for schedule(static)
+    for (int e = 0; e < o->E; ++e) {
+      size_t b = (size_t)e * N;
+      bad += grid_step_env(o, e, actions + b, reward ? reward + e : 0, terminated ? terminated + e : 0,
+                           agent_reward ? agent_reward + b : 0, envflag ? envflag + b : 0,
+                           node ? node + b : 0, edge ? edge + b : 0, avail ? avail + 5 * b : 0, scratch);
+    }
+    free(scratch);
+  }
+  return bad;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * PRIMAL   (mapf_primal.py)
+ * ---------------------------------------------------------------------------------------- */
+
+static const int PRIMAL_DIR[5][2] = {{0, 0}, {0, 1}, {1, 0}, {0, -1}, {-1, 0}}; /* dirDict, PRIMAL:28 */
+static const int PRIMAL_OPPOSITE[5] = {-1, 3, 4, 1, 2};                          /* opposite_actions, PRIMAL:26 */
+
+/* _setWorld with world0/goals0 + State.__init__/scanForAgents, PRIMAL:278-309, 44-66. */
+void oracle_primal_reset(oracle_env* o, const int8_t* map, const int16_t* starts, const int16_t* goals) {
+  size_t cells = (size_t)o->H * o->W;
+  if (map) memcpy(o->map, map, (o->shared_map ? 1 : (size_t)o->E) * cells);
+  if (starts) memcpy(o->start, starts, (size_t)o->E * o->N * 4);
+  if (goals) memcpy(o->goal, goals, (size_t)o->E * o->N * 4);
+  memcpy(o->pos, o->start, (size_t)o->E * o->N * 4);
+  memset(o->step_count, 0, (size_t)o->E * 4);
+#pragma omp parallel for schedule(static) num_threads(o->threads)
+  for (int e = 0; e < o->E; ++e) {
+    const int8_t* m = env_map(o, e);
+    int16_t* st = o->state + (size_t)e * cells;
+    int16_t* gg = o->goals + (size_t)e * cells;
+    for (size_t c = 0; c < cells; ++c) { st[c] = m[c] ? -1 : 0; gg[c] = 0; }
+    for (int i = 0; i < o->N; ++i) {
+      const int16_t* p = o->pos + ((size_t)e * o->N + i) * 2;
+      const int16_t* g = o->goal + ((size_t)e * o->N + i) * 2;
+      st[p[0] * o->W + p[1]] = (int16_t)(i + 1);
+      gg[g[0] * o->W + g[1]] = (int16_t)(i + 1);
+      o->done[(size_t)e * o->N + i] = (uint8_t)(p[0] == g[0] && p[1] == g[1]);
+    }
+  }
+}
+
+/* Overwrite goals of flagged agents (lifelong variant; not in PRIMAL itself). */
+void oracle_primal_set_goals(oracle_env* o, const int16_t* goals, const uint8_t* dirty) {
+  size_t cells = (size_t)o->H * o->W;
+  for (int e = 0; e < o->E; ++e) {
+    int16_t* gg = o->goals + (size_t)e * cells;
+    for (int i = 0; i < o->N; ++i) {
+      size_t k = (size_t)e * o->N + i;
+      if (dirty && !dirty[k]) continue;
+      int16_t* g = o->goal + k * 2;
+      if (gg[g[0] * o->W + g[1]] == i + 1) gg[g[0] * o->W + g[1]] = 0;
+      g[0] = goals[2 * k]; g[1] = goals[2 * k + 1];
+      gg[g[0] * o->W + g[1]] = (int16_t)(i + 1);
+    }
+  }
+}
+
+/* State.moveAgent, PRIMAL:103-135 (DIAGONAL_MOVEMENT off). */
+static int primal_move_agent(oracle_env* o, int e, int id, int action) {
+  const int W = o->W, H = o->H;
+  int16_t* st = o->state + (size_t)e * H * W;
+  const int16_t* gg = o->goals + (size_t)e * H * W;
+  int16_t* p = o->pos + ((size_t)e * o->N + (id - 1)) * 2;
+  int ax = p[0], ay = p[1];
+  int dx = PRIMAL_DIR[action][0], dy = PRIMAL_DIR[action][1];
+  if (dx == 0 && dy == 0) return gg[ax * W + ay] == id ? 1 : 0;
+  if (ax + dx >= H || ax + dx < 0 || ay + dy >= W || ay + dy < 0) return -1;
+  if (st[(ax + dx) * W + ay + dy] < 0) return -2;
+  if (st[(ax + dx) * W + ay + dy] > 0) return -3;
+  st[ax * W + ay] = 0;
+  st[(ax + dx) * W + ay + dy] = (int16_t)id;
+  p[0] = (int16_t)(ax + dx); p[1] = (int16_t)(ay + dy);
+  if (gg[(ax + dx) * W + ay + dy] == id) return 1;
+  if (gg[ax * W + ay] == id) return 2;
+  return 0;
+}
+
+/* State.done, PRIMAL:159-165. */
+static int primal_done(const oracle_env* o, int e) {
+  const int16_t* gg = o->goals + (size_t)e * o->H * o->W;
+  int complete = 0;
+  for (int i = 1; i <= o->N; ++i) {
+    const int16_t* p = o->pos + ((size_t)e * o->N + (i - 1)) * 2;
+    if (gg[p[0] * o->W + p[1]] == i) complete++;
+  }
+  return complete == o->N;
+}
+
+/* _listNextValidActions, PRIMAL:639-667, as a 5-entry mask. */
+static void primal_valid_actions(const oracle_env* o, int e, int id, int prev_action, uint8_t* out5) {
+  const int W = o->W, H = o->H;
+  const int16_t* st = o->state + (size_t)e * H * W;
+  const int16_t* p = o->pos + ((size_t)e * o->N + (id - 1)) * 2;
+  int ax = p[0], ay = p[1];
+  out5[0] = 1;
+  for (int a = 1; a < 5; ++a) {
+    int dx = PRIMAL_DIR[a][0], dy = PRIMAL_DIR[a][1];
+    out5[a] = 0;
+    if (ax + dx >= H || ax + dx < 0 || ay + dy >= W || ay + dy < 0) continue;
+    if (st[(ax + dx) * W + ay + dy] < 0) continue;
+    if (st[(ax + dx) * W + ay + dy] > 0) continue;
+    out5[a] = 1;
+  }
+  int opp = PRIMAL_OPPOSITE[prev_action];
+  if (opp >= 0) out5[opp] = 0;                                      /* PRIMAL:664-665 */
+}
+
+/* One sweep `for id in lo+1..hi: _step((id, a))`, PRIMAL:549-637 without the observation
+ * (observe_all is separate) and with the blocking reward fenced off (returns 0, see refload.py). */
+int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, int8_t* status_out,
+                        double* agent_reward, uint8_t* on_goal_out, uint8_t* valid_out, uint8_t* done_mid,
+                        uint8_t* next_mid, uint8_t* avail, uint8_t* terminated, double* reward) {
+  int bad = 0;
+  const int N = o->N;
+#pragma omp parallel for schedule(static) num_threads(o->threads) reduction(+ : bad)
+  for (int e = 0; e < o->E; ++e) {
+    double total = 0.0;
+    if (lo == 0) o->step_count[e] += 1;
+    for (int i = lo; i < hi; ++i) {
+      size_t k = (size_t)e * N + i;
+      int id = i + 1;
+      int action = actions[k];
+      if (action > 4) { bad++; action = 0; }
+      int status = primal_move_agent(o, e, id, action);            /* world.act, PRIMAL:570 */
+      double r;
+      if (action == 0) {                                            /* PRIMAL:579-587 */
+        if (status == 1) r = o->goal_reward + 0.0 * -1.0;          /* GOAL_REWARD + num_blocking(=0) * BLOCKING_COST */
+        else r = o->idle_cost;
+      } else {                                                      /* PRIMAL:588-596 */
+        if (status == 1) r = o->goal_reward;
+        else if (status < 0) r = o->collision_reward;
+        else r = o->action_cost;
+      }
+      total += r;
+      const int16_t* p = o->pos + k * 2;
+      const int16_t* g = o->goal + k * 2;
+      int on_goal = (p[0] == g[0] && p[1] == g[1]);                 /* PRIMAL:633 */
+      o->done[k] = (uint8_t)on_goal;
+      if (status_out) status_out[k] = (int8_t)status;
+      if (agent_reward) agent_reward[k] = r;
+      if (on_goal_out) on_goal_out[k] = (uint8_t)on_goal;
+      if (valid_out) valid_out[k] = (uint8_t)(status >= 0);         /* PRIMAL:571 */
+      if (done_mid) done_mid[k] = (uint8_t)primal_done(o, e);       /* PRIMAL:626 */
+      if (next_mid) primal_valid_actions(o, e, id, action, next_mid + 5 * k); /* PRIMAL:630 */
+    }
+    if (avail)
+      for (int i = 0; i < N; ++i) {
+        size_t k = (size_t)e * N + i;
+        int prev = (i >= lo && i < hi) ? (actions[k] > 4 ? 0 : actions[k]) : 0;
+        primal_valid_actions(o, e, i + 1, prev, avail + 5 * k);
+      }
+    if (terminated) terminated[e] = (uint8_t)primal_done(o, e);
+    if (reward) reward[e] = total;
+  }
+  return bad;
+}
+
+/* _listNextValidActions(id, prev_action) for every agent on the current state. prev may be NULL (= 0). */
+void oracle_primal_avail(const oracle_env* o, const uint8_t* prev_action, uint8_t* avail) {
+#pragma omp parallel for schedule(static) num_threads(o->threads)
+  for (int e = 0; e < o->E; ++e)
+    for (int i = 0; i < o->N; ++i) {
+      size_t k = (size_t)e * o->N + i;
+      primal_valid_actions(o, e, i + 1, prev_action ? prev_action[k] : 0, avail + 5 * k);
+    }
+}
+
+/* _observe(agent_id), PRIMAL:343-386.  maps: uint8 [4][F][F] in the returned order
+ * [poss_map, goal_map, goals_map, obs_map] (values are exactly 0.0/1.0 in the reference). */
+static void primal_observe_agent(const oracle_env* o, int e, int id, uint8_t* maps, double* vec) {
+  const int H = o->H, W = o->W, F = o->F, N = o->N;
+  const int16_t* st = o->state + (size_t)e * H * W;
+  const int16_t* gg = o->goals + (size_t)e * H * W;
+  const int16_t* p = o->pos + ((size_t)e * N + (id - 1)) * 2;
+  const int16_t* g = o->goal + ((size_t)e * N + (id - 1)) * 2;
+  int tl0 = p[0] - F / 2, tl1 = p[1] - F / 2;                       /* PRIMAL:345-346 */
+  uint8_t* poss_map = maps;
+  uint8_t* goal_map = maps + F * F;
+  uint8_t* goals_map = maps + 2 * F * F;
+  uint8_t* obs_map = maps + 3 * F * F;
+  memset(maps, 0, (size_t)4 * F * F);
+  int visible[256];
+  int nvis = 0;
+  for (int i = tl0; i < tl0 + F; ++i)                               /* PRIMAL:354-372 */
+    for (int j = tl1; j < tl1 + F; ++j) {
+      int w = (i - tl0) * F + (j - tl1);
+      if (i >= H || i < 0 || j >= W || j < 0) { obs_map[w] = 1; continue; }
+      int s = st[i * W + j];
+      if (s == -1) obs_map[w] = 1;
+      if (s == id) poss_map[w] = 1;
+      if (gg[i * W + j] == id) goal_map[w] = 1;
+      if (s > 0 && s != id) { visible[nvis++] = s; poss_map[w] = 1; }
+    }
+  for (int v = 0; v < nvis; ++v) {                                  /* PRIMAL:374-378 */
+    const int16_t* og = o->goal + ((size_t)e * N + (visible[v] - 1)) * 2;
+    int x = og[0], y = og[1];
+    int mx = x < tl0 + F - 1 ? x : tl0 + F - 1; if (mx < tl0) mx = tl0;
+    int my = y < tl1 + F - 1 ? y : tl1 + F - 1; if (my < tl1) my = tl1;
+    goals_map[(mx - tl0) * F + (my - tl1)] = 1;
+  }
+  if (vec) {                                                        /* PRIMAL:380-385 */
+    int dx = g[0] - p[0], dy = g[1] - p[1];
+    double mag = pow((double)(dx * dx + dy * dy), 0.5);
+    double fx = (double)dx, fy = (double)dy;
+    if (mag != 0) { fx = fx / mag; fy = fy / mag; }
+    vec[0] = fx; vec[1] = fy; vec[2] = mag;
+  }
+}
+
+void oracle_primal_observe(const oracle_env* o, uint8_t* obs, double* vec) {
+  const int N = o->N, F = o->F;
+#pragma omp parallel for schedule(static) num_threads(o->threads)
+  for (int e = 0; e < o->E; ++e)
+    for (int i = 0; i < N; ++i) {
+      size_t k = (size_t)e * N + i;
+      primal_observe_agent(o, e, i + 1, obs + k * 4 * F * F, vec ? vec + 3 * k : 0);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Per-goal hop-distance maps
+ *   PARTIAL __setup_agent_goal_dist / __get_path_dist, PARTIAL:931-955: networkx A* length on the
+ *     4-connected unit-weight graph of free cells == BFS hop count (edge attribute 'cost' is
+ *     absent, so every edge weighs 1).
+ *   PRIMAL getAstarCosts, PRIMAL:407-499: exhaustive A* from the goal (runs until the open set is
+ *     empty) == BFS hop count; `costs = state.copy()` first, so walls are -1 and unreachable cells
+ *     keep `state` (0 or an agent id) -- selected with primal_costs != 0.
+ * Output int16[E,N,H,W]: walls -1, unreachable free cells -2 (PARTIAL raises NetworkXNoPath there).
+ * ---------------------------------------------------------------------------------------- */
+void oracle_goal_dist(const oracle_env* o, const uint8_t* dirty, int primal_costs, int16_t* dist) {
+  const int H = o->H, W = o->W, N = o->N;
+  const size_t cells = (size_t)H * W;
+#pragma omp parallel num_threads(o->threads)
+  {
+    int32_t* queue = (int32_t*)malloc(sizeof(int32_t) * cells);
+#pragma omp for schedule(static)
+    for (int e = 0; e < o->E; ++e) {
+      const int8_t* m = env_map(o, e);
+      const int16_t* st = o->state + (size_t)e * cells;
+      for (int i = 0; i < N; ++i) {
+        size_t k = (size_t)e * N + i;
+        if (dirty && !dirty[k]) continue;
+        int16_t* d = dist + k * cells;
+        for (size_t c = 0; c < cells; ++c) d[c] = m[c] ? -1 : -2;
+        const int16_t* g = o->goal + k * 2;
+        int head = 0, tail = 0;
+        int gc = g[0] * W + g[1];
+        if (!m[gc]) { d[gc] = 0; queue[tail++] = gc; }
+        while (head < tail) {
+          int c = queue[head++];
+          int r0 = c / W, c0 = c % W;
+          static const int D[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}};
+          for (int q = 0; q < 4; ++q) {
+            int r1 = r0 + D[q][0], c1 = c0 + D[q][1];
+            if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;
+            int n = r1 * W + c1;
+            if (d[n] != -2) continue;
+            d[n] = (int16_t)(d[c] + 1);
+            queue[tail++] = n;
+          }
+        }
+        if (primal_costs)                                          /* PRIMAL:496-498 */
+          for (size_t c = 0; c < cells; ++c)
+            if (d[c] == -2) d[c] = st[c];
+      }
+    }
+    free(queue);
+  }
+}

@@ -77,7 +77,7 @@ def run_grid(name, obst, starts, goals, actions, step_reward=-0.01, collide_rewa
         obs0 = env.reset()
         avail0 = np.array(env.get_avail_actions(), dtype=np.uint8)
         H, W = obst.shape
-        rec = dict(pos=[], node=[], edge=[], dones=[], reward=[], state=[], avail=[], step_count=[])
+        rec = dict(pos=[], node=[], edge=[], dones=[], reward=[], state=[], avail=[], step_count=[], reward_is_int=[])
         for t in range(T):
             r, dones, info = env.step(actions[t])
             obs = env.get_obs()
@@ -88,6 +88,7 @@ def run_grid(name, obst, starts, goals, actions, step_reward=-0.01, collide_rewa
             rec["edge"].append(np.array(env._edge_collision_agents, dtype=np.int32))
             rec["dones"].append(np.array(dones, dtype=np.uint8))
             rec["reward"].append(float(r))
+            rec["reward_is_int"].append(isinstance(r, int))
             rec["state"].append(st.astype(np.int8))
             rec["avail"].append(np.array(env.get_avail_actions(), dtype=np.uint8))
             rec["step_count"].append(info["_step_count"])
@@ -95,6 +96,8 @@ def run_grid(name, obst, starts, goals, actions, step_reward=-0.01, collide_rewa
         family="GRID", obst=obst.astype(np.uint8), starts=np.array(starts, dtype=np.int16),
         goals=np.array(goals, dtype=np.int16), actions=actions.astype(np.uint8),
         step_reward=np.float64(step_reward), collide_reward=np.float64(collide_reward),
+        step_is_int=np.int64(isinstance(step_reward, int)), collide_is_int=np.int64(isinstance(collide_reward, int)),
+        py_sum_mode=np.int64(sys.version_info >= (3, 12)), reward_is_int=np.array(rec["reward_is_int"], dtype=np.uint8),
         episode_limit=np.int64(episode_limit), obs0=np.asarray(obs0)[0].astype(np.int8),
         avail0=avail0,
         pos=np.array(rec["pos"]), node=np.array(rec["node"]), edge=np.array(rec["edge"]),
@@ -139,6 +142,16 @@ def gen_grid():
     starts = [fc[i] for i in rs.randint(0, len(fc), 10)]
     goals = [fc[i] for i in rs.randint(0, len(fc), 10)]
     run_grid("grid_crowd6", obst, starts, goals, rs.randint(0, 5, [60, 10]))
+    # all-int rewards (the sum stays a Python int) and float-collide / int-step (type tracking in sum())
+    rs = np.random.RandomState(6)
+    obst = rs.rand(9, 9) < 0.15
+    fc = free_cells(obst)
+    starts = [fc[i] for i in rs.randint(0, len(fc), 7)]
+    goals = [fc[i] for i in rs.randint(0, len(fc), 7)]
+    acts = rs.randint(0, 5, [50, 7])
+    run_grid("grid_intint", obst, starts, goals, acts, step_reward=-1, collide_reward=-10)
+    run_grid("grid_fcis", obst, starts, goals, acts, step_reward=-1, collide_reward=-0.3)
+    run_grid("grid_ff", obst, starts, goals, acts, step_reward=-0.1, collide_reward=-0.3, episode_limit=30)
     # real MovingAI map + scen through the reference's own parser (x/y quirk included)
     random.seed(11)
     mp = os.path.join(REF_SRC, "mapf_baseline", "mapf-map", "random-32-32-20.map")
