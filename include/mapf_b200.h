@@ -113,6 +113,14 @@ typedef struct mapf_cfg {
    * `(dx**2 + dy**2) ** .5` (PRIMAL:382).  Must cover s <= (H-1)^2 + (W-1)^2. */
   const double* mag_lut_host;
   int32_t mag_lut_len;
+  /* How `sum(rewards)` (GRID:141) is folded, i.e. which interpreter the drop-in imitates:
+   *   0 = plain left fold (CPython <= 3.11 builtin sum),
+   *   1 = CPython >= 3.12 builtin sum (exact ints, then Neumaier-compensated float adds).
+   * The two *_is_int flags say whether the keyword arguments were Python ints: sum() treats int and
+   * float items differently, so the type of every rewards[i] is part of the result. */
+  int32_t reward_sum_mode;
+  int32_t step_reward_is_int;
+  int32_t collide_reward_is_int;
   int32_t reserved;
 } mapf_cfg;
 
@@ -220,6 +228,11 @@ int mapf_avail(mapf_handle* h, uint8_t* avail_dev, void* stream);
  *   primal_costs != 0 reproduces getAstarCosts' quirk: unreachable cells keep `state` (0 or the id
  *   of the agent standing there, PRIMAL:496-498). */
 int mapf_bfs(mapf_handle* h, const uint8_t* dirty_dev, int16_t* dist_dev, int primal_costs, void* stream);
+
+/* Overrides the stored previous action of every agent (uint8[E,N], PRIMAL action ids).  mapf_avail removes
+ * the opposite of this action, which is how `_listNextValidActions(id, prev_action)` (PRIMAL:639, 664) takes an
+ * explicit prev_action. */
+int mapf_set_prev_actions(mapf_handle* h, const uint8_t* prev_dev, void* stream);
 
 /* State read-back (getPositions/getGoals, PRIMAL:236-246; agent_positions, GRID:61). int16[E,N,2]. */
 int mapf_get_positions(mapf_handle* h, int16_t* pos_dev, void* stream);

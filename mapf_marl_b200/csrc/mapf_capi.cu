@@ -1,0 +1,513 @@
+// mapf_capi.cu -- the C ABI of libmapf_b200.so (include/mapf_b200.h): handle management, argument
+// validation, tile sizing and kernel launches.  No torch types, no exceptions across the boundary.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "mapf_internal.h"
+
+struct mapf_handle {
+  mapf_cfg cfg;
+  MapfDims d;
+  MapfTileLayout L;
+  MapfState S;
+  int device;
+  int fov_fast;        // a specialised tile kernel exists for cfg.fov
+  int64_t launches;
+  int mag_lut_len;
+  // device staging for the *_host entry points (allocated on first use)
+  uint8_t* hs_actions;
+  double* hs_reward;
+  uint8_t* hs_terminated;
+  uint8_t* hs_dones;
+  uint8_t* hs_avail;
+  void* hs_obs;
+  size_t hs_obs_bytes;
+  double* hs_vec;
+  char err[512];
+};
+
+static thread_local char g_create_err[512] = "";
+
+static int fail(mapf_handle* h, int code, const char* fmt, ...) {
+  char* dst = h ? h->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int cuda_fail(mapf_handle* h, cudaError_t e, const char* what) {
+  return fail(h, MAPF_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+#define CK(call)                                               \
+  do {                                                         \
+    cudaError_t _e = (call);                                   \
+    if (_e != cudaSuccess) return cuda_fail(h, _e, #call);     \
+  } while (0)
+
+static int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
+static int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L) {
+  const int na = epb * d.N;
+  const bool fov = d.F > 0;
+  int off = 0;
+  auto take = [&](int bytes) {
+    int o = off;
+    off = align_up(off + bytes, 16);
+    return o;
+  };
+  L->obst_off = take((d.shared_map ? 1 : epb) * d.bm_words * 4);
+  L->agt_off = take(fov ? epb * d.bm_words * 4 : 16);
+  L->grida_off = take(epb * d.grid_bytes);
+  L->gridb_off = take(epb * d.grid_bytes);
+  L->posold_off = take(2 * na);
+  L->posnew_off = take(2 * na);
+  L->goal_off = take(2 * na);
+  L->tgt_off = take(2 * na);
+  L->act_off = take(na);
+  L->status_off = take(na);
+  L->done_off = take(na);
+  L->flag_off = take(na);
+  L->avail_off = take(na);
+  L->nextmid_off = take(na);
+  L->node_off = take(na);
+  L->edge_off = take(na);
+  L->isint_off = take(na);
+  L->rew_off = take(8 * na);
+  L->envrew_off = take(8 * epb);
+  L->envterm_off = take(epb);
+  L->str_off = take(fov ? ((na + d.G - 1) / d.G) * d.GW * 4 + 16 : 16);
+  L->total_bytes = off;
+}
+
+static const int kMaxSmem = 227 * 1024;
+
+// Environments per tile: about 256 agents per 256-thread block, a multiple of the alignment the
+// 16-byte observation chunks need, and enough tiles to cover the 148 SMs at least twice.
+static int choose_epb(MapfDims& d, MapfTileLayout* L) {
+  const int lcm = d.G % 4 == 0 ? d.G : (4 % d.G == 0 ? 4 : d.G * 4 / gcd_i(d.G, 4));
+  const int mult = lcm / gcd_i(d.N, lcm);
+  int epb = (MAPF_TILE_THREADS / d.N) / mult * mult;
+  if (epb < mult) epb = mult;
+  while (epb > mult && (d.E + epb - 1) / epb < 2 * 148 && epb * d.N > 64) epb -= mult;
+  for (;;) {
+    compute_layout(d, epb, L);
+    if (L->total_bytes <= kMaxSmem) break;
+    if (epb <= mult) return -1;
+    epb -= mult;
+  }
+  d.epb = epb;
+  return 0;
+}
+
+extern "C" {
+
+const char* mapf_last_error(const mapf_handle* h) { return h ? h->err : g_create_err; }
+int mapf_abi_version(void) { return MAPF_ABI_VERSION; }
+const char* mapf_build_arch(void) { return "sm_100a"; }
+int64_t mapf_launch_count(const mapf_handle* h) { return h ? h->launches : 0; }
+
+void mapf_default_cfg(mapf_cfg* c) {
+  memset(c, 0, sizeof(*c));
+  c->abi_version = MAPF_ABI_VERSION;
+  c->n_envs = 1;
+  c->n_agents = 4;          /* GRID:25 */
+  c->height = c->width = 10;
+  c->mode = MAPF_MODE_GRID;
+  c->obs_mode = MAPF_OBS_FULLMAP;
+  c->fov = 10;              /* PRIMAL:175 observation_size=10 */
+  c->shared_map = 0;
+  c->episode_limit = 10000; /* GRID:26 */
+  c->goal_dist = 0;
+  c->collect_stats = 1;
+  c->step_reward = -0.01;   /* GRID:29 */
+  c->collide_reward = -10;  /* GRID:30 */
+  c->action_cost = -0.3;    /* PRIMAL:25 */
+  c->idle_cost = -0.5;
+  c->goal_reward = 0.0;
+  c->collision_reward = -2.0;
+  c->reward_sum_mode = 0;
+  c->step_reward_is_int = 0;
+  c->collide_reward_is_int = 1;
+}
+
+int mapf_destroy(mapf_handle* h) {
+  if (!h) return MAPF_OK;
+  cudaFree(h->S.obst_bits);
+  cudaFree(h->S.pos);
+  cudaFree(h->S.goal);
+  cudaFree(h->S.start);
+  cudaFree(h->S.done);
+  cudaFree(h->S.prev_action);
+  cudaFree(h->S.step_count);
+  cudaFree(h->S.goal_dist);
+  cudaFree((void*)h->S.mag_lut);
+  cudaFree(h->S.stats);
+  cudaFree(h->S.err_flags);
+  cudaFree(h->hs_actions);
+  cudaFree(h->hs_reward);
+  cudaFree(h->hs_terminated);
+  cudaFree(h->hs_dones);
+  cudaFree(h->hs_avail);
+  cudaFree(h->hs_obs);
+  cudaFree(h->hs_vec);
+  delete h;
+  return MAPF_OK;
+}
+
+int mapf_create(const mapf_cfg* c, mapf_handle** out) {
+  mapf_handle* h = nullptr;
+  if (!c || !out) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: NULL argument");
+  *out = nullptr;
+  if (c->abi_version != MAPF_ABI_VERSION)
+    return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: abi_version %d, library is %d", c->abi_version,
+                MAPF_ABI_VERSION);
+  if (c->n_envs < 1 || c->n_agents < 1 || c->n_agents > MAPF_MAX_AGENTS || c->height < 1 ||
+      c->height > MAPF_MAX_SIDE || c->width < 1 || c->width > MAPF_MAX_SIDE)
+    return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: need E>=1, 1<=N<=255, 1<=H,W<=255 (got E=%d N=%d H=%d W=%d)",
+                c->n_envs, c->n_agents, c->height, c->width);
+  if (c->mode != MAPF_MODE_GRID && c->mode != MAPF_MODE_PRIMAL)
+    return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: unknown mode %d", c->mode);
+  if (c->obs_mode != MAPF_OBS_FULLMAP && c->obs_mode != MAPF_OBS_PRIMAL_FOV)
+    return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: unknown obs_mode %d", c->obs_mode);
+  if (c->obs_mode == MAPF_OBS_PRIMAL_FOV) {
+    if (c->mode != MAPF_MODE_PRIMAL)
+      return fail(h, MAPF_ERR_UNSUPPORTED,
+                  "mapf_create: the PRIMAL field-of-view observation needs one agent per cell (mode PRIMAL)");
+    if (c->fov < 1 || c->fov > 127) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: fov %d not in [1,127]", c->fov);
+  }
+  const long long need = (long long)(c->height - 1) * (c->height - 1) + (long long)(c->width - 1) * (c->width - 1);
+  if (c->obs_mode == MAPF_OBS_PRIMAL_FOV && (!c->mag_lut_host || c->mag_lut_len <= need))
+    return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: mag_lut_host must cover s in [0, %lld]", need);
+
+  h = new (std::nothrow) mapf_handle();
+  if (!h) return fail(nullptr, MAPF_ERR_ALLOC, "mapf_create: out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->cfg = *c;
+  h->cfg.mag_lut_host = nullptr;
+  cudaError_t e = cudaGetDevice(&h->device);
+  if (e != cudaSuccess) {
+    int rc = cuda_fail(nullptr, e, "cudaGetDevice");
+    delete h;
+    return rc;
+  }
+  MapfDims& d = h->d;
+  d.E = c->n_envs;
+  d.N = c->n_agents;
+  d.H = c->height;
+  d.W = c->width;
+  d.HW = d.H * d.W;
+  d.F = c->obs_mode == MAPF_OBS_PRIMAL_FOV ? c->fov : 0;
+  d.P = d.F / 2 > 1 ? d.F / 2 : 1;
+  d.PR = d.H + 2 * d.P;
+  d.RW = ((d.W + 2 * d.P - 1) >> 5) + 2;
+  d.bm_words = align_up(d.PR * d.RW, 4);
+  d.grid_bytes = align_up(d.HW, 16);
+  d.shared_map = c->shared_map ? 1 : 0;
+  d.mode = c->mode;
+  d.obs_mode = c->obs_mode;
+  d.episode_limit = c->episode_limit;
+  d.sum_mode = c->reward_sum_mode;
+  d.step_is_int = c->step_reward_is_int;
+  d.collide_is_int = c->collide_reward_is_int;
+  d.collect_stats = c->collect_stats;
+  d.step_reward = c->step_reward;
+  d.collide_reward = c->collide_reward;
+  d.action_cost = c->action_cost;
+  d.idle_cost = c->idle_cost;
+  d.goal_reward = c->goal_reward;
+  d.collision_reward = c->collision_reward;
+  h->fov_fast = d.F > 0 && mapf_tile_has_fov(d.F);
+  if (d.F > 0 && h->fov_fast) {
+    const int nb = 4 * d.F * d.F;
+    d.G = 32 / gcd_i(nb, 32);
+    d.GW = d.G * nb / 32;
+  } else {
+    d.G = 1;
+    d.GW = 0;
+  }
+  MapfDims dt = d;
+  if (!h->fov_fast) dt.F = 0;   // the tile kernel then only steps; the generic kernel observes
+  if (choose_epb(dt, &h->L) != 0) {
+    int rc = fail(nullptr, MAPF_ERR_UNSUPPORTED, "mapf_create: one environment needs more than %d bytes of shared memory",
+                  kMaxSmem);
+    delete h;
+    return rc;
+  }
+  d.epb = dt.epb;
+
+#define ALLOC(ptr, bytes)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                                          \
+    if (_e != cudaSuccess) {                                                                       \
+      int rc = fail(nullptr, MAPF_ERR_ALLOC, "mapf_create: cudaMalloc(%zu) for " #ptr ": %s",      \
+                    (size_t)(bytes), cudaGetErrorString(_e));                                      \
+      mapf_destroy(h);                                                                             \
+      return rc;                                                                                   \
+    }                                                                                              \
+  } while (0)
+  const size_t EN = (size_t)d.E * d.N;
+  ALLOC(h->S.obst_bits, (size_t)(d.shared_map ? 1 : d.E) * d.bm_words * 4);
+  ALLOC(h->S.pos, EN * 2);
+  ALLOC(h->S.goal, EN * 2);
+  ALLOC(h->S.start, EN * 2);
+  ALLOC(h->S.done, EN);
+  ALLOC(h->S.prev_action, EN);
+  ALLOC(h->S.step_count, (size_t)d.E * 4);
+  if (c->goal_dist) ALLOC(h->S.goal_dist, EN * d.HW * 2);
+  ALLOC(h->S.stats, MAPF_N_STATS * 8);
+  ALLOC(h->S.err_flags, 4);
+  double* lut = nullptr;
+  const int lut_len = c->mag_lut_host ? c->mag_lut_len : 1;
+  ALLOC(lut, (size_t)lut_len * 8);
+  h->S.mag_lut = lut;
+  h->mag_lut_len = lut_len;
+#undef ALLOC
+  // blocking initialisation: the handle is usable on any stream afterwards
+  e = cudaMemset(h->S.obst_bits, 0xff, (size_t)(d.shared_map ? 1 : d.E) * d.bm_words * 4);
+  if (e == cudaSuccess) e = cudaMemset(h->S.pos, 0, EN * 2);
+  if (e == cudaSuccess) e = cudaMemset(h->S.goal, 0, EN * 2);
+  if (e == cudaSuccess) e = cudaMemset(h->S.start, 0, EN * 2);
+  if (e == cudaSuccess) e = cudaMemset(h->S.done, 0, EN);
+  if (e == cudaSuccess) e = cudaMemset(h->S.prev_action, 0, EN);
+  if (e == cudaSuccess) e = cudaMemset(h->S.step_count, 0, (size_t)d.E * 4);
+  if (e == cudaSuccess) e = cudaMemset(h->S.stats, 0, MAPF_N_STATS * 8);
+  if (e == cudaSuccess) e = cudaMemset(h->S.err_flags, 0, 4);
+  if (e == cudaSuccess) {
+    if (c->mag_lut_host) e = cudaMemcpy(lut, c->mag_lut_host, (size_t)lut_len * 8, cudaMemcpyHostToDevice);
+    else e = cudaMemset(lut, 0, 8);
+  }
+  if (e == cudaSuccess && h->L.total_bytes > 48 * 1024)
+    e = (cudaError_t)mapf_configure_tile(h->fov_fast ? d.F : 0, h->L.total_bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    int rc = cuda_fail(nullptr, e, "mapf_create: initialisation");
+    mapf_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return MAPF_OK;
+}
+
+static int check_aligned(mapf_handle* h, const void* p, const char* name) {
+  if (p && (((uintptr_t)p) & 15) != 0)
+    return fail(h, MAPF_ERR_INVALID_ARG, "%s must be 16-byte aligned", name);
+  return MAPF_OK;
+}
+
+int mapf_reset(mapf_handle* h, const int8_t* map_dev, const int16_t* starts_dev, const int16_t* goals_dev,
+               const uint8_t* env_mask_dev, void* stream) {
+  if (!h) return MAPF_ERR_INVALID_ARG;
+  if (map_dev) {
+    CK((cudaError_t)mapf_launch_build_obst(h->d, h->S, map_dev, env_mask_dev, stream));
+    h->launches++;
+  }
+  CK((cudaError_t)mapf_launch_reset(h->d, h->S, starts_dev, goals_dev, env_mask_dev, stream));
+  h->launches++;
+  return MAPF_OK;
+}
+
+int mapf_set_goals(mapf_handle* h, const int16_t* goals_dev, const uint8_t* dirty_dev, void* stream) {
+  if (!h || !goals_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_set_goals: NULL argument");
+  CK((cudaError_t)mapf_launch_set_goals(h->d, h->S, goals_dev, dirty_dev, stream));
+  h->launches++;
+  return MAPF_OK;
+}
+
+static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, int hi, const mapf_step_out* out,
+                    void* obs, int obs_dtype, double* vec, void* stream) {
+  MapfTileArgs A;
+  memset(&A, 0, sizeof(A));
+  A.actions = actions;
+  A.act_dtype = act_dtype;
+  A.do_step = actions != nullptr;
+  A.agent_lo = lo;
+  A.agent_hi = hi;
+  if (out) A.out = *out;
+  int rc;
+  if ((rc = check_aligned(h, actions, "actions_dev")) != MAPF_OK) return rc;
+  if ((rc = check_aligned(h, obs, "obs_dev")) != MAPF_OK) return rc;
+  if ((rc = check_aligned(h, vec, "vec_dev")) != MAPF_OK) return rc;
+  if (actions && act_dtype != MAPF_U8 && act_dtype != MAPF_I64)
+    return fail(h, MAPF_ERR_INVALID_ARG, "actions must be MAPF_U8 or MAPF_I64");
+  const bool fov = h->d.obs_mode == MAPF_OBS_PRIMAL_FOV;
+  if (obs) {
+    if (fov && obs_dtype != MAPF_U8 && obs_dtype != MAPF_F32)
+      return fail(h, MAPF_ERR_INVALID_ARG, "FOV observations are MAPF_U8 or MAPF_F32");
+    if (!fov && obs_dtype != MAPF_I8) return fail(h, MAPF_ERR_INVALID_ARG, "full-map observations are MAPF_I8");
+  }
+  MapfDims d = h->d;
+  const bool generic_obs = fov && !h->fov_fast && (obs || vec);
+  if (fov && !h->fov_fast) d.F = 0, d.obs_mode = MAPF_OBS_FULLMAP;   // the tile kernel skips the observation
+  if (!generic_obs) {
+    A.obs = obs;
+    A.obs_dtype = obs_dtype;
+    A.vec = fov ? vec : nullptr;
+  }
+  const bool any_out = A.do_step || A.obs || A.vec || A.out.avail_dev;
+  if (any_out) {
+    CK((cudaError_t)mapf_launch_tile(d, h->L, h->S, A, stream));
+    h->launches++;
+  }
+  if (generic_obs) {
+    CK((cudaError_t)mapf_launch_observe_generic(h->d, h->S, obs_dtype == MAPF_U8 ? (uint8_t*)obs : nullptr,
+                                                obs_dtype == MAPF_F32 ? (float*)obs : nullptr, vec, stream));
+    h->launches++;
+  }
+  return MAPF_OK;
+}
+
+int mapf_step_agents(mapf_handle* h, const void* actions_dev, int act_dtype, int agent_lo, int agent_hi,
+                     const mapf_step_out* out, void* stream) {
+  if (!h || !actions_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_step: NULL argument");
+  if (agent_lo < 0 || agent_hi > h->d.N || agent_lo >= agent_hi)
+    return fail(h, MAPF_ERR_INVALID_ARG, "mapf_step_agents: bad range [%d, %d)", agent_lo, agent_hi);
+  if (h->d.mode != MAPF_MODE_PRIMAL && (agent_lo != 0 || agent_hi != h->d.N))
+    return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_step_agents: partial sweeps exist only in PRIMAL mode");
+  return run_tile(h, actions_dev, act_dtype, agent_lo, agent_hi, out, nullptr, 0, nullptr, stream);
+}
+
+int mapf_step(mapf_handle* h, const void* actions_dev, int act_dtype, const mapf_step_out* out, void* stream) {
+  if (!h) return MAPF_ERR_INVALID_ARG;
+  return mapf_step_agents(h, actions_dev, act_dtype, 0, h->d.N, out, stream);
+}
+
+int mapf_observe(mapf_handle* h, void* obs_dev, int obs_dtype, double* vec_dev, void* stream) {
+  if (!h || (!obs_dev && !vec_dev)) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_observe: NULL argument");
+  return run_tile(h, nullptr, 0, 0, h->d.N, nullptr, obs_dev, obs_dtype, vec_dev, stream);
+}
+
+int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, const mapf_step_out* out,
+                      void* obs_dev, int obs_dtype, double* vec_dev, void* stream) {
+  if (!h || !actions_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_step_observe: NULL argument");
+  return run_tile(h, actions_dev, act_dtype, 0, h->d.N, out, obs_dev, obs_dtype, vec_dev, stream);
+}
+
+int mapf_avail(mapf_handle* h, uint8_t* avail_dev, void* stream) {
+  if (!h || !avail_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_avail: NULL argument");
+  mapf_step_out out;
+  memset(&out, 0, sizeof(out));
+  out.avail_dev = avail_dev;
+  return run_tile(h, nullptr, 0, 0, h->d.N, &out, nullptr, 0, nullptr, stream);
+}
+
+int mapf_bfs(mapf_handle* h, const uint8_t* dirty_dev, int16_t* dist_dev, int primal_costs, void* stream) {
+  if (!h) return MAPF_ERR_INVALID_ARG;
+  int16_t* dist = dist_dev ? dist_dev : h->S.goal_dist;
+  if (!dist) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_bfs: no output (dist_dev NULL and cfg.goal_dist == 0)");
+  int rc;
+  if ((rc = check_aligned(h, dist, "dist_dev")) != MAPF_OK) return rc;
+  int n = 0;
+  CK((cudaError_t)mapf_launch_bfs(h->d, h->S, dirty_dev, dist, primal_costs, stream, &n));
+  h->launches += n;
+  return MAPF_OK;
+}
+
+int mapf_set_prev_actions(mapf_handle* h, const uint8_t* prev_dev, void* stream) {
+  if (!h || !prev_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_set_prev_actions: NULL argument");
+  CK(cudaMemcpyAsync(h->S.prev_action, prev_dev, (size_t)h->d.E * h->d.N, cudaMemcpyDeviceToDevice,
+                     (cudaStream_t)stream));
+  return MAPF_OK;
+}
+
+int mapf_get_positions(mapf_handle* h, int16_t* pos_dev, void* stream) {
+  if (!h || !pos_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_get_positions: NULL argument");
+  CK((cudaError_t)mapf_launch_export16(h->d, h->S.pos, pos_dev, stream));
+  h->launches++;
+  return MAPF_OK;
+}
+
+int mapf_get_goals(mapf_handle* h, int16_t* goals_dev, void* stream) {
+  if (!h || !goals_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_get_goals: NULL argument");
+  CK((cudaError_t)mapf_launch_export16(h->d, h->S.goal, goals_dev, stream));
+  h->launches++;
+  return MAPF_OK;
+}
+
+int mapf_get_dones(mapf_handle* h, uint8_t* dones_dev, void* stream) {
+  if (!h || !dones_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_get_dones: NULL argument");
+  CK(cudaMemcpyAsync(dones_dev, h->S.done, (size_t)h->d.E * h->d.N, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return MAPF_OK;
+}
+
+int mapf_get_step_count(mapf_handle* h, int32_t* step_count_dev, void* stream) {
+  if (!h || !step_count_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_get_step_count: NULL argument");
+  CK(cudaMemcpyAsync(step_count_dev, h->S.step_count, (size_t)h->d.E * 4, cudaMemcpyDeviceToDevice,
+                     (cudaStream_t)stream));
+  return MAPF_OK;
+}
+
+int mapf_stats(mapf_handle* h, int64_t* stats_host, void* stream) {
+  if (!h || !stats_host) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_stats: NULL argument");
+  CK(cudaMemcpyAsync(stats_host, h->S.stats, MAPF_N_STATS * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return MAPF_OK;
+}
+
+int mapf_error_flags(mapf_handle* h, uint32_t* flags_host, void* stream) {
+  if (!h || !flags_host) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_error_flags: NULL argument");
+  CK(cudaMemcpyAsync(flags_host, h->S.err_flags, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaMemsetAsync(h->S.err_flags, 0, 4, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return MAPF_OK;
+}
+
+int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream) {
+  if (!h || !io || !io->actions_host) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_step_observe_host: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const MapfDims& d = h->d;
+  const size_t EN = (size_t)d.E * d.N;
+  const bool fov = d.obs_mode == MAPF_OBS_PRIMAL_FOV;
+  size_t obs_bytes = 0;
+  if (io->obs_host) {
+    if (fov) obs_bytes = EN * 4 * d.F * d.F * (io->obs_dtype == MAPF_F32 ? 4 : 1);
+    else obs_bytes = (size_t)d.E * d.HW;
+  }
+#define LAZY(ptr, bytes)                                                \
+  if (!(ptr)) {                                                         \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));               \
+    if (_e != cudaSuccess) return cuda_fail(h, _e, "cudaMalloc " #ptr); \
+  }
+  LAZY(h->hs_actions, EN);
+  if (io->reward_host) LAZY(h->hs_reward, (size_t)d.E * 8);
+  if (io->terminated_host) LAZY(h->hs_terminated, (size_t)d.E);
+  if (io->dones_host) LAZY(h->hs_dones, EN);
+  if (io->avail_host) LAZY(h->hs_avail, EN * 5);
+  if (io->vec_host) LAZY(h->hs_vec, EN * 24);
+#undef LAZY
+  if (obs_bytes > h->hs_obs_bytes) {
+    cudaFree(h->hs_obs);
+    h->hs_obs = nullptr;
+    h->hs_obs_bytes = 0;
+    CK(cudaMalloc(&h->hs_obs, obs_bytes));
+    h->hs_obs_bytes = obs_bytes;
+  }
+  CK(cudaMemcpyAsync(h->hs_actions, io->actions_host, EN, cudaMemcpyHostToDevice, st));
+  mapf_step_out out;
+  memset(&out, 0, sizeof(out));
+  out.reward_dev = io->reward_host ? h->hs_reward : nullptr;
+  out.terminated_dev = io->terminated_host ? h->hs_terminated : nullptr;
+  out.dones_dev = io->dones_host ? h->hs_dones : nullptr;
+  out.avail_dev = io->avail_host ? h->hs_avail : nullptr;
+  int rc = run_tile(h, h->hs_actions, MAPF_U8, 0, d.N, &out, io->obs_host ? h->hs_obs : nullptr, io->obs_dtype,
+                    io->vec_host ? h->hs_vec : nullptr, stream);
+  if (rc != MAPF_OK) return rc;
+  if (io->reward_host) CK(cudaMemcpyAsync(io->reward_host, h->hs_reward, (size_t)d.E * 8, cudaMemcpyDeviceToHost, st));
+  if (io->terminated_host)
+    CK(cudaMemcpyAsync(io->terminated_host, h->hs_terminated, (size_t)d.E, cudaMemcpyDeviceToHost, st));
+  if (io->dones_host) CK(cudaMemcpyAsync(io->dones_host, h->hs_dones, EN, cudaMemcpyDeviceToHost, st));
+  if (io->avail_host) CK(cudaMemcpyAsync(io->avail_host, h->hs_avail, EN * 5, cudaMemcpyDeviceToHost, st));
+  if (io->vec_host) CK(cudaMemcpyAsync(io->vec_host, h->hs_vec, EN * 24, cudaMemcpyDeviceToHost, st));
+  if (io->obs_host) CK(cudaMemcpyAsync(io->obs_host, h->hs_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MAPF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// mapf_internal.h -- structures shared by the host side (mapf_capi.cu) and the kernels.
+// Not part of the public ABI (include/mapf_b200.h is).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/mapf_b200.h"
+
+#define MAPF_TILE_THREADS 256
+#define MAPF_MAX_AGENTS 255
+#define MAPF_MAX_SIDE 255
+
+// Problem dimensions and constants, passed by value to every kernel.
+struct MapfDims {
+  int E, N, H, W, HW;
+  int F;         // FOV side (0 when the obs mode has no window)
+  int P;         // padding of the bitmaps on every side: max(F/2, 1)
+  int PR;        // padded rows  = H + 2P
+  int RW;        // 32-bit words per padded row, including one guard word
+  int bm_words;  // words per padded bitmap, rounded up to a multiple of 4 (16-byte rows for bulk copies)
+  int grid_bytes;  // H*W rounded up to a multiple of 16
+  int shared_map;
+  int mode, obs_mode;
+  int episode_limit;
+  int epb;       // environments per thread block (tile)
+  int G;         // agents per bit-string group (group length is a whole number of 32-bit words)
+  int GW;        // words per group string = G * 4*F*F / 32
+  int sum_mode, step_is_int, collide_is_int;
+  int collect_stats;
+  double step_reward, collide_reward;
+  double action_cost, idle_cost, goal_reward, collision_reward;
+};
+
+// Byte offsets into the dynamic shared memory of a tile kernel.
+struct MapfTileLayout {
+  int obst_off;     // padded obstacle bitmaps: [shared_map ? 1 : epb][bm_words] u32
+  int agt_off;      // padded agent bitmaps:    [epb][bm_words] u32 (FOV only)
+  int grida_off;    // [epb][grid_bytes] u8: PRIMAL live id grid / GRID occupancy counts of the current positions
+  int gridb_off;    // [epb][grid_bytes] u8: PRIMAL pre-sweep id grid / GRID occupancy counts of the new positions
+  int posold_off, posnew_off, goal_off, tgt_off;  // uchar2 [epb*N]
+  int act_off, status_off, done_off, flag_off, avail_off, nextmid_off, node_off, edge_off, isint_off;  // u8 [epb*N]
+  int rew_off;      // double [epb*N]
+  int envrew_off;   // double [epb]
+  int envterm_off;  // u8 [epb] (padded)
+  int str_off;      // bit strings: ceil(epb*N / G) * GW u32
+  int total_bytes;
+};
+
+// Device pointers to the state owned by the handle.
+struct MapfState {
+  uint32_t* obst_bits;     // [Emap][bm_words]
+  uint8_t* pos;            // [E][N][2]
+  uint8_t* goal;           // [E][N][2]
+  uint8_t* start;          // [E][N][2]
+  uint8_t* done;           // [E][N]
+  uint8_t* prev_action;    // [E][N]
+  int32_t* step_count;     // [E]
+  int16_t* goal_dist;      // [E][N][H][W] or NULL
+  const double* mag_lut;   // [mag_lut_len]
+  unsigned long long* stats;  // [MAPF_N_STATS]
+  uint32_t* err_flags;     // [1]
+};
+
+// Per-launch arguments of the tile kernel.
+struct MapfTileArgs {
+  const void* actions;   // [E][N] u8 or i64 (NULL when do_step == 0)
+  int act_dtype;
+  int do_step;
+  int agent_lo, agent_hi;  // PRIMAL sweep range
+  mapf_step_out out;       // any pointer may be NULL
+  void* obs;               // FOV: [E][N][4][F][F] u8/f32 ; FULLMAP: [E][H*W] i8 ; NULL: no observation
+  int obs_dtype;
+  double* vec;             // [E][N][3] or NULL
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+// launchers implemented in mapf_kernels.cu; all return a cudaError_t cast to int
+int mapf_launch_tile(const MapfDims& d, const MapfTileLayout& L, const MapfState& S, const MapfTileArgs& A,
+                     void* stream);
+int mapf_launch_observe_generic(const MapfDims& d, const MapfState& S, uint8_t* obs_u8, float* obs_f32, double* vec,
+                                void* stream);
+int mapf_launch_build_obst(const MapfDims& d, const MapfState& S, const int8_t* map, const uint8_t* env_mask,
+                           void* stream);
+int mapf_launch_reset(const MapfDims& d, const MapfState& S, const int16_t* starts, const int16_t* goals,
+                      const uint8_t* env_mask, void* stream);
+int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, const int16_t* goals, const uint8_t* dirty,
+                          void* stream);
+int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, int16_t* dist, int primal_costs,
+                    void* stream, int* n_launches);
+int mapf_launch_export16(const MapfDims& d, const uint8_t* src_u8x2, int16_t* dst, void* stream);
+int mapf_tile_has_fov(int F);
+int mapf_configure_tile(int F, int smem_bytes);
+#ifdef __cplusplus
+}
+#endif

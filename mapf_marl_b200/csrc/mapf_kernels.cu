@@ -1,0 +1,1147 @@
+// mapf_kernels.cu -- sm_100a kernels of the batched MAPF step/observation engine.
+//
+// Reference semantics reproduced here (paths relative to the reference root):
+//   GRID   = mapf_gridworld.py          step :85-141, avail :203-224, collisions :344-383
+//   PRIMAL = mapf_primal.py             moveAgent :103-135, _step :549-637, _observe :343-386,
+//                                       _listNextValidActions :639-667, getAstarCosts :407-499
+//   PARTIAL= MARL-curve-main/src/envs/marl_partial.py   goal distance maps :931-955
+//
+// Design:
+//   * A thread block owns a TILE of `epb` consecutive environments.  Their whole state
+//     (padded obstacle bitmap, positions, goals, actions, occupancy grid) is staged in
+//     shared memory once; step, collision handling, reward/done, action masks and the
+//     observation are all produced from that copy (one launch, state read from HBM once).
+//   * Sequential semantics: one warp per environment.  The agent-order dependent part of
+//     PRIMAL's sweep (the occupancy claim) is a short serial loop over a shared-memory id
+//     grid; everything that does not depend on agent order runs lane-parallel.
+//   * Field-of-view observation: maps are kept as bit rows padded by F/2 on every side, so an
+//     F-cell window row is one funnel shift.  Each agent assembles its 4*F*F observation bits
+//     in registers, the bit strings of G consecutive agents are concatenated in shared memory,
+//     and the whole tile is expanded to bytes (or floats) with perfectly coalesced 16-byte
+//     streaming stores: thread q writes bytes [16q, 16q+16) of the tile's output.
+//   * No tensor cores: nothing here is a contraction.  The path is bound by HBM writes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mapf_internal.h"
+
+namespace {
+
+constexpr int kThreads = MAPF_TILE_THREADS;
+
+// pre-status codes used inside the PRIMAL sweep (outside the reference's {-3..2})
+constexpr int8_t PRE_SKIP = 10, PRE_STAY = 11, PRE_MOVE = 12, PRE_MOVED = 13;
+
+struct Smem {
+  uint32_t* obst;
+  uint32_t* agt;
+  uint8_t* grida;
+  uint8_t* gridb;
+  uchar2 *posold, *posnew, *goal, *tgt;
+  uint8_t *act, *done, *flag, *avail, *nextmid, *node, *edge, *isint;
+  int8_t* status;
+  double* rew;
+  double* envrew;
+  uint8_t* envterm;
+  uint32_t* str;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char* base, const MapfTileLayout& L) {
+  Smem s;
+  s.obst = (uint32_t*)(base + L.obst_off);
+  s.agt = (uint32_t*)(base + L.agt_off);
+  s.grida = base + L.grida_off;
+  s.gridb = base + L.gridb_off;
+  s.posold = (uchar2*)(base + L.posold_off);
+  s.posnew = (uchar2*)(base + L.posnew_off);
+  s.goal = (uchar2*)(base + L.goal_off);
+  s.tgt = (uchar2*)(base + L.tgt_off);
+  s.act = base + L.act_off;
+  s.status = (int8_t*)(base + L.status_off);
+  s.done = base + L.done_off;
+  s.flag = base + L.flag_off;
+  s.avail = base + L.avail_off;
+  s.nextmid = base + L.nextmid_off;
+  s.node = base + L.node_off;
+  s.edge = base + L.edge_off;
+  s.isint = base + L.isint_off;
+  s.rew = (double*)(base + L.rew_off);
+  s.envrew = (double*)(base + L.envrew_off);
+  s.envterm = base + L.envterm_off;
+  s.str = (uint32_t*)(base + L.str_off);
+  return s;
+}
+
+// Bit test in a padded bitmap; (r, c) are map coordinates and may lie up to P cells outside.
+__device__ __forceinline__ uint32_t bm_test(const uint32_t* bm, int RW, int P, int r, int c) {
+  const int pr = r + P, pc = c + P;
+  return (bm[pr * RW + (pc >> 5)] >> (pc & 31)) & 1u;
+}
+
+// F consecutive bits of padded row `prow` starting at padded column `bit0`.
+__device__ __forceinline__ uint32_t row_field(const uint32_t* bm, int RW, int prow, int bit0, uint32_t fmask) {
+  const uint32_t* r = bm + prow * RW + (bit0 >> 5);
+  return __funnelshift_r(r[0], r[1], bit0) & fmask;
+}
+
+__device__ __forceinline__ void byte_inc(uint8_t* grid, int cell) {
+  atomicAdd((unsigned int*)(grid + (cell & ~3)), 1u << (8 * (cell & 3)));
+}
+
+// 16-byte streaming store (the observation is written once and never re-read by this kernel).
+__device__ __forceinline__ void st_stream16(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// 4 bits -> 4 bytes of 0/1 (bit k lands in byte k).
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+__device__ __forceinline__ void copy_out_bytes(uint8_t* dst, const uint8_t* src, int n, int tid) {
+  if (((((uintptr_t)dst) | ((uintptr_t)src)) & 3) == 0) {
+    const int nw = n >> 2;
+    for (int i = tid; i < nw; i += kThreads) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+    for (int i = (nw << 2) + tid; i < n; i += kThreads) dst[i] = src[i];
+  } else {
+    for (int i = tid; i < n; i += kThreads) dst[i] = src[i];
+  }
+}
+
+// Expands per-agent 5-bit masks to the [na][5] uint8 layout of get_avail_actions.
+__device__ __forceinline__ void write_mask5(uint8_t* dst, const uint8_t* mask, int na, int tid) {
+  const int n = 5 * na;
+  if ((((uintptr_t)dst) & 3) == 0) {
+    const int nw = n >> 2;
+    for (int q = tid; q < nw; q += kThreads) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = 4 * q + k;
+        const int ag = idx / 5;
+        w |= ((mask[ag] >> (idx - 5 * ag)) & 1u) << (8 * k);
+      }
+      ((uint32_t*)dst)[q] = w;
+    }
+    for (int idx = (nw << 2) + tid; idx < n; idx += kThreads) {
+      const int ag = idx / 5;
+      dst[idx] = (mask[ag] >> (idx - 5 * ag)) & 1u;
+    }
+  } else {
+    for (int idx = tid; idx < n; idx += kThreads) {
+      const int ag = idx / 5;
+      dst[idx] = (mask[ag] >> (idx - 5 * ag)) & 1u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// `sum(rewards)` (GRID:141) exactly as the interpreter that runs the reference evaluates it.
+//   sum_mode 0: left fold (CPython <= 3.11).
+//   sum_mode 1: CPython >= 3.12 builtin sum: exact while the items are ints, float(i) + x at the first
+//   float, then Neumaier-compensated adds for floats / plain adds for ints, compensation added last.
+// All operations use explicit round-to-nearest intrinsics so that no FMA contraction can occur.
+// ------------------------------------------------------------------------------------------------
+__device__ double py_sum(const double* x, const uint8_t* is_int, int n, int sum_mode) {
+  double acc = 0.0;
+  if (sum_mode == 0) {
+    for (int i = 0; i < n; ++i) acc = __dadd_rn(acc, x[i]);
+    return acc;
+  }
+  double c = 0.0;
+  bool in_float = false;
+  for (int i = 0; i < n; ++i) {
+    const double xi = x[i];
+    if (!in_float) {
+      acc = __dadd_rn(acc, xi);
+      if (!is_int[i]) in_float = true;
+    } else if (is_int[i]) {
+      acc = __dadd_rn(acc, xi);
+    } else {
+      const double t = __dadd_rn(acc, xi);
+      if (fabs(acc) >= fabs(xi))
+        c = __dadd_rn(c, __dadd_rn(__dsub_rn(acc, t), xi));
+      else
+        c = __dadd_rn(c, __dadd_rn(__dsub_rn(xi, t), acc));
+      acc = t;
+    }
+  }
+  if (in_float && c != 0.0 && isfinite(c)) acc = __dadd_rn(acc, c);
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PRIMAL sweep for one environment (one warp).  State.moveAgent :103-135 applied for ids lo+1..hi
+// in order against the live id grid, then the order-independent parts of _step :549-637.
+// ------------------------------------------------------------------------------------------------
+__device__ void step_primal_env(const MapfDims& d, const Smem& s, int el, int lane, const MapfTileArgs& A,
+                                unsigned int* stat /*smem[8]*/) {
+  const int N = d.N, W = d.W, H = d.H, jb = el * N;
+  const int lo = A.agent_lo, hi = A.agent_hi;
+  uint8_t* grid = s.grida + el * d.grid_bytes;
+  uint8_t* gold = s.gridb + el * d.grid_bytes;
+  const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+  const bool need_mid = (A.out.done_mid_dev != nullptr) || (A.out.next_mid_dev != nullptr);
+
+  if (need_mid)
+    for (int i = lane; i < (d.grid_bytes >> 4); i += 32) ((uint4*)gold)[i] = ((const uint4*)grid)[i];
+
+  // lane-parallel: direction, bounds and wall checks (they do not depend on the other agents)
+  for (int a = lane; a < N; a += 32) {
+    const int j = jb + a;
+    const int act = s.act[j];
+    const uchar2 p = s.posold[j];
+    int8_t st;
+    uchar2 t = p;
+    if (a < lo || a >= hi) {
+      st = PRE_SKIP;
+    } else if (act == 0) {
+      st = PRE_STAY;
+    } else {
+      const int t0 = (int)p.x + (act == 2 ? 1 : (act == 4 ? -1 : 0));  // dirDict, PRIMAL:28
+      const int t1 = (int)p.y + (act == 1 ? 1 : (act == 3 ? -1 : 0));
+      if (bm_test(ob, d.RW, d.P, t0, t1)) {
+        st = (t0 < 0 || t0 >= H || t1 < 0 || t1 >= W) ? -1 : -2;       // PRIMAL:114-118
+      } else {
+        st = PRE_MOVE;
+        t = make_uchar2((unsigned char)t0, (unsigned char)t1);
+      }
+    }
+    s.status[j] = st;
+    s.tgt[j] = t;
+  }
+  __syncwarp();
+
+  // the agent-order dependent part: claim the target cell in the live grid (PRIMAL:119-129)
+  if (lane == 0) {
+    for (int i = lo; i < hi; ++i) {
+      const int j = jb + i;
+      if (s.status[j] == PRE_MOVE) {
+        const uchar2 t = s.tgt[j];
+        const int tc = (int)t.x * W + t.y;
+        if (grid[tc] != 0) {
+          s.status[j] = -3;
+        } else {
+          const uchar2 p = s.posold[j];
+          grid[(int)p.x * W + p.y] = 0;
+          grid[tc] = (uint8_t)(i + 1);
+          s.posnew[j] = t;
+          s.status[j] = PRE_MOVED;
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // lane-parallel epilogue: final status, reward table, on_goal, mid-sweep outputs
+  int tot_old = 0;
+  if (need_mid) {
+    for (int a0 = 0; a0 < N; a0 += 32) {
+      const int a = a0 + lane;
+      bool on_old = false;
+      if (a < N) {
+        const uchar2 p = s.posold[jb + a], g = s.goal[jb + a];
+        on_old = (p.x == g.x && p.y == g.y);
+      }
+      tot_old += __popc(__ballot_sync(0xffffffffu, on_old));
+    }
+  }
+  int new_prefix = 0, old_prefix = 0;
+  bool all_on = true;
+  unsigned int c_env = 0, c_rob = 0, c_arr = 0;
+  for (int a0 = 0; a0 < N; a0 += 32) {
+    const int a = a0 + lane;
+    const bool active = a < N;
+    const int j = jb + (active ? a : 0);
+    const uchar2 po = s.posold[j], pn = s.posnew[j], g = s.goal[j];
+    const bool on_old = active && (po.x == g.x && po.y == g.y);
+    const bool on_new = active && (pn.x == g.x && pn.y == g.y);
+    const int act = s.act[j];
+    int st = s.status[j];
+    const bool swept = active && st != PRE_SKIP;
+    if (st == PRE_STAY) st = on_old ? 1 : 0;                         // PRIMAL:108-110
+    else if (st == PRE_MOVED) st = on_new ? 1 : (on_old ? 2 : 0);    // PRIMAL:130-135
+    else if (st == PRE_SKIP) st = 0;
+    double r = 0.0;
+    if (swept) {
+      if (act == 0) r = (st == 1) ? __dadd_rn(d.goal_reward, -0.0) : d.idle_cost;          // PRIMAL:579-587
+      else r = (st == 1) ? d.goal_reward : (st < 0 ? d.collision_reward : d.action_cost);  // PRIMAL:588-596
+    }
+    const unsigned bn = __ballot_sync(0xffffffffu, on_new);
+    const unsigned bo = __ballot_sync(0xffffffffu, on_old);
+    if (active) {
+      s.status[j] = (int8_t)st;
+      s.rew[j] = r;
+      s.done[j] = on_new ? 1 : 0;                                    // on_goal, PRIMAL:633
+      uint8_t fl = (on_new ? 1 : 0) | ((st >= 0) ? 2 : 0);           // valid_action, PRIMAL:571
+      if (need_mid) {
+        const unsigned le = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
+        const int cnt = new_prefix + __popc(bn & le) + (tot_old - old_prefix - __popc(bo & le));
+        if (cnt == N) fl |= 4;                                       // world.done() right after this agent moved
+        // nextActions as returned by this agent's _step: neighbours at the time it moved.
+        uint8_t m = 1;
+#pragma unroll
+        for (int k = 1; k <= 4; ++k) {
+          const int n0 = (int)pn.x + (k == 2 ? 1 : (k == 4 ? -1 : 0));
+          const int n1 = (int)pn.y + (k == 1 ? 1 : (k == 3 ? -1 : 0));
+          if (!bm_test(ob, d.RW, d.P, n0, n1)) {
+            const int c = n0 * W + n1;
+            const int idn = grid[c], ido = gold[c];
+            const bool occ = (ido > a + 1) || (idn != 0 && idn < a + 1);
+            if (!occ) m |= (uint8_t)(1u << k);
+          }
+        }
+        const int opp = (act == 0) ? -1 : (((act + 1) & 3) + 1);     // opposite_actions, PRIMAL:26
+        if (opp > 0) m &= (uint8_t)~(1u << opp);
+        s.nextmid[j] = swept ? m : 0;
+      }
+      s.flag[j] = fl;
+      if (swept) {
+        c_env += (st == -1 || st == -2);
+        c_rob += (st == -3);
+        c_arr += (on_new && !on_old);
+      }
+      all_on = all_on && on_new;
+    }
+    new_prefix += __popc(bn);
+    old_prefix += __popc(bo);
+  }
+  all_on = __all_sync(0xffffffffu, all_on);
+  if (d.collect_stats) {
+    c_env = __reduce_add_sync(0xffffffffu, c_env);
+    c_rob = __reduce_add_sync(0xffffffffu, c_rob);
+    c_arr = __reduce_add_sync(0xffffffffu, c_arr);
+    if (lane == 0) {
+      atomicAdd(&stat[MAPF_STAT_ENV_STEPS], lo == 0 ? 1u : 0u);
+      atomicAdd(&stat[MAPF_STAT_AGENT_STEPS], (unsigned)(hi - lo));
+      atomicAdd(&stat[MAPF_STAT_ENV_COLLISIONS], c_env);
+      atomicAdd(&stat[MAPF_STAT_NODE_COLLISIONS], c_rob);
+      atomicAdd(&stat[MAPF_STAT_GOAL_ARRIVALS], c_arr);
+      atomicAdd(&stat[MAPF_STAT_EPISODES_DONE], all_on ? 1u : 0u);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    s.envterm[el] = all_on ? 1 : 0;                                  // State.done, PRIMAL:159-165
+    if (A.out.reward_dev) {
+      double tot = 0.0;
+      for (int i = lo; i < hi; ++i) tot = __dadd_rn(tot, s.rew[jb + i]);
+      s.envrew[el] = tot;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GRID step for one environment (one warp).  MAPF_GRID.step, GRID:85-141.
+//   grida: occupancy counts of the positions before the step, gridb: after the step.
+// ------------------------------------------------------------------------------------------------
+__device__ void step_grid_env(const MapfDims& d, const Smem& s, int el, int lane, int step_now,
+                              unsigned int* stat) {
+  const int N = d.N, W = d.W, jb = el * N;
+  uint8_t* cold = s.grida + el * d.grid_bytes;
+  uint8_t* cnew = s.gridb + el * d.grid_bytes;
+  const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+  unsigned int c_env = 0, c_node = 0, c_edge = 0, c_arr = 0;
+
+  for (int a = lane; a < N; a += 32) {                               // GRID:99-118
+    const int j = jb + a;
+    const uchar2 p = s.posold[j], g = s.goal[j];
+    const bool done_old = s.done[j] != 0;
+    uchar2 np = p;
+    double r = 0.0;
+    int flag = 0;
+    if (!done_old) {
+      const int act = s.act[j];
+      if (act < 4) {                                                 // __agent_step, GRID:319-342
+        const int t0 = (int)p.x + (act == 0 ? -1 : (act == 1 ? 1 : 0));
+        const int t1 = (int)p.y + (act == 2 ? -1 : (act == 3 ? 1 : 0));
+        if (bm_test(ob, d.RW, d.P, t0, t1)) flag = 1;
+        else np = make_uchar2((unsigned char)t0, (unsigned char)t1);
+      }
+      if (flag) r = __dadd_rn(r, d.collide_reward);                  // GRID:105-106
+      r = __dadd_rn(r, d.step_reward);                               // GRID:110
+    }
+    bool dn = done_old;
+    const bool reached = (np.x == g.x && np.y == g.y);
+    if (reached) dn = true;                                          // GRID:112-113
+    if (step_now >= d.episode_limit) dn = true;                      // GRID:116-117
+    s.posnew[j] = np;
+    s.status[j] = (int8_t)flag;
+    s.done[j] = dn ? 1 : 0;
+    s.rew[j] = r;
+    s.isint[j] = (uint8_t)(done_old ? d.collide_is_int : (d.collide_is_int && d.step_is_int));
+    byte_inc(cnew, (int)np.x * W + np.y);
+    c_env += flag;
+    c_arr += (reached && !done_old);
+  }
+  __syncwarp();
+  bool all_done = true;
+  for (int a = lane; a < N; a += 32) {
+    const int j = jb + a;
+    const uchar2 p = s.posold[j], np = s.posnew[j];
+    const int nc = (int)np.x * W + np.y;
+    const int node = cnew[nc] > 1 ? 1 : 0;                           // __count_node_collision, GRID:344-362
+    int edge = 0;                                                    // __count_edge_collision, GRID:364-383
+    if ((p.x != np.x || p.y != np.y) && cold[nc] != 0) {
+      for (int k = 0; k < N; ++k) {
+        if (k == a) continue;
+        const uchar2 qo = s.posold[jb + k], qn = s.posnew[jb + k];
+        edge += (qo.x == np.x && qo.y == np.y && qn.x == p.x && qn.y == p.y) ? 1 : 0;
+      }
+    }
+    double r = s.rew[j];
+    r = __dadd_rn(r, __dmul_rn(d.collide_reward, (double)node));     // GRID:128
+    r = __dadd_rn(r, __dmul_rn(d.collide_reward, (double)edge));     // GRID:129
+    s.rew[j] = r;
+    s.node[j] = (uint8_t)node;
+    s.edge[j] = (uint8_t)edge;
+    all_done = all_done && (s.done[j] != 0);
+    c_node += node;
+    c_edge += edge;
+  }
+  all_done = __all_sync(0xffffffffu, all_done);
+  if (d.collect_stats) {
+    c_env = __reduce_add_sync(0xffffffffu, c_env);
+    c_node = __reduce_add_sync(0xffffffffu, c_node);
+    c_edge = __reduce_add_sync(0xffffffffu, c_edge);
+    c_arr = __reduce_add_sync(0xffffffffu, c_arr);
+    if (lane == 0) {
+      atomicAdd(&stat[MAPF_STAT_ENV_STEPS], 1u);
+      atomicAdd(&stat[MAPF_STAT_AGENT_STEPS], (unsigned)N);
+      atomicAdd(&stat[MAPF_STAT_ENV_COLLISIONS], c_env);
+      atomicAdd(&stat[MAPF_STAT_NODE_COLLISIONS], c_node);
+      atomicAdd(&stat[MAPF_STAT_EDGE_COLLISIONS], c_edge);
+      atomicAdd(&stat[MAPF_STAT_GOAL_ARRIVALS], c_arr);
+      atomicAdd(&stat[MAPF_STAT_EPISODES_DONE], all_done ? 1u : 0u);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    s.envrew[el] = py_sum(s.rew + jb, s.isint + jb, N, d.sum_mode);  // GRID:141
+    s.envterm[el] = all_done ? 1 : 0;                                // episode_done, GRID:267
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Field-of-view observation bits of one agent (PRIMAL _observe :343-386), F known at compile time.
+// Bit index == byte index of the [4][F][F] output: channel*F*F + wi*F + wj, channels in the returned
+// order [poss_map, goal_map, goals_map, obs_map] (:386).
+// ------------------------------------------------------------------------------------------------
+template <int F>
+struct Fov {
+  static constexpr int FF = F * F;
+  static constexpr int NB = 4 * FF;
+  static constexpr int NW = (NB + 31) / 32;
+  static constexpr int CW = (FF + 31) / 32;
+  static constexpr uint32_t FMASK = (1u << F) - 1u;
+};
+
+template <int NWORDS>
+__device__ __forceinline__ void or_field(uint32_t (&w)[NWORDS], int off, int bits, uint32_t v) {
+  const int k = off >> 5, sh = off & 31;
+  w[k] |= v << sh;
+  if (sh + bits > 32) w[k + 1] |= v >> (32 - sh);
+}
+
+template <int CW>
+__device__ __forceinline__ void set_bit_dyn(uint32_t (&x)[CW], int idx) {
+  const uint32_t b = 1u << (idx & 31);
+  const int k = idx >> 5;
+#pragma unroll
+  for (int q = 0; q < CW; ++q) x[q] |= (k == q) ? b : 0u;
+}
+
+template <int F>
+__device__ __forceinline__ void fov_agent_bits(uint32_t (&w)[Fov<F>::NW], const MapfDims& d, const uint32_t* ob,
+                                               const uint32_t* ag, const uint8_t* idgrid, const uchar2* goals_env,
+                                               uchar2 p, uchar2 g) {
+  using T = Fov<F>;
+  constexpr int P = F / 2;
+  uint32_t goalp[T::CW], goalsp[T::CW];
+#pragma unroll
+  for (int q = 0; q < T::CW; ++q) goalp[q] = goalsp[q] = 0u;
+#pragma unroll
+  for (int q = 0; q < T::NW; ++q) w[q] = 0u;
+
+  const int gi = (int)g.x - (int)p.x + P, gj = (int)g.y - (int)p.y + P;      // :366-368
+  if ((unsigned)gi < (unsigned)F && (unsigned)gj < (unsigned)F) set_bit_dyn<T::CW>(goalp, gi * F + gj);
+
+#pragma unroll
+  for (int wi = 0; wi < F; ++wi) {
+    // padded row p.x + wi holds map row p.x - P + wi; padded column p.y holds map column p.y - P
+    const uint32_t fo = row_field(ob, d.RW, (int)p.x + wi, (int)p.y, T::FMASK);   // walls + out of bounds, :356-362
+    const uint32_t fa = row_field(ag, d.RW, (int)p.x + wi, (int)p.y, T::FMASK);   // any agent, :363-372
+    or_field<T::NW>(w, 0 * T::FF + wi * F, F, fa);
+    or_field<T::NW>(w, 3 * T::FF + wi * F, F, fo);
+    uint32_t v = fa;
+    if (wi == P) v &= ~(1u << P);                                                   // not the agent itself
+    while (v) {                                                                     // visible_agents, :374-378
+      const int wj = __ffs(v) - 1;
+      v &= v - 1;
+      const int r = (int)p.x - P + wi, c = (int)p.y - P + wj;
+      const int id = idgrid[r * d.W + c];
+      if (id == 0) continue;
+      const uchar2 og = goals_env[id - 1];
+      const int ci = min(max((int)og.x - ((int)p.x - P), 0), F - 1);
+      const int cj = min(max((int)og.y - ((int)p.y - P), 0), F - 1);
+      set_bit_dyn<T::CW>(goalsp, ci * F + cj);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < T::CW; ++q) {
+    const int bits = (T::FF - 32 * q) < 32 ? (T::FF - 32 * q) : 32;
+    or_field<T::NW>(w, 1 * T::FF + 32 * q, bits, goalp[q]);
+    or_field<T::NW>(w, 2 * T::FF + 32 * q, bits, goalsp[q]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The tile kernel: stage -> [step] -> state write-back + small outputs -> [observation].
+// ------------------------------------------------------------------------------------------------
+template <int F>
+__global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, const MapfTileLayout L,
+                                                             const MapfState S, const MapfTileArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned int stat[MAPF_N_STATS];
+  __shared__ unsigned int bad_flag;
+  const Smem s = carve(smem_raw, L);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nwarps = kThreads / 32;
+  const int N = d.N;
+  const int e0 = blockIdx.x * d.epb;
+  const int ne = min(d.epb, d.E - e0);
+  const int na = ne * N;
+  const size_t a0 = (size_t)e0 * N;
+  const bool primal = d.mode == MAPF_MODE_PRIMAL;
+  const bool do_step = A.do_step != 0;
+
+  if (tid < MAPF_N_STATS) stat[tid] = 0;
+  if (tid == 0) bad_flag = 0;
+
+  // ---- stage the tile: obstacle bitmaps (16-byte vectors), agent records, zeroed grids / bitmaps
+  {
+    const int nvec = ((d.shared_map ? 1 : ne) * d.bm_words) >> 2;
+    const uint4* src = (const uint4*)(S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e0 * d.bm_words));
+    uint4* dst = (uint4*)s.obst;
+    for (int i = tid; i < nvec; i += kThreads) dst[i] = __ldg(src + i);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const int ngrid = (ne * d.grid_bytes) >> 4;
+    for (int i = tid; i < ngrid; i += kThreads) {
+      ((uint4*)s.grida)[i] = z;
+      ((uint4*)s.gridb)[i] = z;
+    }
+    if (F > 0) {
+      const int nag = (ne * d.bm_words) >> 2;
+      for (int i = tid; i < nag; i += kThreads) ((uint4*)s.agt)[i] = z;
+    }
+  }
+  __syncthreads();   // stat/bad_flag init + zeroed grids visible
+  for (int j = tid; j < na; j += kThreads) {
+    const uchar2 p = ((const uchar2*)S.pos)[a0 + j];
+    s.posold[j] = p;
+    s.posnew[j] = p;
+    s.goal[j] = ((const uchar2*)S.goal)[a0 + j];
+    s.done[j] = S.done[a0 + j];
+    const int el = j / N, a = j - el * N;
+    int act = S.prev_action[a0 + j];
+    if (do_step && a >= A.agent_lo && a < A.agent_hi) {
+      long long v = (A.act_dtype == MAPF_I64) ? ((const long long*)A.actions)[a0 + j]
+                                              : (long long)((const uint8_t*)A.actions)[a0 + j];
+      if (v < 0 || v > 4) {                                          // GRID:92 / PRIMAL:556 assert
+        bad_flag = 1;
+        v = primal ? 0 : 4;
+      }
+      act = (int)v;
+    }
+    s.act[j] = (uint8_t)act;
+    // occupancy of the current positions: PRIMAL State.state ids (PRIMAL:32-47), GRID agent counts (GRID:299)
+    uint8_t* grid = s.grida + el * d.grid_bytes;
+    const int cell = (int)p.x * d.W + p.y;
+    if (primal) grid[cell] = (uint8_t)(a + 1);
+    else byte_inc(grid, cell);
+  }
+  __syncthreads();
+
+  // ---- step: one warp per environment
+  if (do_step) {
+    for (int el = warp; el < ne; el += nwarps) {
+      if (primal) {
+        step_primal_env(d, s, el, lane, A, stat);
+      } else {
+        int step_now = 0;
+        if (lane == 0) step_now = S.step_count[e0 + el] + 1;         // GRID:93
+        step_now = __shfl_sync(0xffffffffu, step_now, 0);
+        step_grid_env(d, s, el, lane, step_now, stat);
+      }
+      if (lane == 0) {
+        if (!primal || A.agent_lo == 0) S.step_count[e0 + el] += 1;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- agent bitmap of the post-step positions + available-action masks
+  const uint8_t* gridcur = (!primal && do_step) ? s.gridb : s.grida;
+  const bool want_avail = A.out.avail_dev != nullptr;
+  for (int j = tid; j < na; j += kThreads) {
+    const int el = j / N;
+    const uchar2 p = s.posnew[j];
+    if (F > 0) {
+      uint32_t* ag = s.agt + el * d.bm_words;
+      const int pc = (int)p.y + d.P;
+      atomicOr(&ag[((int)p.x + d.P) * d.RW + (pc >> 5)], 1u << (pc & 31));
+    }
+    if (want_avail) {
+      const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+      uint8_t m;
+      if (primal) {                                                  // _listNextValidActions, PRIMAL:639-667
+        const uint8_t* grid = gridcur + el * d.grid_bytes;
+        m = 1;
+#pragma unroll
+        for (int k = 1; k <= 4; ++k) {
+          const int n0 = (int)p.x + (k == 2 ? 1 : (k == 4 ? -1 : 0));
+          const int n1 = (int)p.y + (k == 1 ? 1 : (k == 3 ? -1 : 0));
+          if (!bm_test(ob, d.RW, d.P, n0, n1) && grid[n0 * d.W + n1] == 0) m |= (uint8_t)(1u << k);
+        }
+        const int act = s.act[j];
+        const int opp = (act == 0) ? -1 : (((act + 1) & 3) + 1);
+        if (opp > 0) m &= (uint8_t)~(1u << opp);
+      } else {                                                       // get_avail_agent_actions, GRID:203-224
+        m = 16;
+        m |= bm_test(ob, d.RW, d.P, (int)p.x - 1, (int)p.y) ? 0 : 1;
+        m |= bm_test(ob, d.RW, d.P, (int)p.x + 1, (int)p.y) ? 0 : 2;
+        m |= bm_test(ob, d.RW, d.P, (int)p.x, (int)p.y - 1) ? 0 : 4;
+        m |= bm_test(ob, d.RW, d.P, (int)p.x, (int)p.y + 1) ? 0 : 8;
+      }
+      s.avail[j] = m;
+    }
+  }
+  __syncthreads();
+
+  // ---- state write-back and the small per-agent / per-env outputs (coalesced over the tile)
+  if (do_step) {
+    copy_out_bytes(S.pos + 2 * a0, (const uint8_t*)s.posnew, 2 * na, tid);
+    copy_out_bytes(S.done + a0, s.done, na, tid);
+    copy_out_bytes(S.prev_action + a0, s.act, na, tid);
+    if (A.out.dones_dev) copy_out_bytes(A.out.dones_dev + a0, s.done, na, tid);
+    if (A.out.status_dev) copy_out_bytes((uint8_t*)A.out.status_dev + a0, (const uint8_t*)s.status, na, tid);
+    if (A.out.agent_reward_dev)
+      for (int j = tid; j < na; j += kThreads) A.out.agent_reward_dev[a0 + j] = s.rew[j];
+    if (A.out.reward_dev)
+      for (int el = tid; el < ne; el += kThreads) A.out.reward_dev[e0 + el] = s.envrew[el];
+    if (A.out.terminated_dev)
+      for (int el = tid; el < ne; el += kThreads) A.out.terminated_dev[e0 + el] = s.envterm[el];
+    if (A.out.node_dev)
+      for (int j = tid; j < na; j += kThreads) A.out.node_dev[a0 + j] = primal ? 0 : (int16_t)s.node[j];
+    if (A.out.edge_dev)
+      for (int j = tid; j < na; j += kThreads) A.out.edge_dev[a0 + j] = primal ? 0 : (int16_t)s.edge[j];
+    if (A.out.valid_dev)
+      for (int j = tid; j < na; j += kThreads) A.out.valid_dev[a0 + j] = primal ? ((s.flag[j] >> 1) & 1) : 1;
+    if (primal && A.out.done_mid_dev)
+      for (int j = tid; j < na; j += kThreads) A.out.done_mid_dev[a0 + j] = (s.flag[j] >> 2) & 1;
+    if (primal && A.out.next_mid_dev) write_mask5(A.out.next_mid_dev + 5 * a0, s.nextmid, na, tid);
+  }
+  if (want_avail) write_mask5(A.out.avail_dev + 5 * a0, s.avail, na, tid);
+  if (tid == 0 && bad_flag) atomicOr(S.err_flags, MAPF_FLAG_BAD_ACTION);
+  if (d.collect_stats && do_step && tid < MAPF_N_STATS && stat[tid] != 0)
+    atomicAdd(&S.stats[tid], (unsigned long long)stat[tid]);
+
+  // ---- observation
+  if (A.obs == nullptr && A.vec == nullptr) return;
+
+  if (d.obs_mode == MAPF_OBS_FULLMAP) {
+    // get_obs / get_state, GRID:143-196: -1 on walls, else the number of agents on the cell.
+    if (A.obs == nullptr) return;
+    int8_t* out = (int8_t*)A.obs + (size_t)e0 * d.HW;
+    for (int i = tid; i < ne * d.HW; i += kThreads) {
+      const int el = i / d.HW, cell = i - el * d.HW;
+      const int r = cell / d.W, c = cell - r * d.W;
+      const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+      const int cnt = gridcur[el * d.grid_bytes + cell];
+      out[i] = bm_test(ob, d.RW, d.P, r, c) ? (int8_t)(cnt - 1) : (int8_t)cnt;   // `+= 1` on a -1 cell, GRID:299
+    }
+    return;
+  }
+
+  if constexpr (F > 0) {
+    using T = Fov<F>;
+    // phase 1: one thread per agent builds its 4*F*F bits and the goal vector; G agents share a
+    // word-aligned group string.
+    for (int base = 0; base < na; base += kThreads) {
+      const int j = base + tid;
+      const bool valid = j < na;
+      uint32_t w[T::NW];
+      int w0 = 0, sh = 0;
+      if (valid) {
+        const int el = j / N;
+        const uchar2 p = s.posnew[j], g = s.goal[j];
+        if (A.obs != nullptr) {
+          fov_agent_bits<F>(w, d, s.obst + (d.shared_map ? 0 : el * d.bm_words), s.agt + el * d.bm_words,
+                            gridcur + el * d.grid_bytes, s.goal + el * N, p, g);
+          const int grp = j / d.G, k = j - grp * d.G;
+          const int boff = k * T::NB;
+          w0 = grp * d.GW + (boff >> 5);
+          sh = boff & 31;
+          const int nwords = (sh + T::NB + 31) >> 5;
+          uint32_t prev = 0;
+#pragma unroll
+          for (int q = 0; q <= T::NW; ++q) {
+            const uint32_t cur = (q < T::NW) ? w[q] : 0u;
+            const uint32_t o = __funnelshift_l(prev, cur, sh);     // (cur:prev << sh) >> 32
+            prev = cur;
+            if (q == 0) w[0] = o;                                  // keep for the deferred OR
+            if (q < nwords && !(q == 0 && sh > 0)) s.str[w0 + q] = o;
+          }
+        }
+        if (A.vec != nullptr) {                                      // PRIMAL:380-385
+          const int dx = (int)g.x - (int)p.x, dy = (int)g.y - (int)p.y;
+          const double mag = __ldg(S.mag_lut + (dx * dx + dy * dy));
+          double fx = (double)dx, fy = (double)dy;
+          if (mag != 0.0) {
+            fx = __ddiv_rn(fx, mag);
+            fy = __ddiv_rn(fy, mag);
+          }
+          double* v = A.vec + 3 * (a0 + j);
+          v[0] = fx;
+          v[1] = fy;
+          v[2] = mag;
+        }
+      }
+      __syncthreads();
+      if (valid && sh > 0 && A.obs != nullptr) s.str[w0] |= w[0];   // word shared with the previous agent
+    }
+    __syncthreads();
+    if (A.obs == nullptr) return;
+
+    // phase 2: expand the tile's bit string; thread q writes output bytes [16q, 16q+16)
+    const size_t nbits = (size_t)na * T::NB;
+    if (A.obs_dtype == MAPF_U8) {
+      uint8_t* out = (uint8_t*)A.obs + a0 * T::NB;
+      const int nchunk = (int)(nbits >> 4);
+      const uint16_t* s16 = (const uint16_t*)s.str;
+      for (int q = tid; q < nchunk; q += kThreads) {
+        const uint32_t h = s16[q];
+        uint4 v;
+        v.x = expand4(h & 15u);
+        v.y = expand4((h >> 4) & 15u);
+        v.z = expand4((h >> 8) & 15u);
+        v.w = expand4(h >> 12);
+        st_stream16(out + ((size_t)q << 4), v);
+      }
+      for (int b = (nchunk << 4) + tid; b < (int)nbits; b += kThreads) out[b] = (s.str[b >> 5] >> (b & 31)) & 1u;
+    } else {
+      float* out = (float*)A.obs + a0 * T::NB;
+      const int nchunk = (int)(nbits >> 2);
+      for (int q = tid; q < nchunk; q += kThreads) {
+        const uint32_t nib = (s.str[q >> 3] >> ((q & 7) << 2)) & 15u;
+        uint4 v;
+        v.x = (nib & 1u) ? 0x3f800000u : 0u;
+        v.y = (nib & 2u) ? 0x3f800000u : 0u;
+        v.z = (nib & 4u) ? 0x3f800000u : 0u;
+        v.w = (nib & 8u) ? 0x3f800000u : 0u;
+        st_stream16(out + ((size_t)q << 2), v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic-F observation (any F in [1, 255]); byte-wise gather, used when no specialised tile kernel
+// exists for F and as an independent cross-check of the bit-string path in the tests.
+// One thread per (agent, window cell).
+// ------------------------------------------------------------------------------------------------
+__global__ void mapf_observe_generic_kernel(const MapfDims d, const MapfState S, uint8_t* obs_u8, float* obs_f32,
+                                            double* vec) {
+  const int F = d.F, FF = F * F, Pw = F / 2;
+  const long long total = (long long)d.E * d.N * FF;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long ja = idx / FF;
+    const int cell = (int)(idx - ja * FF);
+    const int e = (int)(ja / d.N), a = (int)(ja - (long long)e * d.N);
+    const int wi = cell / F, wj = cell - wi * F;
+    const uchar2* pos = (const uchar2*)S.pos + (size_t)e * d.N;
+    const uchar2* goal = (const uchar2*)S.goal + (size_t)e * d.N;
+    const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
+    const uchar2 p = pos[a], g = goal[a];
+    const int t0 = (int)p.x - Pw, t1 = (int)p.y - Pw;
+    const int i = t0 + wi, jx = t1 + wj;
+    const bool oob = (i < 0 || i >= d.H || jx < 0 || jx >= d.W);
+    uint8_t c_obs = oob ? 1 : (uint8_t)bm_test(ob, d.RW, d.P, i, jx);
+    uint8_t c_poss = 0, c_goal = 0, c_goals = 0;
+    if (!oob && g.x == i && g.y == jx) c_goal = 1;
+    for (int b = 0; b < d.N; ++b) {
+      const uchar2 q = pos[b];
+      if (q.x == i && q.y == jx) c_poss = 1;
+      if (b != a) {
+        const int bi = (int)q.x - t0, bj = (int)q.y - t1;
+        if ((unsigned)bi < (unsigned)F && (unsigned)bj < (unsigned)F) {   // b is visible to a
+          const uchar2 og = goal[b];
+          const int ci = min(max((int)og.x - t0, 0), F - 1), cj = min(max((int)og.y - t1, 0), F - 1);
+          if (ci == wi && cj == wj) c_goals = 1;
+        }
+      }
+    }
+    const size_t o = (size_t)ja * 4 * FF + cell;
+    if (obs_u8) {
+      obs_u8[o] = c_poss;
+      obs_u8[o + FF] = c_goal;
+      obs_u8[o + 2 * FF] = c_goals;
+      obs_u8[o + 3 * FF] = c_obs;
+    }
+    if (obs_f32) {
+      obs_f32[o] = (float)c_poss;
+      obs_f32[o + FF] = (float)c_goal;
+      obs_f32[o + 2 * FF] = (float)c_goals;
+      obs_f32[o + 3 * FF] = (float)c_obs;
+    }
+    if (vec && cell == 0) {
+      const int dx = (int)g.x - (int)p.x, dy = (int)g.y - (int)p.y;
+      const double mag = S.mag_lut[dx * dx + dy * dy];
+      double fx = (double)dx, fy = (double)dy;
+      if (mag != 0.0) {
+        fx = __ddiv_rn(fx, mag);
+        fy = __ddiv_rn(fy, mag);
+      }
+      vec[3 * ja] = fx;
+      vec[3 * ja + 1] = fy;
+      vec[3 * ja + 2] = mag;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reset-time kernels
+// ------------------------------------------------------------------------------------------------
+// Padded obstacle bitmap: bit = 1 on walls and everywhere outside the map (out of bounds is treated as
+// an obstacle by every consumer: GRID:336-340, PRIMAL:114-118, :356-359).
+__global__ void mapf_build_obst_kernel(const MapfDims d, uint32_t* obst_bits, const int8_t* map,
+                                       const uint8_t* env_mask) {
+  const int emap = d.shared_map ? 1 : d.E;
+  const long long total = (long long)emap * d.bm_words;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(idx / d.bm_words);
+    const int wdx = (int)(idx - (long long)e * d.bm_words);
+    if (env_mask && !d.shared_map && !env_mask[e]) continue;
+    uint32_t bits = 0xffffffffu;
+    const int prow = wdx / d.RW, k = wdx - prow * d.RW;
+    const int r = prow - d.P;
+    if (prow < d.PR && r >= 0 && r < d.H) {
+      const int8_t* mrow = map + ((size_t)e * d.H + r) * d.W;
+      bits = 0;
+      for (int b = 0; b < 32; ++b) {
+        const int c = 32 * k + b - d.P;
+        const bool wall = (c < 0 || c >= d.W) ? true : (mrow[c] != 0);
+        bits |= (wall ? 1u : 0u) << b;
+      }
+    }
+    obst_bits[idx] = bits;
+  }
+}
+
+__global__ void mapf_reset_kernel(const MapfDims d, const MapfState S, const int16_t* starts, const int16_t* goals,
+                                  const uint8_t* env_mask) {
+  const long long total = (long long)d.E * d.N;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total;
+       j += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(j / d.N), a = (int)(j - (long long)e * d.N);
+    if (env_mask && !env_mask[e]) continue;
+    uint32_t flags = 0;
+    uchar2 st = ((const uchar2*)S.start)[j], g = ((const uchar2*)S.goal)[j];
+    if (starts) {
+      int s0 = starts[2 * j], s1 = starts[2 * j + 1];
+      if (s0 < 0 || s0 >= d.H || s1 < 0 || s1 >= d.W) {
+        flags |= MAPF_FLAG_BAD_POSITION;
+        s0 = min(max(s0, 0), d.H - 1);
+        s1 = min(max(s1, 0), d.W - 1);
+      }
+      st = make_uchar2((unsigned char)s0, (unsigned char)s1);
+      ((uchar2*)S.start)[j] = st;
+    }
+    if (goals) {
+      int g0 = goals[2 * j], g1 = goals[2 * j + 1];
+      if (g0 < 0 || g0 >= d.H || g1 < 0 || g1 >= d.W) {
+        flags |= MAPF_FLAG_BAD_POSITION;
+        g0 = min(max(g0, 0), d.H - 1);
+        g1 = min(max(g1, 0), d.W - 1);
+      }
+      g = make_uchar2((unsigned char)g0, (unsigned char)g1);
+      ((uchar2*)S.goal)[j] = g;
+    }
+    const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
+    if (bm_test(ob, d.RW, d.P, st.x, st.y)) flags |= MAPF_FLAG_START_ON_WALL;
+    ((uchar2*)S.pos)[j] = st;                                        // GRID:79
+    S.done[j] = (d.mode == MAPF_MODE_PRIMAL) ? (uint8_t)(st.x == g.x && st.y == g.y) : 0;   // GRID:75
+    S.prev_action[j] = (d.mode == MAPF_MODE_PRIMAL) ? 0 : 4;
+    if (a == 0) S.step_count[e] = 0;                                 // GRID:73
+    if (d.mode == MAPF_MODE_PRIMAL && starts) {                     // one agent per cell, PRIMAL:53-66
+      for (int b = 0; b < a; ++b)
+        if (starts[2 * ((long long)e * d.N + b)] == starts[2 * j] &&
+            starts[2 * ((long long)e * d.N + b) + 1] == starts[2 * j + 1])
+          flags |= MAPF_FLAG_START_OVERLAP;
+    }
+    if (flags) atomicOr(S.err_flags, flags);
+  }
+}
+
+__global__ void mapf_set_goals_kernel(const MapfDims d, const MapfState S, const int16_t* goals,
+                                      const uint8_t* dirty) {
+  const long long total = (long long)d.E * d.N;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total;
+       j += (long long)gridDim.x * blockDim.x) {
+    if (dirty && !dirty[j]) continue;
+    int g0 = goals[2 * j], g1 = goals[2 * j + 1];
+    if (g0 < 0 || g0 >= d.H || g1 < 0 || g1 >= d.W) {
+      atomicOr(S.err_flags, MAPF_FLAG_BAD_POSITION);
+      g0 = min(max(g0, 0), d.H - 1);
+      g1 = min(max(g1, 0), d.W - 1);
+    }
+    ((uchar2*)S.goal)[j] = make_uchar2((unsigned char)g0, (unsigned char)g1);
+    if (d.mode == MAPF_MODE_PRIMAL) {
+      const uchar2 p = ((const uchar2*)S.pos)[j];
+      S.done[j] = (uint8_t)(p.x == g0 && p.y == g1);
+    }
+  }
+}
+
+__global__ void mapf_export16_kernel(long long n, const uint8_t* src, int16_t* dst) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (int16_t)src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-goal BFS distance maps: one warp per (env, agent).  Rows are bit masks; a wavefront step is
+// new = (left | right | up | down neighbours of the frontier) & free & ~visited.
+// (PARTIAL:931-955 == hop distance; PRIMAL getAstarCosts :407-499 == hop distance from the goal.)
+// smem per warp: 4 bitmaps [H][RWB] (free, visited, frontier A/B) and, when it fits, the int16 map.
+// ------------------------------------------------------------------------------------------------
+__global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty, int16_t* dist,
+                                int RWB, int warps_per_block, int stage_dist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long m = (long long)blockIdx.x * warps_per_block + warp;   // (env, agent) index
+  if (m >= (long long)d.E * d.N) return;
+  if (dirty && !dirty[m]) return;
+  const int e = (int)(m / d.N);
+  const int H = d.H, W = d.W, items = H * RWB;
+  const size_t per_warp = (size_t)4 * items * 4 + (stage_dist ? (((size_t)d.HW * 2 + 15) & ~(size_t)15) : 0);
+  unsigned char* base = smem_raw + per_warp * warp;
+  uint32_t* freeb = (uint32_t*)base;
+  uint32_t* vis = freeb + items;
+  uint32_t* fa = vis + items;
+  uint32_t* fb = fa + items;
+  int16_t* sd = (int16_t*)(fb + items);
+  int16_t* gd = dist + (size_t)m * d.HW;
+  int16_t* dd = stage_dist ? sd : gd;
+  const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
+  const uchar2 g = ((const uchar2*)S.goal)[m];
+
+  for (int it = lane; it < items; it += 32) {
+    const int r = it / RWB, k = it - r * RWB;
+    const uint32_t* prow = ob + (r + d.P) * d.RW;
+    const int pb = 32 * k + d.P;
+    uint32_t wall = __funnelshift_r(prow[pb >> 5], prow[(pb >> 5) + 1], pb);
+    const int rem = W - 32 * k;
+    const uint32_t valid = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+    const uint32_t fr = ~wall & valid;
+    freeb[it] = fr;
+    uint32_t start = 0;
+    if (r == g.x && (g.y >> 5) == k) start = (1u << (g.y & 31)) & fr;
+    vis[it] = start;
+    fa[it] = start;
+    for (int b = 0; b < 32 && 32 * k + b < W; ++b) {
+      const int c = 32 * k + b;
+      dd[r * W + c] = ((fr >> b) & 1u) ? (((start >> b) & 1u) ? 0 : -2) : -1;
+    }
+  }
+  __syncwarp();
+  uint32_t* cur = fa;
+  uint32_t* nxt = fb;
+  for (int level = 1; level < 32767; ++level) {
+    uint32_t any = 0;
+    for (int it = lane; it < items; it += 32) {
+      const int r = it / RWB, k = it - r * RWB;
+      const uint32_t f = cur[it];
+      uint32_t nb = (f << 1) | (f >> 1);
+      if (k > 0) nb |= cur[it - 1] >> 31;
+      if (k < RWB - 1) nb |= cur[it + 1] << 31;
+      if (r > 0) nb |= cur[it - RWB];
+      if (r < H - 1) nb |= cur[it + RWB];
+      uint32_t nw = nb & freeb[it] & ~vis[it];
+      vis[it] |= nw;
+      nxt[it] = nw;
+      any |= nw;
+      while (nw) {
+        const int b = __ffs(nw) - 1;
+        nw &= nw - 1;
+        dd[r * W + 32 * k + b] = (int16_t)level;
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, any != 0)) break;
+    uint32_t* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  __syncwarp();
+  if (stage_dist) {
+    if ((d.HW & 7) == 0) {
+      const int nv = d.HW >> 3;
+      for (int i = lane; i < nv; i += 32) ((uint4*)gd)[i] = ((const uint4*)sd)[i];
+    } else {
+      for (int i = lane; i < d.HW; i += 32) gd[i] = sd[i];
+    }
+  }
+}
+
+// getAstarCosts quirk (PRIMAL:496-498): `costs = state.copy()`, so cells the search never reached keep
+// `state`: 0 when free, the agent id when an agent stands there.
+__global__ void mapf_primal_costs_agents_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty,
+                                                int16_t* dist) {
+  const long long total = (long long)d.E * d.N * d.N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / d.N;   // (env, map owner)
+    const int b = (int)(idx - m * d.N);
+    if (dirty && !dirty[m]) continue;
+    const int e = (int)(m / d.N);
+    const uchar2 p = ((const uchar2*)S.pos)[(size_t)e * d.N + b];
+    int16_t* c = dist + (size_t)m * d.HW + (int)p.x * d.W + p.y;
+    if (*c == -2) *c = (int16_t)(b + 1);
+  }
+}
+__global__ void mapf_primal_costs_free_kernel(const MapfDims d, const uint8_t* dirty, int16_t* dist) {
+  const long long total = (long long)d.E * d.N * d.HW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    if (dirty && !dirty[idx / d.HW]) continue;
+    if (dist[idx] == -2) dist[idx] = 0;
+  }
+}
+
+template <int F>
+cudaError_t launch_tile_f(const MapfDims& d, const MapfTileLayout& L, const MapfState& S, const MapfTileArgs& A,
+                          cudaStream_t st) {
+  const int grid = (d.E + d.epb - 1) / d.epb;
+  mapf_tile_kernel<F><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
+  return cudaGetLastError();
+}
+
+int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  if (g > 148LL * 32) g = 148LL * 32;   // grid-stride loops; a multiple of the 148 SMs
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+#define MAPF_FOR_EACH_F(X) X(0) X(3) X(5) X(7) X(9) X(10) X(11)
+
+extern "C" int mapf_tile_has_fov(int F) {
+  switch (F) {
+#define X(f) case f:
+    MAPF_FOR_EACH_F(X)
+#undef X
+    return 1;
+    default:
+      return 0;
+  }
+}
+
+extern "C" int mapf_configure_tile(int F, int smem_bytes) {
+  cudaError_t err = cudaErrorInvalidValue;
+  switch (F) {
+#define X(f)                                                                                                  \
+  case f:                                                                                                     \
+    err = cudaFuncSetAttribute(mapf_tile_kernel<f>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+    break;
+    MAPF_FOR_EACH_F(X)
+#undef X
+    default:
+      break;
+  }
+  return (int)err;
+}
+
+extern "C" int mapf_launch_tile(const MapfDims& d, const MapfTileLayout& L, const MapfState& S, const MapfTileArgs& A,
+                                void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int F = (d.obs_mode == MAPF_OBS_PRIMAL_FOV) ? d.F : 0;
+  switch (F) {
+#define X(f) \
+  case f:    \
+    return (int)launch_tile_f<f>(d, L, S, A, st);
+    MAPF_FOR_EACH_F(X)
+#undef X
+    default:
+      return (int)cudaErrorInvalidValue;
+  }
+}
+
+extern "C" int mapf_launch_observe_generic(const MapfDims& d, const MapfState& S, uint8_t* obs_u8, float* obs_f32,
+                                           double* vec, void* stream) {
+  const long long total = (long long)d.E * d.N * d.F * d.F;
+  mapf_observe_generic_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, S, obs_u8, obs_f32, vec);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_build_obst(const MapfDims& d, const MapfState& S, const int8_t* map,
+                                      const uint8_t* env_mask, void* stream) {
+  const long long total = (long long)(d.shared_map ? 1 : d.E) * d.bm_words;
+  mapf_build_obst_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, S.obst_bits, map, env_mask);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_reset(const MapfDims& d, const MapfState& S, const int16_t* starts, const int16_t* goals,
+                                 const uint8_t* env_mask, void* stream) {
+  mapf_reset_kernel<<<grid_for((long long)d.E * d.N, 256), 256, 0, (cudaStream_t)stream>>>(d, S, starts, goals,
+                                                                                           env_mask);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, const int16_t* goals,
+                                     const uint8_t* dirty, void* stream) {
+  mapf_set_goals_kernel<<<grid_for((long long)d.E * d.N, 256), 256, 0, (cudaStream_t)stream>>>(d, S, goals, dirty);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_export16(const MapfDims& d, const uint8_t* src, int16_t* dst, void* stream) {
+  const long long n = (long long)d.E * d.N * 2;
+  mapf_export16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, src, dst);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, int16_t* dist,
+                               int primal_costs, void* stream, int* n_launches) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int RWB = (d.W + 31) / 32;
+  const size_t bm_bytes = (size_t)4 * d.H * RWB * 4;
+  const size_t dist_bytes = ((size_t)d.HW * 2 + 15) & ~(size_t)15;
+  int stage = 1, warps = 8;
+  while (warps > 1 && (bm_bytes + dist_bytes) * warps > 200 * 1024) warps >>= 1;
+  if ((bm_bytes + dist_bytes) * warps > 200 * 1024) {
+    stage = 0;
+    warps = 8;
+    while (warps > 1 && bm_bytes * warps > 200 * 1024) warps >>= 1;
+  }
+  const size_t smem = (bm_bytes + (stage ? dist_bytes : 0)) * warps;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mapf_bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  const long long maps = (long long)d.E * d.N;
+  const long long grid = (maps + warps - 1) / warps;
+  mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, dirty, dist, RWB, warps, stage);
+  cudaError_t err = cudaGetLastError();
+  *n_launches = 1;
+  if (err == cudaSuccess && primal_costs) {
+    mapf_primal_costs_agents_kernel<<<grid_for(maps * d.N, 256), 256, 0, st>>>(d, S, dirty, dist);
+    mapf_primal_costs_free_kernel<<<grid_for(maps * d.HW, 256), 256, 0, st>>>(d, dirty, dist);
+    err = cudaGetLastError();
+    *n_launches = 3;
+  }
+  return (int)err;
+}

@@ -1,0 +1,336 @@
+"""MapfEngine: thousands of MAPF grid-world environments resident on one B200.
+
+Thin host-side wrapper over the C ABI (include/mapf_b200.h): torch is used only for device
+memory, streams and dtype plumbing.  All arithmetic happens in csrc/mapf_kernels.cu.
+
+Vector API (device tensors, no host round trips):
+    eng = MapfEngine(n_envs=E, n_agents=N, height=H, width=W, mode="primal", fov=11)
+    eng.reset(obst, starts, goals)                       # obst [E,H,W] (or [H,W] shared), starts/goals [E,N,2]
+    out = eng.step_observe(actions)                      # actions uint8/int64 [E,N] on the device
+    out["obs"] [E,N,4,F,F] u8, out["vec"] [E,N,3] f64, out["reward"], out["terminated"], out["avail"], ...
+
+Semantics follow the reference envs (citations in include/mapf_b200.h):
+    mode "grid"   = mapf_gridworld.MAPF_GRID.step (detect-and-penalise collisions)
+    mode "primal" = mapf_primal.MAPFEnv._step swept over agents 1..N (sequential claim)
+"""
+import ctypes
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (F32, I8, I64, MODE_GRID, MODE_PRIMAL, OBS_FULLMAP, OBS_PRIMAL_FOV, STAT_NAMES, STEP_OUT_FIELDS, U8,
+                   MapfCfg, MapfHostIO, MapfStepOut)
+
+_OUT_SPECS = {
+    # name: (dtype, per-env shape suffix builder)
+    "reward": (torch.float64, lambda N: ()),
+    "terminated": (torch.uint8, lambda N: ()),
+    "agent_reward": (torch.float64, lambda N: (N,)),
+    "dones": (torch.uint8, lambda N: (N,)),
+    "status": (torch.int8, lambda N: (N,)),
+    "node": (torch.int16, lambda N: (N,)),
+    "edge": (torch.int16, lambda N: (N,)),
+    "valid": (torch.uint8, lambda N: (N,)),
+    "done_mid": (torch.uint8, lambda N: (N,)),
+    "next_mid": (torch.uint8, lambda N: (N, 5)),
+    "avail": (torch.uint8, lambda N: (N, 5)),
+}
+
+DEFAULT_WANT = ("reward", "terminated", "dones", "avail")
+
+
+class MapfError(RuntimeError):
+    pass
+
+
+def python_sum_mode():
+    """1 when this interpreter's builtin sum() compensates float sums (CPython >= 3.12), else 0."""
+    return 1 if sys.version_info >= (3, 12) else 0
+
+
+def magnitude_lut(height, width):
+    """mag[s] for s = dx*dx + dy*dy, evaluated with the reference's expression (mapf_primal.py:382)."""
+    n = (height - 1) ** 2 + (width - 1) ** 2 + 1
+    return np.array([s ** .5 for s in range(n)], dtype=np.float64)
+
+
+class MapfEngine:
+    def __init__(self, n_envs, n_agents, height, width, mode="primal", obs_mode=None, fov=11, shared_map=False,
+                 episode_limit=10000, step_reward=-0.01, collide_reward=-10, action_cost=-0.3, idle_cost=-0.5,
+                 goal_reward=0.0, collision_reward=-2.0, goal_dist=False, collect_stats=True, device=None,
+                 reward_sum_mode=None):
+        if not torch.cuda.is_available():
+            raise MapfError("MapfEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise MapfError("MapfEngine needs a CUDA device; got %s" % self.device)
+        self.E, self.N, self.H, self.W = int(n_envs), int(n_agents), int(height), int(width)
+        self.mode = {"grid": MODE_GRID, "primal": MODE_PRIMAL}[mode] if isinstance(mode, str) else int(mode)
+        if obs_mode is None:
+            obs_mode = OBS_PRIMAL_FOV if self.mode == MODE_PRIMAL else OBS_FULLMAP
+        elif isinstance(obs_mode, str):
+            obs_mode = {"fullmap": OBS_FULLMAP, "fov": OBS_PRIMAL_FOV}[obs_mode]
+        self.obs_mode = int(obs_mode)
+        self.F = int(fov)
+        self.shared_map = bool(shared_map)
+        self.has_goal_dist = bool(goal_dist)
+        cfg = MapfCfg()
+        self.lib.mapf_default_cfg(ctypes.byref(cfg))
+        cfg.n_envs, cfg.n_agents, cfg.height, cfg.width = self.E, self.N, self.H, self.W
+        cfg.mode, cfg.obs_mode, cfg.fov = self.mode, self.obs_mode, self.F
+        cfg.shared_map = int(self.shared_map)
+        cfg.episode_limit = int(episode_limit)
+        cfg.goal_dist = int(self.has_goal_dist)
+        cfg.collect_stats = int(bool(collect_stats))
+        cfg.step_reward, cfg.collide_reward = float(step_reward), float(collide_reward)
+        cfg.action_cost, cfg.idle_cost = float(action_cost), float(idle_cost)
+        cfg.goal_reward, cfg.collision_reward = float(goal_reward), float(collision_reward)
+        cfg.reward_sum_mode = python_sum_mode() if reward_sum_mode is None else int(reward_sum_mode)
+        cfg.step_reward_is_int = int(isinstance(step_reward, int))
+        cfg.collide_reward_is_int = int(isinstance(collide_reward, int))
+        self._lut = magnitude_lut(self.H, self.W)
+        cfg.mag_lut_host = self._lut.ctypes.data
+        cfg.mag_lut_len = int(self._lut.size)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.mapf_create(ctypes.byref(cfg), ctypes.byref(self._h))
+        if rc != 0:
+            self._h = None
+            raise MapfError("mapf_create failed (%d): %s" % (rc, _lib.last_error(self.lib)))
+        self._bufs = {}
+        self._keep = []   # tensors referenced by asynchronous launches
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mapf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MapfError("%s failed (%d): %s" % (what, rc, _lib.last_error(self.lib, self._h)))
+
+    def _buf(self, name, shape, dtype):
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    def _to_dev(self, x, dtype, shape=None):
+        if x is None:
+            return None
+        if isinstance(x, torch.Tensor):
+            t = x.to(device=self.device, dtype=dtype).contiguous()
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(x), device=self.device).to(dtype).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(t.shape)))
+        return t
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def _actions(self, actions):
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions))
+        if actions.dtype not in (torch.uint8, torch.int64):
+            actions = actions.to(torch.int64)
+        a = actions.to(self.device).contiguous()
+        if tuple(a.shape) != (self.E, self.N):
+            raise ValueError("actions must have shape (%d, %d), got %s" % (self.E, self.N, tuple(a.shape)))
+        return a, (U8 if a.dtype == torch.uint8 else I64)
+
+    def _step_out(self, want):
+        so = MapfStepOut()
+        outs = {}
+        for name in want:
+            if name not in _OUT_SPECS:
+                raise KeyError("unknown step output %r (choose from %s)" % (name, ", ".join(STEP_OUT_FIELDS)))
+            dtype, suffix = _OUT_SPECS[name]
+            t = self._buf("out_" + name, (self.E,) + suffix(self.N), dtype)
+            setattr(so, name + "_dev", t.data_ptr())
+            outs[name] = t
+        return so, outs
+
+    # ------------------------------------------------------------------ state
+    def reset(self, obst=None, starts=None, goals=None, env_mask=None):
+        """obst: non-zero = obstacle, [E,H,W] or [H,W] when shared_map.  starts/goals: [E,N,2] (p0, p1).
+        Any argument may be None to keep the stored value (MAPF_GRID.reset re-uses its start positions)."""
+        mshape = (self.H, self.W) if self.shared_map else (self.E, self.H, self.W)
+        m = self._to_dev(obst, torch.int8, mshape)
+        s = self._to_dev(starts, torch.int16, (self.E, self.N, 2))
+        g = self._to_dev(goals, torch.int16, (self.E, self.N, 2))
+        k = self._to_dev(env_mask, torch.uint8, (self.E,))
+        self._keep = [m, s, g, k]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_reset(self._h, self._ptr(m), self._ptr(s), self._ptr(g), self._ptr(k),
+                                            self._stream()), "mapf_reset")
+
+    def set_goals(self, goals, dirty=None):
+        g = self._to_dev(goals, torch.int16, (self.E, self.N, 2))
+        dmask = self._to_dev(dirty, torch.uint8, (self.E, self.N))
+        self._keep = [g, dmask]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_set_goals(self._h, self._ptr(g), self._ptr(dmask), self._stream()),
+                        "mapf_set_goals")
+
+    def set_prev_actions(self, prev):
+        p = self._to_dev(prev, torch.uint8, (self.E, self.N))
+        self._keep = [p]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_set_prev_actions(self._h, self._ptr(p), self._stream()), "mapf_set_prev_actions")
+
+    def positions(self):
+        out = self._buf("positions", (self.E, self.N, 2), torch.int16)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_get_positions(self._h, self._ptr(out), self._stream()), "mapf_get_positions")
+        return out
+
+    def goals(self):
+        out = self._buf("goals", (self.E, self.N, 2), torch.int16)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_get_goals(self._h, self._ptr(out), self._stream()), "mapf_get_goals")
+        return out
+
+    def dones(self):
+        out = self._buf("dones", (self.E, self.N), torch.uint8)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_get_dones(self._h, self._ptr(out), self._stream()), "mapf_get_dones")
+        return out
+
+    def step_count(self):
+        out = self._buf("step_count", (self.E,), torch.int32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_get_step_count(self._h, self._ptr(out), self._stream()), "mapf_get_step_count")
+        return out
+
+    # ------------------------------------------------------------------ hot path
+    def step(self, actions, want=DEFAULT_WANT, agent_range=None):
+        """One environment step (GRID) / one sweep over agents (PRIMAL).  Returns a dict of device tensors."""
+        a, adt = self._actions(actions)
+        so, outs = self._step_out(want)
+        self._keep = [a]
+        with torch.cuda.device(self.device):
+            if agent_range is None:
+                rc = self.lib.mapf_step(self._h, self._ptr(a), adt, ctypes.byref(so), self._stream())
+            else:
+                rc = self.lib.mapf_step_agents(self._h, self._ptr(a), adt, int(agent_range[0]), int(agent_range[1]),
+                                               ctypes.byref(so), self._stream())
+        self._check(rc, "mapf_step")
+        return outs
+
+    def _obs_buffers(self, dtype, want_vec):
+        if self.obs_mode == OBS_PRIMAL_FOV:
+            if dtype not in (torch.uint8, torch.float32):
+                raise ValueError("FOV observations are uint8 or float32")
+            obs = self._buf("obs_%s" % dtype, (self.E, self.N, 4, self.F, self.F), dtype)
+            vec = self._buf("vec", (self.E, self.N, 3), torch.float64) if want_vec else None
+            return obs, vec, (U8 if dtype == torch.uint8 else F32)
+        obs = self._buf("state", (self.E, self.H * self.W), torch.int8)
+        return obs, None, I8
+
+    def observe(self, dtype=torch.uint8, want_vec=True):
+        """FOV: (obs [E,N,4,F,F], vec [E,N,3]); full map: (state int8 [E,H*W], None)."""
+        obs, vec, odt = self._obs_buffers(dtype, want_vec)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_observe(self._h, self._ptr(obs), odt, self._ptr(vec), self._stream()),
+                        "mapf_observe")
+        return obs, vec
+
+    def step_observe(self, actions, want=DEFAULT_WANT, dtype=torch.uint8, want_vec=True):
+        """Fused step + observation: one kernel launch."""
+        a, adt = self._actions(actions)
+        so, outs = self._step_out(want)
+        obs, vec, odt = self._obs_buffers(dtype, want_vec)
+        self._keep = [a]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_step_observe(self._h, self._ptr(a), adt, ctypes.byref(so), self._ptr(obs), odt,
+                                                   self._ptr(vec), self._stream()), "mapf_step_observe")
+        outs["obs"] = obs
+        if vec is not None:
+            outs["vec"] = vec
+        return outs
+
+    def avail(self):
+        out = self._buf("out_avail", (self.E, self.N, 5), torch.uint8)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_avail(self._h, self._ptr(out), self._stream()), "mapf_avail")
+        return out
+
+    def goal_dist(self, dirty=None, primal_costs=False, out=None):
+        """int16 [E,N,H,W] hop distance to every agent's goal (walls -1, unreachable -2)."""
+        dmask = self._to_dev(dirty, torch.uint8, (self.E, self.N))
+        if out is None and not self.has_goal_dist:
+            out = self._buf("goal_dist", (self.E, self.N, self.H, self.W), torch.int16)
+        self._keep = [dmask]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_bfs(self._h, self._ptr(dmask), self._ptr(out), int(bool(primal_costs)),
+                                          self._stream()), "mapf_bfs")
+        return out
+
+    # ------------------------------------------------------------------ host-buffer path (what e2e times)
+    def make_host_io(self, obs_dtype=torch.uint8, want=("reward", "terminated", "dones", "avail", "obs", "vec")):
+        """Pinned host buffers + the mapf_host_io descriptor for step_observe_host()."""
+        E, N = self.E, self.N
+        bufs = {"actions": torch.empty((E, N), dtype=torch.uint8).pin_memory()}
+        if "reward" in want:
+            bufs["reward"] = torch.empty((E,), dtype=torch.float64).pin_memory()
+        if "terminated" in want:
+            bufs["terminated"] = torch.empty((E,), dtype=torch.uint8).pin_memory()
+        if "dones" in want:
+            bufs["dones"] = torch.empty((E, N), dtype=torch.uint8).pin_memory()
+        if "avail" in want:
+            bufs["avail"] = torch.empty((E, N, 5), dtype=torch.uint8).pin_memory()
+        odt = I8
+        if "obs" in want:
+            if self.obs_mode == OBS_PRIMAL_FOV:
+                bufs["obs"] = torch.empty((E, N, 4, self.F, self.F), dtype=obs_dtype).pin_memory()
+                odt = U8 if obs_dtype == torch.uint8 else F32
+            else:
+                bufs["obs"] = torch.empty((E, self.H * self.W), dtype=torch.int8).pin_memory()
+        if "vec" in want and self.obs_mode == OBS_PRIMAL_FOV:
+            bufs["vec"] = torch.empty((E, N, 3), dtype=torch.float64).pin_memory()
+        io = MapfHostIO()
+        io.actions_host = bufs["actions"].data_ptr()
+        for k in ("reward", "terminated", "dones", "avail", "obs", "vec"):
+            setattr(io, k + "_host", bufs[k].data_ptr() if k in bufs else None)
+        io.obs_dtype = odt
+        h2d = bufs["actions"].numel()
+        d2h = sum(t.numel() * t.element_size() for k, t in bufs.items() if k != "actions")
+        return io, bufs, h2d, d2h
+
+    def step_observe_host(self, io):
+        """Host buffers in, host buffers out; returns when the outputs are on the host."""
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_step_observe_host(self._h, ctypes.byref(io), self._stream()),
+                        "mapf_step_observe_host")
+
+    # ------------------------------------------------------------------ diagnostics
+    def stats(self):
+        buf = (ctypes.c_int64 * _lib.N_STATS)()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_stats(self._h, buf, self._stream()), "mapf_stats")
+        return dict(zip(STAT_NAMES, [int(v) for v in buf]))
+
+    def error_flags(self):
+        v = ctypes.c_uint32(0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_error_flags(self._h, ctypes.byref(v), self._stream()), "mapf_error_flags")
+        return int(v.value)
+
+    def launch_count(self):
+        return int(self.lib.mapf_launch_count(self._h))

@@ -1,0 +1,138 @@
+"""CPU-side tests: the C-ABI library builds for sm_100a, loads, and exports every symbol that
+include/mapf_b200.h declares; struct layouts agree between the header and the ctypes binding; the host
+logic (map ingestion, synthetic worlds, LUT, sharding arithmetic) behaves.  No kernel is launched."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "mapf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(mapf_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    import mapf_marl_b200
+    from mapf_marl_b200 import _lib
+    path = mapf_marl_b200.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    declared = _declared_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libmapf_b200.so lacks %s" % name
+    assert set(declared) == set(_lib.PROTOTYPES), set(declared) ^ set(_lib.PROTOTYPES)
+    assert lib.mapf_abi_version() == _lib.ABI_VERSION
+    assert lib.mapf_build_arch() == b"sm_100a"
+
+
+def test_library_has_no_torch_dependency_and_carries_sm100a_code():
+    from mapf_marl_b200 import _lib
+    out = subprocess.run(["ldd", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "torch" not in out and "c10" not in out
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if os.path.exists(cuobjdump):
+        out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+        assert "sm_100a" in out
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """Compile a tiny C program against the header and compare sizeof/offsetof with ctypes."""
+    from mapf_marl_b200 import _lib
+    prog = tmp_path / "layout.c"
+    fields_cfg = [f[0] for f in _lib.MapfCfg._fields_]
+    fields_out = [f[0] for f in _lib.MapfStepOut._fields_]
+    fields_io = [f[0] for f in _lib.MapfHostIO._fields_]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mapf_b200.h"', 'int main(void){']
+    lines.append('printf("%zu %zu %zu\\n", sizeof(mapf_cfg), sizeof(mapf_step_out), sizeof(mapf_host_io));')
+    for f in fields_cfg:
+        lines.append('printf("%%zu\\n", offsetof(mapf_cfg, %s));' % f)
+    for f in fields_out:
+        lines.append('printf("%%zu\\n", offsetof(mapf_step_out, %s));' % f)
+    for f in fields_io:
+        lines.append('printf("%%zu\\n", offsetof(mapf_host_io, %s));' % f)
+    lines.append('return 0;}')
+    prog.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True).stdout.split()
+    sizes = [int(x) for x in out[:3]]
+    assert sizes == [ctypes.sizeof(_lib.MapfCfg), ctypes.sizeof(_lib.MapfStepOut), ctypes.sizeof(_lib.MapfHostIO)]
+    offs = [int(x) for x in out[3:]]
+    expect = [getattr(_lib.MapfCfg, f).offset for f in fields_cfg] + \
+             [getattr(_lib.MapfStepOut, f).offset for f in fields_out] + \
+             [getattr(_lib.MapfHostIO, f).offset for f in fields_io]
+    assert offs == expect
+
+
+def test_default_cfg_carries_the_reference_defaults():
+    from mapf_marl_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.MapfCfg()
+    lib.mapf_default_cfg(ctypes.byref(cfg))
+    assert (cfg.n_agents, cfg.episode_limit, cfg.step_reward, cfg.collide_reward) == (4, 10000, -0.01, -10.0)
+    assert (cfg.action_cost, cfg.idle_cost, cfg.goal_reward, cfg.collision_reward) == (-0.3, -0.5, 0.0, -2.0)
+    assert cfg.fov == 10 and cfg.collide_reward_is_int == 1 and cfg.step_reward_is_int == 0
+
+
+def test_engine_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mapf_marl_b200.engine import MapfEngine, MapfError
+    with pytest.raises(MapfError):
+        MapfEngine(2, 2, 4, 4)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mapf_marl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("test oracle", ""), os.path.join(dirpath, f)
+
+
+def test_movingai_ingestion(tmp_path):
+    from mapf_marl_b200 import maps
+    mp = tmp_path / "a.map"
+    mp.write_text("type octile\nheight 3\nwidth 4\nmap\n..@.\n.T..\n@@..\n")
+    m = maps.read_movingai_map(str(mp))
+    assert m.tolist() == [[0, 0, 1, 0], [0, 1, 0, 0], [1, 1, 0, 0]]
+    sc = tmp_path / "a-1.scen"
+    sc.write_text("version 1\n0\ta.map\t4\t3\t0\t1\t3\t2\t4.0\n5\ta.map\t4\t3\t3\t0\t0\t0\t3.0\n")
+    lines = maps.read_scen_lines(str(sc))
+    assert [maps.scen_fields(ln) for ln in lines] == [(0, 1, 3, 2), (3, 0, 0, 0)]
+
+
+def test_synthetic_batch_is_a_function_of_the_global_env_index():
+    from mapf_marl_b200 import maps
+    full = maps.synthetic_batch(9, 12, 10, 10, 0.2, 4, distinct=0)
+    a = maps.synthetic_batch(9, 6, 10, 10, 0.2, 4, env_offset=0, distinct=0)
+    b = maps.synthetic_batch(9, 6, 10, 10, 0.2, 4, env_offset=6, distinct=0)
+    for k in range(3):
+        assert np.array_equal(full[k], np.concatenate([a[k], b[k]]))
+    obst, starts, goals = full
+    for e in range(12):
+        assert len({tuple(p) for p in starts[e].tolist()}) == 4 and len({tuple(p) for p in goals[e].tolist()}) == 4
+        lab = maps.label_components(obst[e])
+        for k in range(4):
+            assert obst[e][tuple(starts[e, k])] == 0 and obst[e][tuple(goals[e, k])] == 0
+            assert lab[tuple(starts[e, k])] == lab[tuple(goals[e, k])]
+
+
+def test_magnitude_lut_uses_the_reference_expression():
+    from mapf_marl_b200.engine import magnitude_lut
+    lut = magnitude_lut(32, 32)
+    assert len(lut) == 2 * 31 * 31 + 1
+    for dx, dy in ((0, 0), (3, 4), (-7, 19), (31, -31), (1, 2)):
+        assert lut[dx * dx + dy * dy] == (dx ** 2 + dy ** 2) ** .5

@@ -1,0 +1,484 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against
+  (a) traces recorded from the live reference (tests/golden/*.npz), and
+  (b) the CPU oracle on seeded random batches, and
+  (c) size-independent invariants at BASELINE.json's full sizes.
+Integer / byte / index outputs and float64 rewards / goal vectors are all compared bit-for-bit.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(*a, **k):
+    from mapf_marl_b200.engine import MapfEngine
+    return MapfEngine(*a, **k)
+
+
+def _oracle(*a, **k):
+    from oracle import Oracle
+    return Oracle(*a, **k)
+
+
+def _bits(x):
+    return np.ascontiguousarray(x).view(np.uint64)
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+GRID_WANT = ("reward", "terminated", "agent_reward", "dones", "status", "node", "edge", "avail")
+PRIMAL_WANT = ("reward", "terminated", "agent_reward", "dones", "status", "valid", "done_mid", "next_mid", "avail")
+
+
+# ------------------------------------------------------------------------------------------ golden traces
+@pytest.mark.parametrize("name", golden_names("GRID"))
+def test_grid_engine_matches_reference_trace(name):
+    g = load_golden(name)
+    H, W = g["obst"].shape
+    N = g["starts"].shape[0]
+    sr = int(g["step_reward"]) if g["step_is_int"] else float(g["step_reward"])
+    cr = int(g["collide_reward"]) if g["collide_is_int"] else float(g["collide_reward"])
+    eng = _engine(1, N, H, W, mode="grid", episode_limit=int(g["episode_limit"]), step_reward=sr,
+                  collide_reward=cr, reward_sum_mode=int(g["py_sum_mode"]))
+    eng.reset(g["obst"][None], g["starts"][None], g["goals"][None])
+    assert np.array_equal(_np(eng.observe()[0])[0], g["obs0"])
+    assert np.array_equal(_np(eng.avail())[0], g["avail0"])
+    for t in range(g["actions"].shape[0]):
+        out = eng.step(torch.as_tensor(g["actions"][t][None]), want=GRID_WANT)
+        assert np.array_equal(_np(eng.positions())[0], g["pos"][t]), t
+        assert np.array_equal(_np(out["node"])[0], g["node"][t]), t
+        assert np.array_equal(_np(out["edge"])[0], g["edge"][t]), t
+        assert np.array_equal(_np(out["dones"])[0], g["dones"][t]), t
+        assert _bits(_np(out["reward"]))[0] == _bits(g["reward"][t:t + 1])[0], (t, _np(out["reward"]), g["reward"][t])
+        assert np.array_equal(_np(eng.observe()[0])[0], g["state"][t]), t
+        assert np.array_equal(_np(out["avail"])[0], g["avail"][t]), t
+        assert _np(eng.step_count())[0] == g["step_count"][t]
+        assert _np(out["terminated"])[0] == int(g["dones"][t].all())
+    assert eng.error_flags() == 0
+
+
+@pytest.mark.parametrize("name", golden_names("PRIMAL"))
+def test_primal_engine_matches_reference_trace(name):
+    g = load_golden(name)
+    H, W = g["obst"].shape
+    N = g["starts"].shape[0]
+    F = int(g["fov"])
+    eng = _engine(1, N, H, W, mode="primal", fov=F)
+    eng.reset(g["obst"][None], g["starts"][None], g["goals"][None])
+    obs, vec = eng.observe()
+    assert np.array_equal(_np(obs)[0], g["obs0"])
+    assert np.array_equal(_bits(_np(vec)[0]), _bits(g["vec0"]))
+    assert np.array_equal(_np(eng.avail())[0], g["avail0"])
+    nc = g["costs0"].shape[0]
+    assert np.array_equal(_np(eng.goal_dist(primal_costs=True))[0, :nc], g["costs0"])
+    for t in range(g["actions"].shape[0]):
+        fused = (t % 2 == 0)
+        a = torch.as_tensor(g["actions"][t][None])
+        if fused:
+            out = eng.step_observe(a, want=PRIMAL_WANT)
+            obs, vec = out["obs"], out["vec"]
+        else:
+            out = eng.step(a, want=PRIMAL_WANT)
+            obs, vec = eng.observe()
+        assert np.array_equal(_np(out["status"])[0], g["status"][t]), t
+        assert np.array_equal(_bits(_np(out["agent_reward"])[0]), _bits(g["reward"][t])), t
+        assert np.array_equal(_np(out["done_mid"])[0], g["done_mid"][t]), t
+        assert np.array_equal(_np(out["next_mid"])[0], g["next_mid"][t]), t
+        assert np.array_equal(_np(out["dones"])[0], g["on_goal"][t]), t
+        assert np.array_equal(_np(out["valid"])[0], g["valid"][t]), t
+        assert np.array_equal(_np(eng.positions())[0], g["pos"][t]), t
+        assert np.array_equal(_np(out["avail"])[0], g["avail"][t]), t
+        assert _np(out["terminated"])[0] == g["done"][t]
+        assert np.array_equal(_np(obs)[0], g["obs"][t]), t
+        assert np.array_equal(_bits(_np(vec)[0]), _bits(g["vec"][t])), t
+    assert np.array_equal(_np(eng.goal_dist(primal_costs=True))[0, :nc], g["costsT"])
+    assert eng.error_flags() == 0
+
+
+@pytest.mark.parametrize("name", golden_names("PDIST"))
+def test_goal_dist_matches_partial_reference(name):
+    g = load_golden(name)
+    H, W = g["obst"].shape
+    N = g["goals"].shape[0]
+    eng = _engine(1, N, H, W, mode="primal", fov=5)
+    eng.reset(g["obst"][None], g["starts"][None], g["goals"][None])
+    d = _np(eng.goal_dist())[0].astype(np.int32)
+    free = ~g["obst"].astype(bool)
+    assert np.array_equal(d[:, free], g["dist"][:, free])
+    assert (d[:, ~free] == -1).all()
+
+
+# ------------------------------------------------------------------------------------------ drop-in classes
+def _write_movingai(tmp_path, obst, n_lines=40):
+    H, W = obst.shape
+    mp = tmp_path / "m.map"
+    with open(mp, "w") as f:
+        f.write("type octile\nheight %d\nwidth %d\nmap\n" % (H, W))
+        for r in range(H):
+            f.write("".join("@" if v else "." for v in obst[r]) + "\n")
+    free = [(i, j) for i in range(H) for j in range(W) if not obst[i, j]]
+    for k in range(1, 26):
+        with open(tmp_path / ("s-%d.scen" % k), "w") as f:
+            f.write("version 1\n")
+            for n in range(n_lines):
+                a, b = free[(n * 7 + k) % len(free)], free[(n * 13 + 3 * k + 1) % len(free)]
+                f.write("0\tm.map\t%d\t%d\t%d\t%d\t%d\t%d\t1.0\n" % (W, H, a[0], a[1], b[0], b[1]))
+    return str(mp), str(tmp_path / "s-")
+
+
+@pytest.mark.parametrize("name", ["grid_kat_b1", "grid_c1", "grid_crowd6", "grid_intint"])
+def test_mapf_grid_dropin_class(name, tmp_path):
+    """The MAPF_GRID class with the reference's constructor, return types and attribute names."""
+    from mapf_marl_b200.mapf_gridworld import MAPF_GRID
+    g = load_golden(name)
+    mp, sp = _write_movingai(tmp_path, g["obst"])
+    N = g["starts"].shape[0]
+    sr = int(g["step_reward"]) if g["step_is_int"] else float(g["step_reward"])
+    cr = int(g["collide_reward"]) if g["collide_is_int"] else float(g["collide_reward"])
+    env = MAPF_GRID(mp, sp, n_agents=N, episode_limit=int(g["episode_limit"]), seed=1, render="none",
+                    step_reward=sr, collide_reward=cr)
+    env.set_starts_goals(g["starts"], g["goals"])
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (N, g["obst"].size) and obs.dtype == np.int64
+    assert np.array_equal(obs[0], g["obs0"]) and np.array_equal(obs[-1], g["obs0"])
+    info = env.get_env_info()
+    assert info == {"state_shape": g["obst"].size, "obs_shape": g["obst"].size, "n_actions": 5, "n_agents": N,
+                    "episode_limit": int(g["episode_limit"])}
+    for t in range(min(40, g["actions"].shape[0])):
+        acts = torch.as_tensor(g["actions"][t].astype(np.int64)) if t % 2 else g["actions"][t]
+        reward, dones, info = env.step(acts)
+        assert isinstance(dones, list) and dones is env._agent_dones
+        assert float(reward) == g["reward"][t] and isinstance(reward, int) == bool(g["reward_is_int"][t])
+        assert [int(x) for x in dones] == g["dones"][t].tolist()
+        assert info == {"_step_count": int(g["step_count"][t])}
+        assert env.agent_positions == [tuple(p) for p in g["pos"][t].tolist()]
+        assert env._node_collision_agents == g["node"][t].tolist()
+        assert env._edge_collision_agents == g["edge"][t].tolist()
+        assert env.get_avail_actions() == g["avail"][t].tolist()
+        assert np.array_equal(env.get_state(), g["state"][t])
+        assert np.array_equal(env.get_obs()[N - 1], g["state"][t])
+        assert env.episode_done() == bool(g["dones"][t].all())
+    with pytest.raises(AssertionError):
+        env.step([0] * (N - 1) + [7])
+
+
+@pytest.mark.parametrize("name", ["primal_kat_b2", "primal_crowd", "primal_f10"])
+def test_mapfenv_dropin_class_single_agent_steps(name):
+    """MAPFEnv._step((id, action)) one agent at a time, exactly as PRIMAL drives it."""
+    from mapf_marl_b200.mapf_primal import MAPFEnv
+    g = load_golden(name)
+    N = g["starts"].shape[0]
+    F = int(g["fov"])
+    world0 = -g["obst"].astype(int)
+    goals0 = np.zeros_like(world0)
+    for k in range(N):
+        world0[tuple(g["starts"][k])] = k + 1
+        goals0[tuple(g["goals"][k])] = k + 1
+    env = MAPFEnv(num_agents=N, observation_size=F, world0=world0, goals0=goals0)
+    assert env.getPositions() == [tuple(p) for p in g["starts"].tolist()]
+    assert env.getGoals() == [tuple(p) for p in g["goals"].tolist()]
+    assert np.array_equal(env.getObstacleMap(), g["obst"].astype(int))
+    for i in range(1, N + 1):
+        assert env._listNextValidActions(i) == [a for a in range(5) if g["avail0"][i - 1, a]]
+    for t in range(min(12, g["actions"].shape[0])):
+        for i in range(1, N + 1):
+            a = int(g["actions"][t, i - 1])
+            state, reward, done, nxt, on_goal, blocking, valid = env._step((i, a))
+            assert reward == g["reward"][t, i - 1]
+            assert done == bool(g["done_mid"][t, i - 1])
+            assert nxt == [k for k in range(5) if g["next_mid"][t, i - 1, k]]
+            assert on_goal == bool(g["on_goal"][t, i - 1]) and valid == bool(g["valid"][t, i - 1])
+            assert blocking is False
+        assert env.getPositions() == [tuple(p) for p in g["pos"][t].tolist()]
+        for i in range(1, N + 1):
+            maps4, vec = env._observe(i)
+            for c in range(4):
+                assert maps4[c].dtype == np.float64 and np.array_equal(maps4[c], g["obs"][t, i - 1, c])
+            assert np.array_equal(_bits(np.array(vec, dtype=np.float64)), _bits(g["vec"][t, i - 1]))
+            assert env._listNextValidActions(i, int(g["actions"][t, i - 1])) == \
+                [k for k in range(5) if g["avail"][t, i - 1, k]]
+        assert env.world.done() == bool(g["done"][t])
+    nc = g["costs0"].shape[0]
+    if g["actions"].shape[0] <= 12:
+        for k in range(nc):
+            costs = env.getAstarCosts(env.world.getPos(k + 1), env.world.getGoal(k + 1))
+            assert np.array_equal(costs, g["costsT"][k])
+
+
+# ------------------------------------------------------------------------------------------ differential vs oracle
+PRIMAL_CASES = [
+    # E, N, H, W, F, density, shared, T
+    (512, 8, 20, 20, 11, 0.2, False, 12),    # c2 shape
+    (256, 32, 32, 32, 11, 0.3, False, 8),    # c3 shape
+    (37, 7, 40, 40, 11, 0.25, False, 8),     # ragged: N % 4 != 0, E not a multiple of the tile, W > 32
+    (64, 5, 9, 13, 3, 0.1, False, 10),       # tiny FOV, rectangular
+    (64, 12, 8, 8, 5, 0.05, False, 20),      # crowded
+    (48, 6, 12, 12, 10, 0.15, False, 8),     # even FOV
+    (32, 128, 64, 64, 11, 0.0, True, 4),     # c4 shape: 128 agents, one shared warehouse map
+    (16, 9, 16, 16, 6, 0.2, False, 6),       # FOV without a specialised kernel -> generic observation kernel
+    (3, 1, 5, 5, 7, 0.0, False, 6),          # single agent
+]
+
+
+@pytest.mark.parametrize("case", PRIMAL_CASES, ids=lambda c: "E%d_N%d_%dx%d_F%d" % c[:5])
+def test_primal_batch_matches_oracle(case):
+    from mapf_marl_b200 import maps
+    from oracle.oracle import MODE_PRIMAL
+    E, N, H, W, F, dens, shared, T = case
+    if shared:
+        obst = maps.warehouse_layout(H, W)
+        _, starts, goals = maps.synthetic_batch(7, E, H, W, 0.0, N, shared_map=True)
+        rs = np.random.RandomState(5)
+        free = np.argwhere(obst == 0)
+        for e in range(E):
+            idx = rs.permutation(len(free))
+            starts[e] = free[idx[:N]]
+            goals[e] = free[rs.permutation(len(free))[:N]]
+    else:
+        obst, starts, goals = maps.synthetic_batch(100 + E, E, H, W, dens, N, distinct=0)
+    eng = _engine(E, N, H, W, mode="primal", fov=F, shared_map=shared)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F, shared_map=shared)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    robs, rvec = orc.primal_observe()
+    obs, vec = eng.observe()
+    assert np.array_equal(_np(obs), robs)
+    assert np.array_equal(_bits(_np(vec)), _bits(rvec))
+    f32, _ = eng.observe(dtype=torch.float32)
+    assert np.array_equal(_np(f32), robs.astype(np.float32))
+    assert np.array_equal(_np(eng.avail()), orc.primal_avail())
+    rs = np.random.RandomState(E + N)
+    for t in range(T):
+        a = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        ad = torch.as_tensor(a.astype(np.int64) if t % 3 == 1 else a, device="cuda")
+        if t % 2 == 0:
+            out = eng.step_observe(ad, want=PRIMAL_WANT)
+            obs, vec = out["obs"], out["vec"]
+        else:
+            out = eng.step(ad, want=PRIMAL_WANT)
+            obs, vec = eng.observe()
+        ref = orc.primal_sweep(a)
+        robs, rvec = orc.primal_observe()
+        for k in ("status", "dones", "valid", "done_mid", "next_mid", "avail", "terminated"):
+            assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        assert np.array_equal(_bits(_np(out["agent_reward"])), _bits(ref["agent_reward"])), t
+        assert np.array_equal(_bits(_np(out["reward"])), _bits(ref["reward"])), t
+        assert np.array_equal(_np(eng.positions()), orc.positions()), t
+        assert np.array_equal(_np(obs), robs), t
+        assert np.array_equal(_bits(_np(vec)), _bits(rvec)), t
+    assert np.array_equal(_np(eng.goal_dist()), orc.goal_dist())
+    assert np.array_equal(_np(eng.goal_dist(primal_costs=True)), orc.goal_dist(primal_costs=True))
+    assert eng.error_flags() == 0
+    st = eng.stats()
+    assert st["env_steps"] == E * T and st["agent_steps"] == E * N * T
+
+
+GRID_CASES = [
+    (300, 4, 10, 10, 0.0, -0.01, -10, 25, 10000),
+    (64, 12, 16, 16, 0.2, -0.013, -0.7, 30, 10000),
+    (33, 10, 6, 6, 0.05, -0.01, -10, 40, 25),       # crowded, episode limit reached
+    (16, 32, 32, 32, 0.2, -1, -10, 12, 10000),       # all-int rewards
+    (8, 130, 40, 40, 0.1, -0.01, -0.5, 6, 10000),    # more than 128 agents
+]
+
+
+@pytest.mark.parametrize("case", GRID_CASES, ids=lambda c: "E%d_N%d_%dx%d" % c[:4])
+@pytest.mark.parametrize("sum_mode", [0, 1])
+def test_grid_batch_matches_oracle(case, sum_mode):
+    from oracle.oracle import MODE_GRID
+    E, N, H, W, dens, sr, cr, T, limit = case
+    rs = np.random.RandomState(E * 7 + N)
+    obst = (rs.rand(E, H, W) < dens).astype(np.uint8)
+    starts = np.zeros((E, N, 2), np.int16)
+    goals = np.zeros((E, N, 2), np.int16)
+    for e in range(E):
+        free = np.argwhere(obst[e] == 0)
+        starts[e] = free[rs.randint(0, len(free), N)]      # overlapping starts are legal in GRID
+        goals[e] = free[rs.randint(0, len(free), N)]
+    eng = _engine(E, N, H, W, mode="grid", episode_limit=limit, step_reward=sr, collide_reward=cr,
+                  reward_sum_mode=sum_mode)
+    orc = _oracle(E, N, H, W, MODE_GRID, episode_limit=limit, step_reward=sr, collide_reward=cr, sum_mode=sum_mode)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    assert np.array_equal(_np(eng.observe()[0]), orc.grid_state())
+    assert np.array_equal(_np(eng.avail()), orc.grid_avail())
+    for t in range(T):
+        a = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        if t % 2 == 0:
+            out = eng.step_observe(torch.as_tensor(a, device="cuda"), want=GRID_WANT)
+            state = out["obs"]
+        else:
+            out = eng.step(torch.as_tensor(a, device="cuda"), want=GRID_WANT)
+            state = eng.observe()[0]
+        ref = orc.grid_step(a)
+        for k in ("terminated", "dones", "status", "node", "edge", "avail"):
+            assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        assert np.array_equal(_bits(_np(out["agent_reward"])), _bits(ref["agent_reward"])), t
+        assert np.array_equal(_bits(_np(out["reward"])), _bits(ref["reward"])), t
+        assert np.array_equal(_np(eng.positions()), orc.positions()), t
+        assert np.array_equal(_np(state), orc.grid_state()), t
+        assert np.array_equal(_np(eng.step_count()), orc.step_count()), t
+    assert eng.error_flags() == 0
+
+
+# ------------------------------------------------------------------------------------------ API behaviour
+def test_partial_sweeps_equal_full_sweep_and_masked_reset():
+    from mapf_marl_b200 import maps
+    E, N, H, W, F = 40, 8, 12, 12, 5
+    obst, starts, goals = maps.synthetic_batch(3, E, H, W, 0.1, N, distinct=0)
+    a = _engine(E, N, H, W, mode="primal", fov=F)
+    b = _engine(E, N, H, W, mode="primal", fov=F)
+    a.reset(obst, starts, goals)
+    b.reset(obst, starts, goals)
+    rs = np.random.RandomState(0)
+    for t in range(6):
+        act = torch.as_tensor(rs.randint(0, 5, (E, N)).astype(np.uint8), device="cuda")
+        full = {k: v.clone() for k, v in a.step(act, want=PRIMAL_WANT).items()}
+        for i in range(N):
+            part = b.step(act, want=PRIMAL_WANT, agent_range=(i, i + 1))
+            for k in ("status", "valid", "done_mid", "next_mid", "dones"):
+                assert torch.equal(part[k][:, i], full[k][:, i]), (k, t, i)
+        assert torch.equal(a.positions(), b.positions())
+    # masked reset: only the selected environments go back to their start cells
+    mask = np.zeros(E, np.uint8)
+    mask[::3] = 1
+    before = a.positions().clone()
+    a.reset(env_mask=mask)
+    after = _np(a.positions())
+    assert np.array_equal(after[mask == 1], starts[mask == 1])
+    assert np.array_equal(after[mask == 0], _np(before)[mask == 0])
+    assert (_np(a.step_count())[mask == 1] == 0).all() and (_np(a.step_count())[mask == 0] == 6).all()
+
+
+def test_bad_action_sets_device_flag_and_bad_args_are_rejected():
+    from mapf_marl_b200 import _lib
+    from mapf_marl_b200.engine import MapfError
+    eng = _engine(4, 3, 6, 6, mode="primal", fov=5)
+    eng.reset(np.zeros((4, 6, 6), np.uint8), np.tile(np.array([[0, 0], [1, 1], [2, 2]], np.int16), (4, 1, 1)),
+              np.tile(np.array([[5, 5], [4, 4], [3, 3]], np.int16), (4, 1, 1)))
+    assert eng.error_flags() == 0
+    bad = torch.zeros((4, 3), dtype=torch.uint8, device="cuda")
+    bad[2, 1] = 9
+    eng.step(bad)
+    assert eng.error_flags() == _lib.FLAG_BAD_ACTION
+    assert eng.error_flags() == 0          # reading clears
+    with pytest.raises(ValueError):
+        eng.step(torch.zeros((4, 2), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(MapfError):
+        eng.step(torch.zeros((4, 3), dtype=torch.uint8, device="cuda"), agent_range=(2, 1))
+    with pytest.raises(MapfError):
+        _engine(4, 3, 6, 6, mode="grid", obs_mode="fov")   # FOV needs one agent per cell
+    with pytest.raises(MapfError):
+        _engine(4, 300, 6, 6)
+    # start on a wall / out of bounds / overlapping starts are flagged
+    obst = np.zeros((4, 6, 6), np.uint8)
+    obst[:, 0, 0] = 1
+    eng.reset(obst, np.tile(np.array([[0, 0], [1, 1], [1, 1]], np.int16), (4, 1, 1)),
+              np.tile(np.array([[5, 5], [4, 4], [9, 3]], np.int16), (4, 1, 1)))
+    f = eng.error_flags()
+    assert f & _lib.FLAG_START_ON_WALL and f & _lib.FLAG_BAD_POSITION and f & _lib.FLAG_START_OVERLAP
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    from mapf_marl_b200 import maps
+    E, N, H, W, F = 96, 8, 20, 20, 11
+    obst, starts, goals = maps.synthetic_batch(11, E, H, W, 0.2, N, distinct=0)
+    a = _engine(E, N, H, W, mode="primal", fov=F)
+    b = _engine(E, N, H, W, mode="primal", fov=F)
+    a.reset(obst, starts, goals)
+    b.reset(obst, starts, goals)
+    io, bufs, h2d, d2h = b.make_host_io()
+    assert h2d == E * N and d2h == E * 8 + E + E * N + E * N * 5 + E * N * 4 * F * F + E * N * 24
+    rs = np.random.RandomState(1)
+    for t in range(5):
+        act = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        out = a.step_observe(torch.as_tensor(act, device="cuda"))
+        bufs["actions"].copy_(torch.as_tensor(act))
+        b.step_observe_host(io)
+        for k in ("reward", "terminated", "dones", "avail", "obs", "vec"):
+            assert torch.equal(out[k].cpu(), bufs[k]), (k, t)
+
+
+def test_set_goals_and_dirty_bfs():
+    from mapf_marl_b200 import maps
+    from oracle.oracle import MODE_PRIMAL
+    E, N, H, W = 24, 6, 16, 16
+    obst, starts, goals = maps.synthetic_batch(5, E, H, W, 0.2, N, distinct=0)
+    eng = _engine(E, N, H, W, mode="primal", fov=5, goal_dist=True)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=5)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    dist = torch.full((E, N, H, W), -9, dtype=torch.int16, device="cuda")
+    eng.goal_dist(out=dist)
+    ref = orc.goal_dist()
+    assert np.array_equal(_np(dist), ref)
+    rs = np.random.RandomState(2)
+    dirty = (rs.rand(E, N) < 0.3).astype(np.uint8)
+    new_goals = goals.copy()
+    for e in range(E):
+        free = np.argwhere(obst[e] == 0)
+        new_goals[e] = free[rs.permutation(len(free))[:N]]
+    eng.set_goals(new_goals, dirty)
+    orc.set_goals(new_goals, dirty)
+    eng.goal_dist(dirty=dirty, out=dist)
+    orc.goal_dist(dirty=dirty, out=ref)
+    assert np.array_equal(_np(dist), ref)
+    assert np.array_equal(_np(eng.goals()), np.where(dirty[..., None] != 0, new_goals, goals))
+    obs, vec = eng.observe()
+    robs, rvec = orc.primal_observe()
+    assert np.array_equal(_np(obs), robs) and np.array_equal(_bits(_np(vec)), _bits(rvec))
+
+
+# ------------------------------------------------------------------------------------------ full-size invariants
+@pytest.mark.parametrize("cfg", [(4096, 8, 20, 20, 0.2), (16384, 32, 32, 32, 0.3)], ids=["c2", "c3"])
+def test_full_size_invariants(cfg):
+    """BASELINE sizes, where the scalar oracle would take minutes: properties that hold for any input."""
+    from mapf_marl_b200 import maps
+    from oracle.oracle import MODE_PRIMAL
+    E, N, H, W, dens = cfg
+    F = 11
+    obst, starts, goals = maps.synthetic_batch(1000, E, H, W, dens, N, distinct=64)
+    eng = _engine(E, N, H, W, mode="primal", fov=F)
+    eng.reset(obst, starts, goals)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    obst_d = torch.as_tensor(obst, device="cuda").bool()
+    for t in range(6):
+        act = torch.randint(0, 5, (E, N), generator=gen, device="cuda", dtype=torch.uint8)
+        out = eng.step_observe(act, want=("status", "dones", "valid", "avail", "terminated"))
+        pos = eng.positions().long()
+        # agents stand on free cells and never share a cell (sequential claim)
+        e_idx = torch.arange(E, device="cuda")[:, None].expand(E, N)
+        assert not obst_d[e_idx, pos[..., 0], pos[..., 1]].any()
+        cell = pos[..., 0] * W + pos[..., 1]
+        assert (torch.sort(cell, dim=1).values.diff(dim=1) != 0).all()
+        obs = out["obs"].clone()
+        assert obs.max().item() <= 1
+        c = F // 2
+        assert (obs[:, :, 0, c, c] == 1).all()                       # the agent sees itself
+        assert (obs[:, :, 3, c, c] == 0).all()                       # ... on a free cell
+        # number of visible agents == agents within the window (computed independently with torch)
+        d = (pos[:, :, None, :] - pos[:, None, :, :])
+        vis = ((d[..., 0] >= -c) & (d[..., 0] <= F - 1 - c) & (d[..., 1] >= -c) & (d[..., 1] <= F - 1 - c)).sum(-1)
+        assert torch.equal(obs[:, :, 0].flatten(2).sum(-1).long(), vis)
+        assert (obs[:, :, 1].flatten(2).sum(-1) <= 1).all()
+        # the fused kernel, the separate observe launch and the byte-wise generic kernel agree
+        sep, vec = eng.observe()
+        assert torch.equal(sep, obs)
+        assert torch.equal((out["status"] >= 0), out["valid"].bool())
+    # the first environments against the oracle (the batch repeats 64 distinct worlds)
+    n = 64
+    orc = _oracle(n, N, H, W, MODE_PRIMAL, fov=F)
+    orc.reset(obst[:n], starts[:n], goals[:n])
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(6):
+        act = torch.randint(0, 5, (E, N), generator=gen, device="cuda", dtype=torch.uint8)
+        orc.primal_sweep(_np(act[:n]))
+    robs, rvec = orc.primal_observe()
+    assert np.array_equal(_np(obs[:n]), robs)
+    assert np.array_equal(_bits(_np(vec[:n])), _bits(rvec))
+    assert np.array_equal(_np(eng.positions()[:n]), orc.positions())
