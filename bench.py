@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s (step + observation) of the batched MAPF engine on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+
+One "step" = one pass of the hot path over one batch: every agent of every environment is advanced one
+environment step and receives its observation, action mask, reward and done flag (one fused kernel
+launch).  Workloads (BASELINE.json configs):
+    c2  20x20 map, density 0.2,  8 agents, FOV 11,  4096 envs per GPU
+    c3  32x32 map, density 0.3, 32 agents, FOV 11, 16384 envs per GPU   <- default: the config the
+        north-star target (>= 1e9 agent-steps/s on 8 GPUs, obs kernel >= 50 % of HBM roofline) is quoted on
+    c4  64x64 warehouse layout (one shared map), 128 agents, FOV 11, 8192 envs per GPU
+Multi-GPU: environments shard by index, `--gpus N` ranks under torchrun each own the same number of
+environments (weak scaling); there is no data-path collective, NCCL only reduces the statistics vector.
+
+The JSON line carries: value (device-resident inputs), e2e (host buffers in / host buffers out through
+mapf_step_observe_host), roofline of the fused kernel against the measured HBM peak, and cpu_baseline
+(the CPU oracle port on this box's host cores, bounded sample).  `--impl reference` times that CPU port
+alone (the reference itself is pure Python and does not travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (H, W, density, N, F, envs per GPU, shared warehouse map, algorithmic bytes per agent-step)
+    "c2": dict(H=20, W=20, density=0.2, N=8, F=11, E=4096, warehouse=False, bytes_per_agent_step=578),
+    "c3": dict(H=32, W=32, density=0.3, N=32, F=11, E=16384, warehouse=False, bytes_per_agent_step=559),
+    "c4": dict(H=64, W=64, density=0.0, N=128, F=11, E=8192, warehouse=True, bytes_per_agent_step=526),
+}
+METRIC = "agent-steps/sec (step+obs)"
+UNIT = "agent-steps/s"
+
+
+def make_world(wl, n_envs, env_offset, seed=1000):
+    from mapf_marl_b200 import maps
+    if wl["warehouse"]:
+        obst = maps.warehouse_layout(wl["H"], wl["W"])
+        free = np.argwhere(obst == 0)
+        starts = np.zeros((n_envs, wl["N"], 2), np.int16)
+        goals = np.zeros((n_envs, wl["N"], 2), np.int16)
+        base = {}
+        for e in range(n_envs):
+            k = (env_offset + e) % 64
+            if k not in base:
+                rs = np.random.RandomState(seed + k)
+                base[k] = (free[rs.permutation(len(free))[:wl["N"]]], free[rs.permutation(len(free))[:wl["N"]]])
+            starts[e], goals[e] = base[k]
+        return obst, starts, goals
+    return maps.synthetic_batch(seed, n_envs, wl["H"], wl["W"], wl["density"], wl["N"], env_offset=env_offset,
+                                distinct=64)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and clock-event (throttle) reasons through NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.sm, self.bits, self.max_mhz, self._stop_evt = index, [], 0, None, threading.Event()
+        self.err = None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop_evt.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.bits |= int(get_reasons(h))
+                self._stop_evt.wait(0.002)
+        except Exception as ex:  # keep the benchmark alive; the record says why clocks are missing
+            self.err = repr(ex)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.bits & bit)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": reasons, "samples": len(self.sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
+
+
+def cpu_port_rate(wl, n_envs, steps, warmup, threads=0, want_obs=True):
+    """The CPU oracle port stepping + observing `n_envs` environments of the workload; agent-steps/s."""
+    from oracle import Oracle, oracle_max_threads
+    from oracle.oracle import MODE_PRIMAL
+    obst, starts, goals = make_world(wl, n_envs, 0)
+    orc = Oracle(n_envs, wl["N"], wl["H"], wl["W"], MODE_PRIMAL, fov=wl["F"], shared_map=wl["warehouse"],
+                 threads=threads)
+    orc.reset(obst, starts, goals)
+    rs = np.random.RandomState(0)
+    acts = rs.randint(0, 5, (4, n_envs, wl["N"])).astype(np.uint8)
+    want = ("agent_reward", "dones", "avail", "terminated", "reward")
+    obs = np.empty((n_envs, wl["N"], 4, wl["F"], wl["F"]), np.uint8)
+    vec = np.empty((n_envs, wl["N"], 3), np.float64)
+    import ctypes
+
+    def one(t):
+        orc.primal_sweep(acts[t % 4], want=want)
+        if want_obs:
+            orc._lib.oracle_primal_observe(orc._h, obs.ctypes.data_as(ctypes.c_void_p),
+                                           vec.ctypes.data_as(ctypes.c_void_p))
+    for t in range(warmup):
+        one(t)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        one(t)
+    dt = time.perf_counter() - t0
+    return n_envs * wl["N"] * steps / dt, dt, (threads or oracle_max_threads())
+
+
+def run_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    from oracle import oracle_max_threads
+    # each step is a bounded sample of the workload, sized so that K steps take about two minutes at most
+    r0, _, _ = cpu_port_rate(wl, min(wl["E"], 1024), 3, 1)
+    n_envs = int(min(wl["E"], 2048, max(16, r0 * 120.0 / (max(args.steps, 1) * wl["N"]))))
+    rate, dt, cores = cpu_port_rate(wl, n_envs, args.steps, min(args.warmup, 10))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args.workload, wl, args.gpus),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d envs x %d agents x %d steps of %s (C oracle port, OpenMP over envs, %d threads)"
+                                   % (n_envs, wl["N"], args.steps, args.workload, oracle_max_threads())},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python and cannot travel to the GPU box; this is the C oracle port, "
+                "pinned bit-exact to the live reference by tests/test_oracle_golden.py",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, wl, gpus):
+    return {"workload": "%s: %dx%d map, density %.2f, %d agents, FOV %d, %d envs per GPU%s" % (
+        name, wl["H"], wl["W"], wl["density"], wl["N"], wl["F"], wl["E"],
+        ", shared warehouse map" if wl["warehouse"] else ""),
+        "mode": "primal (sequential claim) + 4-channel FOV observation + goal vector, fused step+obs kernel",
+        "n_envs_total": wl["E"] * gpus, "n_agents": wl["N"],
+        "l2": "per-step working set (obs output %.0f MB) exceeds the 126 MB L2" % (
+            wl["E"] * wl["N"] * 4 * wl["F"] ** 2 / 1e6),
+        "parallelism": "envs sharded by index over %d GPU(s), no data-path collective" % gpus}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--f32", action="store_true", help="emit float32 observations instead of uint8")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.envs:
+        wl["E"] = args.envs
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        from oracle import build_oracle
+        if rank == 0:
+            build_oracle()
+        run_reference_arm(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mapf_marl_b200
+    from mapf_marl_b200.engine import MapfEngine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (use --impl reference for the CPU arm)")
+    mapf_marl_b200.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, N, F = wl["E"], wl["N"], wl["F"]
+    obst, starts, goals = make_world(wl, E, rank * E)
+    eng = MapfEngine(E, N, wl["H"], wl["W"], mode="primal", fov=F, shared_map=wl["warehouse"], goal_dist=True,
+                     device=dev)
+    eng.reset(obst, starts, goals)
+    # goal-distance maps: computed at reset (and on goal reassignment), reported separately
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.goal_dist()
+    torch.cuda.synchronize()
+    ev0.record()
+    eng.goal_dist()
+    ev1.record()
+    torch.cuda.synchronize()
+    bfs_ms = ev0.elapsed_time(ev1)
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = torch.randint(0, 5, (16, E, N), generator=gen, device=dev, dtype=torch.uint8)
+    want = ("reward", "terminated", "dones", "avail")
+    odt = torch.float32 if args.f32 else torch.uint8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for t in range(warmup):
+            fn(t)
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for t in range(steps):
+            fn(t)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput (the fused step+observation kernel), clocks sampled meanwhile
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launch_count()
+    if sampler:
+        sampler.start()
+    ms_total = timed(lambda t: eng.step_observe(pool[t % 16], want=want, dtype=odt), args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count() - launches0 - args.warmup
+    ms_step = ms_total / args.steps
+    value = world * E * N * args.steps / (ms_total * 1e-3)
+
+    # ---- breakdown: the step-only and observe-only launches of the same tile kernel
+    ms_obs = timed(lambda t: eng.observe(dtype=odt), max(args.steps // 4, 5), 3) / max(args.steps // 4, 5)
+    ms_stp = timed(lambda t: eng.step(pool[t % 16], want=want), max(args.steps // 4, 5), 3) / max(args.steps // 4, 5)
+
+    # ---- end to end: pinned host actions in, every output back on the host, through the C-ABI host entry point
+    io, bufs, h2d, d2h = eng.make_host_io(obs_dtype=odt)
+    host_pool = pool[:4].cpu()
+
+    def e2e_step(t):
+        bufs["actions"].copy_(host_pool[t % 4])
+        eng.step_observe_host(io)
+    ms_e2e = timed(e2e_step, args.e2e_steps, 3)
+    e2e_value = world * E * N * args.e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- statistics: the only collective of the path (one all-reduce of 8 int64 over NCCL)
+    stats = eng.stats()
+    svec = torch.tensor([stats[k] for k in sorted(stats)], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(svec, op=dist.ReduceOp.SUM)
+    flags = eng.error_flags()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bytes_per = wl["bytes_per_agent_step"] + (3 * 4 * F * F if args.f32 else 0)
+        alg_bytes = bytes_per * E * N
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_fused_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 obs / u8 state" if args.f32 else "u8", "data": "synthetic",
+            "config": workload_config(args.workload, wl, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.e2e_steps, "steps": args.e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "mapf_tile_kernel<%d> (fused step+obs)" % F,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "algorithmic_bytes_per_agent_step": bytes_per},
+            "breakdown_ms": {"fused_step_obs": ms_step, "observe_only": ms_obs, "step_only": ms_stp,
+                             "observe_only_GBps": (4 * F * F * (4 if args.f32 else 1) + 24 + 8 +
+                                                   wl["H"] * wl["W"] / N) * E * N / (ms_obs * 1e-3) / 1e9,
+                             "goal_bfs_all_maps": bfs_ms, "goal_maps_per_s": E * N / (bfs_ms * 1e-3)},
+            "clocks": clocks,
+            "stats": dict(zip(sorted(stats), [int(v) for v in svec.tolist()])),
+            "device_error_flags": flags,
+        }
+        if not args.no_cpu:
+            n_cpu = min(E, 2048)
+            r0, dt0, cores = cpu_port_rate(wl, n_cpu, 4, 1)
+            n_steps = int(max(8, min(20000, 10.0 / max(dt0 / 4, 1e-6))))      # about 10 s of CPU work
+            rate, dt, cores = cpu_port_rate(wl, n_cpu, n_steps, 2)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d envs x %d agents x %d steps of %s (step+obs), C oracle port, OpenMP over envs on "
+                          "%d threads, %.1f s" % (n_cpu, N, n_steps, args.workload, cores, dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

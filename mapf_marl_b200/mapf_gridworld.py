@@ -15,7 +15,7 @@ import random
 import numpy as np
 import torch
 
-from . import maps
+from . import _lib, maps
 from .engine import MapfEngine
 from .multiagentenv import MultiAgentEnv
 
@@ -107,8 +107,10 @@ class MAPF_GRID(MultiAgentEnv):
         """Returns initial observations (mapf_gridworld.py:70-83)."""
         self.engine.reset(self._obst, self._starts, self._goals)
         flags = self.engine.error_flags()
-        if flags and self._strict:
-            raise AssertionError("invalid start/goal cells (device flags 0x%x)" % flags)
+        # a start cell on an obstacle is legal in the reference (the .scen x/y transposition produces them,
+        # mapf_gridworld.py:443-445); only out-of-range cells, which would raise IndexError there, are rejected
+        if (flags & _lib.FLAG_BAD_POSITION) and self._strict:
+            raise AssertionError("start/goal cells outside the map (device flags 0x%x)" % flags)
         self._step_count = 0
         self._agent_dones = [False for _ in self.agents]
         self._node_collision_agents = [0 for _ in self.agents]

@@ -59,7 +59,10 @@ def test_grid_engine_matches_reference_trace(name):
         assert np.array_equal(_np(out["avail"])[0], g["avail"][t]), t
         assert _np(eng.step_count())[0] == g["step_count"][t]
         assert _np(out["terminated"])[0] == int(g["dones"][t].all())
-    assert eng.error_flags() == 0
+    # grid_real32 goes through the reference's own .scen parser, whose x/y transposition (GRID:443-445) puts
+    # some agents on obstacle cells; the trace is reproduced all the same and the engine reports the fact.
+    from mapf_marl_b200 import _lib
+    assert eng.error_flags() == (_lib.FLAG_START_ON_WALL if name == "grid_real32" else 0)
 
 
 @pytest.mark.parametrize("name", golden_names("PRIMAL"))
