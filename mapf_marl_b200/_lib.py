@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libmapf_b200.so")
+LIB_PATH = os.environ.get("MAPF_B200_LIB") or os.path.join(_HERE, "libmapf_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mapf_b200.h")
 
 ABI_VERSION = 1

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -70,7 +71,8 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L) {
   L->posold_off = take(2 * na);
   L->posnew_off = take(2 * na);
   L->goal_off = take(2 * na);
-  L->tgt_off = take(2 * na);
+  L->mv_off = take(4 * na);
+  L->moved_off = take(32 * epb);
   L->act_off = take(na);
   L->status_off = take(na);
   L->done_off = take(na);
@@ -83,6 +85,7 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L) {
   L->rew_off = take(8 * na);
   L->envrew_off = take(8 * epb);
   L->envterm_off = take(epb);
+  L->envcnt_off = take(4 * epb);
   L->str_off = take(fov ? ((na + d.G - 1) / d.G) * d.GW * 4 + 16 : 16);
   L->total_bytes = off;
 }
@@ -97,6 +100,10 @@ static int choose_epb(MapfDims& d, MapfTileLayout* L) {
   int epb = (MAPF_TILE_THREADS / d.N) / mult * mult;
   if (epb < mult) epb = mult;
   while (epb > mult && (d.E + epb - 1) / epb < 2 * 148 && epb * d.N > 64) epb -= mult;
+  if (const char* env = getenv("MAPF_B200_EPB")) {   // tuning knob for experiments: environments per tile
+    const int want = atoi(env);
+    if (want >= mult) epb = want / mult * mult;
+  }
   for (;;) {
     compute_layout(d, epb, L);
     if (L->total_bytes <= kMaxSmem) break;

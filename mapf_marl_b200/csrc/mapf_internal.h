@@ -5,7 +5,9 @@
 
 #include "../../include/mapf_b200.h"
 
-#define MAPF_TILE_THREADS 256
+#ifndef MAPF_TILE_THREADS
+#define MAPF_TILE_THREADS 128
+#endif
 #define MAPF_MAX_AGENTS 255
 #define MAPF_MAX_SIDE 255
 
@@ -36,11 +38,14 @@ struct MapfTileLayout {
   int agt_off;      // padded agent bitmaps:    [epb][bm_words] u32 (FOV only)
   int grida_off;    // [epb][grid_bytes] u8: PRIMAL live id grid / GRID occupancy counts of the current positions
   int gridb_off;    // [epb][grid_bytes] u8: PRIMAL pre-sweep id grid / GRID occupancy counts of the new positions
-  int posold_off, posnew_off, goal_off, tgt_off;  // uchar2 [epb*N]
+  int posold_off, posnew_off, goal_off;  // uchar2 [epb*N]
+  int mv_off;       // u32 [epb*N]
+  int moved_off;    // u32 [epb][8]
   int act_off, status_off, done_off, flag_off, avail_off, nextmid_off, node_off, edge_off, isint_off;  // u8 [epb*N]
   int rew_off;      // double [epb*N]
   int envrew_off;   // double [epb]
   int envterm_off;  // u8 [epb] (padded)
+  int envcnt_off;   // int [epb]: per-environment counters (agents on goal / done)
   int str_off;      // bit strings: ceil(epb*N / G) * GW u32
   int total_bytes;
 };

@@ -28,6 +28,7 @@
 namespace {
 
 constexpr int kThreads = MAPF_TILE_THREADS;
+static_assert(kThreads % 32 == 0 && kThreads >= 32 && kThreads <= 1024, "tile block size");
 
 // pre-status codes used inside the PRIMAL sweep (outside the reference's {-3..2})
 constexpr int8_t PRE_SKIP = 10, PRE_STAY = 11, PRE_MOVE = 12, PRE_MOVED = 13;
@@ -37,7 +38,9 @@ struct Smem {
   uint32_t* agt;
   uint8_t* grida;
   uint8_t* gridb;
-  uchar2 *posold, *posnew, *goal, *tgt;
+  uchar2 *posold, *posnew, *goal;
+  uint32_t* mv;      // [epb*N] old cell | target cell << 16
+  uint32_t* moved;   // [epb][8] bit i: agent i's move was carried out
   uint8_t *act, *done, *flag, *avail, *nextmid, *node, *edge, *isint;
   int8_t* status;
   double* rew;
@@ -55,7 +58,8 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const MapfTileLayout&
   s.posold = (uchar2*)(base + L.posold_off);
   s.posnew = (uchar2*)(base + L.posnew_off);
   s.goal = (uchar2*)(base + L.goal_off);
-  s.tgt = (uchar2*)(base + L.tgt_off);
+  s.mv = (uint32_t*)(base + L.mv_off);
+  s.moved = (uint32_t*)(base + L.moved_off);
   s.act = base + L.act_off;
   s.status = (int8_t*)(base + L.status_off);
   s.done = base + L.done_off;
@@ -170,71 +174,119 @@ __device__ double py_sum(const double* x, const uint8_t* is_int, int n, int sum_
 }
 
 // ------------------------------------------------------------------------------------------------
-// PRIMAL sweep for one environment (one warp).  State.moveAgent :103-135 applied for ids lo+1..hi
-// in order against the live id grid, then the order-independent parts of _step :549-637.
+// Step phases.  Both modes share the structure
+//   A  thread per agent : occupancy of the current positions + everything that does not depend on
+//                         the other agents (direction, bounds / wall checks, GRID done latch)
+//   B  (PRIMAL only) LANE per environment: the agent-order dependent occupancy claim
+//   C  thread per agent : outcome, reward, collisions, statistics
+//   D  thread per environment: done flag, team reward, step counter
 // ------------------------------------------------------------------------------------------------
-__device__ void step_primal_env(const MapfDims& d, const Smem& s, int el, int lane, const MapfTileArgs& A,
-                                unsigned int* stat /*smem[8]*/) {
-  const int N = d.N, W = d.W, H = d.H, jb = el * N;
-  const int lo = A.agent_lo, hi = A.agent_hi;
-  uint8_t* grid = s.grida + el * d.grid_bytes;
-  uint8_t* gold = s.gridb + el * d.grid_bytes;
+
+// PRIMAL phase A for agent j: State.moveAgent's checks that do not involve other robots (PRIMAL:107-118).
+// mv[j] = old cell | target cell << 16 (0xffff: no claim to make); status[j] = pre-status.
+__device__ __forceinline__ void primal_phase_a(const MapfDims& d, const Smem& s, const MapfTileArgs& A, int j, int el,
+                                               int a) {
   const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
-  const bool need_mid = (A.out.done_mid_dev != nullptr) || (A.out.next_mid_dev != nullptr);
-
-  if (need_mid)
-    for (int i = lane; i < (d.grid_bytes >> 4); i += 32) ((uint4*)gold)[i] = ((const uint4*)grid)[i];
-
-  // lane-parallel: direction, bounds and wall checks (they do not depend on the other agents)
-  for (int a = lane; a < N; a += 32) {
-    const int j = jb + a;
-    const int act = s.act[j];
-    const uchar2 p = s.posold[j];
-    int8_t st;
-    uchar2 t = p;
-    if (a < lo || a >= hi) {
-      st = PRE_SKIP;
-    } else if (act == 0) {
-      st = PRE_STAY;
+  const int act = s.act[j];
+  const uchar2 p = s.posold[j];
+  const uint32_t oc = (uint32_t)((int)p.x * d.W + p.y);
+  uint32_t tc = 0xffffu;
+  int8_t st;
+  if (a < A.agent_lo || a >= A.agent_hi) {
+    st = PRE_SKIP;
+  } else if (act == 0) {
+    st = PRE_STAY;
+  } else {
+    const int t0 = (int)p.x + (act == 2 ? 1 : (act == 4 ? -1 : 0));  // dirDict, PRIMAL:28
+    const int t1 = (int)p.y + (act == 1 ? 1 : (act == 3 ? -1 : 0));
+    if (bm_test(ob, d.RW, d.P, t0, t1)) {
+      st = (t0 < 0 || t0 >= d.H || t1 < 0 || t1 >= d.W) ? -1 : -2;   // PRIMAL:114-118
     } else {
-      const int t0 = (int)p.x + (act == 2 ? 1 : (act == 4 ? -1 : 0));  // dirDict, PRIMAL:28
-      const int t1 = (int)p.y + (act == 1 ? 1 : (act == 3 ? -1 : 0));
-      if (bm_test(ob, d.RW, d.P, t0, t1)) {
-        st = (t0 < 0 || t0 >= H || t1 < 0 || t1 >= W) ? -1 : -2;       // PRIMAL:114-118
-      } else {
-        st = PRE_MOVE;
-        t = make_uchar2((unsigned char)t0, (unsigned char)t1);
-      }
+      st = PRE_MOVE;
+      tc = (uint32_t)(t0 * d.W + t1);
     }
-    s.status[j] = st;
-    s.tgt[j] = t;
   }
-  __syncwarp();
+  s.status[j] = st;
+  s.mv[j] = oc | (tc << 16);
+}
 
-  // the agent-order dependent part: claim the target cell in the live grid (PRIMAL:119-129)
-  if (lane == 0) {
-    for (int i = lo; i < hi; ++i) {
-      const int j = jb + i;
-      if (s.status[j] == PRE_MOVE) {
-        const uchar2 t = s.tgt[j];
-        const int tc = (int)t.x * W + t.y;
-        if (grid[tc] != 0) {
-          s.status[j] = -3;
-        } else {
-          const uchar2 p = s.posold[j];
-          grid[(int)p.x * W + p.y] = 0;
+// PRIMAL phase B: claim the target cell in the live id grid (PRIMAL:119-129), strictly in agent order.
+// One lane per environment; up to 32 environments' sweeps advance in lockstep inside one warp.
+// Result: bit i of moved[el][i / 32] says whether agent i's move was carried out.
+__device__ __forceinline__ void primal_phase_b(const MapfDims& d, const Smem& s, const MapfTileArgs& A, int el) {
+  uint8_t* grid = s.grida + el * d.grid_bytes;
+  const uint32_t* mv = s.mv + el * d.N;
+  uint32_t* moved = s.moved + el * 8;
+  const int lo = A.agent_lo, hi = A.agent_hi;
+  for (int c0 = (lo & ~31); c0 < hi; c0 += 32) {
+    uint32_t mask = 0;
+    const int i0 = max(c0, lo), i1 = min(c0 + 32, hi);
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) {
+      const uint32_t m = mv[i];
+      const uint32_t tc = m >> 16;
+      if (tc != 0xffffu) {
+        if (grid[tc] == 0) {                 // nobody stands there NOW: earlier ids have moved, later ids have not
+          grid[m & 0xffffu] = 0;
           grid[tc] = (uint8_t)(i + 1);
-          s.posnew[j] = t;
-          s.status[j] = PRE_MOVED;
+          mask |= 1u << (i & 31);
         }
       }
     }
+    moved[c0 >> 5] = mask;
   }
-  __syncwarp();
+}
 
-  // lane-parallel epilogue: final status, reward table, on_goal, mid-sweep outputs
-  int tot_old = 0;
-  if (need_mid) {
+// PRIMAL phase C for agent j: final status (PRIMAL:108-110, 130-135), reward table (:579-597), on_goal (:633).
+__device__ __forceinline__ bool primal_phase_c(const MapfDims& d, const Smem& s, int j, int el, int a,
+                                               unsigned int& c_env, unsigned int& c_rob, unsigned int& c_arr) {
+  const uchar2 po = s.posold[j], g = s.goal[j];
+  int st = s.status[j];
+  const bool swept = st != PRE_SKIP;
+  uchar2 pn = po;
+  if (st == PRE_MOVE) {
+    if ((s.moved[el * 8 + (a >> 5)] >> (a & 31)) & 1u) {
+      const uint32_t tc = s.mv[j] >> 16;
+      const uint32_t t0 = tc / (uint32_t)d.W;
+      pn = make_uchar2((unsigned char)t0, (unsigned char)(tc - t0 * d.W));
+      st = PRE_MOVED;
+    } else {
+      st = -3;                                                       // collide with robot, PRIMAL:119-120
+    }
+  }
+  const bool on_old = (po.x == g.x && po.y == g.y);
+  const bool on_new = (pn.x == g.x && pn.y == g.y);
+  const int act = s.act[j];
+  if (st == PRE_STAY) st = on_old ? 1 : 0;
+  else if (st == PRE_MOVED) st = on_new ? 1 : (on_old ? 2 : 0);
+  else if (st == PRE_SKIP) st = 0;
+  double r = 0.0;
+  if (swept) {
+    if (act == 0) r = (st == 1) ? __dadd_rn(d.goal_reward, -0.0) : d.idle_cost;
+    else r = (st == 1) ? d.goal_reward : (st < 0 ? d.collision_reward : d.action_cost);
+    c_env += (st == -1 || st == -2);
+    c_rob += (st == -3);
+    c_arr += (on_new && !on_old);
+  }
+  s.posnew[j] = pn;
+  s.status[j] = (int8_t)st;
+  s.rew[j] = r;
+  s.done[j] = on_new ? 1 : 0;
+  s.flag[j] = (uint8_t)((on_new ? 1 : 0) | ((st >= 0) ? 2 : 0));     // valid_action, PRIMAL:571
+  return on_new;
+}
+
+// `done` and `nextActions` exactly as the i-th _step call of the sweep returned them (PRIMAL:626-630): at that
+// moment agents < i stand on their new cells and agents > i still on their old ones.  One warp per environment.
+// gridb holds the pre-sweep id grid.  Only used when the caller asks for the mid-sweep outputs.
+__device__ void primal_mid_outputs(const MapfDims& d, const Smem& s, const MapfTileArgs& A, int ne, int tid) {
+  const int N = d.N, W = d.W, lane = tid & 31, warp = tid >> 5;
+  for (int el = warp; el < ne; el += kThreads / 32) {
+    const int jb = el * N;
+    const uint8_t* grid = s.grida + el * d.grid_bytes;
+    const uint8_t* gold = s.gridb + el * d.grid_bytes;
+    const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+    int tot_old = 0;
     for (int a0 = 0; a0 < N; a0 += 32) {
       const int a = a0 + lane;
       bool on_old = false;
@@ -244,40 +296,21 @@ __device__ void step_primal_env(const MapfDims& d, const Smem& s, int el, int la
       }
       tot_old += __popc(__ballot_sync(0xffffffffu, on_old));
     }
-  }
-  int new_prefix = 0, old_prefix = 0;
-  bool all_on = true;
-  unsigned int c_env = 0, c_rob = 0, c_arr = 0;
-  for (int a0 = 0; a0 < N; a0 += 32) {
-    const int a = a0 + lane;
-    const bool active = a < N;
-    const int j = jb + (active ? a : 0);
-    const uchar2 po = s.posold[j], pn = s.posnew[j], g = s.goal[j];
-    const bool on_old = active && (po.x == g.x && po.y == g.y);
-    const bool on_new = active && (pn.x == g.x && pn.y == g.y);
-    const int act = s.act[j];
-    int st = s.status[j];
-    const bool swept = active && st != PRE_SKIP;
-    if (st == PRE_STAY) st = on_old ? 1 : 0;                         // PRIMAL:108-110
-    else if (st == PRE_MOVED) st = on_new ? 1 : (on_old ? 2 : 0);    // PRIMAL:130-135
-    else if (st == PRE_SKIP) st = 0;
-    double r = 0.0;
-    if (swept) {
-      if (act == 0) r = (st == 1) ? __dadd_rn(d.goal_reward, -0.0) : d.idle_cost;          // PRIMAL:579-587
-      else r = (st == 1) ? d.goal_reward : (st < 0 ? d.collision_reward : d.action_cost);  // PRIMAL:588-596
-    }
-    const unsigned bn = __ballot_sync(0xffffffffu, on_new);
-    const unsigned bo = __ballot_sync(0xffffffffu, on_old);
-    if (active) {
-      s.status[j] = (int8_t)st;
-      s.rew[j] = r;
-      s.done[j] = on_new ? 1 : 0;                                    // on_goal, PRIMAL:633
-      uint8_t fl = (on_new ? 1 : 0) | ((st >= 0) ? 2 : 0);           // valid_action, PRIMAL:571
-      if (need_mid) {
+    int new_prefix = 0, old_prefix = 0;
+    for (int a0 = 0; a0 < N; a0 += 32) {
+      const int a = a0 + lane;
+      const bool active = a < N;
+      const int j = jb + (active ? a : 0);
+      const uchar2 po = s.posold[j], pn = s.posnew[j], g = s.goal[j];
+      const bool on_old = active && (po.x == g.x && po.y == g.y);
+      const bool on_new = active && (pn.x == g.x && pn.y == g.y);
+      const unsigned bn = __ballot_sync(0xffffffffu, on_new);
+      const unsigned bo = __ballot_sync(0xffffffffu, on_old);
+      if (active) {
+        const bool swept = (a >= A.agent_lo && a < A.agent_hi);
         const unsigned le = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
         const int cnt = new_prefix + __popc(bn & le) + (tot_old - old_prefix - __popc(bo & le));
-        if (cnt == N) fl |= 4;                                       // world.done() right after this agent moved
-        // nextActions as returned by this agent's _step: neighbours at the time it moved.
+        if (cnt == N) s.flag[j] |= 4;
         uint8_t m = 1;
 #pragma unroll
         for (int k = 1; k <= 4; ++k) {
@@ -290,139 +323,81 @@ __device__ void step_primal_env(const MapfDims& d, const Smem& s, int el, int la
             if (!occ) m |= (uint8_t)(1u << k);
           }
         }
+        const int act = s.act[j];
         const int opp = (act == 0) ? -1 : (((act + 1) & 3) + 1);     // opposite_actions, PRIMAL:26
         if (opp > 0) m &= (uint8_t)~(1u << opp);
         s.nextmid[j] = swept ? m : 0;
       }
-      s.flag[j] = fl;
-      if (swept) {
-        c_env += (st == -1 || st == -2);
-        c_rob += (st == -3);
-        c_arr += (on_new && !on_old);
-      }
-      all_on = all_on && on_new;
-    }
-    new_prefix += __popc(bn);
-    old_prefix += __popc(bo);
-  }
-  all_on = __all_sync(0xffffffffu, all_on);
-  if (d.collect_stats) {
-    c_env = __reduce_add_sync(0xffffffffu, c_env);
-    c_rob = __reduce_add_sync(0xffffffffu, c_rob);
-    c_arr = __reduce_add_sync(0xffffffffu, c_arr);
-    if (lane == 0) {
-      atomicAdd(&stat[MAPF_STAT_ENV_STEPS], lo == 0 ? 1u : 0u);
-      atomicAdd(&stat[MAPF_STAT_AGENT_STEPS], (unsigned)(hi - lo));
-      atomicAdd(&stat[MAPF_STAT_ENV_COLLISIONS], c_env);
-      atomicAdd(&stat[MAPF_STAT_NODE_COLLISIONS], c_rob);
-      atomicAdd(&stat[MAPF_STAT_GOAL_ARRIVALS], c_arr);
-      atomicAdd(&stat[MAPF_STAT_EPISODES_DONE], all_on ? 1u : 0u);
-    }
-  }
-  __syncwarp();
-  if (lane == 0) {
-    s.envterm[el] = all_on ? 1 : 0;                                  // State.done, PRIMAL:159-165
-    if (A.out.reward_dev) {
-      double tot = 0.0;
-      for (int i = lo; i < hi; ++i) tot = __dadd_rn(tot, s.rew[jb + i]);
-      s.envrew[el] = tot;
+      new_prefix += __popc(bn);
+      old_prefix += __popc(bo);
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// GRID step for one environment (one warp).  MAPF_GRID.step, GRID:85-141.
-//   grida: occupancy counts of the positions before the step, gridb: after the step.
-// ------------------------------------------------------------------------------------------------
-__device__ void step_grid_env(const MapfDims& d, const Smem& s, int el, int lane, int step_now,
-                              unsigned int* stat) {
-  const int N = d.N, W = d.W, jb = el * N;
-  uint8_t* cold = s.grida + el * d.grid_bytes;
-  uint8_t* cnew = s.gridb + el * d.grid_bytes;
+// GRID phase A for agent j (GRID:99-118): move unless wall / border, done latch, new-position counts.
+__device__ __forceinline__ void grid_phase_a(const MapfDims& d, const Smem& s, int j, int el, int step_now,
+                                             unsigned int& c_env, unsigned int& c_arr) {
   const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
-  unsigned int c_env = 0, c_node = 0, c_edge = 0, c_arr = 0;
+  const uchar2 p = s.posold[j], g = s.goal[j];
+  const bool done_old = s.done[j] != 0;
+  uchar2 np = p;
+  double r = 0.0;
+  int flag = 0;
+  if (!done_old) {
+    const int act = s.act[j];
+    if (act < 4) {                                                   // __agent_step, GRID:319-342
+      const int t0 = (int)p.x + (act == 0 ? -1 : (act == 1 ? 1 : 0));
+      const int t1 = (int)p.y + (act == 2 ? -1 : (act == 3 ? 1 : 0));
+      if (bm_test(ob, d.RW, d.P, t0, t1)) flag = 1;
+      else np = make_uchar2((unsigned char)t0, (unsigned char)t1);
+    }
+    if (flag) r = __dadd_rn(r, d.collide_reward);                    // GRID:105-106
+    r = __dadd_rn(r, d.step_reward);                                 // GRID:110
+  }
+  bool dn = done_old;
+  const bool reached = (np.x == g.x && np.y == g.y);
+  if (reached) dn = true;                                            // GRID:112-113
+  if (step_now >= d.episode_limit) dn = true;                        // GRID:116-117
+  s.posnew[j] = np;
+  s.status[j] = (int8_t)flag;
+  s.done[j] = dn ? 1 : 0;
+  s.rew[j] = r;
+  s.isint[j] = (uint8_t)(done_old ? d.collide_is_int : (d.collide_is_int && d.step_is_int));
+  byte_inc(s.gridb + el * d.grid_bytes, (int)np.x * d.W + np.y);
+  c_env += flag;
+  c_arr += (reached && !done_old);
+}
 
-  for (int a = lane; a < N; a += 32) {                               // GRID:99-118
-    const int j = jb + a;
-    const uchar2 p = s.posold[j], g = s.goal[j];
-    const bool done_old = s.done[j] != 0;
-    uchar2 np = p;
-    double r = 0.0;
-    int flag = 0;
-    if (!done_old) {
-      const int act = s.act[j];
-      if (act < 4) {                                                 // __agent_step, GRID:319-342
-        const int t0 = (int)p.x + (act == 0 ? -1 : (act == 1 ? 1 : 0));
-        const int t1 = (int)p.y + (act == 2 ? -1 : (act == 3 ? 1 : 0));
-        if (bm_test(ob, d.RW, d.P, t0, t1)) flag = 1;
-        else np = make_uchar2((unsigned char)t0, (unsigned char)t1);
-      }
-      if (flag) r = __dadd_rn(r, d.collide_reward);                  // GRID:105-106
-      r = __dadd_rn(r, d.step_reward);                               // GRID:110
-    }
-    bool dn = done_old;
-    const bool reached = (np.x == g.x && np.y == g.y);
-    if (reached) dn = true;                                          // GRID:112-113
-    if (step_now >= d.episode_limit) dn = true;                      // GRID:116-117
-    s.posnew[j] = np;
-    s.status[j] = (int8_t)flag;
-    s.done[j] = dn ? 1 : 0;
-    s.rew[j] = r;
-    s.isint[j] = (uint8_t)(done_old ? d.collide_is_int : (d.collide_is_int && d.step_is_int));
-    byte_inc(cnew, (int)np.x * W + np.y);
-    c_env += flag;
-    c_arr += (reached && !done_old);
-  }
-  __syncwarp();
-  bool all_done = true;
-  for (int a = lane; a < N; a += 32) {
-    const int j = jb + a;
-    const uchar2 p = s.posold[j], np = s.posnew[j];
-    const int nc = (int)np.x * W + np.y;
-    const int node = cnew[nc] > 1 ? 1 : 0;                           // __count_node_collision, GRID:344-362
-    int edge = 0;                                                    // __count_edge_collision, GRID:364-383
-    if ((p.x != np.x || p.y != np.y) && cold[nc] != 0) {
-      for (int k = 0; k < N; ++k) {
-        if (k == a) continue;
-        const uchar2 qo = s.posold[jb + k], qn = s.posnew[jb + k];
-        edge += (qo.x == np.x && qo.y == np.y && qn.x == p.x && qn.y == p.y) ? 1 : 0;
-      }
-    }
-    double r = s.rew[j];
-    r = __dadd_rn(r, __dmul_rn(d.collide_reward, (double)node));     // GRID:128
-    r = __dadd_rn(r, __dmul_rn(d.collide_reward, (double)edge));     // GRID:129
-    s.rew[j] = r;
-    s.node[j] = (uint8_t)node;
-    s.edge[j] = (uint8_t)edge;
-    all_done = all_done && (s.done[j] != 0);
-    c_node += node;
-    c_edge += edge;
-  }
-  all_done = __all_sync(0xffffffffu, all_done);
-  if (d.collect_stats) {
-    c_env = __reduce_add_sync(0xffffffffu, c_env);
-    c_node = __reduce_add_sync(0xffffffffu, c_node);
-    c_edge = __reduce_add_sync(0xffffffffu, c_edge);
-    c_arr = __reduce_add_sync(0xffffffffu, c_arr);
-    if (lane == 0) {
-      atomicAdd(&stat[MAPF_STAT_ENV_STEPS], 1u);
-      atomicAdd(&stat[MAPF_STAT_AGENT_STEPS], (unsigned)N);
-      atomicAdd(&stat[MAPF_STAT_ENV_COLLISIONS], c_env);
-      atomicAdd(&stat[MAPF_STAT_NODE_COLLISIONS], c_node);
-      atomicAdd(&stat[MAPF_STAT_EDGE_COLLISIONS], c_edge);
-      atomicAdd(&stat[MAPF_STAT_GOAL_ARRIVALS], c_arr);
-      atomicAdd(&stat[MAPF_STAT_EPISODES_DONE], all_done ? 1u : 0u);
+// GRID phase C for agent j: node flag (GRID:344-362), edge count (GRID:364-383), collision penalties (:127-130).
+__device__ __forceinline__ bool grid_phase_c(const MapfDims& d, const Smem& s, int j, int el, int a,
+                                             unsigned int& c_node, unsigned int& c_edge) {
+  const int N = d.N, jb = el * N;
+  const uint8_t* cold = s.grida + el * d.grid_bytes;
+  const uint8_t* cnew = s.gridb + el * d.grid_bytes;
+  const uchar2 p = s.posold[j], np = s.posnew[j];
+  const int nc = (int)np.x * d.W + np.y;
+  const int node = cnew[nc] > 1 ? 1 : 0;
+  int edge = 0;
+  if ((p.x != np.x || p.y != np.y) && cold[nc] != 0) {
+    for (int k = 0; k < N; ++k) {
+      if (k == a) continue;
+      const uchar2 qo = s.posold[jb + k], qn = s.posnew[jb + k];
+      edge += (qo.x == np.x && qo.y == np.y && qn.x == p.x && qn.y == p.y) ? 1 : 0;
     }
   }
-  __syncwarp();
-  if (lane == 0) {
-    s.envrew[el] = py_sum(s.rew + jb, s.isint + jb, N, d.sum_mode);  // GRID:141
-    s.envterm[el] = all_done ? 1 : 0;                                // episode_done, GRID:267
-  }
+  double r = s.rew[j];
+  r = __dadd_rn(r, __dmul_rn(d.collide_reward, (double)node));       // GRID:128
+  r = __dadd_rn(r, __dmul_rn(d.collide_reward, (double)edge));       // GRID:129
+  s.rew[j] = r;
+  s.node[j] = (uint8_t)node;
+  s.edge[j] = (uint8_t)edge;
+  c_node += node;
+  c_edge += edge;
+  return s.done[j] != 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Field-of-view observation bits of one agent (PRIMAL _observe :343-386), F known at compile time.
+// Field-of-view observation (PRIMAL _observe :343-386), F known at compile time.
 // Bit index == byte index of the [4][F][F] output: channel*F*F + wi*F + wj, channels in the returned
 // order [poss_map, goal_map, goals_map, obs_map] (:386).
 // ------------------------------------------------------------------------------------------------
@@ -433,6 +408,9 @@ struct Fov {
   static constexpr int NW = (NB + 31) / 32;
   static constexpr int CW = (FF + 31) / 32;
   static constexpr uint32_t FMASK = (1u << F) - 1u;
+  // goal_map / goals_map bits never fall into a string word shared with a neighbouring agent iff channel 0
+  // and channel 3 each cover a whole word
+  static constexpr bool kInterior = FF >= 32;
 };
 
 template <int NWORDS>
@@ -442,29 +420,13 @@ __device__ __forceinline__ void or_field(uint32_t (&w)[NWORDS], int off, int bit
   if (sh + bits > 32) w[k + 1] |= v >> (32 - sh);
 }
 
-template <int CW>
-__device__ __forceinline__ void set_bit_dyn(uint32_t (&x)[CW], int idx) {
-  const uint32_t b = 1u << (idx & 31);
-  const int k = idx >> 5;
-#pragma unroll
-  for (int q = 0; q < CW; ++q) x[q] |= (k == q) ? b : 0u;
-}
-
+// poss_map (channel 0) and obs_map (channel 3): 2 x F window rows, each one funnel shift of a padded bit row.
 template <int F>
-__device__ __forceinline__ void fov_agent_bits(uint32_t (&w)[Fov<F>::NW], const MapfDims& d, const uint32_t* ob,
-                                               const uint32_t* ag, const uint8_t* idgrid, const uchar2* goals_env,
-                                               uchar2 p, uchar2 g) {
+__device__ __forceinline__ void fov_window_planes(uint32_t (&w)[Fov<F>::NW], const MapfDims& d, const uint32_t* ob,
+                                                  const uint32_t* ag, uchar2 p) {
   using T = Fov<F>;
-  constexpr int P = F / 2;
-  uint32_t goalp[T::CW], goalsp[T::CW];
-#pragma unroll
-  for (int q = 0; q < T::CW; ++q) goalp[q] = goalsp[q] = 0u;
 #pragma unroll
   for (int q = 0; q < T::NW; ++q) w[q] = 0u;
-
-  const int gi = (int)g.x - (int)p.x + P, gj = (int)g.y - (int)p.y + P;      // :366-368
-  if ((unsigned)gi < (unsigned)F && (unsigned)gj < (unsigned)F) set_bit_dyn<T::CW>(goalp, gi * F + gj);
-
 #pragma unroll
   for (int wi = 0; wi < F; ++wi) {
     // padded row p.x + wi holds map row p.x - P + wi; padded column p.y holds map column p.y - P
@@ -472,25 +434,38 @@ __device__ __forceinline__ void fov_agent_bits(uint32_t (&w)[Fov<F>::NW], const 
     const uint32_t fa = row_field(ag, d.RW, (int)p.x + wi, (int)p.y, T::FMASK);   // any agent, :363-372
     or_field<T::NW>(w, 0 * T::FF + wi * F, F, fa);
     or_field<T::NW>(w, 3 * T::FF + wi * F, F, fo);
-    uint32_t v = fa;
-    if (wi == P) v &= ~(1u << P);                                                   // not the agent itself
-    while (v) {                                                                     // visible_agents, :374-378
-      const int wj = __ffs(v) - 1;
-      v &= v - 1;
-      const int r = (int)p.x - P + wi, c = (int)p.y - P + wj;
-      const int id = idgrid[r * d.W + c];
-      if (id == 0) continue;
-      const uchar2 og = goals_env[id - 1];
-      const int ci = min(max((int)og.x - ((int)p.x - P), 0), F - 1);
-      const int cj = min(max((int)og.y - ((int)p.y - P), 0), F - 1);
-      set_bit_dyn<T::CW>(goalsp, ci * F + cj);
-    }
   }
+}
+
+// goal_map (own goal cell, :366-368) and goals_map (goals of the visible other agents clamped into the window,
+// :374-378): single bits OR-ed into the agent's string in shared memory.  `vis` = poss_map without the agent itself.
+template <int F, bool ATOMIC>
+__device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, const uint32_t (&vis)[Fov<F>::CW], int W,
+                                              const uint8_t* idgrid, const uchar2* goals_env, uchar2 p, uchar2 g) {
+  using T = Fov<F>;
+  constexpr int P = F / 2;
+  auto set = [&](int pos) {
+    const int b = bit0 + pos;
+    if (ATOMIC) atomicOr(&str[b >> 5], 1u << (b & 31));
+    else str[b >> 5] |= 1u << (b & 31);
+  };
+  const int t0 = (int)p.x - P, t1 = (int)p.y - P;
+  const int gi = (int)g.x - t0, gj = (int)g.y - t1;
+  if ((unsigned)gi < (unsigned)F && (unsigned)gj < (unsigned)F) set(T::FF + gi * F + gj);
 #pragma unroll
   for (int q = 0; q < T::CW; ++q) {
-    const int bits = (T::FF - 32 * q) < 32 ? (T::FF - 32 * q) : 32;
-    or_field<T::NW>(w, 1 * T::FF + 32 * q, bits, goalp[q]);
-    or_field<T::NW>(w, 2 * T::FF + 32 * q, bits, goalsp[q]);
+    uint32_t v = vis[q];
+    while (v) {
+      const int idx = 32 * q + __ffs(v) - 1;
+      v &= v - 1;
+      const int wi = idx / F, wj = idx - wi * F;
+      const int id = idgrid[(t0 + wi) * W + t1 + wj];
+      if (id == 0) continue;
+      const uchar2 og = goals_env[id - 1];
+      const int ci = min(max((int)og.x - t0, 0), F - 1);
+      const int cj = min(max((int)og.y - t1, 0), F - 1);
+      set(2 * T::FF + ci * F + cj);
+    }
   }
 }
 
@@ -504,8 +479,8 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   __shared__ unsigned int stat[MAPF_N_STATS];
   __shared__ unsigned int bad_flag;
   const Smem s = carve(smem_raw, L);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int nwarps = kThreads / 32;
+  int* envcnt = (int*)(smem_raw + L.envcnt_off);
+  const int tid = threadIdx.x, lane = tid & 31;
   const int N = d.N;
   const int e0 = blockIdx.x * d.epb;
   const int ne = min(d.epb, d.E - e0);
@@ -513,28 +488,19 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   const size_t a0 = (size_t)e0 * N;
   const bool primal = d.mode == MAPF_MODE_PRIMAL;
   const bool do_step = A.do_step != 0;
+  const bool need_mid = primal && do_step && ((A.out.done_mid_dev != nullptr) || (A.out.next_mid_dev != nullptr));
 
+  // ---- stage the tile (one exposed global-memory latency): obstacle bitmaps, per-agent records, zeroed grids
   if (tid < MAPF_N_STATS) stat[tid] = 0;
   if (tid == 0) bad_flag = 0;
-
-  // ---- stage the tile: obstacle bitmaps (16-byte vectors), agent records, zeroed grids / bitmaps
+  for (int el = tid; el < ne; el += kThreads) envcnt[el] = 0;
   {
     const int nvec = ((d.shared_map ? 1 : ne) * d.bm_words) >> 2;
     const uint4* src = (const uint4*)(S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e0 * d.bm_words));
     uint4* dst = (uint4*)s.obst;
     for (int i = tid; i < nvec; i += kThreads) dst[i] = __ldg(src + i);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    const int ngrid = (ne * d.grid_bytes) >> 4;
-    for (int i = tid; i < ngrid; i += kThreads) {
-      ((uint4*)s.grida)[i] = z;
-      ((uint4*)s.gridb)[i] = z;
-    }
-    if (F > 0) {
-      const int nag = (ne * d.bm_words) >> 2;
-      for (int i = tid; i < nag; i += kThreads) ((uint4*)s.agt)[i] = z;
-    }
   }
-  __syncthreads();   // stat/bad_flag init + zeroed grids visible
+  bool bad = false;
   for (int j = tid; j < na; j += kThreads) {
     const uchar2 p = ((const uchar2*)S.pos)[a0 + j];
     s.posold[j] = p;
@@ -547,37 +513,88 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       long long v = (A.act_dtype == MAPF_I64) ? ((const long long*)A.actions)[a0 + j]
                                               : (long long)((const uint8_t*)A.actions)[a0 + j];
       if (v < 0 || v > 4) {                                          // GRID:92 / PRIMAL:556 assert
-        bad_flag = 1;
+        bad = true;
         v = primal ? 0 : 4;
       }
       act = (int)v;
     }
     s.act[j] = (uint8_t)act;
-    // occupancy of the current positions: PRIMAL State.state ids (PRIMAL:32-47), GRID agent counts (GRID:299)
-    uint8_t* grid = s.grida + el * d.grid_bytes;
-    const int cell = (int)p.x * d.W + p.y;
-    if (primal) grid[cell] = (uint8_t)(a + 1);
-    else byte_inc(grid, cell);
   }
-  __syncthreads();
-
-  // ---- step: one warp per environment
-  if (do_step) {
-    for (int el = warp; el < ne; el += nwarps) {
-      if (primal) {
-        step_primal_env(d, s, el, lane, A, stat);
-      } else {
-        int step_now = 0;
-        if (lane == 0) step_now = S.step_count[e0 + el] + 1;         // GRID:93
-        step_now = __shfl_sync(0xffffffffu, step_now, 0);
-        step_grid_env(d, s, el, lane, step_now, stat);
-      }
-      if (lane == 0) {
-        if (!primal || A.agent_lo == 0) S.step_count[e0 + el] += 1;
-      }
+  {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const int ngrid = (ne * d.grid_bytes) >> 4;
+    for (int i = tid; i < ngrid; i += kThreads) ((uint4*)s.grida)[i] = z;
+    if (!primal && do_step)
+      for (int i = tid; i < ngrid; i += kThreads) ((uint4*)s.gridb)[i] = z;
+    if (F > 0) {
+      const int nag = (ne * d.bm_words) >> 2;
+      for (int i = tid; i < nag; i += kThreads) ((uint4*)s.agt)[i] = z;
     }
   }
   __syncthreads();
+  if (bad) bad_flag = 1;
+
+  // ---- phase A: occupancy of the current positions (PRIMAL State.state ids, PRIMAL:32-47; GRID agent counts,
+  //      GRID:299) and the agent-independent part of the step
+  unsigned int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  for (int j = tid; j < na; j += kThreads) {
+    const int el = j / N, a = j - el * N;
+    const uchar2 p = s.posold[j];
+    uint8_t* grid = s.grida + el * d.grid_bytes;
+    const int cell = (int)p.x * d.W + p.y;
+    if (primal) {
+      grid[cell] = (uint8_t)(a + 1);
+      if (do_step) primal_phase_a(d, s, A, j, el, a);
+    } else {
+      byte_inc(grid, cell);
+      if (do_step) grid_phase_a(d, s, j, el, S.step_count[e0 + el] + 1, c0, c3);   // GRID:93
+    }
+  }
+  __syncthreads();
+
+  if (do_step) {
+    // ---- phase B (PRIMAL): the sequential claim, one lane per environment
+    if (primal) {
+      if (need_mid)   // keep the pre-sweep id grid for the mid-sweep outputs
+        for (int i = tid; i < ((ne * d.grid_bytes) >> 4); i += kThreads)
+          ((uint4*)s.gridb)[i] = ((const uint4*)s.grida)[i];
+      __syncthreads();
+      for (int el = tid; el < ne; el += kThreads) primal_phase_b(d, s, A, el);
+      __syncthreads();
+    }
+    // ---- phase C
+    for (int j0 = 0; j0 < na; j0 += kThreads) {
+      const int j = j0 + tid;
+      const bool active = j < na;
+      int el = -1;
+      bool flag = false;
+      if (active) {
+        el = j / N;
+        const int a = j - el * N;
+        flag = primal ? primal_phase_c(d, s, j, el, a, c0, c1, c3) : grid_phase_c(d, s, j, el, a, c1, c2);
+      }
+      // per-environment count of agents on goal (PRIMAL) / done (GRID), one shared-memory atomic per (warp, env)
+      const unsigned peers = __match_any_sync(0xffffffffu, el);
+      const unsigned bf = __ballot_sync(0xffffffffu, flag);
+      if (active && lane == __ffs(peers) - 1) atomicAdd(&envcnt[el], __popc(bf & peers));
+    }
+    if (d.collect_stats) {
+      c0 = __reduce_add_sync(0xffffffffu, c0);
+      c1 = __reduce_add_sync(0xffffffffu, c1);
+      c2 = __reduce_add_sync(0xffffffffu, c2);
+      c3 = __reduce_add_sync(0xffffffffu, c3);
+      if (lane == 0) {
+        if (c0) atomicAdd(&stat[MAPF_STAT_ENV_COLLISIONS], c0);
+        if (c1) atomicAdd(&stat[MAPF_STAT_NODE_COLLISIONS], c1);
+        if (c2) atomicAdd(&stat[MAPF_STAT_EDGE_COLLISIONS], c2);
+        if (c3) atomicAdd(&stat[MAPF_STAT_GOAL_ARRIVALS], c3);
+      }
+    }
+    if (need_mid) {
+      __syncthreads();
+      primal_mid_outputs(d, s, A, ne, tid);
+    }
+  }
 
   // ---- agent bitmap of the post-step positions + available-action masks
   const uint8_t* gridcur = (!primal && do_step) ? s.gridb : s.grida;
@@ -617,8 +634,25 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   }
   __syncthreads();
 
-  // ---- state write-back and the small per-agent / per-env outputs (coalesced over the tile)
+  // ---- phase D + state write-back + the small per-agent / per-env outputs (coalesced over the tile)
   if (do_step) {
+    for (int el = tid; el < ne; el += kThreads) {
+      const bool all = envcnt[el] == N;        // PRIMAL State.done (:159-165) / GRID episode_done (:267)
+      if (A.out.terminated_dev) A.out.terminated_dev[e0 + el] = all ? 1 : 0;
+      if (primal) {
+        if (A.out.reward_dev) {
+          double tot = 0.0;
+          for (int i = A.agent_lo; i < A.agent_hi; ++i) tot = __dadd_rn(tot, s.rew[el * N + i]);
+          A.out.reward_dev[e0 + el] = tot;
+        }
+        if (A.agent_lo == 0) S.step_count[e0 + el] += 1;
+      } else {
+        if (A.out.reward_dev)
+          A.out.reward_dev[e0 + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // GRID:141
+        S.step_count[e0 + el] += 1;
+      }
+      if (d.collect_stats && all) atomicAdd(&stat[MAPF_STAT_EPISODES_DONE], 1u);
+    }
     copy_out_bytes(S.pos + 2 * a0, (const uint8_t*)s.posnew, 2 * na, tid);
     copy_out_bytes(S.done + a0, s.done, na, tid);
     copy_out_bytes(S.prev_action + a0, s.act, na, tid);
@@ -626,10 +660,6 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     if (A.out.status_dev) copy_out_bytes((uint8_t*)A.out.status_dev + a0, (const uint8_t*)s.status, na, tid);
     if (A.out.agent_reward_dev)
       for (int j = tid; j < na; j += kThreads) A.out.agent_reward_dev[a0 + j] = s.rew[j];
-    if (A.out.reward_dev)
-      for (int el = tid; el < ne; el += kThreads) A.out.reward_dev[e0 + el] = s.envrew[el];
-    if (A.out.terminated_dev)
-      for (int el = tid; el < ne; el += kThreads) A.out.terminated_dev[e0 + el] = s.envterm[el];
     if (A.out.node_dev)
       for (int j = tid; j < na; j += kThreads) A.out.node_dev[a0 + j] = primal ? 0 : (int16_t)s.node[j];
     if (A.out.edge_dev)
@@ -639,11 +669,18 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     if (primal && A.out.done_mid_dev)
       for (int j = tid; j < na; j += kThreads) A.out.done_mid_dev[a0 + j] = (s.flag[j] >> 2) & 1;
     if (primal && A.out.next_mid_dev) write_mask5(A.out.next_mid_dev + 5 * a0, s.nextmid, na, tid);
+    if (d.collect_stats) {   // one global atomic per counter per tile
+      __syncthreads();
+      if (tid == 0) {
+        stat[MAPF_STAT_ENV_STEPS] = (!primal || A.agent_lo == 0) ? (unsigned)ne : 0u;
+        stat[MAPF_STAT_AGENT_STEPS] = (unsigned)(ne * (primal ? A.agent_hi - A.agent_lo : N));
+      }
+      __syncthreads();
+      if (tid < MAPF_N_STATS && stat[tid] != 0) atomicAdd(&S.stats[tid], (unsigned long long)stat[tid]);
+    }
   }
   if (want_avail) write_mask5(A.out.avail_dev + 5 * a0, s.avail, na, tid);
   if (tid == 0 && bad_flag) atomicOr(S.err_flags, MAPF_FLAG_BAD_ACTION);
-  if (d.collect_stats && do_step && tid < MAPF_N_STATS && stat[tid] != 0)
-    atomicAdd(&S.stats[tid], (unsigned long long)stat[tid]);
 
   // ---- observation
   if (A.obs == nullptr && A.vec == nullptr) return;
@@ -668,46 +705,62 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     // word-aligned group string.
     for (int base = 0; base < na; base += kThreads) {
       const int j = base + tid;
-      const bool valid = j < na;
-      uint32_t w[T::NW];
-      int w0 = 0, sh = 0;
+      const bool valid = (j < na) && (A.obs != nullptr);
+      uint32_t first = 0;
+      uint32_t vis[T::CW];
+      int w0 = 0, sh = 0, el = 0;
+      uchar2 p = make_uchar2(0, 0), g = make_uchar2(0, 0);
+      if (j < na) {
+        el = j / N;
+        p = s.posnew[j];
+        g = s.goal[j];
+      }
       if (valid) {
-        const int el = j / N;
-        const uchar2 p = s.posnew[j], g = s.goal[j];
-        if (A.obs != nullptr) {
-          fov_agent_bits<F>(w, d, s.obst + (d.shared_map ? 0 : el * d.bm_words), s.agt + el * d.bm_words,
-                            gridcur + el * d.grid_bytes, s.goal + el * N, p, g);
-          const int grp = j / d.G, k = j - grp * d.G;
-          const int boff = k * T::NB;
-          w0 = grp * d.GW + (boff >> 5);
-          sh = boff & 31;
-          const int nwords = (sh + T::NB + 31) >> 5;
-          uint32_t prev = 0;
+        uint32_t w[T::NW];
+        fov_window_planes<F>(w, d, s.obst + (d.shared_map ? 0 : el * d.bm_words), s.agt + el * d.bm_words, p);
 #pragma unroll
-          for (int q = 0; q <= T::NW; ++q) {
-            const uint32_t cur = (q < T::NW) ? w[q] : 0u;
-            const uint32_t o = __funnelshift_l(prev, cur, sh);     // (cur:prev << sh) >> 32
-            prev = cur;
-            if (q == 0) w[0] = o;                                  // keep for the deferred OR
-            if (q < nwords && !(q == 0 && sh > 0)) s.str[w0 + q] = o;
-          }
+        for (int q = 0; q < T::CW; ++q) vis[q] = w[q];
+        if ((T::FF & 31) != 0) vis[T::CW - 1] &= (1u << (T::FF & 31)) - 1u;
+        vis[((F / 2) * F + F / 2) >> 5] &= ~(1u << (((F / 2) * F + F / 2) & 31));   // not the agent itself
+        const int grp = j / d.G, k = j - grp * d.G;
+        const int boff = k * T::NB;
+        w0 = grp * d.GW + (boff >> 5);
+        sh = boff & 31;
+        const int nwords = (sh + T::NB + 31) >> 5;
+        uint32_t prev = 0;
+#pragma unroll
+        for (int q = 0; q <= T::NW; ++q) {
+          const uint32_t cur = (q < T::NW) ? w[q] : 0u;
+          const uint32_t o = __funnelshift_l(prev, cur, sh);     // (cur:prev << sh) >> 32
+          prev = cur;
+          if (q == 0) first = o;                                 // word shared with the previous agent: OR-ed below
+          if (q < nwords && !(q == 0 && sh > 0)) s.str[w0 + q] = o;
         }
-        if (A.vec != nullptr) {                                      // PRIMAL:380-385
-          const int dx = (int)g.x - (int)p.x, dy = (int)g.y - (int)p.y;
-          const double mag = __ldg(S.mag_lut + (dx * dx + dy * dy));
-          double fx = (double)dx, fy = (double)dy;
-          if (mag != 0.0) {
-            fx = __ddiv_rn(fx, mag);
-            fy = __ddiv_rn(fy, mag);
-          }
-          double* v = A.vec + 3 * (a0 + j);
-          v[0] = fx;
-          v[1] = fy;
-          v[2] = mag;
+        if (T::kInterior)
+          fov_goal_bits<F, false>(s.str + w0, sh, vis, d.W, gridcur + el * d.grid_bytes, s.goal + el * N, p, g);
+      }
+      if (j < na && A.vec != nullptr) {                              // PRIMAL:380-385
+        const int dx = (int)g.x - (int)p.x, dy = (int)g.y - (int)p.y;
+        const double mag = __ldg(S.mag_lut + (dx * dx + dy * dy));
+        double fx = (double)dx, fy = (double)dy;
+        if (mag != 0.0) {
+          fx = __ddiv_rn(fx, mag);
+          fy = __ddiv_rn(fy, mag);
         }
+        double* v = A.vec + 3 * (a0 + j);
+        v[0] = fx;
+        v[1] = fy;
+        v[2] = mag;
       }
       __syncthreads();
-      if (valid && sh > 0 && A.obs != nullptr) s.str[w0] |= w[0];   // word shared with the previous agent
+      if (valid) {
+        if (T::kInterior) {
+          if (sh > 0) s.str[w0] |= first;
+        } else {
+          if (sh > 0) atomicOr(&s.str[w0], first);
+          fov_goal_bits<F, true>(s.str + w0, sh, vis, d.W, gridcur + el * d.grid_bytes, s.goal + el * N, p, g);
+        }
+      }
     }
     __syncthreads();
     if (A.obs == nullptr) return;
