@@ -225,6 +225,8 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   d.step_is_int = c->step_reward_is_int;
   d.collide_is_int = c->collide_reward_is_int;
   d.collect_stats = c->collect_stats;
+  d.invN = (uint32_t)((0x100000000ULL + d.N - 1) / d.N);
+  d.invW = (uint32_t)((0x100000000ULL + d.W - 1) / d.W);
   d.step_reward = c->step_reward;
   d.collide_reward = c->collide_reward;
   d.action_cost = c->action_cost;

@@ -28,6 +28,7 @@ struct MapfDims {
   int GW;        // words per group string = G * 4*F*F / 32
   int sum_mode, step_is_int, collide_is_int;
   int collect_stats;
+  uint32_t invN, invW;  // ceil(2^32 / N), ceil(2^32 / W): exact division of values < 65536 by IMAD.HI
   double step_reward, collide_reward;
   double action_cost, idle_cost, goal_reward, collision_reward;
 };

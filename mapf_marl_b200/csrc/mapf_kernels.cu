@@ -76,6 +76,11 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const MapfTileLayout&
   return s;
 }
 
+// j / N for j < 65536 with inv = ceil(2^32 / N) (exact for N <= 255): one IMAD.HI instead of an integer division.
+__device__ __forceinline__ int fast_div(int j, uint32_t inv) {
+  return inv ? (int)__umulhi((uint32_t)j, inv) : j;   // inv == 0 encodes a divisor of 1
+}
+
 // Bit test in a padded bitmap; (r, c) are map coordinates and may lie up to P cells outside.
 __device__ __forceinline__ uint32_t bm_test(const uint32_t* bm, int RW, int P, int r, int c) {
   const int pr = r + P, pc = c + P;
@@ -101,7 +106,7 @@ __device__ __forceinline__ void st_stream16(void* p, uint4 v) {
 // 4 bits -> 4 bytes of 0/1 (bit k lands in byte k).
 __device__ __forceinline__ uint32_t expand4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
-__device__ __forceinline__ void copy_out_bytes(uint8_t* dst, const uint8_t* src, int n, int tid) {
+__device__ __noinline__ void copy_out_bytes(uint8_t* dst, const uint8_t* src, int n, int tid) {
   if (((((uintptr_t)dst) | ((uintptr_t)src)) & 3) == 0) {
     const int nw = n >> 2;
     for (int i = tid; i < nw; i += kThreads) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
@@ -112,7 +117,7 @@ __device__ __forceinline__ void copy_out_bytes(uint8_t* dst, const uint8_t* src,
 }
 
 // Expands per-agent 5-bit masks to the [na][5] uint8 layout of get_avail_actions.
-__device__ __forceinline__ void write_mask5(uint8_t* dst, const uint8_t* mask, int na, int tid) {
+__device__ __noinline__ void write_mask5(uint8_t* dst, const uint8_t* mask, int na, int tid) {
   const int n = 5 * na;
   if ((((uintptr_t)dst) & 3) == 0) {
     const int nw = n >> 2;
@@ -247,7 +252,7 @@ __device__ __forceinline__ bool primal_phase_c(const MapfDims& d, const Smem& s,
   if (st == PRE_MOVE) {
     if ((s.moved[el * 8 + (a >> 5)] >> (a & 31)) & 1u) {
       const uint32_t tc = s.mv[j] >> 16;
-      const uint32_t t0 = tc / (uint32_t)d.W;
+      const uint32_t t0 = (uint32_t)fast_div((int)tc, d.invW);
       pn = make_uchar2((unsigned char)t0, (unsigned char)(tc - t0 * d.W));
       st = PRE_MOVED;
     } else {
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     s.posnew[j] = p;
     s.goal[j] = ((const uchar2*)S.goal)[a0 + j];
     s.done[j] = S.done[a0 + j];
-    const int el = j / N, a = j - el * N;
+    const int el = fast_div(j, d.invN), a = j - el * N;
     int act = S.prev_action[a0 + j];
     if (do_step && a >= A.agent_lo && a < A.agent_hi) {
       long long v = (A.act_dtype == MAPF_I64) ? ((const long long*)A.actions)[a0 + j]
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   //      GRID:299) and the agent-independent part of the step
   unsigned int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   for (int j = tid; j < na; j += kThreads) {
-    const int el = j / N, a = j - el * N;
+    const int el = fast_div(j, d.invN), a = j - el * N;
     const uchar2 p = s.posold[j];
     uint8_t* grid = s.grida + el * d.grid_bytes;
     const int cell = (int)p.x * d.W + p.y;
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       int el = -1;
       bool flag = false;
       if (active) {
-        el = j / N;
+        el = fast_div(j, d.invN);
         const int a = j - el * N;
         flag = primal ? primal_phase_c(d, s, j, el, a, c0, c1, c3) : grid_phase_c(d, s, j, el, a, c1, c2);
       }
@@ -600,7 +605,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   const uint8_t* gridcur = (!primal && do_step) ? s.gridb : s.grida;
   const bool want_avail = A.out.avail_dev != nullptr;
   for (int j = tid; j < na; j += kThreads) {
-    const int el = j / N;
+    const int el = fast_div(j, d.invN);
     const uchar2 p = s.posnew[j];
     if (F > 0) {
       uint32_t* ag = s.agt + el * d.bm_words;
@@ -711,7 +716,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       int w0 = 0, sh = 0, el = 0;
       uchar2 p = make_uchar2(0, 0), g = make_uchar2(0, 0);
       if (j < na) {
-        el = j / N;
+        el = fast_div(j, d.invN);
         p = s.posnew[j];
         g = s.goal[j];
       }
