@@ -110,8 +110,10 @@ class ClockSampler(threading.Thread):
 
 def cpu_port_rate(wl, n_envs, steps, warmup, threads=0, want_obs=True):
     """The CPU oracle port stepping + observing `n_envs` environments of the workload; agent-steps/s."""
-    from oracle import Oracle, oracle_max_threads
+    from oracle import Oracle
     from oracle.oracle import MODE_PRIMAL
+    if not threads:   # all host threads this process may use (torchrun pins OMP_NUM_THREADS=1, so ask the OS)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     obst, starts, goals = make_world(wl, n_envs, 0)
     orc = Oracle(n_envs, wl["N"], wl["H"], wl["W"], MODE_PRIMAL, fov=wl["F"], shared_map=wl["warehouse"],
                  threads=threads)
@@ -134,13 +136,12 @@ def cpu_port_rate(wl, n_envs, steps, warmup, threads=0, want_obs=True):
     for t in range(steps):
         one(t)
     dt = time.perf_counter() - t0
-    return n_envs * wl["N"] * steps / dt, dt, (threads or oracle_max_threads())
+    return n_envs * wl["N"] * steps / dt, dt, threads
 
 
 def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
-    from oracle import oracle_max_threads
     # each step is a bounded sample of the workload, sized so that K steps take about two minutes at most
     r0, _, _ = cpu_port_rate(wl, min(wl["E"], 1024), 3, 1)
     n_envs = int(min(wl["E"], 2048, max(16, r0 * 120.0 / (max(args.steps, 1) * wl["N"]))))
@@ -152,7 +153,7 @@ def run_reference_arm(args, wl, rank):
         "config": workload_config(args.workload, wl, args.gpus),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d envs x %d agents x %d steps of %s (C oracle port, OpenMP over envs, %d threads)"
-                                   % (n_envs, wl["N"], args.steps, args.workload, oracle_max_threads())},
+                                   % (n_envs, wl["N"], args.steps, args.workload, cores)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference is pure Python and cannot travel to the GPU box; this is the C oracle port, "
