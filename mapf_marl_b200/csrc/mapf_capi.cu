@@ -72,7 +72,8 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L) {
   L->posnew_off = take(2 * na);
   L->goal_off = take(2 * na);
   L->mv_off = take(4 * na);
-  L->moved_off = take(32 * epb);
+  L->res_off = take(na);
+  L->dep_off = take(na);
   L->act_off = take(na);
   L->status_off = take(na);
   L->done_off = take(na);
@@ -216,7 +217,8 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   d.PR = d.H + 2 * d.P;
   d.RW = ((d.W + 2 * d.P - 1) >> 5) + 2;
   d.bm_words = align_up(d.PR * d.RW, 4);
-  d.grid_bytes = align_up(d.HW, 16);
+  d.GS = d.W + 2;
+  d.grid_bytes = align_up((d.H + 2) * (d.W + 2), 16);
   d.shared_map = c->shared_map ? 1 : 0;
   d.mode = c->mode;
   d.obs_mode = c->obs_mode;

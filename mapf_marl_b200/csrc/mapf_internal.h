@@ -19,7 +19,8 @@ struct MapfDims {
   int PR;        // padded rows  = H + 2P
   int RW;        // 32-bit words per padded row, including one guard word
   int bm_words;  // words per padded bitmap, rounded up to a multiple of 4 (16-byte rows for bulk copies)
-  int grid_bytes;  // H*W rounded up to a multiple of 16
+  int GS;          // row stride of the occupancy grids = W + 2 (one cell of padding on every side)
+  int grid_bytes;  // (H+2)*(W+2) rounded up to a multiple of 16
   int shared_map;
   int mode, obs_mode;
   int episode_limit;
@@ -41,7 +42,7 @@ struct MapfTileLayout {
   int gridb_off;    // [epb][grid_bytes] u8: PRIMAL pre-sweep id grid / GRID occupancy counts of the new positions
   int posold_off, posnew_off, goal_off;  // uchar2 [epb*N]
   int mv_off;       // u32 [epb*N]
-  int moved_off;    // u32 [epb][8]
+  int res_off, dep_off;  // u8 [epb*N]
   int act_off, status_off, done_off, flag_off, avail_off, nextmid_off, node_off, edge_off, isint_off;  // u8 [epb*N]
   int rew_off;      // double [epb*N]
   int envrew_off;   // double [epb]

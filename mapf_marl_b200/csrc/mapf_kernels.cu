@@ -39,8 +39,9 @@ struct Smem {
   uint8_t* grida;
   uint8_t* gridb;
   uchar2 *posold, *posnew, *goal;
-  uint32_t* mv;      // [epb*N] old cell | target cell << 16
-  uint32_t* moved;   // [epb][8] bit i: agent i's move was carried out
+  uint32_t* mv;      // [epb*N] padded target cell of the agent's move (0xffffffff: none)
+  uint8_t* res;      // [epb*N] outcome of the move: RES_*
+  uint8_t* dep;      // [epb*N] lower-id agent whose outcome decides this one
   uint8_t *act, *done, *flag, *avail, *nextmid, *node, *edge, *isint;
   int8_t* status;
   double* rew;
@@ -59,7 +60,8 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const MapfTileLayout&
   s.posnew = (uchar2*)(base + L.posnew_off);
   s.goal = (uchar2*)(base + L.goal_off);
   s.mv = (uint32_t*)(base + L.mv_off);
-  s.moved = (uint32_t*)(base + L.moved_off);
+  s.res = base + L.res_off;
+  s.dep = base + L.dep_off;
   s.act = base + L.act_off;
   s.status = (int8_t*)(base + L.status_off);
   s.done = base + L.done_off;
@@ -187,15 +189,20 @@ __device__ double py_sum(const double* x, const uint8_t* is_int, int n, int sum_
 //   D  thread per environment: done flag, team reward, step counter
 // ------------------------------------------------------------------------------------------------
 
+// Occupancy grids are padded by one cell on every side (stride GS = W + 2): the four neighbours of any map cell
+// can be read without bounds checks, the padding is never occupied.
+__device__ __forceinline__ int gcell(const MapfDims& d, int r, int c) { return (r + 1) * d.GS + c + 1; }
+
+constexpr uint8_t RES_UNRESOLVED = 0, RES_MOVED = 1, RES_STAYS = 2;
+
 // PRIMAL phase A for agent j: State.moveAgent's checks that do not involve other robots (PRIMAL:107-118).
-// mv[j] = old cell | target cell << 16 (0xffff: no claim to make); status[j] = pre-status.
+// mv[j] = padded target cell (0xffffffff: no claim to make); status[j] = pre-status.
 __device__ __forceinline__ void primal_phase_a(const MapfDims& d, const Smem& s, const MapfTileArgs& A, int j, int el,
                                                int a) {
   const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
   const int act = s.act[j];
   const uchar2 p = s.posold[j];
-  const uint32_t oc = (uint32_t)((int)p.x * d.W + p.y);
-  uint32_t tc = 0xffffu;
+  uint32_t tc = 0xffffffffu;
   int8_t st;
   if (a < A.agent_lo || a >= A.agent_hi) {
     st = PRE_SKIP;
@@ -208,38 +215,44 @@ __device__ __forceinline__ void primal_phase_a(const MapfDims& d, const Smem& s,
       st = (t0 < 0 || t0 >= d.H || t1 < 0 || t1 >= d.W) ? -1 : -2;   // PRIMAL:114-118
     } else {
       st = PRE_MOVE;
-      tc = (uint32_t)(t0 * d.W + t1);
+      tc = (uint32_t)gcell(d, t0, t1);
     }
   }
   s.status[j] = st;
-  s.mv[j] = oc | (tc << 16);
+  s.mv[j] = tc;
 }
 
-// PRIMAL phase B: claim the target cell in the live id grid (PRIMAL:119-129), strictly in agent order.
-// One lane per environment; up to 32 environments' sweeps advance in lockstep inside one warp.
-// Result: bit i of moved[el][i / 32] says whether agent i's move was carried out.
-__device__ __forceinline__ void primal_phase_b(const MapfDims& d, const Smem& s, const MapfTileArgs& A, int el) {
-  uint8_t* grid = s.grida + el * d.grid_bytes;
+// PRIMAL phase B: the outcome of the ordered sweep `for id in 1..N: moveAgent(id)` (PRIMAL:119-129) WITHOUT walking
+// the agents one by one.  Agent a's move succeeds iff its target cell t is free when a's turn comes.  With k = the
+// agent standing on t before the sweep (if any) and "claimants" = agents whose target is t (they sit on t's four
+// neighbours), the ordered semantics reduce to
+//     k > a                       : k has not moved yet                                        -> blocked
+//     a claimant b with k < b < a : b found t free earlier (t was empty, or k had left) and took it -> blocked
+//     otherwise, t empty (no k)   : nobody could have entered before a                          -> moves
+//     otherwise, k < a            : a moves iff k itself moved away (k's own outcome, a lower id) -> depends on k
+// (claimants below k always fail: k is still there at their turn).  Only the last case is order dependent, and only
+// on a LOWER id, so the dependencies resolve in rounds; a round is one barrier, and random traffic needs one or two.
+// Equivalence to the serial walk is checked bit-for-bit against the reference traces and the oracle.
+__device__ __forceinline__ uint8_t primal_classify(const MapfDims& d, const Smem& s, int j, int el, int a) {
+  if (s.status[j] != PRE_MOVE) return RES_STAYS;
+  const uint8_t* grid = s.grida + el * d.grid_bytes;   // ids before the sweep
   const uint32_t* mv = s.mv + el * d.N;
-  uint32_t* moved = s.moved + el * 8;
-  const int lo = A.agent_lo, hi = A.agent_hi;
-  for (int c0 = (lo & ~31); c0 < hi; c0 += 32) {
-    uint32_t mask = 0;
-    const int i0 = max(c0, lo), i1 = min(c0 + 32, hi);
-#pragma unroll 4
-    for (int i = i0; i < i1; ++i) {
-      const uint32_t m = mv[i];
-      const uint32_t tc = m >> 16;
-      if (tc != 0xffffu) {
-        if (grid[tc] == 0) {                 // nobody stands there NOW: earlier ids have moved, later ids have not
-          grid[m & 0xffffu] = 0;
-          grid[tc] = (uint8_t)(i + 1);
-          mask |= 1u << (i & 31);
-        }
-      }
-    }
-    moved[c0 >> 5] = mask;
+  const int8_t* st = s.status + el * d.N;
+  const int tc = (int)s.mv[j];
+  const int occ = grid[tc];
+  if (occ > a + 1) return RES_STAYS;
+  const int k = occ - 1;
+  bool taken = false;
+  const int nb[4] = {tc - 1, tc + 1, tc - d.GS, tc + d.GS};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int b = (int)grid[nb[q]] - 1;
+    if (b > k && b < a && st[b] == PRE_MOVE && (int)mv[b] == tc) taken = true;
   }
+  if (taken) return RES_STAYS;
+  if (k < 0) return RES_MOVED;
+  s.dep[j] = (uint8_t)k;
+  return RES_UNRESOLVED;
 }
 
 // PRIMAL phase C for agent j: final status (PRIMAL:108-110, 130-135), reward table (:579-597), on_goal (:633).
@@ -249,11 +262,12 @@ __device__ __forceinline__ bool primal_phase_c(const MapfDims& d, const Smem& s,
   int st = s.status[j];
   const bool swept = st != PRE_SKIP;
   uchar2 pn = po;
+  const int act = s.act[j];
   if (st == PRE_MOVE) {
-    if ((s.moved[el * 8 + (a >> 5)] >> (a & 31)) & 1u) {
-      const uint32_t tc = s.mv[j] >> 16;
-      const uint32_t t0 = (uint32_t)fast_div((int)tc, d.invW);
-      pn = make_uchar2((unsigned char)t0, (unsigned char)(tc - t0 * d.W));
+    if (s.res[j] == RES_MOVED) {
+      pn = make_uchar2((unsigned char)((int)po.x + (act == 2 ? 1 : (act == 4 ? -1 : 0))),
+                       (unsigned char)((int)po.y + (act == 1 ? 1 : (act == 3 ? -1 : 0))));
+      s.grida[el * d.grid_bytes + s.mv[j]] = (uint8_t)(a + 1);       // old cells were cleared before this phase
       st = PRE_MOVED;
     } else {
       st = -3;                                                       // collide with robot, PRIMAL:119-120
@@ -261,7 +275,6 @@ __device__ __forceinline__ bool primal_phase_c(const MapfDims& d, const Smem& s,
   }
   const bool on_old = (po.x == g.x && po.y == g.y);
   const bool on_new = (pn.x == g.x && pn.y == g.y);
-  const int act = s.act[j];
   if (st == PRE_STAY) st = on_old ? 1 : 0;
   else if (st == PRE_MOVED) st = on_new ? 1 : (on_old ? 2 : 0);
   else if (st == PRE_SKIP) st = 0;
@@ -285,7 +298,7 @@ __device__ __forceinline__ bool primal_phase_c(const MapfDims& d, const Smem& s,
 // moment agents < i stand on their new cells and agents > i still on their old ones.  One warp per environment.
 // gridb holds the pre-sweep id grid.  Only used when the caller asks for the mid-sweep outputs.
 __device__ void primal_mid_outputs(const MapfDims& d, const Smem& s, const MapfTileArgs& A, int ne, int tid) {
-  const int N = d.N, W = d.W, lane = tid & 31, warp = tid >> 5;
+  const int N = d.N, lane = tid & 31, warp = tid >> 5;
   for (int el = warp; el < ne; el += kThreads / 32) {
     const int jb = el * N;
     const uint8_t* grid = s.grida + el * d.grid_bytes;
@@ -322,7 +335,7 @@ __device__ void primal_mid_outputs(const MapfDims& d, const Smem& s, const MapfT
           const int n0 = (int)pn.x + (k == 2 ? 1 : (k == 4 ? -1 : 0));
           const int n1 = (int)pn.y + (k == 1 ? 1 : (k == 3 ? -1 : 0));
           if (!bm_test(ob, d.RW, d.P, n0, n1)) {
-            const int c = n0 * W + n1;
+            const int c = gcell(d, n0, n1);
             const int idn = grid[c], ido = gold[c];
             const bool occ = (ido > a + 1) || (idn != 0 && idn < a + 1);
             if (!occ) m |= (uint8_t)(1u << k);
@@ -368,7 +381,7 @@ __device__ __forceinline__ void grid_phase_a(const MapfDims& d, const Smem& s, i
   s.done[j] = dn ? 1 : 0;
   s.rew[j] = r;
   s.isint[j] = (uint8_t)(done_old ? d.collide_is_int : (d.collide_is_int && d.step_is_int));
-  byte_inc(s.gridb + el * d.grid_bytes, (int)np.x * d.W + np.y);
+  byte_inc(s.gridb + el * d.grid_bytes, gcell(d, np.x, np.y));
   c_env += flag;
   c_arr += (reached && !done_old);
 }
@@ -380,7 +393,7 @@ __device__ __forceinline__ bool grid_phase_c(const MapfDims& d, const Smem& s, i
   const uint8_t* cold = s.grida + el * d.grid_bytes;
   const uint8_t* cnew = s.gridb + el * d.grid_bytes;
   const uchar2 p = s.posold[j], np = s.posnew[j];
-  const int nc = (int)np.x * d.W + np.y;
+  const int nc = gcell(d, np.x, np.y);
   const int node = cnew[nc] > 1 ? 1 : 0;
   int edge = 0;
   if ((p.x != np.x || p.y != np.y) && cold[nc] != 0) {
@@ -445,7 +458,7 @@ __device__ __forceinline__ void fov_window_planes(uint32_t (&w)[Fov<F>::NW], con
 // goal_map (own goal cell, :366-368) and goals_map (goals of the visible other agents clamped into the window,
 // :374-378): single bits OR-ed into the agent's string in shared memory.  `vis` = poss_map without the agent itself.
 template <int F, bool ATOMIC>
-__device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, const uint32_t (&vis)[Fov<F>::CW], int W,
+__device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, const uint32_t (&vis)[Fov<F>::CW], int GS,
                                               const uint8_t* idgrid, const uchar2* goals_env, uchar2 p, uchar2 g) {
   using T = Fov<F>;
   constexpr int P = F / 2;
@@ -464,7 +477,7 @@ __device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, const uin
       const int idx = 32 * q + __ffs(v) - 1;
       v &= v - 1;
       const int wi = idx / F, wj = idx - wi * F;
-      const int id = idgrid[(t0 + wi) * W + t1 + wj];
+      const int id = idgrid[(t0 + wi + 1) * GS + t1 + wj + 1];
       if (id == 0) continue;
       const uchar2 og = goals_env[id - 1];
       const int ci = min(max((int)og.x - t0, 0), F - 1);
@@ -546,7 +559,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     const int el = fast_div(j, d.invN), a = j - el * N;
     const uchar2 p = s.posold[j];
     uint8_t* grid = s.grida + el * d.grid_bytes;
-    const int cell = (int)p.x * d.W + p.y;
+    const int cell = gcell(d, p.x, p.y);
     if (primal) {
       grid[cell] = (uint8_t)(a + 1);
       if (do_step) primal_phase_a(d, s, A, j, el, a);
@@ -558,13 +571,33 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   __syncthreads();
 
   if (do_step) {
-    // ---- phase B (PRIMAL): the sequential claim, one lane per environment
+    // ---- phase B (PRIMAL): outcome of the ordered sweep, resolved in parallel (see primal_classify)
     if (primal) {
       if (need_mid)   // keep the pre-sweep id grid for the mid-sweep outputs
         for (int i = tid; i < ((ne * d.grid_bytes) >> 4); i += kThreads)
           ((uint4*)s.gridb)[i] = ((const uint4*)s.grida)[i];
-      __syncthreads();
-      for (int el = tid; el < ne; el += kThreads) primal_phase_b(d, s, A, el);
+      bool pending = false;
+      for (int j = tid; j < na; j += kThreads) {
+        const int el = fast_div(j, d.invN), a = j - el * N;
+        const uint8_t r = primal_classify(d, s, j, el, a);
+        s.res[j] = r;
+        pending |= (r == RES_UNRESOLVED);
+      }
+      while (__syncthreads_or(pending)) {      // an agent waits only for a LOWER id: every round makes progress
+        pending = false;
+        for (int j = tid; j < na; j += kThreads) {
+          if (s.res[j] != RES_UNRESOLVED) continue;
+          const int el = fast_div(j, d.invN);
+          const uint8_t rk = s.res[el * N + s.dep[j]];
+          if (rk == RES_UNRESOLVED) pending = true;
+          else s.res[j] = rk;                  // moves iff the agent ahead of it moved away
+        }
+      }
+      for (int j = tid; j < na; j += kThreads)   // vacate the old cells; phase C enters the new ones
+        if (s.res[j] == RES_MOVED) {
+          const uchar2 p = s.posold[j];
+          s.grida[fast_div(j, d.invN) * d.grid_bytes + gcell(d, p.x, p.y)] = 0;
+        }
       __syncthreads();
     }
     // ---- phase C
@@ -595,10 +628,8 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
         if (c3) atomicAdd(&stat[MAPF_STAT_GOAL_ARRIVALS], c3);
       }
     }
-    if (need_mid) {
-      __syncthreads();
-      primal_mid_outputs(d, s, A, ne, tid);
-    }
+    if (primal) __syncthreads();   // phase C entered the new cells into the id grid
+    if (need_mid) primal_mid_outputs(d, s, A, ne, tid);
   }
 
   // ---- agent bitmap of the post-step positions + available-action masks
@@ -622,7 +653,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
         for (int k = 1; k <= 4; ++k) {
           const int n0 = (int)p.x + (k == 2 ? 1 : (k == 4 ? -1 : 0));
           const int n1 = (int)p.y + (k == 1 ? 1 : (k == 3 ? -1 : 0));
-          if (!bm_test(ob, d.RW, d.P, n0, n1) && grid[n0 * d.W + n1] == 0) m |= (uint8_t)(1u << k);
+          if (!bm_test(ob, d.RW, d.P, n0, n1) && grid[gcell(d, n0, n1)] == 0) m |= (uint8_t)(1u << k);
         }
         const int act = s.act[j];
         const int opp = (act == 0) ? -1 : (((act + 1) & 3) + 1);
@@ -698,7 +729,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       const int el = i / d.HW, cell = i - el * d.HW;
       const int r = cell / d.W, c = cell - r * d.W;
       const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
-      const int cnt = gridcur[el * d.grid_bytes + cell];
+      const int cnt = gridcur[el * d.grid_bytes + gcell(d, r, c)];
       out[i] = bm_test(ob, d.RW, d.P, r, c) ? (int8_t)(cnt - 1) : (int8_t)cnt;   // `+= 1` on a -1 cell, GRID:299
     }
     return;
@@ -742,7 +773,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
           if (q < nwords && !(q == 0 && sh > 0)) s.str[w0 + q] = o;
         }
         if (T::kInterior)
-          fov_goal_bits<F, false>(s.str + w0, sh, vis, d.W, gridcur + el * d.grid_bytes, s.goal + el * N, p, g);
+          fov_goal_bits<F, false>(s.str + w0, sh, vis, d.GS, gridcur + el * d.grid_bytes, s.goal + el * N, p, g);
       }
       if (j < na && A.vec != nullptr) {                              // PRIMAL:380-385
         const int dx = (int)g.x - (int)p.x, dy = (int)g.y - (int)p.y;
@@ -763,7 +794,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
           if (sh > 0) s.str[w0] |= first;
         } else {
           if (sh > 0) atomicOr(&s.str[w0], first);
-          fov_goal_bits<F, true>(s.str + w0, sh, vis, d.W, gridcur + el * d.grid_bytes, s.goal + el * N, p, g);
+          fov_goal_bits<F, true>(s.str + w0, sh, vis, d.GS, gridcur + el * d.grid_bytes, s.goal + el * N, p, g);
         }
       }
     }

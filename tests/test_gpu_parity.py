@@ -485,3 +485,55 @@ def test_full_size_invariants(cfg):
     assert np.array_equal(_np(obs[:n]), robs)
     assert np.array_equal(_bits(_np(vec[:n])), _bits(rvec))
     assert np.array_equal(_np(eng.positions()[:n]), orc.positions())
+
+
+def test_primal_convoys_cycles_and_long_dependency_chains_match_oracle():
+    """The ordered sweep is resolved in parallel rounds on the device (primal_classify): stress the cases where
+    an agent's outcome depends on a chain of lower ids -- convoys in ascending / descending / shuffled id order,
+    rotating 2x2 cycles, three-way races for one cell -- against the serial oracle."""
+    from oracle.oracle import MODE_PRIMAL
+    H, W, N = 6, 40, 36
+    rs = np.random.RandomState(42)
+    envs = []
+    # rows 1 and 3 are corridors; agents stand shoulder to shoulder and all push the same way
+    for order in ("asc", "desc", "shuffle", "shuffle2"):
+        ids = np.arange(N)
+        if order == "desc":
+            ids = ids[::-1].copy()
+        elif order.startswith("shuffle"):
+            ids = rs.permutation(N)
+        starts = np.zeros((N, 2), np.int16)
+        for slot, a in enumerate(ids):       # slot 0 is the head of the convoy (nearest the free space ahead)
+            starts[a] = (1 + 2 * (slot // 18), 30 - (slot % 18))
+        envs.append(starts)
+    # 2x2 rotating blocks and 3-way races, packed anywhere
+    for _ in range(12):
+        cells = [(r, c) for r in range(H) for c in range(W)]
+        idx = rs.permutation(len(cells))[:N]
+        envs.append(np.array([cells[i] for i in idx], np.int16))
+    E = len(envs)
+    starts = np.stack(envs)
+    goals = np.zeros((E, N, 2), np.int16)
+    for e in range(E):
+        cells = [(r, c) for r in range(H) for c in range(W)]
+        goals[e] = np.array([cells[i] for i in rs.permutation(len(cells))[:N]], np.int16)
+    obst = np.zeros((E, H, W), np.uint8)
+    eng = _engine(E, N, H, W, mode="primal", fov=5)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=5)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    for t in range(30):
+        a = np.zeros((E, N), np.uint8)
+        a[:4] = 1 if t % 6 < 4 else 3                    # convoys push east (PRIMAL action 1 = (0,+1)), then back west
+        a[4:] = rs.randint(0, 5, (E - 4, N))
+        if t % 5 == 4:
+            a[4:] = rs.randint(1, 5)                      # everybody tries the same direction: long chains
+        out = eng.step_observe(torch.as_tensor(a, device="cuda"), want=PRIMAL_WANT)
+        ref = orc.primal_sweep(a)
+        robs, _ = orc.primal_observe()
+        for k in ("status", "dones", "valid", "done_mid", "next_mid", "avail", "terminated"):
+            assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        assert np.array_equal(_np(eng.positions()), orc.positions()), t
+        assert np.array_equal(_np(out["obs"]), robs), t
+    # the ascending convoy moved as a whole in its first step, the descending one only at its head
+    assert eng.error_flags() == 0
