@@ -52,19 +52,28 @@ typedef enum mapf_mode {
   /* mode B "sequential claim": State.moveAgent swept over ids 1..N, PRIMAL:103-135 and
    * MAPFEnv._step, PRIMAL:549-637.  Actions {0:stay 1:(0,+1) 2:(+1,0) 3:(0,-1) 4:(-1,0)}
    * (dirDict, PRIMAL:28). */
-  MAPF_MODE_PRIMAL = 1
+  MAPF_MODE_PRIMAL = 1,
+  /* mode A with the rewards and bookkeeping of MARL_PARTIAL_ENV.step (output == False), PARTIAL:169-310: move /
+   * stay / stay-on-goal costs, goal-distance shaping `(dist[old] - dist[new]) / episode_limit` from the BFS maps
+   * (:229-234), at_goal recomputed every step, termination at the limit or when all agents are on goal, with the
+   * completion bonus (:291-299).  The same GRID action deltas on (row, col). */
+  MAPF_MODE_PARTIAL = 2
 } mapf_mode;
 
 typedef enum mapf_obs_mode {
   MAPF_OBS_FULLMAP = 0,   /* GRID get_obs/get_state, GRID:143-196: int8[E, H*W], -1 wall else agent count */
-  MAPF_OBS_PRIMAL_FOV = 1 /* PRIMAL _observe, PRIMAL:343-386: [E, N, 4, F, F] + double[E, N, 3] */
+  MAPF_OBS_PRIMAL_FOV = 1, /* PRIMAL _observe, PRIMAL:343-386: [E, N, 4, F, F] + double[E, N, 3] */
+  /* PARTIAL get_obs_agent, PARTIAL:319-382: double[E, N, 2*W*W + 13*K]: W x W obstacle map, W x W agent-count map,
+   * K nearest agents x 13 features (self first, stable sort by L2 distance, missing rows -1). */
+  MAPF_OBS_PARTIAL_WINDOW = 2
 } mapf_obs_mode;
 
 typedef enum mapf_dtype {
   MAPF_U8 = 0,
   MAPF_I64 = 1,
   MAPF_F32 = 2,
-  MAPF_I8 = 3
+  MAPF_I8 = 3,
+  MAPF_F64 = 4
 } mapf_dtype;
 
 /* Device-side error flag bits (mapf_error_flags). */
@@ -122,6 +131,16 @@ typedef struct mapf_cfg {
   int32_t step_reward_is_int;
   int32_t collide_reward_is_int;
   int32_t reserved;
+  /* MAPF_MODE_PARTIAL: constructor keywords of MARL_PARTIAL_ENV, PARTIAL:26-45. */
+  int32_t obs_window;         /* W */
+  int32_t obs_knn_agents;     /* K */
+  double move_reward, stay_reward, stay_goal_reward;
+  double node_collide_reward, edge_collide_reward, env_collide_reward;
+  /* complete_lut_host[t] = the bonus every agent receives when all agents are on goal at step t:
+   * `(complete_reward / (gamma ** (episode_limit - t))) * complete_fac` (PARTIAL:296), evaluated by the host. */
+  const double* complete_lut_host;
+  int32_t complete_lut_len;
+  int32_t reserved2;
 } mapf_cfg;
 
 /* Outputs of one step.  Every pointer is a device pointer and may be NULL (not written). */
@@ -240,6 +259,12 @@ int mapf_get_goals(mapf_handle* h, int16_t* goals_dev, void* stream);
 /* uint8[E,N] `_agent_dones` (GRID) / on_goal (PRIMAL); int32[E] `_step_count` (GRID:93). */
 int mapf_get_dones(mapf_handle* h, uint8_t* dones_dev, void* stream);
 int mapf_get_step_count(mapf_handle* h, int32_t* step_count_dev, void* stream);
+
+/* MAPF_MODE_PARTIAL read-backs.  state_dev int64[E,3] = get_state() (PARTIAL:384-393): [total collisions, step
+ * count, sum of per-agent goal costs]; at_goal_dev uint8[E,N] (`_agent_at_goals`), goal_cost_dev int32[E,N]
+ * (`_each_goal_cost`), agent_steps_dev int32[E,N] (`_agent_step_count`); any pointer may be NULL. */
+int mapf_partial_state(mapf_handle* h, int64_t* state_dev, uint8_t* at_goal_dev, int32_t* goal_cost_dev,
+                       int32_t* agent_steps_dev, void* stream);
 
 /* Copies the int64[MAPF_N_STATS] counters to stats_host (waits for the stream). */
 int mapf_stats(mapf_handle* h, int64_t* stats_host, void* stream);

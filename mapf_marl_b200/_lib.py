@@ -17,9 +17,9 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mapf_b200.h")
 ABI_VERSION = 1
 
 MAPF_OK = 0
-MODE_GRID, MODE_PRIMAL = 0, 1
-OBS_FULLMAP, OBS_PRIMAL_FOV = 0, 1
-U8, I64, F32, I8 = 0, 1, 2, 3
+MODE_GRID, MODE_PRIMAL, MODE_PARTIAL = 0, 1, 2
+OBS_FULLMAP, OBS_PRIMAL_FOV, OBS_PARTIAL_WINDOW = 0, 1, 2
+U8, I64, F32, I8, F64 = 0, 1, 2, 3, 4
 FLAG_BAD_ACTION, FLAG_BAD_POSITION, FLAG_START_ON_WALL, FLAG_START_OVERLAP = 1, 2, 4, 8
 N_STATS = 8
 STAT_NAMES = ("env_steps", "agent_steps", "env_collisions", "node_collisions", "edge_collisions",
@@ -40,6 +40,11 @@ class MapfCfg(ctypes.Structure):
         ("mag_lut_host", _vp), ("mag_lut_len", ctypes.c_int32),
         ("reward_sum_mode", ctypes.c_int32), ("step_reward_is_int", ctypes.c_int32),
         ("collide_reward_is_int", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("obs_window", ctypes.c_int32), ("obs_knn_agents", ctypes.c_int32),
+        ("move_reward", ctypes.c_double), ("stay_reward", ctypes.c_double), ("stay_goal_reward", ctypes.c_double),
+        ("node_collide_reward", ctypes.c_double), ("edge_collide_reward", ctypes.c_double),
+        ("env_collide_reward", ctypes.c_double),
+        ("complete_lut_host", _vp), ("complete_lut_len", ctypes.c_int32), ("reserved2", ctypes.c_int32),
     ]
 
 
@@ -80,6 +85,7 @@ PROTOTYPES = {
     "mapf_get_goals": (_i, [_vp, _vp, _vp]),
     "mapf_get_dones": (_i, [_vp, _vp, _vp]),
     "mapf_get_step_count": (_i, [_vp, _vp, _vp]),
+    "mapf_partial_state": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_stats": (_i, [_vp, _vp, _vp]),
     "mapf_error_flags": (_i, [_vp, _vp, _vp]),
     "mapf_launch_count": (_i64, [_vp]),

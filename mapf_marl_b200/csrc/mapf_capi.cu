@@ -87,6 +87,8 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L) {
   L->envrew_off = take(8 * epb);
   L->envterm_off = take(epb);
   L->envcnt_off = take(4 * epb);
+  L->envcnt2_off = take(4 * epb);
+  L->atgoal_off = take(na);
   L->str_off = take(fov ? ((na + d.G - 1) / d.G) * d.GW * 4 + 16 : 16);
   L->total_bytes = off;
 }
@@ -159,6 +161,14 @@ int mapf_destroy(mapf_handle* h) {
   cudaFree((void*)h->S.mag_lut);
   cudaFree(h->S.stats);
   cudaFree(h->S.err_flags);
+  cudaFree(h->S.at_goal);
+  cudaFree(h->S.goal_cost);
+  cudaFree(h->S.agent_steps);
+  cudaFree(h->S.pnode);
+  cudaFree(h->S.pedge);
+  cudaFree(h->S.total_coll);
+  cudaFree(h->S.terminated);
+  cudaFree((void*)h->S.complete_lut);
   cudaFree(h->hs_actions);
   cudaFree(h->hs_reward);
   cudaFree(h->hs_terminated);
@@ -181,10 +191,20 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
       c->height > MAPF_MAX_SIDE || c->width < 1 || c->width > MAPF_MAX_SIDE)
     return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: need E>=1, 1<=N<=255, 1<=H,W<=255 (got E=%d N=%d H=%d W=%d)",
                 c->n_envs, c->n_agents, c->height, c->width);
-  if (c->mode != MAPF_MODE_GRID && c->mode != MAPF_MODE_PRIMAL)
+  if (c->mode != MAPF_MODE_GRID && c->mode != MAPF_MODE_PRIMAL && c->mode != MAPF_MODE_PARTIAL)
     return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: unknown mode %d", c->mode);
-  if (c->obs_mode != MAPF_OBS_FULLMAP && c->obs_mode != MAPF_OBS_PRIMAL_FOV)
+  if (c->obs_mode != MAPF_OBS_FULLMAP && c->obs_mode != MAPF_OBS_PRIMAL_FOV && c->obs_mode != MAPF_OBS_PARTIAL_WINDOW)
     return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: unknown obs_mode %d", c->obs_mode);
+  if (c->obs_mode == MAPF_OBS_PARTIAL_WINDOW && c->mode != MAPF_MODE_PARTIAL)
+    return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_create: the PARTIAL window observation needs mode PARTIAL");
+  if (c->mode == MAPF_MODE_PARTIAL) {
+    if (c->obs_window < 1 || c->obs_window > 255 || c->obs_knn_agents < 1 || c->obs_knn_agents > 254)
+      return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: obs_window %d / obs_knn_agents %d out of range",
+                  c->obs_window, c->obs_knn_agents);
+    if (!c->complete_lut_host || c->complete_lut_len < 1)
+      return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: mode PARTIAL needs complete_lut_host");
+    if (c->episode_limit < 1) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: episode_limit must be >= 1");
+  }
   if (c->obs_mode == MAPF_OBS_PRIMAL_FOV) {
     if (c->mode != MAPF_MODE_PRIMAL)
       return fail(h, MAPF_ERR_UNSUPPORTED,
@@ -227,6 +247,16 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   d.step_is_int = c->step_reward_is_int;
   d.collide_is_int = c->collide_reward_is_int;
   d.collect_stats = c->collect_stats;
+  d.pW = c->obs_window;
+  d.pK = c->obs_knn_agents;
+  d.posz = 2 * d.pW * d.pW + 13 * d.pK;
+  d.complete_len = c->complete_lut_len;
+  d.p_move = c->move_reward;
+  d.p_stay = c->stay_reward;
+  d.p_stay_goal = c->stay_goal_reward;
+  d.p_nc = c->node_collide_reward;
+  d.p_ec = c->edge_collide_reward;
+  d.p_envc = c->env_collide_reward;
   d.invN = (uint32_t)((0x100000000ULL + d.N - 1) / d.N);
   d.invW = (uint32_t)((0x100000000ULL + d.W - 1) / d.W);
   d.step_reward = c->step_reward;
@@ -272,7 +302,19 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   ALLOC(h->S.done, EN);
   ALLOC(h->S.prev_action, EN);
   ALLOC(h->S.step_count, (size_t)d.E * 4);
-  if (c->goal_dist) ALLOC(h->S.goal_dist, EN * d.HW * 2);
+  if (c->goal_dist || c->mode == MAPF_MODE_PARTIAL) ALLOC(h->S.goal_dist, EN * d.HW * 2);
+  if (c->mode == MAPF_MODE_PARTIAL) {
+    ALLOC(h->S.at_goal, EN);
+    ALLOC(h->S.goal_cost, EN * 4);
+    ALLOC(h->S.agent_steps, EN * 4);
+    ALLOC(h->S.pnode, EN);
+    ALLOC(h->S.pedge, EN);
+    ALLOC(h->S.total_coll, (size_t)d.E * 8);
+    ALLOC(h->S.terminated, (size_t)d.E);
+    double* clut = nullptr;
+    ALLOC(clut, (size_t)c->complete_lut_len * 8);
+    h->S.complete_lut = clut;
+  }
   ALLOC(h->S.stats, MAPF_N_STATS * 8);
   ALLOC(h->S.err_flags, 4);
   double* lut = nullptr;
@@ -294,6 +336,17 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   if (e == cudaSuccess) {
     if (c->mag_lut_host) e = cudaMemcpy(lut, c->mag_lut_host, (size_t)lut_len * 8, cudaMemcpyHostToDevice);
     else e = cudaMemset(lut, 0, 8);
+  }
+  if (e == cudaSuccess && c->mode == MAPF_MODE_PARTIAL) {
+    e = cudaMemcpy((void*)h->S.complete_lut, c->complete_lut_host, (size_t)c->complete_lut_len * 8,
+                   cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(h->S.at_goal, 0, EN);
+    if (e == cudaSuccess) e = cudaMemset(h->S.goal_cost, 0xff, EN * 4);
+    if (e == cudaSuccess) e = cudaMemset(h->S.agent_steps, 0, EN * 4);
+    if (e == cudaSuccess) e = cudaMemset(h->S.pnode, 0, EN);
+    if (e == cudaSuccess) e = cudaMemset(h->S.pedge, 0, EN);
+    if (e == cudaSuccess) e = cudaMemset(h->S.total_coll, 0, (size_t)d.E * 8);
+    if (e == cudaSuccess) e = cudaMemset(h->S.terminated, 0, (size_t)d.E);
   }
   if (e == cudaSuccess && h->L.total_bytes > 48 * 1024)
     e = (cudaError_t)mapf_configure_tile(h->fov_fast ? d.F : 0, h->L.total_bytes);
@@ -322,6 +375,11 @@ int mapf_reset(mapf_handle* h, const int8_t* map_dev, const int16_t* starts_dev,
   }
   CK((cudaError_t)mapf_launch_reset(h->d, h->S, starts_dev, goals_dev, env_mask_dev, stream));
   h->launches++;
+  if (h->d.mode == MAPF_MODE_PARTIAL) {   // __setup_agent_goal_dist runs inside the reference's reset, PARTIAL:130, 928
+    int n = 0;
+    CK((cudaError_t)mapf_launch_bfs(h->d, h->S, nullptr, env_mask_dev, h->S.goal_dist, 0, stream, &n));
+    h->launches += n;
+  }
   return MAPF_OK;
 }
 
@@ -349,15 +407,18 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
   if (actions && act_dtype != MAPF_U8 && act_dtype != MAPF_I64)
     return fail(h, MAPF_ERR_INVALID_ARG, "actions must be MAPF_U8 or MAPF_I64");
   const bool fov = h->d.obs_mode == MAPF_OBS_PRIMAL_FOV;
+  const bool pwin = h->d.obs_mode == MAPF_OBS_PARTIAL_WINDOW;
   if (obs) {
     if (fov && obs_dtype != MAPF_U8 && obs_dtype != MAPF_F32)
       return fail(h, MAPF_ERR_INVALID_ARG, "FOV observations are MAPF_U8 or MAPF_F32");
-    if (!fov && obs_dtype != MAPF_I8) return fail(h, MAPF_ERR_INVALID_ARG, "full-map observations are MAPF_I8");
+    if (pwin && obs_dtype != MAPF_F64) return fail(h, MAPF_ERR_INVALID_ARG, "PARTIAL window observations are MAPF_F64");
+    if (!fov && !pwin && obs_dtype != MAPF_I8)
+      return fail(h, MAPF_ERR_INVALID_ARG, "full-map observations are MAPF_I8");
   }
   MapfDims d = h->d;
   const bool generic_obs = fov && !h->fov_fast && (obs || vec);
   if (fov && !h->fov_fast) d.F = 0, d.obs_mode = MAPF_OBS_FULLMAP;   // the tile kernel skips the observation
-  if (!generic_obs) {
+  if (!generic_obs && !pwin) {
     A.obs = obs;
     A.obs_dtype = obs_dtype;
     A.vec = fov ? vec : nullptr;
@@ -365,6 +426,10 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
   const bool any_out = A.do_step || A.obs || A.vec || A.out.avail_dev;
   if (any_out) {
     CK((cudaError_t)mapf_launch_tile(d, h->L, h->S, A, stream));
+    h->launches++;
+  }
+  if (pwin && obs) {
+    CK((cudaError_t)mapf_launch_partial_obs(h->d, h->S, (double*)obs, stream));
     h->launches++;
   }
   if (generic_obs) {
@@ -416,7 +481,7 @@ int mapf_bfs(mapf_handle* h, const uint8_t* dirty_dev, int16_t* dist_dev, int pr
   int rc;
   if ((rc = check_aligned(h, dist, "dist_dev")) != MAPF_OK) return rc;
   int n = 0;
-  CK((cudaError_t)mapf_launch_bfs(h->d, h->S, dirty_dev, dist, primal_costs, stream, &n));
+  CK((cudaError_t)mapf_launch_bfs(h->d, h->S, dirty_dev, nullptr, dist, primal_costs, stream, &n));
   h->launches += n;
   return MAPF_OK;
 }
@@ -455,6 +520,22 @@ int mapf_get_step_count(mapf_handle* h, int32_t* step_count_dev, void* stream) {
   return MAPF_OK;
 }
 
+int mapf_partial_state(mapf_handle* h, int64_t* state_dev, uint8_t* at_goal_dev, int32_t* goal_cost_dev,
+                       int32_t* agent_steps_dev, void* stream) {
+  if (!h) return MAPF_ERR_INVALID_ARG;
+  if (h->d.mode != MAPF_MODE_PARTIAL) return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_partial_state: mode is not PARTIAL");
+  const size_t EN = (size_t)h->d.E * h->d.N;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (state_dev) {
+    CK((cudaError_t)mapf_launch_partial_state(h->d, h->S, (long long*)state_dev, stream));
+    h->launches++;
+  }
+  if (at_goal_dev) CK(cudaMemcpyAsync(at_goal_dev, h->S.at_goal, EN, cudaMemcpyDeviceToDevice, st));
+  if (goal_cost_dev) CK(cudaMemcpyAsync(goal_cost_dev, h->S.goal_cost, EN * 4, cudaMemcpyDeviceToDevice, st));
+  if (agent_steps_dev) CK(cudaMemcpyAsync(agent_steps_dev, h->S.agent_steps, EN * 4, cudaMemcpyDeviceToDevice, st));
+  return MAPF_OK;
+}
+
 int mapf_stats(mapf_handle* h, int64_t* stats_host, void* stream) {
   if (!h || !stats_host) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_stats: NULL argument");
   CK(cudaMemcpyAsync(stats_host, h->S.stats, MAPF_N_STATS * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -479,6 +560,7 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   size_t obs_bytes = 0;
   if (io->obs_host) {
     if (fov) obs_bytes = EN * 4 * d.F * d.F * (io->obs_dtype == MAPF_F32 ? 4 : 1);
+    else if (d.obs_mode == MAPF_OBS_PARTIAL_WINDOW) obs_bytes = EN * d.posz * 8;
     else obs_bytes = (size_t)d.E * d.HW;
   }
 #define LAZY(ptr, bytes)                                                \

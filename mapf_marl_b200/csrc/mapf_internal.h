@@ -32,6 +32,10 @@ struct MapfDims {
   uint32_t invN, invW;  // ceil(2^32 / N), ceil(2^32 / W): exact division of values < 65536 by IMAD.HI
   double step_reward, collide_reward;
   double action_cost, idle_cost, goal_reward, collision_reward;
+  // MAPF_MODE_PARTIAL
+  int pW, pK, posz;      // obs window, K nearest agents, obs size = 2*W*W + 13*K
+  int complete_len;
+  double p_move, p_stay, p_stay_goal, p_nc, p_ec, p_envc;
 };
 
 // Byte offsets into the dynamic shared memory of a tile kernel.
@@ -48,6 +52,8 @@ struct MapfTileLayout {
   int envrew_off;   // double [epb]
   int envterm_off;  // u8 [epb] (padded)
   int envcnt_off;   // int [epb]: per-environment counters (agents on goal / done)
+  int envcnt2_off;  // int [epb]: PARTIAL: sum of node flags + edge counts
+  int atgoal_off;   // u8 [epb*N]: PARTIAL _agent_at_goals
   int str_off;      // bit strings: ceil(epb*N / G) * GW u32
   int total_bytes;
 };
@@ -64,6 +70,15 @@ struct MapfState {
   int16_t* goal_dist;      // [E][N][H][W] or NULL
   const double* mag_lut;   // [mag_lut_len]
   unsigned long long* stats;  // [MAPF_N_STATS]
+  // MAPF_MODE_PARTIAL
+  uint8_t* at_goal;        // [E][N]
+  int32_t* goal_cost;      // [E][N]
+  int32_t* agent_steps;    // [E][N]
+  uint8_t* pnode;          // [E][N]
+  uint8_t* pedge;          // [E][N]
+  long long* total_coll;   // [E]
+  uint8_t* terminated;     // [E]
+  const double* complete_lut;
   uint32_t* err_flags;     // [1]
 };
 
@@ -93,8 +108,10 @@ int mapf_launch_reset(const MapfDims& d, const MapfState& S, const int16_t* star
                       const uint8_t* env_mask, void* stream);
 int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, const int16_t* goals, const uint8_t* dirty,
                           void* stream);
-int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, int16_t* dist, int primal_costs,
-                    void* stream, int* n_launches);
+int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, const uint8_t* env_mask, int16_t* dist,
+                    int primal_costs, void* stream, int* n_launches);
+int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, double* obs, void* stream);
+int mapf_launch_partial_state(const MapfDims& d, const MapfState& S, long long* state, void* stream);
 int mapf_launch_export16(const MapfDims& d, const uint8_t* src_u8x2, int16_t* dst, void* stream);
 int mapf_tile_has_fov(int F);
 int mapf_configure_tile(int F, int smem_bytes);

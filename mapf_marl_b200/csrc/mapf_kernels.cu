@@ -47,6 +47,7 @@ struct Smem {
   double* rew;
   double* envrew;
   uint8_t* envterm;
+  uint8_t* atgoal;
   uint32_t* str;
 };
 
@@ -74,6 +75,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const MapfTileLayout&
   s.rew = (double*)(base + L.rew_off);
   s.envrew = (double*)(base + L.envrew_off);
   s.envterm = base + L.envterm_off;
+  s.atgoal = base + L.atgoal_off;
   s.str = (uint32_t*)(base + L.str_off);
   return s;
 }
@@ -232,7 +234,7 @@ __device__ __forceinline__ void primal_phase_a(const MapfDims& d, const Smem& s,
 //     otherwise, k < a            : a moves iff k itself moved away (k's own outcome, a lower id) -> depends on k
 // (claimants below k always fail: k is still there at their turn).  Only the last case is order dependent, and only
 // on a LOWER id, so the dependencies resolve in rounds; a round is one barrier, and random traffic needs one or two.
-// Equivalence to the serial walk is checked bit-for-bit against the reference traces and the oracle.
+// Equivalence to the serial walk is checked bit-for-bit against the reference traces (tests/test_gpu_parity.py).
 __device__ __forceinline__ uint8_t primal_classify(const MapfDims& d, const Smem& s, int j, int el, int a) {
   if (s.status[j] != PRE_MOVE) return RES_STAYS;
   const uint8_t* grid = s.grida + el * d.grid_bytes;   // ids before the sweep
@@ -386,9 +388,51 @@ __device__ __forceinline__ void grid_phase_a(const MapfDims& d, const Smem& s, i
   c_arr += (reached && !done_old);
 }
 
-// GRID phase C for agent j: node flag (GRID:344-362), edge count (GRID:364-383), collision penalties (:127-130).
-__device__ __forceinline__ bool grid_phase_c(const MapfDims& d, const Smem& s, int j, int el, int a,
-                                             unsigned int& c_node, unsigned int& c_edge) {
+// PARTIAL phase A for agent j (PARTIAL:192-235): move unless wall / border, action cost, at_goal, limit latch and the
+// goal-distance shaping term from the BFS maps.
+__device__ __forceinline__ void partial_phase_a(const MapfDims& d, const Smem& s, const MapfState& S, size_t gj, int j,
+                                                int el, int step_now, unsigned int& c_env, unsigned int& c_arr) {
+  const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+  const uchar2 p = s.posold[j], g = s.goal[j];
+  const bool done_old = s.done[j] != 0;
+  const bool at_old = s.atgoal[j] != 0;
+  uchar2 np = p;
+  double r = 0.0;
+  int flag = 0;
+  if (!done_old) {
+    S.agent_steps[gj] += 1;                                          // _agent_step_count, :194
+    const int act = s.act[j];
+    if (act < 4) {                                                   // __agent_step, :618-643
+      const int t0 = (int)p.x + (act == 0 ? -1 : (act == 1 ? 1 : 0));
+      const int t1 = (int)p.y + (act == 2 ? -1 : (act == 3 ? 1 : 0));
+      if (bm_test(ob, d.RW, d.P, t0, t1)) flag = 1;
+      else np = make_uchar2((unsigned char)t0, (unsigned char)t1);
+    }
+    if (flag) r = __dadd_rn(r, d.p_envc);                            // :203-205
+    if (act < 4) r = __dadd_rn(r, d.p_move);                         // :207-208
+    else r = __dadd_rn(r, at_old ? d.p_stay_goal : d.p_stay);        // :209-213
+  }
+  const bool at_new = (np.x == g.x && np.y == g.y);                  // :217-222
+  if (at_new) S.goal_cost[gj] = step_now;
+  const bool dn = done_old || (step_now >= d.episode_limit);         // :224-227
+  const int16_t* dm = S.goal_dist + gj * d.HW;                       // :229-234
+  const int opd = dm[(int)p.x * d.W + p.y], npd = dm[(int)np.x * d.W + np.y];
+  r = __dadd_rn(r, __ddiv_rn((double)(opd - npd), (double)d.episode_limit));
+  s.posnew[j] = np;
+  s.status[j] = (int8_t)flag;
+  s.done[j] = dn ? 1 : 0;
+  s.atgoal[j] = at_new ? 1 : 0;
+  s.rew[j] = r;
+  s.isint[j] = 0;                                                    // closer_rew is always a float
+  byte_inc(s.gridb + el * d.grid_bytes, gcell(d, np.x, np.y));
+  c_env += flag;
+  c_arr += (at_new && !at_old);
+}
+
+// GRID / PARTIAL phase C for agent j: node flag (GRID:344-362, PARTIAL:713-737), edge count (GRID:364-383,
+// PARTIAL:822-857), collision penalties (GRID:127-130, PARTIAL:255-259).
+__device__ __forceinline__ bool grid_phase_c(const MapfDims& d, const Smem& s, int j, int el, int a, bool partial,
+                                             int* envcnt2, unsigned int& c_node, unsigned int& c_edge) {
   const int N = d.N, jb = el * N;
   const uint8_t* cold = s.grida + el * d.grid_bytes;
   const uint8_t* cnew = s.gridb + el * d.grid_bytes;
@@ -404,13 +448,17 @@ __device__ __forceinline__ bool grid_phase_c(const MapfDims& d, const Smem& s, i
     }
   }
   double r = s.rew[j];
-  r = __dadd_rn(r, __dmul_rn(d.collide_reward, (double)node));       // GRID:128
-  r = __dadd_rn(r, __dmul_rn(d.collide_reward, (double)edge));       // GRID:129
+  r = __dadd_rn(r, __dmul_rn(partial ? d.p_nc : d.collide_reward, (double)node));
+  r = __dadd_rn(r, __dmul_rn(partial ? d.p_ec : d.collide_reward, (double)edge));
   s.rew[j] = r;
   s.node[j] = (uint8_t)node;
   s.edge[j] = (uint8_t)edge;
   c_node += node;
   c_edge += edge;
+  if (partial) {
+    if (node + edge) atomicAdd(&envcnt2[el], node + edge);           // _total_number_collisions, PARTIAL:250
+    return s.atgoal[j] != 0;
+  }
   return s.done[j] != 0;
 }
 
@@ -505,13 +553,18 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   const int na = ne * N;
   const size_t a0 = (size_t)e0 * N;
   const bool primal = d.mode == MAPF_MODE_PRIMAL;
+  const bool partial = d.mode == MAPF_MODE_PARTIAL;
+  int* envcnt2 = (int*)(smem_raw + L.envcnt2_off);
   const bool do_step = A.do_step != 0;
   const bool need_mid = primal && do_step && ((A.out.done_mid_dev != nullptr) || (A.out.next_mid_dev != nullptr));
 
   // ---- stage the tile (one exposed global-memory latency): obstacle bitmaps, per-agent records, zeroed grids
   if (tid < MAPF_N_STATS) stat[tid] = 0;
   if (tid == 0) bad_flag = 0;
-  for (int el = tid; el < ne; el += kThreads) envcnt[el] = 0;
+  for (int el = tid; el < ne; el += kThreads) {
+    envcnt[el] = 0;
+    envcnt2[el] = 0;
+  }
   {
     const int nvec = ((d.shared_map ? 1 : ne) * d.bm_words) >> 2;
     const uint4* src = (const uint4*)(S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e0 * d.bm_words));
@@ -525,6 +578,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     s.posnew[j] = p;
     s.goal[j] = ((const uchar2*)S.goal)[a0 + j];
     s.done[j] = S.done[a0 + j];
+    if (partial) s.atgoal[j] = S.at_goal[a0 + j];
     const int el = fast_div(j, d.invN), a = j - el * N;
     int act = S.prev_action[a0 + j];
     if (do_step && a >= A.agent_lo && a < A.agent_hi) {
@@ -565,7 +619,11 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       if (do_step) primal_phase_a(d, s, A, j, el, a);
     } else {
       byte_inc(grid, cell);
-      if (do_step) grid_phase_a(d, s, j, el, S.step_count[e0 + el] + 1, c0, c3);   // GRID:93
+      if (do_step) {
+        const int step_now = S.step_count[e0 + el] + 1;              // GRID:93, PARTIAL:178
+        if (partial) partial_phase_a(d, s, S, a0 + j, j, el, step_now, c0, c3);
+        else grid_phase_a(d, s, j, el, step_now, c0, c3);
+      }
     }
   }
   __syncthreads();
@@ -609,7 +667,8 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       if (active) {
         el = fast_div(j, d.invN);
         const int a = j - el * N;
-        flag = primal ? primal_phase_c(d, s, j, el, a, c0, c1, c3) : grid_phase_c(d, s, j, el, a, c1, c2);
+        flag = primal ? primal_phase_c(d, s, j, el, a, c0, c1, c3)
+                      : grid_phase_c(d, s, j, el, a, partial, envcnt2, c1, c2);
       }
       // per-environment count of agents on goal (PRIMAL) / done (GRID), one shared-memory atomic per (warp, env)
       const unsigned peers = __match_any_sync(0xffffffffu, el);
@@ -682,12 +741,35 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
           A.out.reward_dev[e0 + el] = tot;
         }
         if (A.agent_lo == 0) S.step_count[e0 + el] += 1;
+      } else if (partial) {
+        const int step_now = S.step_count[e0 + el] + 1;
+        bool term = (S.terminated[e0 + el] != 0) || (step_now >= d.episode_limit);     // PARTIAL:224-226
+        if (all) {                                                                     // all at goal, PARTIAL:291-299
+          term = true;
+          const double bonus = S.complete_lut[min(step_now, d.complete_len - 1)];
+          for (int i = 0; i < N; ++i) {
+            s.done[el * N + i] = 1;
+            s.rew[el * N + i] = __dadd_rn(s.rew[el * N + i], bonus);
+          }
+        }
+        if (A.out.reward_dev)
+          A.out.reward_dev[e0 + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // PARTIAL:310
+        if (A.out.terminated_dev) A.out.terminated_dev[e0 + el] = term ? 1 : 0;
+        S.terminated[e0 + el] = term ? 1 : 0;
+        S.total_coll[e0 + el] += envcnt2[el] / 2;                                      // PARTIAL:250
+        S.step_count[e0 + el] = step_now;
       } else {
         if (A.out.reward_dev)
           A.out.reward_dev[e0 + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // GRID:141
         S.step_count[e0 + el] += 1;
       }
       if (d.collect_stats && all) atomicAdd(&stat[MAPF_STAT_EPISODES_DONE], 1u);
+    }
+    if (partial) {   // phase D changed done / rewards of whole environments
+      __syncthreads();
+      copy_out_bytes(S.at_goal + a0, s.atgoal, na, tid);
+      copy_out_bytes(S.pnode + a0, s.node, na, tid);
+      copy_out_bytes(S.pedge + a0, s.edge, na, tid);
     }
     copy_out_bytes(S.pos + 2 * a0, (const uint8_t*)s.posnew, 2 * na, tid);
     copy_out_bytes(S.done + a0, s.done, na, tid);
@@ -963,6 +1045,17 @@ __global__ void mapf_reset_kernel(const MapfDims d, const MapfState S, const int
     S.done[j] = (d.mode == MAPF_MODE_PRIMAL) ? (uint8_t)(st.x == g.x && st.y == g.y) : 0;   // GRID:75
     S.prev_action[j] = (d.mode == MAPF_MODE_PRIMAL) ? 0 : 4;
     if (a == 0) S.step_count[e] = 0;                                 // GRID:73
+    if (d.mode == MAPF_MODE_PARTIAL) {                               // PARTIAL:135-150
+      S.at_goal[j] = 0;
+      S.goal_cost[j] = -1;
+      S.agent_steps[j] = 0;
+      S.pnode[j] = 0;
+      S.pedge[j] = 0;
+      if (a == 0) {
+        S.total_coll[e] = 0;
+        S.terminated[e] = 0;
+      }
+    }
     if (d.mode == MAPF_MODE_PRIMAL && starts) {                     // one agent per cell, PRIMAL:53-66
       for (int b = 0; b < a; ++b)
         if (starts[2 * ((long long)e * d.N + b)] == starts[2 * j] &&
@@ -1004,14 +1097,15 @@ __global__ void mapf_export16_kernel(long long n, const uint8_t* src, int16_t* d
 // (PARTIAL:931-955 == hop distance; PRIMAL getAstarCosts :407-499 == hop distance from the goal.)
 // smem per warp: 4 bitmaps [H][RWB] (free, visited, frontier A/B) and, when it fits, the int16 map.
 // ------------------------------------------------------------------------------------------------
-__global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty, int16_t* dist,
-                                int RWB, int warps_per_block, int stage_dist) {
+__global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty, const uint8_t* env_mask,
+                                int16_t* dist, int RWB, int warps_per_block, int stage_dist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long m = (long long)blockIdx.x * warps_per_block + warp;   // (env, agent) index
   if (m >= (long long)d.E * d.N) return;
   if (dirty && !dirty[m]) return;
   const int e = (int)(m / d.N);
+  if (env_mask && !env_mask[e]) return;
   const int H = d.H, W = d.W, items = H * RWB;
   const size_t per_warp = (size_t)4 * items * 4 + (stage_dist ? (((size_t)d.HW * 2 + 15) & ~(size_t)15) : 0);
   unsigned char* base = smem_raw + per_warp * warp;
@@ -1108,6 +1202,114 @@ __global__ void mapf_primal_costs_free_kernel(const MapfDims d, const uint8_t* d
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// PARTIAL observation (get_obs_agent, PARTIAL:319-382): double[E][N][2*W*W + 13*K].
+// One block per environment: the agent-count grid is built in shared memory, each agent's K-1 nearest agents are
+// selected (stable order by L2 distance == order by squared integer distance, ties by index; the agent itself has
+// distance H*W, :560-567), then thread q writes element q of the environment's observation block (coalesced).
+// ------------------------------------------------------------------------------------------------
+__global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, double* obs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int e = blockIdx.x, N = d.N, W = d.W, H = d.H, Wn = d.pW, K = d.pK;
+  uint8_t* cnt = smem_raw;                                   // [H*W] agents per cell
+  uint8_t* knn = cnt + ((d.HW + 15) & ~15);                  // [N][K] ids, 255 = empty row
+  const uchar2* pos = (const uchar2*)S.pos + (size_t)e * N;
+  const uchar2* goal = (const uchar2*)S.goal + (size_t)e * N;
+  const uchar2* start = (const uchar2*)S.start + (size_t)e * N;
+  const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
+  for (int i = threadIdx.x; i < ((d.HW + 15) >> 4); i += blockDim.x) ((uint4*)cnt)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int a = threadIdx.x; a < N; a += blockDim.x) byte_inc(cnt, (int)pos[a].x * W + pos[a].y);
+  const int k_m1 = min(N, K) - 1;
+  const long long self_key = (long long)d.HW * d.HW;
+  for (int a = threadIdx.x; a < N; a += blockDim.x) {
+    const uchar2 p = pos[a];
+    long long last_key = -1;
+    int last_idx = -1;
+    knn[a * K] = (uint8_t)a;                                 // knn_agents.insert(0, agent_id), :352
+    for (int r = 0; r < K - 1; ++r) {
+      int best = -1;
+      long long best_key = 0;
+      if (r < k_m1) {
+        for (int b = 0; b < N; ++b) {
+          const int dx = (int)p.x - (int)pos[b].x, dy = (int)p.y - (int)pos[b].y;
+          const long long key = (b == a) ? self_key : (long long)(dx * dx + dy * dy);
+          const bool after_last = key > last_key || (key == last_key && b > last_idx);
+          if (after_last && (best < 0 || key < best_key)) {
+            best = b;
+            best_key = key;
+          }
+        }
+        last_key = best_key;
+        last_idx = best;
+      }
+      knn[a * K + 1 + r] = best < 0 ? (uint8_t)255 : (uint8_t)best;
+    }
+  }
+  __syncthreads();
+  const int osz = d.posz, ww = Wn * Wn;
+  double* out = obs + (size_t)e * N * osz;
+  for (int q = threadIdx.x; q < N * osz; q += blockDim.x) {
+    const int a = q / osz, idx = q - a * osz;
+    const uchar2 p = pos[a];
+    double v;
+    if (idx < 2 * ww) {                                      // the two W x W maps, :326-342
+      const int c = idx < ww ? idx : idx - ww;
+      const int wi = c / Wn, wj = c - wi * Wn;
+      const int i = (int)p.x - Wn / 2 + wi, jx = (int)p.y - Wn / 2 + wj;
+      const bool oob = (i < 0 || i >= H || jx < 0 || jx >= W);
+      const bool wall = oob || bm_test(ob, d.RW, d.P, i, jx);
+      if (idx < ww) v = wall ? 1.0 : 0.0;
+      else v = wall ? 0.0 : (double)cnt[i * W + jx];
+    } else {                                                 // K x 13 features, :344-371
+      const int f0 = idx - 2 * ww;
+      const int row = f0 / 13, f = f0 - 13 * row;
+      const int na = knn[a * K + row];
+      if (na == 255) {
+        v = -1.0;
+      } else {
+        const uchar2 q0 = pos[na], g = goal[na], st = start[na];
+        const int dx = (int)g.x - (int)q0.x, dy = (int)g.y - (int)q0.y;
+        switch (f) {
+          case 0: v = q0.x; break;
+          case 1: v = q0.y; break;
+          case 2: v = st.x; break;
+          case 3: v = st.y; break;
+          case 4: v = g.x; break;
+          case 5: v = g.y; break;
+          case 6:
+          case 7: {                                          // __update_goal_vectors, :957-972
+            const double norm = __dsqrt_rn((double)(dx * dx + dy * dy));
+            v = norm != 0.0 ? __ddiv_rn((double)(f == 6 ? dx : dy), norm) : 0.0;
+            break;
+          }
+          case 8: v = __dsqrt_rn((double)(dx * dx + dy * dy)); break;
+          case 9: v = S.pnode[(size_t)e * N + na]; break;
+          case 10: v = S.pedge[(size_t)e * N + na]; break;
+          case 11: {
+            const int ex = (int)p.x - (int)q0.x, ey = (int)p.y - (int)q0.y;
+            v = (na == a) ? (double)d.HW : __dsqrt_rn((double)(ex * ex + ey * ey));
+            break;
+          }
+          default: v = S.agent_steps[(size_t)e * N + na]; break;
+        }
+      }
+    }
+    out[q] = v;
+  }
+}
+
+// get_state, PARTIAL:384-393: [total collisions, step count, sum of per-agent goal costs].
+__global__ void mapf_partial_state_kernel(const MapfDims d, const MapfState S, long long* state) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.E; e += gridDim.x * blockDim.x) {
+    long long sum = 0;
+    for (int i = 0; i < d.N; ++i) sum += S.goal_cost[(size_t)e * d.N + i];
+    state[3 * e] = S.total_coll[e];
+    state[3 * e + 1] = S.step_count[e];
+    state[3 * e + 2] = sum;
+  }
+}
+
 template <int F>
 cudaError_t launch_tile_f(const MapfDims& d, const MapfTileLayout& L, const MapfState& S, const MapfTileArgs& A,
                           cudaStream_t st) {
@@ -1195,14 +1397,29 @@ extern "C" int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, cons
   return (int)cudaGetLastError();
 }
 
+extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, double* obs, void* stream) {
+  const size_t smem = ((size_t)(d.HW + 15) & ~(size_t)15) + (size_t)d.N * d.pK + 16;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(mapf_partial_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  mapf_partial_obs_kernel<<<d.E, 128, smem, (cudaStream_t)stream>>>(d, S, obs);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_partial_state(const MapfDims& d, const MapfState& S, long long* state, void* stream) {
+  mapf_partial_state_kernel<<<grid_for(d.E, 256), 256, 0, (cudaStream_t)stream>>>(d, S, state);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int mapf_launch_export16(const MapfDims& d, const uint8_t* src, int16_t* dst, void* stream) {
   const long long n = (long long)d.E * d.N * 2;
   mapf_export16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, src, dst);
   return (int)cudaGetLastError();
 }
 
-extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, int16_t* dist,
-                               int primal_costs, void* stream, int* n_launches) {
+extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, const uint8_t* env_mask,
+                               int16_t* dist, int primal_costs, void* stream, int* n_launches) {
   cudaStream_t st = (cudaStream_t)stream;
   const int RWB = (d.W + 31) / 32;
   const size_t bm_bytes = (size_t)4 * d.H * RWB * 4;
@@ -1223,7 +1440,7 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
   }
   const long long maps = (long long)d.E * d.N;
   const long long grid = (maps + warps - 1) / warps;
-  mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, dirty, dist, RWB, warps, stage);
+  mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, dirty, env_mask, dist, RWB, warps, stage);
   cudaError_t err = cudaGetLastError();
   *n_launches = 1;
   if (err == cudaSuccess && primal_costs) {

@@ -20,8 +20,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (F32, I8, I64, MODE_GRID, MODE_PRIMAL, OBS_FULLMAP, OBS_PRIMAL_FOV, STAT_NAMES, STEP_OUT_FIELDS, U8,
-                   MapfCfg, MapfHostIO, MapfStepOut)
+from ._lib import (F32, F64, I8, I64, MODE_GRID, MODE_PARTIAL, MODE_PRIMAL, OBS_FULLMAP, OBS_PARTIAL_WINDOW,
+                   OBS_PRIMAL_FOV, STAT_NAMES, STEP_OUT_FIELDS, U8, MapfCfg, MapfHostIO, MapfStepOut)
 
 _OUT_SPECS = {
     # name: (dtype, per-env shape suffix builder)
@@ -60,7 +60,9 @@ class MapfEngine:
     def __init__(self, n_envs, n_agents, height, width, mode="primal", obs_mode=None, fov=11, shared_map=False,
                  episode_limit=10000, step_reward=-0.01, collide_reward=-10, action_cost=-0.3, idle_cost=-0.5,
                  goal_reward=0.0, collision_reward=-2.0, goal_dist=False, collect_stats=True, device=None,
-                 reward_sum_mode=None):
+                 reward_sum_mode=None, obs_window=5, obs_knn_agents=5, move_reward=-0.01, stay_reward=-0.02,
+                 stay_goal_reward=0, node_collide_reward=-1, edge_collide_reward=-1, env_collide_reward=-1,
+                 complete_reward=1000, complete_fac=1.5, gamma=0.99):
         if not torch.cuda.is_available():
             raise MapfError("MapfEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -68,15 +70,18 @@ class MapfEngine:
         if self.device.type != "cuda":
             raise MapfError("MapfEngine needs a CUDA device; got %s" % self.device)
         self.E, self.N, self.H, self.W = int(n_envs), int(n_agents), int(height), int(width)
-        self.mode = {"grid": MODE_GRID, "primal": MODE_PRIMAL}[mode] if isinstance(mode, str) else int(mode)
+        self.mode = ({"grid": MODE_GRID, "primal": MODE_PRIMAL, "partial": MODE_PARTIAL}[mode]
+                     if isinstance(mode, str) else int(mode))
         if obs_mode is None:
-            obs_mode = OBS_PRIMAL_FOV if self.mode == MODE_PRIMAL else OBS_FULLMAP
+            obs_mode = {MODE_PRIMAL: OBS_PRIMAL_FOV, MODE_PARTIAL: OBS_PARTIAL_WINDOW}.get(self.mode, OBS_FULLMAP)
         elif isinstance(obs_mode, str):
-            obs_mode = {"fullmap": OBS_FULLMAP, "fov": OBS_PRIMAL_FOV}[obs_mode]
+            obs_mode = {"fullmap": OBS_FULLMAP, "fov": OBS_PRIMAL_FOV, "window": OBS_PARTIAL_WINDOW}[obs_mode]
         self.obs_mode = int(obs_mode)
         self.F = int(fov)
         self.shared_map = bool(shared_map)
-        self.has_goal_dist = bool(goal_dist)
+        self.has_goal_dist = bool(goal_dist) or self.mode == MODE_PARTIAL
+        self.obs_window, self.obs_knn_agents = int(obs_window), int(obs_knn_agents)
+        self.obs_size = 2 * self.obs_window ** 2 + 13 * self.obs_knn_agents
         cfg = MapfCfg()
         self.lib.mapf_default_cfg(ctypes.byref(cfg))
         cfg.n_envs, cfg.n_agents, cfg.height, cfg.width = self.E, self.N, self.H, self.W
@@ -94,6 +99,18 @@ class MapfEngine:
         self._lut = magnitude_lut(self.H, self.W)
         cfg.mag_lut_host = self._lut.ctypes.data
         cfg.mag_lut_len = int(self._lut.size)
+        if self.mode == MODE_PARTIAL:
+            cfg.obs_window, cfg.obs_knn_agents = self.obs_window, self.obs_knn_agents
+            cfg.move_reward, cfg.stay_reward = float(move_reward), float(stay_reward)
+            cfg.stay_goal_reward = float(stay_goal_reward)
+            cfg.node_collide_reward, cfg.edge_collide_reward = float(node_collide_reward), float(edge_collide_reward)
+            cfg.env_collide_reward = float(env_collide_reward)
+            # the completion bonus per step index, with the reference's own expression (marl_partial.py:296)
+            limit = int(episode_limit)
+            self._clut = np.array([(complete_reward / (gamma ** (limit - t))) * complete_fac
+                                   for t in range(limit + 65)], dtype=np.float64)
+            cfg.complete_lut_host = self._clut.ctypes.data
+            cfg.complete_lut_len = int(self._clut.size)
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             rc = self.lib.mapf_create(ctypes.byref(cfg), ctypes.byref(self._h))
@@ -240,6 +257,8 @@ class MapfEngine:
             obs = self._buf("obs_%s" % dtype, (self.E, self.N, 4, self.F, self.F), dtype)
             vec = self._buf("vec", (self.E, self.N, 3), torch.float64) if want_vec else None
             return obs, vec, (U8 if dtype == torch.uint8 else F32)
+        if self.obs_mode == OBS_PARTIAL_WINDOW:
+            return self._buf("obs_partial", (self.E, self.N, self.obs_size), torch.float64), None, F64
         obs = self._buf("state", (self.E, self.H * self.W), torch.int8)
         return obs, None, I8
 
@@ -280,6 +299,23 @@ class MapfEngine:
         with torch.cuda.device(self.device):
             self._check(self.lib.mapf_bfs(self._h, self._ptr(dmask), self._ptr(out), int(bool(primal_costs)),
                                           self._stream()), "mapf_bfs")
+        return out
+
+    def partial_state(self, want=("state", "at_goal", "goal_cost", "agent_steps")):
+        """MARL_PARTIAL_ENV bookkeeping: state int64 [E,3] = get_state(); at_goal u8, goal_cost / agent_steps i32 [E,N]."""
+        out = {}
+        if "state" in want:
+            out["state"] = self._buf("p_state", (self.E, 3), torch.int64)
+        if "at_goal" in want:
+            out["at_goal"] = self._buf("p_at_goal", (self.E, self.N), torch.uint8)
+        if "goal_cost" in want:
+            out["goal_cost"] = self._buf("p_goal_cost", (self.E, self.N), torch.int32)
+        if "agent_steps" in want:
+            out["agent_steps"] = self._buf("p_agent_steps", (self.E, self.N), torch.int32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_partial_state(self._h, self._ptr(out.get("state")), self._ptr(out.get("at_goal")),
+                                                    self._ptr(out.get("goal_cost")), self._ptr(out.get("agent_steps")),
+                                                    self._stream()), "mapf_partial_state")
         return out
 
     # ------------------------------------------------------------------ host-buffer path (what e2e times)

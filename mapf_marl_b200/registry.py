@@ -4,6 +4,7 @@ from functools import partial
 
 from .mapf_gridworld import MAPF_GRID
 from .mapf_primal import MAPFEnv
+from .marl_partial import MARL_PARTIAL_ENV
 from .multiagentenv import MultiAgentEnv
 
 
@@ -14,3 +15,4 @@ def env_fn(env, **kwargs) -> MultiAgentEnv:
 REGISTRY = {}
 REGISTRY["mapf_gridworld"] = partial(env_fn, env=MAPF_GRID)
 REGISTRY["mapf_primal"] = partial(env_fn, env=MAPFEnv)
+REGISTRY["marl_partial"] = partial(env_fn, env=MARL_PARTIAL_ENV)   # the one the reference registers

@@ -47,6 +47,17 @@ typedef struct oracle_env {
   uint8_t* done;     /* [E,N]  GRID _agent_dones */
   int32_t* step_count; /* [E] */
   int threads;
+  /* PARTIAL (marl_partial.py) */
+  int pW, pK;                                   /* obs_window, obs_knn_agents */
+  double p_move, p_stay, p_stay_goal, p_nc, p_ec, p_envc, p_complete, p_fac, p_gamma;
+  uint8_t* at_goal;    /* [E,N] _agent_at_goals */
+  int32_t* goal_cost;  /* [E,N] _each_goal_cost */
+  int32_t* agent_steps;/* [E,N] _agent_step_count */
+  int16_t* pnode;      /* [E,N] _node_collision_agents */
+  int16_t* pedge;      /* [E,N] _edge_collision_agents */
+  int64_t* total_coll; /* [E]   _total_number_collisions */
+  uint8_t* terminated; /* [E]   _terminated */
+  int16_t* pdist;      /* [E,N,H,W] _goal_dist */
 } oracle_env;
 
 static const int8_t* env_map(const oracle_env* o, int e) {
@@ -83,13 +94,23 @@ oracle_env* oracle_create(int E, int N, int H, int W, int F, int shared_map, int
   o->done = (uint8_t*)calloc((size_t)E * N, 1);
   o->step_count = (int32_t*)calloc((size_t)E, sizeof(int32_t));
   o->threads = threads > 0 ? threads : oracle_max_threads();
+  o->at_goal = (uint8_t*)calloc((size_t)E * N, 1);
+  o->goal_cost = (int32_t*)calloc((size_t)E * N, sizeof(int32_t));
+  o->agent_steps = (int32_t*)calloc((size_t)E * N, sizeof(int32_t));
+  o->pnode = (int16_t*)calloc((size_t)E * N, sizeof(int16_t));
+  o->pedge = (int16_t*)calloc((size_t)E * N, sizeof(int16_t));
+  o->total_coll = (int64_t*)calloc((size_t)E, sizeof(int64_t));
+  o->terminated = (uint8_t*)calloc((size_t)E, 1);
+  o->pdist = NULL;
   return o;
 }
 
 void oracle_destroy(oracle_env* o) {
   if (!o) return;
   free(o->map); free(o->state); free(o->goals); free(o->pos); free(o->goal); free(o->start);
-  free(o->done); free(o->step_count); free(o);
+  free(o->done); free(o->step_count);
+  free(o->at_goal); free(o->goal_cost); free(o->agent_steps); free(o->pnode); free(o->pedge);
+  free(o->total_coll); free(o->terminated); free(o->pdist); free(o);
 }
 
 void oracle_get_positions(const oracle_env* o, int16_t* out) { memcpy(out, o->pos, (size_t)o->E * o->N * 4); }
@@ -538,4 +559,212 @@ void oracle_goal_dist(const oracle_env* o, const uint8_t* dirty, int primal_cost
     }
     free(queue);
   }
+}
+
+
+/* ------------------------------------------------------------------------------------------
+ * PARTIAL   (MARL-curve-main/src/envs/marl_partial.py) -- the env the reference registers
+ * ---------------------------------------------------------------------------------------- */
+void oracle_partial_config(oracle_env* o, int obs_window, int obs_knn, double move, double stay, double stay_goal,
+                           double nc, double ec, double envc, double complete, double fac, double gamma) {
+  o->pW = obs_window; o->pK = obs_knn;
+  o->p_move = move; o->p_stay = stay; o->p_stay_goal = stay_goal;
+  o->p_nc = nc; o->p_ec = ec; o->p_envc = envc;
+  o->p_complete = complete; o->p_fac = fac; o->p_gamma = gamma;
+}
+
+/* reset, PARTIAL:125-167 with pinned starts/goals (the reference samples them from a random .scen,
+ * :907-927) + __setup_agent_goal_dist :931-945. */
+void oracle_partial_reset(oracle_env* o, const int8_t* map, const int16_t* starts, const int16_t* goals) {
+  oracle_grid_reset(o, map, starts, goals);
+  size_t EN = (size_t)o->E * o->N;
+  memset(o->at_goal, 0, EN);
+  for (size_t k = 0; k < EN; ++k) { o->goal_cost[k] = -1; o->agent_steps[k] = 0; o->pnode[k] = 0; o->pedge[k] = 0; }
+  memset(o->total_coll, 0, sizeof(int64_t) * (size_t)o->E);
+  memset(o->terminated, 0, (size_t)o->E);
+  if (!o->pdist) o->pdist = (int16_t*)malloc(EN * o->H * o->W * sizeof(int16_t));
+  oracle_goal_dist(o, NULL, 0, o->pdist);
+}
+
+/* step, PARTIAL:169-310 (output == False) for one environment. */
+static int partial_step_env(oracle_env* o, int e, const uint8_t* act, double* reward, uint8_t* terminated_out,
+                            double* agent_reward, uint8_t* avail, int16_t* scratch) {
+  const int N = o->N, W = o->W, H = o->H;
+  const int8_t* m = env_map(o, e);
+  int16_t* pos = o->pos + (size_t)e * N * 2;
+  const int16_t* goal = o->goal + (size_t)e * N * 2;
+  uint8_t* done = o->done + (size_t)e * N;
+  uint8_t* at_goal = o->at_goal + (size_t)e * N;
+  int16_t* newp = scratch;
+  int16_t* cnt = scratch + 2 * N;
+  double rew[256];
+  uint8_t isint[256];
+  int bad = 0;
+  o->step_count[e] += 1;                                              /* :178 */
+  const int step = o->step_count[e];
+  for (int i = 0; i < N; ++i) {                                       /* :192-235 */
+    int n0 = pos[2 * i], n1 = pos[2 * i + 1];
+    double r = 0.0;
+    if (!done[i]) {
+      o->agent_steps[(size_t)e * N + i] += 1;
+      int a = act[i];
+      int t0 = n0, t1 = n1, flag = 0;                                 /* __agent_step :618-643 */
+      if (a == 0) t0 -= 1; else if (a == 1) t0 += 1; else if (a == 2) t1 -= 1; else if (a == 3) t1 += 1;
+      else if (a != 4) bad++;
+      if (a >= 0 && a <= 3) {
+        if (grid_free(o, m, t0, t1)) { n0 = t0; n1 = t1; } else flag = 1;
+      }
+      if (flag) r += o->p_envc;                                       /* :203-205 */
+      if (a >= 0 && a <= 3) r += o->p_move;                           /* :207-208 */
+      else r += at_goal[i] ? o->p_stay_goal : o->p_stay;              /* :209-213 */
+    }
+    newp[2 * i] = (int16_t)n0; newp[2 * i + 1] = (int16_t)n1;
+    at_goal[i] = 0;                                                   /* :217-222 */
+    if (n0 == goal[2 * i] && n1 == goal[2 * i + 1]) {
+      o->goal_cost[(size_t)e * N + i] = step;
+      at_goal[i] = 1;
+    }
+    if (step >= o->episode_limit) { o->terminated[e] = 1; done[i] = 1; }   /* :224-227 */
+    const int16_t* dm = o->pdist + ((size_t)e * N + i) * H * W;       /* :229-234 */
+    int opd = dm[pos[2 * i] * W + pos[2 * i + 1]], npd = dm[n0 * W + n1];
+    double closer = (double)(opd - npd) / (double)o->episode_limit;
+    r += closer;
+    rew[i] = r;
+    isint[i] = 0;                                                     /* closer_rew is always a float */
+  }
+  memset(cnt, 0, sizeof(int16_t) * (size_t)H * W);                    /* __check_node_collisions :713-737 */
+  for (int i = 0; i < N; ++i) cnt[newp[2 * i] * W + newp[2 * i + 1]] += 1;
+  long nsum = 0, esum = 0;
+  for (int i = 0; i < N; ++i) {                                       /* __check_edge_collisions :822-857 */
+    int node = cnt[newp[2 * i] * W + newp[2 * i + 1]] > 1 ? 1 : 0;
+    int edge = 0;
+    int io0 = pos[2 * i], io1 = pos[2 * i + 1], in0 = newp[2 * i], in1 = newp[2 * i + 1];
+    if (!(io0 == in0 && io1 == in1))
+      for (int j = 0; j < N; ++j) {
+        if (j == i) continue;
+        if (pos[2 * j] == in0 && pos[2 * j + 1] == in1 && newp[2 * j] == io0 && newp[2 * j + 1] == io1) edge++;
+      }
+    o->pnode[(size_t)e * N + i] = (int16_t)node;
+    o->pedge[(size_t)e * N + i] = (int16_t)edge;
+    nsum += node; esum += edge;
+    rew[i] += o->p_nc * node;                                         /* :255-259 */
+    rew[i] += o->p_ec * edge;
+  }
+  o->total_coll[e] += (nsum + esum) / 2;                              /* :250 */
+  for (int i = 0; i < 2 * N; ++i) pos[i] = newp[i];                   /* :279-283 */
+  grid_rebuild_full_obs(o, e);
+  int all_goal = 1;
+  for (int i = 0; i < N; ++i) all_goal &= at_goal[i];
+  if (all_goal) {                                                     /* :291-299 */
+    for (int i = 0; i < N; ++i) done[i] = 1;
+    o->terminated[e] = 1;
+    double tmp = (o->p_complete / pow(o->p_gamma, (double)(o->episode_limit - step))) * o->p_fac;
+    for (int i = 0; i < N; ++i) rew[i] += tmp;
+  }
+  if (reward) *reward = py_sum(rew, isint, N, o->sum_mode);           /* :310 */
+  if (terminated_out) *terminated_out = o->terminated[e];
+  if (agent_reward) for (int i = 0; i < N; ++i) agent_reward[i] = rew[i];
+  if (avail) for (int i = 0; i < N; ++i) grid_avail_agent(o, m, pos[2 * i], pos[2 * i + 1], avail + 5 * i);
+  return bad;
+}
+
+int oracle_partial_step(oracle_env* o, const uint8_t* actions, double* reward, uint8_t* terminated,
+                        double* agent_reward, uint8_t* avail) {
+  int bad = 0;
+  const int N = o->N;
+#pragma omp parallel num_threads(o->threads) reduction(+ : bad)
+  {
+    int16_t* scratch = (int16_t*)malloc(sizeof(int16_t) * (2 * (size_t)N + (size_t)o->H * o->W));
+#pragma omp for schedule(static)
+    for (int e = 0; e < o->E; ++e) {
+      size_t b = (size_t)e * N;
+      bad += partial_step_env(o, e, actions + b, reward ? reward + e : 0, terminated ? terminated + e : 0,
+                              agent_reward ? agent_reward + b : 0, avail ? avail + 5 * b : 0, scratch);
+    }
+    free(scratch);
+  }
+  return bad;
+}
+
+void oracle_partial_get(const oracle_env* o, uint8_t* at_goal, int32_t* goal_cost, int32_t* agent_steps,
+                        int16_t* node, int16_t* edge) {
+  size_t EN = (size_t)o->E * o->N;
+  if (at_goal) memcpy(at_goal, o->at_goal, EN);
+  if (goal_cost) memcpy(goal_cost, o->goal_cost, EN * 4);
+  if (agent_steps) memcpy(agent_steps, o->agent_steps, EN * 4);
+  if (node) memcpy(node, o->pnode, EN * 2);
+  if (edge) memcpy(edge, o->pedge, EN * 2);
+}
+
+/* get_state, PARTIAL:384-393: [total collisions, step count, sum of per-agent goal costs]. */
+void oracle_partial_state(const oracle_env* o, int64_t* out) {
+  for (int e = 0; e < o->E; ++e) {
+    int64_t sum = 0;
+    for (int i = 0; i < o->N; ++i) sum += o->goal_cost[(size_t)e * o->N + i];
+    out[3 * e] = o->total_coll[e];
+    out[3 * e + 1] = o->step_count[e];
+    out[3 * e + 2] = sum;
+  }
+}
+
+/* get_obs_agent, PARTIAL:319-382: W x W obstacle map, W x W agent-count map, K x 13 nearest-agent features. */
+static void partial_observe_agent(const oracle_env* o, int e, int id, double* out) {
+  const int H = o->H, W = o->W, N = o->N, Wn = o->pW, K = o->pK;
+  const int16_t* st = o->state + (size_t)e * H * W;
+  const int16_t* pos = o->pos + (size_t)e * N * 2;
+  const int16_t* goal = o->goal + (size_t)e * N * 2;
+  const int16_t* start = o->start + (size_t)e * N * 2;
+  int tl0 = pos[2 * id] - Wn / 2, tl1 = pos[2 * id + 1] - Wn / 2;     /* :326-327 */
+  double* obstacle_map = out;
+  double* agents_map = out + Wn * Wn;
+  double* knn = out + 2 * Wn * Wn;
+  for (int k = 0; k < 2 * Wn * Wn; ++k) out[k] = 0.0;
+  for (int i = tl0; i < tl0 + Wn; ++i)                                 /* :332-342 */
+    for (int j = tl1; j < tl1 + Wn; ++j) {
+      int w = (i - tl0) * Wn + (j - tl1);
+      if (!(0 <= i && i < H && 0 <= j && j < W)) { obstacle_map[w] = 1.0; continue; }
+      if (st[i * W + j] == -1) obstacle_map[w] = 1.0;
+      else if (st[i * W + j] > 0) agents_map[w] = (double)st[i * W + j];
+    }
+  for (int k = 0; k < K * 13; ++k) knn[k] = -1.0;                      /* :346 */
+  /* agent_distance_matrix row (:548-567) and the stable sort by distance (:351-352) */
+  double dist[256];
+  int order[256];
+  for (int j = 0; j < N; ++j) {
+    if (j == id) dist[j] = (double)(H * W);
+    else {
+      int dx = pos[2 * id] - pos[2 * j], dy = pos[2 * id + 1] - pos[2 * j + 1];
+      dist[j] = sqrt((double)(dx * dx + dy * dy));
+    }
+    order[j] = j;
+  }
+  for (int a = 1; a < N; ++a) {                                         /* insertion sort == stable */
+    int v = order[a], b = a - 1;
+    while (b >= 0 && dist[order[b]] > dist[v]) { order[b + 1] = order[b]; --b; }
+    order[b + 1] = v;
+  }
+  int k_m1 = (N < K ? N : K) - 1;
+  for (int row = 0; row <= k_m1; ++row) {                               /* :353-371 */
+    int na = row == 0 ? id : order[row - 1];
+    int dx = goal[2 * na] - pos[2 * na], dy = goal[2 * na + 1] - pos[2 * na + 1];
+    double norm = sqrt((double)(dx * dx + dy * dy));                    /* __update_goal_vectors :957-972 */
+    double ux = 0.0, uy = 0.0;
+    if (norm != 0) { ux = (double)dx / norm; uy = (double)dy / norm; }
+    double* f = knn + 13 * row;
+    f[0] = pos[2 * na]; f[1] = pos[2 * na + 1];
+    f[2] = start[2 * na]; f[3] = start[2 * na + 1];
+    f[4] = goal[2 * na]; f[5] = goal[2 * na + 1];
+    f[6] = ux; f[7] = uy; f[8] = norm;
+    f[9] = o->pnode[(size_t)e * N + na]; f[10] = o->pedge[(size_t)e * N + na];
+    f[11] = dist[na];
+    f[12] = o->agent_steps[(size_t)e * N + na];
+  }
+}
+
+void oracle_partial_observe(const oracle_env* o, double* obs) {
+  const int N = o->N;
+  const size_t osz = (size_t)2 * o->pW * o->pW + (size_t)13 * o->pK;
+#pragma omp parallel for schedule(static) num_threads(o->threads)
+  for (int e = 0; e < o->E; ++e)
+    for (int i = 0; i < N; ++i) partial_observe_agent(o, e, i, obs + ((size_t)e * N + i) * osz);
 }

@@ -11,6 +11,7 @@ _LIB = None
 
 MODE_GRID = 0
 MODE_PRIMAL = 1
+MODE_PARTIAL = 2
 
 
 def build_oracle(force=False):
@@ -42,6 +43,18 @@ def _lib():
         lib.oracle_primal_sweep.restype = i
         lib.oracle_goal_dist.argtypes = [vp, vp, i, vp]
         lib.oracle_goal_dist.restype = None
+        lib.oracle_partial_config.argtypes = [vp, i, i] + [d] * 9
+        lib.oracle_partial_config.restype = None
+        lib.oracle_partial_reset.argtypes = [vp] * 4
+        lib.oracle_partial_reset.restype = None
+        lib.oracle_partial_step.argtypes = [vp] * 6
+        lib.oracle_partial_step.restype = i
+        lib.oracle_partial_get.argtypes = [vp] * 6
+        lib.oracle_partial_get.restype = None
+        lib.oracle_partial_state.argtypes = [vp] * 2
+        lib.oracle_partial_state.restype = None
+        lib.oracle_partial_observe.argtypes = [vp] * 2
+        lib.oracle_partial_observe.restype = None
         _LIB = lib
     return _LIB
 
@@ -93,7 +106,8 @@ class Oracle:
         for a in (s, g):
             if a is not None:
                 assert a.shape == (self.E, self.N, 2)
-        fn = self._lib.oracle_grid_reset if self.mode == MODE_GRID else self._lib.oracle_primal_reset
+        fn = {MODE_GRID: self._lib.oracle_grid_reset, MODE_PRIMAL: self._lib.oracle_primal_reset,
+              MODE_PARTIAL: self._lib.oracle_partial_reset}[self.mode]
         fn(self._h, _p(m), _p(s), _p(g))
 
     def set_goals(self, goals, dirty=None):
@@ -183,3 +197,44 @@ class Oracle:
         dm = None if dirty is None else np.ascontiguousarray(dirty, dtype=np.uint8)
         self._lib.oracle_goal_dist(self._h, _p(dm), int(bool(primal_costs)), _p(out))
         return out
+
+    # ---- PARTIAL (marl_partial.py)
+    def partial_config(self, obs_window=5, obs_knn_agents=5, move_reward=-0.01, stay_reward=-0.02, stay_goal_reward=0,
+                       node_collide_reward=-1, edge_collide_reward=-1, env_collide_reward=-1, complete_reward=1000,
+                       complete_fac=1.5, gamma=0.99):
+        self.pW, self.pK = int(obs_window), int(obs_knn_agents)
+        self._lib.oracle_partial_config(self._h, self.pW, self.pK, float(move_reward), float(stay_reward),
+                                        float(stay_goal_reward), float(node_collide_reward),
+                                        float(edge_collide_reward), float(env_collide_reward), float(complete_reward),
+                                        float(complete_fac), float(gamma))
+
+    def partial_step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        assert a.shape == (self.E, self.N)
+        E, N = self.E, self.N
+        out = dict(reward=np.empty(E, np.float64), terminated=np.empty(E, np.uint8),
+                   agent_reward=np.empty((E, N), np.float64), avail=np.empty((E, N, 5), np.uint8))
+        out["bad_actions"] = self._lib.oracle_partial_step(self._h, _p(a), _p(out["reward"]), _p(out["terminated"]),
+                                                           _p(out["agent_reward"]), _p(out["avail"]))
+        out.update(self.partial_get())
+        out["dones"] = self.dones()
+        return out
+
+    def partial_get(self):
+        E, N = self.E, self.N
+        out = dict(at_goal=np.empty((E, N), np.uint8), goal_cost=np.empty((E, N), np.int32),
+                   agent_steps=np.empty((E, N), np.int32), node=np.empty((E, N), np.int16),
+                   edge=np.empty((E, N), np.int16))
+        self._lib.oracle_partial_get(self._h, _p(out["at_goal"]), _p(out["goal_cost"]), _p(out["agent_steps"]),
+                                     _p(out["node"]), _p(out["edge"]))
+        return out
+
+    def partial_state(self):
+        out = np.empty((self.E, 3), np.int64)
+        self._lib.oracle_partial_state(self._h, _p(out))
+        return out
+
+    def partial_observe(self):
+        obs = np.empty((self.E, self.N, 2 * self.pW * self.pW + 13 * self.pK), np.float64)
+        self._lib.oracle_partial_observe(self._h, _p(obs))
+        return obs

@@ -305,11 +305,106 @@ def gen_pdist():
     run_pdist("pdist_rand32", "random-32-32-20.map", "random-32-32-20-random-", 4, 22)
 
 
+# --------------------------------------------------------------------------- PARTIAL step / observation traces
+def run_partial(name, map_file, scen_prefix, n, T, seed, policy, **kw):
+    """Traces of MARL_PARTIAL_ENV (the env the reference actually registers): step :169-310, get_obs :319-382,
+    get_state :384-393, avail :409-434.  policy: 'random' or 'greedy' (walk down the goal-distance map)."""
+    random.seed(seed)
+    mp = os.path.join(REF_SRC, "mapf_baseline", "mapf-map", map_file)
+    sp = os.path.join(REF_SRC, "mapf_baseline", "scen-random", scen_prefix)
+    env = PARTIAL.MARL_PARTIAL_ENV(mp, sp, n_agents=n, render="none", **kw)
+    obs0 = env.reset()
+    grid = env._original_grid
+    H, W = len(grid), len(grid[0])
+    obst = np.array([[c != "." for c in row] for row in grid])
+    starts = np.array(env._agent_init_pos, dtype=np.int16)
+    goals = np.array(env._agent_goal_pos, dtype=np.int16)
+    dist = np.full((n, H, W), -1, np.int32)
+    for a in range(n):
+        for num, d in env._goal_dist[a].items():
+            dist[a, num // W, num % W] = d
+    rs = np.random.RandomState(seed)
+    delta = {0: (-1, 0), 1: (1, 0), 2: (0, -1), 3: (0, 1)}
+    rec = {k: [] for k in ("actions", "pos", "node", "edge", "at_goal", "dones", "reward", "terminated", "obs",
+                           "state", "avail", "goal_cost", "agent_steps")}
+    avail0 = np.array(env.get_avail_actions(), dtype=np.uint8)
+    state0 = np.array(env.get_state(), dtype=np.int64)
+    extra = 0
+    for t in range(T):
+        acts = rs.randint(0, 5, n)
+        if policy == "greedy":
+            for a in range(n):
+                if rs.rand() < 0.85:
+                    p = env._agent_positions[a]
+                    if p == env._agent_goal_pos[a]:
+                        acts[a] = 4
+                    else:
+                        best, bd = 4, dist[a, p[0], p[1]]
+                        for k, (dr, dc) in delta.items():
+                            q = (p[0] + dr, p[1] + dc)
+                            if 0 <= q[0] < H and 0 <= q[1] < W and not obst[q] and dist[a, q[0], q[1]] < bd:
+                                best, bd = k, dist[a, q[0], q[1]]
+                        acts[a] = best
+        r, term, info = env.step(acts)
+        rec["actions"].append(acts.astype(np.uint8))
+        rec["pos"].append(np.array(env._agent_positions, dtype=np.int16))
+        rec["node"].append(np.array(env._node_collision_agents, dtype=np.int32))
+        rec["edge"].append(np.array(env._edge_collision_agents, dtype=np.int32))
+        rec["at_goal"].append(np.array(env._agent_at_goals, dtype=np.uint8))
+        rec["dones"].append(np.array(env._agent_dones, dtype=np.uint8))
+        rec["reward"].append(float(r))
+        rec["terminated"].append(bool(term))
+        rec["obs"].append(np.array(env.get_obs(), dtype=np.float64))
+        rec["state"].append(np.array(env.get_state(), dtype=np.int64))
+        rec["avail"].append(np.array(env.get_avail_actions(), dtype=np.uint8))
+        rec["goal_cost"].append(np.array(env._each_goal_cost, dtype=np.int32))
+        rec["agent_steps"].append(np.array(env._agent_step_count, dtype=np.int32))
+        assert info == {"_step_count": t + 1}
+        if term:
+            extra += 1
+            if extra > 2:
+                break
+    cfg = dict(obs_window=5, obs_knn_agents=5, episode_limit=100, move_reward=-0.01, stay_reward=-0.02,
+               stay_goal_reward=0, node_collide_reward=-1, edge_collide_reward=-1, env_collide_reward=-1,
+               complete_reward=1000, complete_fac=1.5, gamma=0.99)
+    cfg.update(kw)
+    out = dict(family="PARTIAL", obst=obst.astype(np.uint8), starts=starts, goals=goals, dist=dist,
+               obs0=np.array(obs0, dtype=np.float64), avail0=avail0, state0=state0,
+               py_sum_mode=np.int64(sys.version_info >= (3, 12)),
+               **{k: np.array(v) for k, v in rec.items()})
+    for k, v in cfg.items():
+        out["cfg_" + k] = np.float64(v)
+        out["cfgint_" + k] = np.int64(isinstance(v, int))
+    out["terminated"] = out["terminated"].astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "T=%d N=%d HxW=%dx%d terminated_at=%s collisions=%d sum_reward=%.4f" % (
+        len(rec["reward"]), n, H, W, (int(np.argmax(out["terminated"])) + 1) if out["terminated"].any() else None,
+        int(out["state"][-1][0]), float(np.sum(out["reward"]))))
+
+
+def gen_partial():
+    yaml_like = dict(move_reward=0, stay_reward=-0.1, stay_goal_reward=1, node_collide_reward=-2000,
+                     edge_collide_reward=-2000, env_collide_reward=-2000, complete_reward=1000, complete_fac=1.5,
+                     gamma=0.99)
+    run_partial("partial_empty8_yaml", "empty-8-8.map", "empty-8-8-random-", 6, 60, 31, "greedy",
+                obs_window=5, obs_knn_agents=5, episode_limit=100, **yaml_like)
+    run_partial("partial_empty8_crowd", "empty-8-8.map", "empty-8-8-random-", 12, 40, 32, "random",
+                obs_window=3, obs_knn_agents=3, episode_limit=25)
+    run_partial("partial_rand32", "random-32-32-20.map", "random-32-32-20-random-", 5, 40, 33, "greedy",
+                obs_window=11, obs_knn_agents=8, episode_limit=60)
+    run_partial("partial_k1", "empty-8-8.map", "empty-8-8-random-", 4, 30, 34, "greedy",
+                obs_window=4, obs_knn_agents=1, episode_limit=40, move_reward=-0.05, stay_reward=-0.25,
+                stay_goal_reward=0.5, node_collide_reward=-1.5, edge_collide_reward=-2.5, env_collide_reward=-0.75,
+                complete_reward=10.0, complete_fac=1.1, gamma=0.9)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["grid", "primal", "pdist"]
+    which = sys.argv[1:] or ["grid", "primal", "pdist", "partial"]
     if "grid" in which:
         gen_grid()
     if "primal" in which:
         gen_primal()
     if "pdist" in which:
         gen_pdist()
+    if "partial" in which:
+        gen_partial()

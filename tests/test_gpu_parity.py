@@ -537,3 +537,131 @@ def test_primal_convoys_cycles_and_long_dependency_chains_match_oracle():
         assert np.array_equal(_np(out["obs"]), robs), t
     # the ascending convoy moved as a whole in its first step, the descending one only at its head
     assert eng.error_flags() == 0
+
+
+# ------------------------------------------------------------------------------------------ PARTIAL (marl_partial.py)
+def _partial_kwargs(g):
+    keys = ("obs_window", "obs_knn_agents", "move_reward", "stay_reward", "stay_goal_reward", "node_collide_reward",
+            "edge_collide_reward", "env_collide_reward", "complete_reward", "complete_fac", "gamma")
+    return {k: (int(g["cfg_" + k]) if g["cfgint_" + k] else float(g["cfg_" + k])) for k in keys}
+
+
+PARTIAL_WANT = ("reward", "terminated", "agent_reward", "dones", "status", "node", "edge", "avail")
+
+
+@pytest.mark.parametrize("name", golden_names("PARTIAL"))
+def test_partial_engine_matches_reference_trace(name):
+    g = load_golden(name)
+    H, W = g["obst"].shape
+    N = g["starts"].shape[0]
+    eng = _engine(1, N, H, W, mode="partial", episode_limit=int(g["cfg_episode_limit"]),
+                  reward_sum_mode=int(g["py_sum_mode"]), **_partial_kwargs(g))
+    eng.reset(g["obst"][None], g["starts"][None], g["goals"][None])
+    free = ~g["obst"].astype(bool)
+    assert np.array_equal(_np(eng.goal_dist())[0][:, free].astype(np.int32), g["dist"][:, free])
+    assert np.array_equal(_bits(_np(eng.observe()[0])[0]), _bits(g["obs0"]))
+    assert np.array_equal(_np(eng.avail())[0], g["avail0"])
+    assert np.array_equal(_np(eng.partial_state()["state"])[0], g["state0"])
+    for t in range(g["actions"].shape[0]):
+        out = eng.step(torch.as_tensor(g["actions"][t][None]), want=PARTIAL_WANT)
+        ps = eng.partial_state()
+        assert np.array_equal(_np(eng.positions())[0], g["pos"][t]), t
+        assert np.array_equal(_np(out["node"])[0], g["node"][t]), t
+        assert np.array_equal(_np(out["edge"])[0], g["edge"][t]), t
+        assert np.array_equal(_np(ps["at_goal"])[0], g["at_goal"][t]), t
+        assert np.array_equal(_np(out["dones"])[0], g["dones"][t]), t
+        assert np.array_equal(_np(ps["goal_cost"])[0], g["goal_cost"][t]), t
+        assert np.array_equal(_np(ps["agent_steps"])[0], g["agent_steps"][t]), t
+        assert _bits(_np(out["reward"]))[0] == _bits(g["reward"][t:t + 1])[0], (t, _np(out["reward"]), g["reward"][t])
+        assert _np(out["terminated"])[0] == g["terminated"][t]
+        assert np.array_equal(_np(out["avail"])[0], g["avail"][t]), t
+        assert np.array_equal(_np(ps["state"])[0], g["state"][t]), t
+        assert np.array_equal(_bits(_np(eng.observe()[0])[0]), _bits(g["obs"][t])), t
+    assert eng.error_flags() == 0
+
+
+@pytest.mark.parametrize("case", [(96, 15, 8, 8, 0.0, 5, 5, 30), (40, 32, 32, 32, 0.2, 11, 8, 60),
+                                  (25, 7, 12, 12, 0.1, 4, 9, 20), (8, 100, 24, 24, 0.05, 3, 4, 15)],
+                         ids=lambda c: "E%d_N%d_%dx%d" % c[:4])
+def test_partial_batch_matches_oracle(case):
+    from oracle.oracle import MODE_PARTIAL
+    E, N, H, W, dens, Wn, K, limit = case
+    rs = np.random.RandomState(E + N)
+    obst = np.zeros((E, H, W), np.uint8)
+    starts = np.zeros((E, N, 2), np.int16)
+    goals = np.zeros((E, N, 2), np.int16)
+    from mapf_marl_b200 import maps
+    for e in range(E):
+        while True:
+            m = (rs.rand(H, W) < dens).astype(np.uint8)
+            lab = maps.label_components(m)
+            big = np.argmax(np.bincount(lab[lab >= 0]))
+            m[lab != big] = 1                       # one connected region: PARTIAL needs every goal reachable
+            free = np.argwhere(m == 0)
+            if len(free) >= 2 * N:
+                break
+        obst[e] = m
+        starts[e] = free[rs.randint(0, len(free), N)]
+        goals[e] = free[rs.randint(0, len(free), N)]
+    kw = dict(obs_window=Wn, obs_knn_agents=K, move_reward=-0.01, stay_reward=-0.02, stay_goal_reward=0.3,
+              node_collide_reward=-1, edge_collide_reward=-1.5, env_collide_reward=-1, complete_reward=100,
+              complete_fac=1.5, gamma=0.97)
+    eng = _engine(E, N, H, W, mode="partial", episode_limit=limit, **kw)
+    orc = _oracle(E, N, H, W, MODE_PARTIAL, episode_limit=limit)
+    orc.partial_config(**kw)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    assert np.array_equal(_bits(_np(eng.observe()[0])), _bits(orc.partial_observe()))
+    for t in range(limit + 3):
+        a = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        if t % 2 == 0:
+            out = eng.step_observe(torch.as_tensor(a, device="cuda"), want=PARTIAL_WANT)
+            obs = out["obs"]
+        else:
+            out = eng.step(torch.as_tensor(a, device="cuda"), want=PARTIAL_WANT)
+            obs = eng.observe()[0]
+        ref = orc.partial_step(a)
+        ps = eng.partial_state()
+        for k in ("terminated", "dones", "node", "edge", "avail"):
+            assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        for k in ("at_goal", "goal_cost", "agent_steps"):
+            assert np.array_equal(_np(ps[k]), ref[k]), (k, t)
+        assert np.array_equal(_bits(_np(out["agent_reward"])), _bits(ref["agent_reward"])), t
+        assert np.array_equal(_bits(_np(out["reward"])), _bits(ref["reward"])), t
+        assert np.array_equal(_np(eng.positions()), orc.positions()), t
+        assert np.array_equal(_np(ps["state"]), orc.partial_state()), t
+        assert np.array_equal(_bits(_np(obs)), _bits(orc.partial_observe())), t
+    assert eng.error_flags() == 0
+
+
+def test_marl_partial_dropin_class(tmp_path):
+    """MARL_PARTIAL_ENV with the reference's constructor, reset/step/get_obs/get_state types."""
+    from mapf_marl_b200.marl_partial import MARL_PARTIAL_ENV
+    g = load_golden("partial_empty8_yaml")
+    mp, sp = _write_movingai(tmp_path, g["obst"])
+    N = g["starts"].shape[0]
+    kw = _partial_kwargs(g)
+    env = MARL_PARTIAL_ENV(mp, sp, n_agents=N, episode_limit=int(g["cfg_episode_limit"]), render="none", **kw)
+    env.set_starts_goals(g["starts"], g["goals"])
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.dtype == np.float64 and obs.shape == (N, env.get_obs_size())
+    assert np.array_equal(_bits(obs), _bits(g["obs0"]))
+    assert env.get_env_info() == {"state_shape": 3, "obs_shape": obs.shape[1], "n_actions": 5, "n_agents": N,
+                                  "episode_limit": int(g["cfg_episode_limit"])}
+    for t in range(g["actions"].shape[0]):
+        reward, terminated, info = env.step(torch.as_tensor(g["actions"][t].astype(np.int64)))
+        assert isinstance(reward, float) and isinstance(terminated, bool)
+        assert np.float64(reward).view(np.uint64) == g["reward"][t:t + 1].view(np.uint64)[0]
+        assert terminated == bool(g["terminated"][t]) and info == {"_step_count": t + 1}
+        assert [env.agent_pos(a) for a in range(N)] == [tuple(p) for p in g["pos"][t].tolist()]
+        assert env.get_avail_actions() == g["avail"][t].tolist()
+        assert np.array_equal(env.get_state(), g["state"][t])
+        assert np.array_equal(_bits(env.get_obs()), _bits(g["obs"][t]))
+        assert env.episode_done() == bool(g["dones"][t].all())
+    # re-sampling reset: starts / goals come from the .scen files and are free cells
+    env2 = MARL_PARTIAL_ENV(mp, sp, n_agents=N, render="none")
+    random_obs = env2.reset()
+    assert random_obs.shape == (N, env2.get_obs_size())
+    from mapf_marl_b200.registry import REGISTRY
+    env3 = REGISTRY["marl_partial"](grid_file_path=mp, agents_path=sp, n_agents=3, render="none")
+    assert env3.reset().shape == (3, env3.get_obs_size())

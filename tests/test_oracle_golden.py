@@ -9,7 +9,7 @@ import pytest
 
 from conftest import golden_names, load_golden
 from oracle import Oracle
-from oracle.oracle import MODE_GRID, MODE_PRIMAL
+from oracle.oracle import MODE_GRID, MODE_PARTIAL, MODE_PRIMAL
 
 
 @pytest.mark.parametrize("name", golden_names("GRID"))
@@ -115,3 +115,36 @@ def test_oracle_batch_is_independent_per_env():
         for e in range(E):
             assert np.array_equal(obs[e], g["obs"][t])
             assert np.array_equal(o.positions()[e], g["pos"][t])
+
+
+def partial_kwargs(g):
+    keys = ("obs_window", "obs_knn_agents", "move_reward", "stay_reward", "stay_goal_reward", "node_collide_reward",
+            "edge_collide_reward", "env_collide_reward", "complete_reward", "complete_fac", "gamma")
+    return {k: (int(g["cfg_" + k]) if g["cfgint_" + k] else float(g["cfg_" + k])) for k in keys}
+
+
+@pytest.mark.parametrize("name", golden_names("PARTIAL"))
+def test_partial_oracle_matches_reference_trace(name):
+    g = load_golden(name)
+    H, W = g["obst"].shape
+    N = g["starts"].shape[0]
+    o = Oracle(1, N, H, W, MODE_PARTIAL, episode_limit=int(g["cfg_episode_limit"]), sum_mode=int(g["py_sum_mode"]))
+    o.partial_config(**partial_kwargs(g))
+    o.reset(g["obst"][None], g["starts"][None], g["goals"][None])
+    assert np.array_equal(o.partial_observe()[0].view(np.uint64), g["obs0"].view(np.uint64))
+    assert np.array_equal(o.grid_avail()[0], g["avail0"])
+    assert np.array_equal(o.partial_state()[0], g["state0"])
+    for t in range(g["actions"].shape[0]):
+        out = o.partial_step(g["actions"][t][None])
+        assert np.array_equal(o.positions()[0], g["pos"][t]), t
+        assert np.array_equal(out["node"][0], g["node"][t]), t
+        assert np.array_equal(out["edge"][0], g["edge"][t]), t
+        assert np.array_equal(out["at_goal"][0], g["at_goal"][t]), t
+        assert np.array_equal(out["dones"][0], g["dones"][t]), t
+        assert np.array_equal(out["goal_cost"][0], g["goal_cost"][t]), t
+        assert np.array_equal(out["agent_steps"][0], g["agent_steps"][t]), t
+        assert out["reward"].view(np.uint64)[0] == g["reward"][t:t + 1].view(np.uint64)[0], (t, out["reward"], g["reward"][t])
+        assert out["terminated"][0] == g["terminated"][t]
+        assert np.array_equal(out["avail"][0], g["avail"][t]), t
+        assert np.array_equal(o.partial_state()[0], g["state"][t]), t
+        assert np.array_equal(o.partial_observe()[0].view(np.uint64), g["obs"][t].view(np.uint64)), t
