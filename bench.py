@@ -216,10 +216,10 @@ def main():
     eng.reset(obst, starts, goals)
     # goal-distance maps: computed at reset (and on goal reassignment), reported separately
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.goal_dist()
+    eng.refresh_goal_dist()
     torch.cuda.synchronize()
     ev0.record()
-    eng.goal_dist()
+    eng.refresh_goal_dist()
     ev1.record()
     torch.cuda.synchronize()
     bfs_ms = ev0.elapsed_time(ev1)

@@ -291,15 +291,23 @@ class MapfEngine:
         return out
 
     def goal_dist(self, dirty=None, primal_costs=False, out=None):
-        """int16 [E,N,H,W] hop distance to every agent's goal (walls -1, unreachable -2)."""
+        """int16 [E,N,H,W] hop distance to every agent's goal (walls -1, unreachable -2), computed into `out`
+        (or an engine-owned tensor)."""
         dmask = self._to_dev(dirty, torch.uint8, (self.E, self.N))
-        if out is None and not self.has_goal_dist:
+        if out is None:
             out = self._buf("goal_dist", (self.E, self.N, self.H, self.W), torch.int16)
         self._keep = [dmask]
         with torch.cuda.device(self.device):
             self._check(self.lib.mapf_bfs(self._h, self._ptr(dmask), self._ptr(out), int(bool(primal_costs)),
                                           self._stream()), "mapf_bfs")
         return out
+
+    def refresh_goal_dist(self, dirty=None):
+        """Recompute the handle's own distance maps (cfg.goal_dist / mode PARTIAL) for the flagged agents."""
+        dmask = self._to_dev(dirty, torch.uint8, (self.E, self.N))
+        self._keep = [dmask]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_bfs(self._h, self._ptr(dmask), None, 0, self._stream()), "mapf_bfs")
 
     def partial_state(self, want=("state", "at_goal", "goal_cost", "agent_steps")):
         """MARL_PARTIAL_ENV bookkeeping: state int64 [E,3] = get_state(); at_goal u8, goal_cost / agent_steps i32 [E,N]."""
