@@ -13,7 +13,8 @@
 struct mapf_handle {
   mapf_cfg cfg;
   MapfDims d;
-  MapfTileLayout L;
+  MapfTileLayout L;       // full layout
+  MapfTileLayout L_lite;  // PRIMAL without mid-sweep outputs: no second occupancy grid (more resident tiles per SM)
   MapfState S;
   int device;
   int fov_fast;        // a specialised tile kernel exists for cfg.fov
@@ -55,7 +56,7 @@ static int cuda_fail(mapf_handle* h, cudaError_t e, const char* what) {
 static int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L) {
+static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L, bool second_grid = true) {
   const int na = epb * d.N;
   const bool fov = d.F > 0;
   int off = 0;
@@ -67,7 +68,8 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L) {
   L->obst_off = take((d.shared_map ? 1 : epb) * d.bm_words * 4);
   L->agt_off = take(fov ? epb * d.bm_words * 4 : 16);
   L->grida_off = take(epb * d.grid_bytes);
-  L->gridb_off = take(epb * d.grid_bytes);
+  // PRIMAL needs the second grid only for the mid-sweep outputs (a copy of the pre-sweep ids)
+  L->gridb_off = second_grid ? take(epb * d.grid_bytes) : L->grida_off;
   L->posold_off = take(2 * na);
   L->posnew_off = take(2 * na);
   L->goal_off = take(2 * na);
@@ -88,6 +90,7 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L) {
   L->envterm_off = take(epb);
   L->envcnt_off = take(4 * epb);
   L->envcnt2_off = take(4 * epb);
+  L->envstep_off = take(4 * epb);
   L->atgoal_off = take(na);
   L->str_off = take(fov ? ((na + d.G - 1) / d.G) * d.GW * 4 + 16 : 16);
   L->total_bytes = off;
@@ -283,6 +286,8 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
     return rc;
   }
   d.epb = dt.epb;
+  dt.epb = d.epb;
+  compute_layout(dt, d.epb, &h->L_lite, d.mode != MAPF_MODE_PRIMAL);
 
 #define ALLOC(ptr, bytes)                                                                          \
   do {                                                                                             \
@@ -425,7 +430,8 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
   }
   const bool any_out = A.do_step || A.obs || A.vec || A.out.avail_dev;
   if (any_out) {
-    CK((cudaError_t)mapf_launch_tile(d, h->L, h->S, A, stream));
+    const bool need_mid = A.out.done_mid_dev || A.out.next_mid_dev;
+    CK((cudaError_t)mapf_launch_tile(d, need_mid ? h->L : h->L_lite, h->S, A, stream));
     h->launches++;
   }
   if (pwin && obs) {

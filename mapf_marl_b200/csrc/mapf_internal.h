@@ -53,6 +53,7 @@ struct MapfTileLayout {
   int envterm_off;  // u8 [epb] (padded)
   int envcnt_off;   // int [epb]: per-environment counters (agents on goal / done)
   int envcnt2_off;  // int [epb]: PARTIAL: sum of node flags + edge counts
+  int envstep_off;  // int [epb]: step counter before this step
   int atgoal_off;   // u8 [epb*N]: PARTIAL _agent_at_goals
   int str_off;      // bit strings: ceil(epb*N / G) * GW u32
   int total_bytes;

@@ -25,6 +25,13 @@
 
 #include "mapf_internal.h"
 
+#ifdef MAPF_PHASE_TIMING
+__device__ long long g_phase_clk[32];
+#define PHASE_MARK(i) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) g_phase_clk[i] = clock64(); } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kThreads = MAPF_TILE_THREADS;
@@ -558,12 +565,15 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   const bool do_step = A.do_step != 0;
   const bool need_mid = primal && do_step && ((A.out.done_mid_dev != nullptr) || (A.out.next_mid_dev != nullptr));
 
+  PHASE_MARK(0);
   // ---- stage the tile (one exposed global-memory latency): obstacle bitmaps, per-agent records, zeroed grids
   if (tid < MAPF_N_STATS) stat[tid] = 0;
   if (tid == 0) bad_flag = 0;
+  int* envstep = (int*)(smem_raw + L.envstep_off);
   for (int el = tid; el < ne; el += kThreads) {
     envcnt[el] = 0;
     envcnt2[el] = 0;
+    envstep[el] = S.step_count[e0 + el];   // staged with the other global loads: no mid-kernel round trip
   }
   {
     const int nvec = ((d.shared_map ? 1 : ne) * d.bm_words) >> 2;
@@ -606,6 +616,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   __syncthreads();
   if (bad) bad_flag = 1;
 
+  PHASE_MARK(1);
   // ---- phase A: occupancy of the current positions (PRIMAL State.state ids, PRIMAL:32-47; GRID agent counts,
   //      GRID:299) and the agent-independent part of the step
   unsigned int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
@@ -620,7 +631,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     } else {
       byte_inc(grid, cell);
       if (do_step) {
-        const int step_now = S.step_count[e0 + el] + 1;              // GRID:93, PARTIAL:178
+        const int step_now = envstep[el] + 1;                        // GRID:93, PARTIAL:178
         if (partial) partial_phase_a(d, s, S, a0 + j, j, el, step_now, c0, c3);
         else grid_phase_a(d, s, j, el, step_now, c0, c3);
       }
@@ -629,6 +640,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   __syncthreads();
 
   if (do_step) {
+  PHASE_MARK(2);
     // ---- phase B (PRIMAL): outcome of the ordered sweep, resolved in parallel (see primal_classify)
     if (primal) {
       if (need_mid)   // keep the pre-sweep id grid for the mid-sweep outputs
@@ -658,6 +670,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
         }
       __syncthreads();
     }
+  PHASE_MARK(3);
     // ---- phase C
     for (int j0 = 0; j0 < na; j0 += kThreads) {
       const int j = j0 + tid;
@@ -691,6 +704,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     if (need_mid) primal_mid_outputs(d, s, A, ne, tid);
   }
 
+  PHASE_MARK(4);
   // ---- agent bitmap of the post-step positions + available-action masks
   const uint8_t* gridcur = (!primal && do_step) ? s.gridb : s.grida;
   const bool want_avail = A.out.avail_dev != nullptr;
@@ -729,6 +743,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   }
   __syncthreads();
 
+  PHASE_MARK(5);
   // ---- phase D + state write-back + the small per-agent / per-env outputs (coalesced over the tile)
   if (do_step) {
     for (int el = tid; el < ne; el += kThreads) {
@@ -740,9 +755,9 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
           for (int i = A.agent_lo; i < A.agent_hi; ++i) tot = __dadd_rn(tot, s.rew[el * N + i]);
           A.out.reward_dev[e0 + el] = tot;
         }
-        if (A.agent_lo == 0) S.step_count[e0 + el] += 1;
+        if (A.agent_lo == 0) S.step_count[e0 + el] = envstep[el] + 1;
       } else if (partial) {
-        const int step_now = S.step_count[e0 + el] + 1;
+        const int step_now = envstep[el] + 1;
         bool term = (S.terminated[e0 + el] != 0) || (step_now >= d.episode_limit);     // PARTIAL:224-226
         if (all) {                                                                     // all at goal, PARTIAL:291-299
           term = true;
@@ -761,9 +776,17 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       } else {
         if (A.out.reward_dev)
           A.out.reward_dev[e0 + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // GRID:141
-        S.step_count[e0 + el] += 1;
+        S.step_count[e0 + el] = envstep[el] + 1;
       }
-      if (d.collect_stats && all) atomicAdd(&stat[MAPF_STAT_EPISODES_DONE], 1u);
+      if (d.collect_stats && all) atomicAdd(&S.stats[MAPF_STAT_EPISODES_DONE], 1ull);
+    }
+    if (d.collect_stats) {   // one global atomic per counter per tile; the per-agent counters were complete at the barrier
+      if (tid == 0) {
+        if (!primal || A.agent_lo == 0) atomicAdd(&S.stats[MAPF_STAT_ENV_STEPS], (unsigned long long)ne);
+        atomicAdd(&S.stats[MAPF_STAT_AGENT_STEPS], (unsigned long long)(ne * (primal ? A.agent_hi - A.agent_lo : N)));
+      } else if (tid < MAPF_N_STATS && stat[tid] != 0) {
+        atomicAdd(&S.stats[tid], (unsigned long long)stat[tid]);
+      }
     }
     if (partial) {   // phase D changed done / rewards of whole environments
       __syncthreads();
@@ -787,19 +810,11 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     if (primal && A.out.done_mid_dev)
       for (int j = tid; j < na; j += kThreads) A.out.done_mid_dev[a0 + j] = (s.flag[j] >> 2) & 1;
     if (primal && A.out.next_mid_dev) write_mask5(A.out.next_mid_dev + 5 * a0, s.nextmid, na, tid);
-    if (d.collect_stats) {   // one global atomic per counter per tile
-      __syncthreads();
-      if (tid == 0) {
-        stat[MAPF_STAT_ENV_STEPS] = (!primal || A.agent_lo == 0) ? (unsigned)ne : 0u;
-        stat[MAPF_STAT_AGENT_STEPS] = (unsigned)(ne * (primal ? A.agent_hi - A.agent_lo : N));
-      }
-      __syncthreads();
-      if (tid < MAPF_N_STATS && stat[tid] != 0) atomicAdd(&S.stats[tid], (unsigned long long)stat[tid]);
-    }
   }
   if (want_avail) write_mask5(A.out.avail_dev + 5 * a0, s.avail, na, tid);
   if (tid == 0 && bad_flag) atomicOr(S.err_flags, MAPF_FLAG_BAD_ACTION);
 
+  PHASE_MARK(6);
   // ---- observation
   if (A.obs == nullptr && A.vec == nullptr) return;
 
@@ -819,6 +834,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
 
   if constexpr (F > 0) {
     using T = Fov<F>;
+    PHASE_MARK(7);
     // phase 1: one thread per agent builds its 4*F*F bits and the goal vector; G agents share a
     // word-aligned group string.
     for (int base = 0; base < na; base += kThreads) {
@@ -883,6 +899,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     __syncthreads();
     if (A.obs == nullptr) return;
 
+  PHASE_MARK(8);
     // phase 2: expand the tile's bit string; thread q writes output bytes [16q, 16q+16)
     const size_t nbits = (size_t)na * T::NB;
     if (A.obs_dtype == MAPF_U8) {
@@ -913,6 +930,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       }
     }
   }
+  PHASE_MARK(9);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1328,6 +1346,12 @@ int grid_for(long long total, int block) {
 }  // namespace
 
 #define MAPF_FOR_EACH_F(X) X(0) X(3) X(5) X(7) X(9) X(10) X(11)
+
+#ifdef MAPF_PHASE_TIMING
+extern "C" int mapf_debug_phase_clocks(long long* out32) {
+  return (int)cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(long long) * 32);
+}
+#endif
 
 extern "C" int mapf_tile_has_fov(int F) {
   switch (F) {
