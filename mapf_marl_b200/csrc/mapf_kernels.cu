@@ -525,6 +525,7 @@ __device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, const uin
   const int t0 = (int)p.x - P, t1 = (int)p.y - P;
   const int gi = (int)g.x - t0, gj = (int)g.y - t1;
   if ((unsigned)gi < (unsigned)F && (unsigned)gj < (unsigned)F) set(T::FF + gi * F + gj);
+  const uint8_t* gbase = idgrid + (t0 + 1) * GS + t1 + 1;
 #pragma unroll
   for (int q = 0; q < T::CW; ++q) {
     uint32_t v = vis[q];
@@ -532,9 +533,8 @@ __device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, const uin
       const int idx = 32 * q + __ffs(v) - 1;
       v &= v - 1;
       const int wi = idx / F, wj = idx - wi * F;
-      const int id = idgrid[(t0 + wi + 1) * GS + t1 + wj + 1];
-      if (id == 0) continue;
-      const uchar2 og = goals_env[id - 1];
+      const int id = gbase[wi * GS + wj];          // the agent bit map says somebody stands here: id >= 1
+      const uchar2 og = goals_env[max(id, 1) - 1];
       const int ci = min(max((int)og.x - t0, 0), F - 1);
       const int cj = min(max((int)og.y - t1, 0), F - 1);
       set(2 * T::FF + ci * F + cj);
@@ -906,6 +906,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       uint8_t* out = (uint8_t*)A.obs + a0 * T::NB;
       const int nchunk = (int)(nbits >> 4);
       const uint16_t* s16 = (const uint16_t*)s.str;
+#pragma unroll 2
       for (int q = tid; q < nchunk; q += kThreads) {
         const uint32_t h = s16[q];
         uint4 v;
