@@ -81,6 +81,7 @@ typedef enum mapf_dtype {
 #define MAPF_FLAG_BAD_POSITION 2u /* start/goal out of bounds at reset */
 #define MAPF_FLAG_START_ON_WALL 4u
 #define MAPF_FLAG_START_OVERLAP 8u /* PRIMAL only: two agents on one cell (State.scanForAgents, PRIMAL:53-66) */
+#define MAPF_FLAG_GOAL_OVERLAP 16u /* PRIMAL only: two agents share a goal cell (State.goals holds one id per cell) */
 
 /* Indices into the int64[MAPF_N_STATS] vector returned by mapf_stats. */
 enum {

@@ -1081,6 +1081,12 @@ __global__ void mapf_reset_kernel(const MapfDims d, const MapfState S, const int
             starts[2 * ((long long)e * d.N + b) + 1] == starts[2 * j + 1])
           flags |= MAPF_FLAG_START_OVERLAP;
     }
+    if (d.mode == MAPF_MODE_PRIMAL && goals) {
+      for (int b = 0; b < a; ++b)
+        if (goals[2 * ((long long)e * d.N + b)] == goals[2 * j] &&
+            goals[2 * ((long long)e * d.N + b) + 1] == goals[2 * j + 1])
+          flags |= MAPF_FLAG_GOAL_OVERLAP;
+    }
     if (flags) atomicOr(S.err_flags, flags);
   }
 }

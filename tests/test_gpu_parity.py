@@ -665,3 +665,55 @@ def test_marl_partial_dropin_class(tmp_path):
     from mapf_marl_b200.registry import REGISTRY
     env3 = REGISTRY["marl_partial"](grid_file_path=mp, agents_path=sp, n_agents=3, render="none")
     assert env3.reset().shape == (3, env3.get_obs_size())
+
+
+def test_c4_shape_lifelong_goal_reassignment_matches_oracle():
+    """BASELINE config c4: 64x64 warehouse layout, 128 agents, goals popped from a per-agent queue on arrival,
+    distance maps recomputed only for the reassigned goals."""
+    from mapf_marl_b200 import maps
+    from mapf_marl_b200.lifelong import LifelongGoals
+    from oracle.oracle import MODE_PRIMAL
+    E, N, H, W, F, Q = 12, 128, 64, 64, 11, 4
+    rs = np.random.RandomState(3)
+    obst = maps.warehouse_layout(H, W)
+    free = np.argwhere(obst == 0)
+    # PRIMAL's `goals` grid holds one id per cell, so goal cells must be distinct at all times: every agent draws its
+    # start, first goal and queued goals from a private pool of cells
+    assert len(free) >= N * (Q + 2)
+    starts = np.zeros((E, N, 2), np.int16)
+    goals = np.zeros((E, N, 2), np.int16)
+    queue = np.zeros((E, N, Q, 2), np.int16)
+    for e in range(E):
+        pool = free[rs.permutation(len(free))[:N * (Q + 2)]].reshape(N, Q + 2, 2)
+        starts[e] = pool[:, 0]
+        goals[e] = pool[:, 1]
+        near = rs.rand(N) < 0.5
+        goals[e][near] = starts[e][near]             # half of the agents start on their goal: immediate reassignment
+        queue[e] = pool[:, 2:]
+    eng = _engine(E, N, H, W, mode="primal", fov=F, shared_map=True, goal_dist=True)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F, shared_map=True)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    life = LifelongGoals(eng, queue)
+    dist = torch.full((E, N, H, W), -9, dtype=torch.int16, device="cuda")
+    eng.goal_dist(out=dist)
+    ref_dist = orc.goal_dist()
+    head = np.zeros((E, N), np.int64)
+    for t in range(8):
+        a = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        out = eng.step_observe(torch.as_tensor(a, device="cuda"), want=("dones", "status", "avail", "terminated"))
+        ref = orc.primal_sweep(a)
+        assert np.array_equal(_np(out["status"]), ref["status"]) and np.array_equal(_np(out["dones"]), ref["dones"])
+        dirty = _np(life.reassign(out["dones"]))
+        ref_dirty = ((ref["dones"] != 0) & (head < Q)).astype(np.uint8)
+        assert np.array_equal(dirty, ref_dirty)
+        new_goals = np.take_along_axis(queue, np.minimum(head, Q - 1)[..., None, None].repeat(2, -1), 2)[:, :, 0, :]
+        head += ref_dirty
+        orc.set_goals(new_goals, ref_dirty)
+        orc.goal_dist(dirty=ref_dirty, out=ref_dist)
+        eng.goal_dist(dirty=dirty, out=dist)
+        assert np.array_equal(_np(dist), ref_dist), t
+        obs, vec = eng.observe()
+        robs, rvec = orc.primal_observe()
+        assert np.array_equal(_np(obs), robs) and np.array_equal(_bits(_np(vec)), _bits(rvec)), t
+    assert int(head.sum()) > E * N // 4          # several hundred reassignments happened
