@@ -274,6 +274,16 @@ def main():
     ms_e2e = timed(e2e_step, args.e2e_steps, 3)
     e2e_value = world * E * N * args.e2e_steps / (ms_e2e * 1e-3)
 
+    # ---- the same host entry point when the policy lives on the GPU (pymarl's controller does): actions come from
+    #      the host, reward / terminated go back, the observation stays in device memory for the agent network
+    io2, bufs2, h2d2, d2h2 = eng.make_host_io(obs_dtype=odt, want=("reward", "terminated"))
+
+    def e2e_dev_obs(t):
+        bufs2["actions"].copy_(host_pool[t % 4])
+        eng.step_observe_host(io2)
+        eng.observe(dtype=odt)
+    ms_e2e2 = timed(e2e_dev_obs, max(args.e2e_steps * 10, 50), 3) / max(args.e2e_steps * 10, 50)
+
     # ---- statistics: the only collective of the path (one all-reduce of 8 int64 over NCCL)
     stats = eng.stats()
     svec = torch.tensor([stats[k] for k in sorted(stats)], device=dev, dtype=torch.int64)
@@ -300,6 +310,10 @@ def main():
             "config": workload_config(args.workload, wl, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.e2e_steps, "steps": args.e2e_steps},
+            "e2e_obs_on_device": {"value": world * E * N / (ms_e2e2 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e2,
+                                  "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2,
+                                  "note": "informational: host actions in, reward/terminated out, observation left "
+                                          "in HBM for a GPU-resident policy (two launches: step, observe)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
