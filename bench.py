@@ -276,12 +276,19 @@ def main():
 
     # ---- the same host entry point when the policy lives on the GPU (pymarl's controller does): actions come from
     #      the host, reward / terminated go back, the observation stays in device memory for the agent network
-    io2, bufs2, h2d2, d2h2 = eng.make_host_io(obs_dtype=odt, want=("reward", "terminated"))
+    acts_dev = torch.empty((E, N), dtype=torch.uint8, device=dev)
+    pin_act = torch.empty((E, N), dtype=torch.uint8).pin_memory()
+    pin_rew = torch.empty((E,), dtype=torch.float64).pin_memory()
+    pin_term = torch.empty((E,), dtype=torch.uint8).pin_memory()
+    h2d2, d2h2 = E * N, E * 9
 
     def e2e_dev_obs(t):
-        bufs2["actions"].copy_(host_pool[t % 4])
-        eng.step_observe_host(io2)
-        eng.observe(dtype=odt)
+        pin_act.copy_(host_pool[t % 4])
+        acts_dev.copy_(pin_act, non_blocking=True)
+        out = eng.step_observe(acts_dev, want=want, dtype=odt)       # one fused launch, observation stays in HBM
+        pin_rew.copy_(out["reward"], non_blocking=True)
+        pin_term.copy_(out["terminated"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
     ms_e2e2 = timed(e2e_dev_obs, max(args.e2e_steps * 10, 50), 3) / max(args.e2e_steps * 10, 50)
 
     # ---- statistics: the only collective of the path (one all-reduce of 8 int64 over NCCL)
@@ -313,7 +320,7 @@ def main():
             "e2e_obs_on_device": {"value": world * E * N / (ms_e2e2 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e2,
                                   "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2,
                                   "note": "informational: host actions in, reward/terminated out, observation left "
-                                          "in HBM for a GPU-resident policy (two launches: step, observe)"},
+                                          "in HBM for a GPU-resident policy (one fused launch per step)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
