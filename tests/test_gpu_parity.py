@@ -717,3 +717,60 @@ def test_c4_shape_lifelong_goal_reassignment_matches_oracle():
         robs, rvec = orc.primal_observe()
         assert np.array_equal(_np(obs), robs) and np.array_equal(_bits(_np(vec)), _bits(rvec)), t
     assert int(head.sum()) > E * N // 4          # several hundred reassignments happened
+
+
+def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path):
+    """The pymarl rollout loop over a device-resident vector env: what lands in the batch equals a rollout of the
+    CPU oracle driven by the same actions (PARTIAL env, the one the reference registers)."""
+    from mapf_marl_b200.batched_runner import BatchedRunner
+    from mapf_marl_b200.marl_partial import MARL_PARTIAL_ENV
+    from oracle.oracle import MODE_PARTIAL
+    g = load_golden("partial_empty8_crowd")
+    mp, sp = _write_movingai(tmp_path, g["obst"])
+    B, N, limit = 24, 6, 12
+    kw = dict(obs_window=5, obs_knn_agents=4, move_reward=-0.01, stay_reward=-0.02, stay_goal_reward=0,
+              node_collide_reward=-1, edge_collide_reward=-1, env_collide_reward=-1, complete_reward=1000,
+              complete_fac=1.5, gamma=0.99)
+    env = MARL_PARTIAL_ENV(mp, sp, n_agents=N, episode_limit=limit, render="none", n_envs=B, **kw)
+
+    class RandomMAC:
+        def __init__(self):
+            self.gen = torch.Generator(device="cuda").manual_seed(5)
+            self.log = []
+
+        def init_hidden(self, batch_size):
+            self.batch_size = batch_size
+
+        def select_actions(self, batch, t_ep, t_env, bs, test_mode=False):
+            avail = batch["avail_actions"][bs, t_ep]                      # [len(bs), N, 5]
+            probs = avail.float() + 1e-9
+            a = torch.multinomial(probs.reshape(-1, 5), 1, generator=self.gen).reshape(len(bs), -1)
+            self.log.append((list(bs), a.cpu().numpy()))
+            return a
+
+    mac = RandomMAC()
+    runner = BatchedRunner(env, mac)
+    batch = runner.run(test_mode=False)
+    H, W = g["obst"].shape
+    orc = _oracle(B, N, H, W, MODE_PARTIAL, episode_limit=limit)
+    orc.partial_config(**kw)
+    orc.reset(np.repeat(g["obst"][None], B, 0), env._starts, env._goals)
+    obs0 = orc.partial_observe()
+    assert np.array_equal(_np(batch["obs"][:, 0]), obs0.astype(np.float32))
+    assert (_np(batch["filled"][:, 0]) == 1).all()
+    alive = np.ones(B, bool)
+    for t, (bs, a) in enumerate(mac.log):
+        assert bs == np.nonzero(alive)[0].tolist()
+        full = np.full((B, N), 4, np.uint8)
+        full[bs] = a
+        ref = orc.partial_step(full)
+        robs = orc.partial_observe()
+        assert np.array_equal(_np(batch["actions"][bs, t, :, 0]), a)
+        assert np.array_equal(_np(batch["reward"][bs, t, 0]), ref["reward"][bs].astype(np.float32))
+        assert np.array_equal(_np(batch["obs"][bs, t + 1]), robs[bs].astype(np.float32))
+        assert np.array_equal(_np(batch["avail_actions"][bs, t + 1]), ref["avail"][bs].astype(np.int32))
+        assert np.array_equal(_np(batch["state"][bs, t + 1]), orc.partial_state()[bs].astype(np.float32))
+        assert np.array_equal(_np(batch["terminated"][bs, t, 0]), ref["terminated"][bs])
+        alive &= ~ref["terminated"].astype(bool)
+    assert runner.t_env == sum(len(bs) for bs, _ in mac.log)
+    assert runner.train_stats["n_episodes"] == B and len(runner.train_returns) == B
