@@ -127,3 +127,44 @@ def warehouse_layout(height=64, width=64, lane_every=8):
     obst[0, :] = obst[-1, :] = 0
     obst[:, 0] = obst[:, -1] = 0
     return obst
+
+
+# --------------------------------------------------------------------------- highway_layout_v19.py outputs
+HIGHWAY_ALPHABET = "@.`LnsewIX"
+
+
+def parse_highway_rows(rows):
+    """Rows written by highway_layout_v19.py (get_output_hw_label :1158-1180 / get_output_global_label :1183-1205):
+    '@' obstacle (in highways.txt town cells are '@' too), '.' or '`' free town cell, 'L' lock, 'n' 's' 'e' 'w'
+    one-way highway cell, 'I' intersection, 'X' highway end.  Rows are top row first (the script writes y from
+    nrows-1 down to 0, :1454-1465).  Returns dict(obst u8[H,W], lane i8[H,W] (0 none, 1 n, 2 s, 3 e, 4 w),
+    lock u8[H,W], junction u8[H,W]); only `obst` matters to the step/observation path."""
+    import numpy as np
+    H, W = len(rows), len(rows[0])
+    obst = np.zeros((H, W), np.uint8)
+    lane = np.zeros((H, W), np.int8)
+    lock = np.zeros((H, W), np.uint8)
+    junction = np.zeros((H, W), np.uint8)
+    code = {"n": 1, "s": 2, "e": 3, "w": 4}
+    for r, row in enumerate(rows):
+        assert len(row) == W, "ragged highway map"
+        for c, ch in enumerate(row):
+            if ch not in HIGHWAY_ALPHABET:
+                raise ValueError("unknown highway map symbol %r at (%d, %d)" % (ch, r, c))
+            obst[r, c] = ch == "@"
+            lane[r, c] = code.get(ch, 0)
+            lock[r, c] = ch == "L"
+            junction[r, c] = ch in "IX"
+    return dict(obst=obst, lane=lane, lock=lock, junction=junction)
+
+
+def read_highway_map(path):
+    """highways.txt as written by highway_layout_v19.py to_file (:1536-1546): three header lines
+    (`height (n_rows): H`, `width (n_cols): W`, `Highway Map:`) then H rows."""
+    with open(path, "r") as f:
+        lines = [ln.rstrip("\n") for ln in f.readlines()]
+    h = int(lines[0].split(":")[1])
+    w = int(lines[1].split(":")[1])
+    rows = [ln for ln in lines[3:3 + h]]
+    assert len(rows) == h and all(len(r) == w for r in rows)
+    return parse_highway_rows(rows)

@@ -136,3 +136,17 @@ def test_magnitude_lut_uses_the_reference_expression():
     assert len(lut) == 2 * 31 * 31 + 1
     for dx, dy in ((0, 0), (3, 4), (-7, 19), (31, -31), (1, 2)):
         assert lut[dx * dx + dy * dy] == (dx ** 2 + dy ** 2) ** .5
+
+
+def test_highway_layout_alphabet(tmp_path):
+    from mapf_marl_b200 import maps
+    p = tmp_path / "highways.txt"
+    p.write_text("height (n_rows): 3\nwidth (n_cols): 5\nHighway Map:\n@eeI@\n@n.s@\nXwwL`\n")
+    m = maps.read_highway_map(str(p))
+    assert m["obst"].tolist() == [[1, 0, 0, 0, 1], [1, 0, 0, 0, 1], [0, 0, 0, 0, 0]]
+    assert m["lane"].tolist() == [[0, 3, 3, 0, 0], [0, 1, 0, 2, 0], [0, 4, 4, 0, 0]]
+    assert m["lock"][2, 3] == 1 and m["junction"][0, 3] == 1 and m["junction"][2, 0] == 1
+    with pytest.raises(ValueError):
+        maps.parse_highway_rows(["@?"])
+    w = maps.warehouse_layout(64, 64)
+    assert w.shape == (64, 64) and w[0].sum() == 0 and 0.3 < w.mean() < 0.8
