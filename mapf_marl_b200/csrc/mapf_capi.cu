@@ -354,7 +354,7 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
     if (e == cudaSuccess) e = cudaMemset(h->S.terminated, 0, (size_t)d.E);
   }
   if (e == cudaSuccess && h->L.total_bytes > 48 * 1024)
-    e = (cudaError_t)mapf_configure_tile(h->fov_fast ? d.F : 0, h->L.total_bytes);
+    e = (cudaError_t)mapf_configure_tile(h->fov_fast ? d.F : 0, d.mode, h->L.total_bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     int rc = cuda_fail(nullptr, e, "mapf_create: initialisation");

@@ -115,7 +115,7 @@ int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, double* obs, 
 int mapf_launch_partial_state(const MapfDims& d, const MapfState& S, long long* state, void* stream);
 int mapf_launch_export16(const MapfDims& d, const uint8_t* src_u8x2, int16_t* dst, void* stream);
 int mapf_tile_has_fov(int F);
-int mapf_configure_tile(int F, int smem_bytes);
+int mapf_configure_tile(int F, int mode, int smem_bytes);
 #ifdef __cplusplus
 }
 #endif

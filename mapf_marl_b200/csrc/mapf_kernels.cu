@@ -545,7 +545,7 @@ __device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, const uin
 // ------------------------------------------------------------------------------------------------
 // The tile kernel: stage -> [step] -> state write-back + small outputs -> [observation].
 // ------------------------------------------------------------------------------------------------
-template <int F>
+template <int F, int MODE>
 __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, const MapfTileLayout L,
                                                              const MapfState S, const MapfTileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -559,8 +559,8 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   const int ne = min(d.epb, d.E - e0);
   const int na = ne * N;
   const size_t a0 = (size_t)e0 * N;
-  const bool primal = d.mode == MAPF_MODE_PRIMAL;
-  const bool partial = d.mode == MAPF_MODE_PARTIAL;
+  constexpr bool primal = MODE == MAPF_MODE_PRIMAL;     // the mode is a template parameter: the other modes' code is
+  constexpr bool partial = MODE == MAPF_MODE_PARTIAL;   // not even in this kernel's instruction stream
   int* envcnt2 = (int*)(smem_raw + L.envcnt2_off);
   const bool do_step = A.do_step != 0;
   const bool need_mid = primal && do_step && ((A.out.done_mid_dev != nullptr) || (A.out.next_mid_dev != nullptr));
@@ -1335,11 +1335,11 @@ __global__ void mapf_partial_state_kernel(const MapfDims d, const MapfState S, l
   }
 }
 
-template <int F>
+template <int F, int MODE>
 cudaError_t launch_tile_f(const MapfDims& d, const MapfTileLayout& L, const MapfState& S, const MapfTileArgs& A,
                           cudaStream_t st) {
   const int grid = (d.E + d.epb - 1) / d.epb;
-  mapf_tile_kernel<F><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
+  mapf_tile_kernel<F, MODE><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
   return cudaGetLastError();
 }
 
@@ -1352,18 +1352,14 @@ int grid_for(long long total, int block) {
 
 }  // namespace
 
-#define MAPF_FOR_EACH_F(X) X(0) X(3) X(5) X(7) X(9) X(10) X(11)
-
-#ifdef MAPF_PHASE_TIMING
-extern "C" int mapf_debug_phase_clocks(long long* out32) {
-  return (int)cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(long long) * 32);
-}
-#endif
+// Specialised tile kernels: PRIMAL with a field of view F (and F = 0: step only, the observation of an unlisted F
+// comes from the generic kernel), GRID and PARTIAL without a window.
+#define MAPF_FOR_EACH_FOV(X) X(3) X(5) X(7) X(9) X(10) X(11)
 
 extern "C" int mapf_tile_has_fov(int F) {
   switch (F) {
 #define X(f) case f:
-    MAPF_FOR_EACH_F(X)
+    MAPF_FOR_EACH_FOV(X)
 #undef X
     return 1;
     default:
@@ -1371,17 +1367,19 @@ extern "C" int mapf_tile_has_fov(int F) {
   }
 }
 
-extern "C" int mapf_configure_tile(int F, int smem_bytes) {
+extern "C" int mapf_configure_tile(int F, int mode, int smem_bytes) {
   cudaError_t err = cudaErrorInvalidValue;
-  switch (F) {
-#define X(f)                                                                                                  \
-  case f:                                                                                                     \
-    err = cudaFuncSetAttribute(mapf_tile_kernel<f>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
-    break;
-    MAPF_FOR_EACH_F(X)
+  const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  if (mode == MAPF_MODE_GRID) err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_GRID>, attr, smem_bytes);
+  else if (mode == MAPF_MODE_PARTIAL) err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_PARTIAL>, attr, smem_bytes);
+  else {
+    switch (F) {
+      case 0: err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_PRIMAL>, attr, smem_bytes); break;
+#define X(f) case f: err = cudaFuncSetAttribute(mapf_tile_kernel<f, MAPF_MODE_PRIMAL>, attr, smem_bytes); break;
+      MAPF_FOR_EACH_FOV(X)
 #undef X
-    default:
-      break;
+      default: break;
+    }
   }
   return (int)err;
 }
@@ -1389,12 +1387,13 @@ extern "C" int mapf_configure_tile(int F, int smem_bytes) {
 extern "C" int mapf_launch_tile(const MapfDims& d, const MapfTileLayout& L, const MapfState& S, const MapfTileArgs& A,
                                 void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (d.mode == MAPF_MODE_GRID) return (int)launch_tile_f<0, MAPF_MODE_GRID>(d, L, S, A, st);
+  if (d.mode == MAPF_MODE_PARTIAL) return (int)launch_tile_f<0, MAPF_MODE_PARTIAL>(d, L, S, A, st);
   const int F = (d.obs_mode == MAPF_OBS_PRIMAL_FOV) ? d.F : 0;
   switch (F) {
-#define X(f) \
-  case f:    \
-    return (int)launch_tile_f<f>(d, L, S, A, st);
-    MAPF_FOR_EACH_F(X)
+    case 0: return (int)launch_tile_f<0, MAPF_MODE_PRIMAL>(d, L, S, A, st);
+#define X(f) case f: return (int)launch_tile_f<f, MAPF_MODE_PRIMAL>(d, L, S, A, st);
+    MAPF_FOR_EACH_FOV(X)
 #undef X
     default:
       return (int)cudaErrorInvalidValue;
