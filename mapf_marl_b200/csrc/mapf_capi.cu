@@ -65,14 +65,18 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L, bool s
     off = align_up(off + bytes, 16);
     return o;
   };
+  // ---- alive for the whole kernel: maps, occupancy, positions, goals
   L->obst_off = take((d.shared_map ? 1 : epb) * d.bm_words * 4);
   L->agt_off = take(fov ? epb * d.bm_words * 4 : 16);
   L->grida_off = take(epb * d.grid_bytes);
   // PRIMAL needs the second grid only for the mid-sweep outputs (a copy of the pre-sweep ids)
   L->gridb_off = second_grid ? take(epb * d.grid_bytes) : L->grida_off;
-  L->posold_off = take(2 * na);
   L->posnew_off = take(2 * na);
   L->goal_off = take(2 * na);
+  // ---- step-phase scratch; dead once the state has been written back, so the observation's bit strings reuse
+  //      the same bytes (the kernel puts a barrier between the two uses)
+  const int scratch0 = off;
+  L->posold_off = take(2 * na);
   L->mv_off = take(4 * na);
   L->res_off = take(na);
   L->dep_off = take(na);
@@ -85,14 +89,17 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L, bool s
   L->node_off = take(na);
   L->edge_off = take(na);
   L->isint_off = take(na);
+  L->atgoal_off = take(na);
   L->rew_off = take(8 * na);
   L->envrew_off = take(8 * epb);
   L->envterm_off = take(epb);
   L->envcnt_off = take(4 * epb);
   L->envcnt2_off = take(4 * epb);
   L->envstep_off = take(4 * epb);
-  L->atgoal_off = take(na);
-  L->str_off = take(fov ? ((na + d.G - 1) / d.G) * d.GW * 4 + 16 : 16);
+  const int scratch1 = off;
+  const int str_bytes = fov ? ((na + d.G - 1) / d.G) * d.GW * 4 + 16 : 16;
+  L->str_off = scratch0;
+  off = align_up(scratch0 + (str_bytes > scratch1 - scratch0 ? str_bytes : scratch1 - scratch0), 16);
   L->total_bytes = off;
 }
 

@@ -835,6 +835,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   if constexpr (F > 0) {
     using T = Fov<F>;
     PHASE_MARK(7);
+    __syncthreads();   // the bit strings reuse the step-phase scratch: everybody has finished the write-back
     // phase 1: one thread per agent builds its 4*F*F bits and the goal vector; G agents share a
     // word-aligned group string.
     for (int base = 0; base < na; base += kThreads) {
