@@ -1463,11 +1463,9 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
     while (warps > 1 && bm_bytes * warps > 200 * 1024) warps >>= 1;
   }
   const size_t smem = (bm_bytes + (stage ? dist_bytes : 0)) * warps;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {   // per device and cheap: set it on every launch that needs it
     cudaError_t e = cudaFuncSetAttribute(mapf_bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
   }
   const long long maps = (long long)d.E * d.N;
   const long long grid = (maps + warps - 1) / warps;
