@@ -120,7 +120,18 @@ static int choose_epb(MapfDims& d, MapfTileLayout* L) {
   for (;;) {
     compute_layout(d, epb, L);
     if (L->total_bytes <= kMaxSmem) break;
-    if (epb <= mult) return -1;
+    if (epb <= mult) {
+      // large maps with an agent count that is not a multiple of the group size: give up the 16-byte alignment of
+      // the tile's observation block (the kernel has a path for it) rather than refuse the configuration
+      epb = mult - 1;
+      while (epb >= 1) {
+        compute_layout(d, epb, L);
+        if (L->total_bytes <= kMaxSmem) break;
+        --epb;
+      }
+      if (epb < 1) return -1;
+      break;
+    }
     epb -= mult;
   }
   d.epb = epb;

@@ -905,19 +905,40 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     const size_t nbits = (size_t)na * T::NB;
     if (A.obs_dtype == MAPF_U8) {
       uint8_t* out = (uint8_t*)A.obs + a0 * T::NB;
-      const int nchunk = (int)(nbits >> 4);
-      const uint16_t* s16 = (const uint16_t*)s.str;
+      const int lead = (int)((16 - ((uintptr_t)out & 15)) & 15);   // 0 unless the tile holds an odd number of groups
+      if (lead == 0) {
+        const int nchunk = (int)(nbits >> 4);
+        const uint16_t* s16 = (const uint16_t*)s.str;
 #pragma unroll 2
-      for (int q = tid; q < nchunk; q += kThreads) {
-        const uint32_t h = s16[q];
-        uint4 v;
-        v.x = expand4(h & 15u);
-        v.y = expand4((h >> 4) & 15u);
-        v.z = expand4((h >> 8) & 15u);
-        v.w = expand4(h >> 12);
-        st_stream16(out + ((size_t)q << 4), v);
+        for (int q = tid; q < nchunk; q += kThreads) {
+          const uint32_t h = s16[q];
+          uint4 v;
+          v.x = expand4(h & 15u);
+          v.y = expand4((h >> 4) & 15u);
+          v.z = expand4((h >> 8) & 15u);
+          v.w = expand4(h >> 12);
+          st_stream16(out + ((size_t)q << 4), v);
+        }
+        for (int b = (nchunk << 4) + tid; b < (int)nbits; b += kThreads) out[b] = (s.str[b >> 5] >> (b & 31)) & 1u;
+      } else {
+        // tile start not 16-byte aligned (environments-per-tile had to drop below the aligned multiple to fit shared
+        // memory): bytes up to the first boundary one by one, then aligned chunks taken at a 4-bit-aligned string offset
+        const int first = min(lead, (int)nbits);
+        for (int b = tid; b < first; b += kThreads) out[b] = (s.str[b >> 5] >> (b & 31)) & 1u;
+        const int nchunk = ((int)nbits - first) >> 4;
+        for (int q = tid; q < nchunk; q += kThreads) {
+          const int bit = first + (q << 4);
+          const uint32_t h = __funnelshift_r(s.str[bit >> 5], s.str[(bit >> 5) + 1], bit) & 0xffffu;
+          uint4 v;
+          v.x = expand4(h & 15u);
+          v.y = expand4((h >> 4) & 15u);
+          v.z = expand4((h >> 8) & 15u);
+          v.w = expand4(h >> 12);
+          st_stream16(out + first + ((size_t)q << 4), v);
+        }
+        for (int b = first + (nchunk << 4) + tid; b < (int)nbits; b += kThreads)
+          out[b] = (s.str[b >> 5] >> (b & 31)) & 1u;
       }
-      for (int b = (nchunk << 4) + tid; b < (int)nbits; b += kThreads) out[b] = (s.str[b >> 5] >> (b & 31)) & 1u;
     } else {
       float* out = (float*)A.obs + a0 * T::NB;
       const int nchunk = (int)(nbits >> 2);

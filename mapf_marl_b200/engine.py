@@ -152,7 +152,7 @@ class MapfEngine:
         if isinstance(x, torch.Tensor):
             t = x.to(device=self.device, dtype=dtype).contiguous()
         else:
-            t = torch.as_tensor(np.ascontiguousarray(x), device=self.device).to(dtype).contiguous()
+            t = torch.as_tensor(np.array(x, copy=True), device=self.device).to(dtype).contiguous()
         if shape is not None and tuple(t.shape) != tuple(shape):
             raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(t.shape)))
         return t

@@ -774,3 +774,33 @@ def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path
         alive &= ~ref["terminated"].astype(bool)
     assert runner.t_env == sum(len(bs) for bs, _ in mac.log)
     assert runner.train_stats["n_episodes"] == B and len(runner.train_returns) == B
+
+
+@pytest.mark.parametrize("case", [(3, 255, 40, 40, 11, 0.05), (3, 7, 200, 200, 11, 0.2), (2, 5, 255, 255, 9, 0.1),
+                                  (5, 3, 150, 90, 7, 0.3)], ids=lambda c: "E%d_N%d_%dx%d" % c[:4])
+def test_extreme_sizes_match_oracle(case):
+    """The limits of the ABI (255 agents, 255 x 255 maps) and maps so large that a tile cannot hold the aligned
+    number of environments (the kernel's unaligned observation path)."""
+    from mapf_marl_b200 import maps
+    from oracle.oracle import MODE_PRIMAL
+    E, N, H, W, F, dens = case
+    obst, starts, goals = maps.synthetic_batch(900 + N, E, H, W, dens, N, distinct=0)
+    eng = _engine(E, N, H, W, mode="primal", fov=F)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    rs = np.random.RandomState(N)
+    for t in range(5):
+        a = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        out = eng.step_observe(torch.as_tensor(a, device="cuda"), want=PRIMAL_WANT)
+        ref = orc.primal_sweep(a)
+        robs, rvec = orc.primal_observe()
+        for k in ("status", "dones", "valid", "done_mid", "next_mid", "avail", "terminated"):
+            assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        assert np.array_equal(_np(eng.positions()), orc.positions()), t
+        assert np.array_equal(_np(out["obs"]), robs), t
+        assert np.array_equal(_bits(_np(out["vec"])), _bits(rvec)), t
+        f32, _ = eng.observe(dtype=torch.float32)
+        assert np.array_equal(_np(f32), robs.astype(np.float32)), t
+    assert np.array_equal(_np(eng.goal_dist()), orc.goal_dist())
+    assert eng.error_flags() == 0
