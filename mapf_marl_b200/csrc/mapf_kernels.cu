@@ -1374,6 +1374,14 @@ int grid_for(long long total, int block) {
 
 }  // namespace
 
+#ifdef MAPF_PHASE_TIMING
+// debug builds only (-DMAPF_PHASE_TIMING): clock64() at the phase boundaries of the middle block, see
+// profiles/phase_probe.py
+extern "C" int mapf_debug_phase_clocks(long long* out32) {
+  return (int)cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(long long) * 32);
+}
+#endif
+
 // Specialised tile kernels: PRIMAL with a field of view F (and F = 0: step only, the observation of an unlisted F
 // comes from the generic kernel), GRID and PARTIAL without a window.
 #define MAPF_FOR_EACH_FOV(X) X(3) X(5) X(7) X(9) X(10) X(11)
