@@ -1224,6 +1224,88 @@ __global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-synchronous BFS for maps up to 64 x 64: the whole map lives in registers, lane l holds rows
+// [l*RPL, (l+1)*RPL) as W-bit masks (Row = uint32_t or uint64_t).  One wavefront step is two shuffles (the rows
+// above and below) and a handful of logic ops per row; no shared-memory traffic except the int16 distance map
+// that is staged for the final coalesced store.
+// ------------------------------------------------------------------------------------------------
+template <typename Row, int RPL>
+__global__ void mapf_bfs_warp_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty,
+                                     const uint8_t* env_mask, int16_t* dist, int warps_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long m = (long long)blockIdx.x * warps_per_block + warp;
+  if (m >= (long long)d.E * d.N) return;
+  if (dirty && !dirty[m]) return;
+  const int e = (int)(m / d.N);
+  if (env_mask && !env_mask[e]) return;
+  const int H = d.H, W = d.W;
+  constexpr int RB = sizeof(Row) * 8;
+  int16_t* sd = (int16_t*)(smem_raw + (size_t)warp * (((size_t)d.HW * 2 + 15) & ~(size_t)15));
+  int16_t* gd = dist + (size_t)m * d.HW;
+  const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
+  const uchar2 g = ((const uchar2*)S.goal)[m];
+  const Row valid = (W >= RB) ? ~(Row)0 : (((Row)1 << W) - 1);
+  Row freeR[RPL], vis[RPL], f[RPL];
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) {
+    const int r = lane * RPL + k;
+    Row fr = 0;
+    if (r < H) {
+      const uint32_t* prow = ob + (r + d.P) * d.RW + (d.P >> 5);
+      Row wall = __funnelshift_r(prow[0], prow[1], d.P);
+      if (RB == 64) wall |= (Row)__funnelshift_r(prow[1], prow[2], d.P) << (RB / 2);
+      fr = ~wall & valid;
+    }
+    freeR[k] = fr;
+    const Row start = (r == g.x) ? (((Row)1 << g.y) & fr) : 0;
+    vis[k] = start;
+    f[k] = start;
+  }
+  // distance map staging: walls -1, free -2, goal 0; lanes walk the cells linearly (conflict-free stores), the row's
+  // free mask comes from the lane that owns the row
+  for (int r = 0; r < H; ++r) {
+    const Row fr = __shfl_sync(0xffffffffu, freeR[RPL == 1 ? 0 : (r % RPL)], r / RPL);
+    for (int c = lane; c < W; c += 32) sd[r * W + c] = ((fr >> c) & 1) ? -2 : -1;
+  }
+  __syncwarp();
+  if (lane == 0 && (int)g.x < H && (int)g.y < W && sd[(int)g.x * W + g.y] == -2) sd[(int)g.x * W + g.y] = 0;
+  __syncwarp();
+  for (int level = 1; level < 32767; ++level) {
+    const Row from_above = __shfl_up_sync(0xffffffffu, f[RPL - 1], 1);     // last row of the lane above
+    const Row from_below = __shfl_down_sync(0xffffffffu, f[0], 1);         // first row of the lane below
+    Row nw[RPL];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      const Row up = (k > 0) ? f[k - 1] : (lane > 0 ? from_above : 0);
+      const Row dn = (k < RPL - 1) ? f[k + 1] : (lane < 31 ? from_below : 0);
+      nw[k] = ((f[k] << 1) | (f[k] >> 1) | up | dn) & freeR[k] & ~vis[k];
+      any |= nw[k] != 0;
+    }
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      vis[k] |= nw[k];
+      f[k] = nw[k];
+      Row x = nw[k];
+      const int r = lane * RPL + k;
+      while (x) {
+        const int b = (RB == 64) ? (__ffsll((long long)x) - 1) : (__ffs((int)x) - 1);
+        x &= x - 1;
+        sd[r * W + b] = (int16_t)level;
+      }
+    }
+    if (!__any_sync(0xffffffffu, any)) break;
+  }
+  __syncwarp();
+  if ((d.HW & 7) == 0) {
+    for (int i = lane; i < (d.HW >> 3); i += 32) ((uint4*)gd)[i] = ((const uint4*)sd)[i];
+  } else {
+    for (int i = lane; i < d.HW; i += 32) gd[i] = sd[i];
+  }
+}
+
 // getAstarCosts quirk (PRIMAL:496-498): `costs = state.copy()`, so cells the search never reached keep
 // `state`: 0 when free, the agent id when an agent stands there.
 __global__ void mapf_primal_costs_agents_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty,
@@ -1497,8 +1579,30 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
     if (e != cudaSuccess) return (int)e;
   }
   const long long maps = (long long)d.E * d.N;
-  const long long grid = (maps + warps - 1) / warps;
-  mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, dirty, env_mask, dist, RWB, warps, stage);
+  if (d.W <= 64 && d.H <= 64) {
+    // register-resident warp-synchronous kernel; shared memory only stages the int16 map for the coalesced store
+    const int w2 = 8;
+    const size_t sm2 = dist_bytes * w2;
+    const long long g2 = (maps + w2 - 1) / w2;
+    const bool wide = d.W > 32, tall = d.H > 32;
+#define BFS_LAUNCH(ROW, RPL)                                                                                       \
+  do {                                                                                                             \
+    if (sm2 > 48 * 1024) {                                                                                         \
+      cudaError_t e_ = cudaFuncSetAttribute(mapf_bfs_warp_kernel<ROW, RPL>,                                        \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);                \
+      if (e_ != cudaSuccess) return (int)e_;                                                                       \
+    }                                                                                                              \
+    mapf_bfs_warp_kernel<ROW, RPL><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, dirty, env_mask, dist, w2);           \
+  } while (0)
+    if (!wide && !tall) BFS_LAUNCH(uint32_t, 1);
+    else if (!wide && tall) BFS_LAUNCH(uint32_t, 2);
+    else if (wide && !tall) BFS_LAUNCH(unsigned long long, 1);
+    else BFS_LAUNCH(unsigned long long, 2);
+#undef BFS_LAUNCH
+  } else {
+    const long long grid = (maps + warps - 1) / warps;
+    mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, dirty, env_mask, dist, RWB, warps, stage);
+  }
   cudaError_t err = cudaGetLastError();
   *n_launches = 1;
   if (err == cudaSuccess && primal_costs) {
