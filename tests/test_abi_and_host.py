@@ -150,3 +150,19 @@ def test_highway_layout_alphabet(tmp_path):
         maps.parse_highway_rows(["@?"])
     w = maps.warehouse_layout(64, 64)
     assert w.shape == (64, 64) and w[0].sum() == 0 and 0.3 < w.mean() < 0.8
+
+
+def test_multiagentenv_contract_is_enforced():
+    from mapf_marl_b200.multiagentenv import CONTRACT, MultiAgentEnv
+    from mapf_marl_b200.mapf_gridworld import MAPF_GRID
+    from mapf_marl_b200.marl_partial import MARL_PARTIAL_ENV
+    for cls in (MAPF_GRID, MARL_PARTIAL_ENV):
+        assert issubclass(cls, MultiAgentEnv)
+        for name in CONTRACT:
+            assert getattr(cls, name) is not getattr(MultiAgentEnv, name)
+    with pytest.raises(TypeError):
+        class Broken(MultiAgentEnv):          # forgets most of the contract
+            def reset(self):
+                return None
+    with pytest.raises(NotImplementedError):
+        MultiAgentEnv().step(None)
