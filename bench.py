@@ -10,6 +10,7 @@ launch).  Workloads (BASELINE.json configs):
     c3  32x32 map, density 0.3, 32 agents, FOV 11, 16384 envs per GPU   <- default: the config the
         north-star target (>= 1e9 agent-steps/s on 8 GPUs, obs kernel >= 50 % of HBM roofline) is quoted on
     c4  64x64 warehouse layout (one shared map), 128 agents, FOV 11, 8192 envs per GPU
+    c5  the c3 shape with 1 048 576 envs in TOTAL, split evenly over the GPUs (strong scaling)
 Multi-GPU: environments shard by index, `--gpus N` ranks under torchrun each own the same number of
 environments (weak scaling); there is no data-path collective, NCCL only reduces the statistics vector.
 
@@ -37,6 +38,8 @@ WORKLOADS = {
     "c2": dict(H=20, W=20, density=0.2, N=8, F=11, E=4096, warehouse=False, bytes_per_agent_step=578),
     "c3": dict(H=32, W=32, density=0.3, N=32, F=11, E=16384, warehouse=False, bytes_per_agent_step=559),
     "c4": dict(H=64, W=64, density=0.0, N=128, F=11, E=8192, warehouse=True, bytes_per_agent_step=526),
+    # c5: the 1M-env sweep of the c3 shape; E is the TOTAL, split evenly over the GPUs (strong scaling)
+    "c5": dict(H=32, W=32, density=0.3, N=32, F=11, E=1048576, warehouse=False, bytes_per_agent_step=559, total=True),
 }
 METRIC = "agent-steps/sec (step+obs)"
 UNIT = "agent-steps/s"
@@ -190,6 +193,9 @@ def main():
         wl["E"] = args.envs
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    strong = bool(wl.get("total"))
+    if strong:
+        wl["E"] = wl["E"] // max(world, 1)        # the same total work on any number of GPUs
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         from oracle import build_oracle
@@ -312,7 +318,8 @@ def main():
                 traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32 obs / u8 state" if args.f32 else "u8", "data": "synthetic",
             "config": workload_config(args.workload, wl, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
