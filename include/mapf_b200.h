@@ -141,7 +141,13 @@ typedef struct mapf_cfg {
    * `(complete_reward / (gamma ** (episode_limit - t))) * complete_fac` (PARTIAL:296), evaluated by the host. */
   const double* complete_lut_host;
   int32_t complete_lut_len;
-  int32_t reserved2;
+  /* MAPF_MODE_PRIMAL: 1 = add get_blocking_reward (PRIMAL:513-546) to the reward of an agent that stays on its goal:
+   * -1 (blocking_cost) for every visible robot (ids 1..N-1, the reference's loop skips the last id) whose
+   * single-robot shortest path to its goal is cut, or lengthened by more than 10, by this agent.  The reference
+   * gets those path lengths from the un-vendored od_mstar3 (optimal single-robot paths); here they are BFS hop
+   * counts.  Maps up to 64 x 64. */
+  int32_t blocking_reward;
+  double blocking_cost;      /* BLOCKING_COST, PRIMAL:25 (-1.0) */
 } mapf_cfg;
 
 /* Outputs of one step.  Every pointer is a device pointer and may be NULL (not written). */
@@ -171,6 +177,8 @@ typedef struct mapf_step_out {
   /* [E, N, 5] available-action mask after the step.  GRID: get_avail_actions (GRID:198-224).
    * PRIMAL: _listNextValidActions(i, action_i) evaluated after the whole sweep (PRIMAL:639-667). */
   uint8_t* avail_dev;
+  /* [E, N] PRIMAL `blocking` as returned by _step (PRIMAL:578-585, 637); needs cfg.blocking_reward. */
+  uint8_t* blocking_dev;
 } mapf_step_out;
 
 /* Host-buffer mirror of the outputs used by mapf_step_observe_host (pinned memory recommended). */

@@ -44,12 +44,13 @@ class MapfCfg(ctypes.Structure):
         ("move_reward", ctypes.c_double), ("stay_reward", ctypes.c_double), ("stay_goal_reward", ctypes.c_double),
         ("node_collide_reward", ctypes.c_double), ("edge_collide_reward", ctypes.c_double),
         ("env_collide_reward", ctypes.c_double),
-        ("complete_lut_host", _vp), ("complete_lut_len", ctypes.c_int32), ("reserved2", ctypes.c_int32),
+        ("complete_lut_host", _vp), ("complete_lut_len", ctypes.c_int32), ("blocking_reward", ctypes.c_int32),
+        ("blocking_cost", ctypes.c_double),
     ]
 
 
 STEP_OUT_FIELDS = ("reward", "terminated", "agent_reward", "dones", "status", "node", "edge", "valid",
-                   "done_mid", "next_mid", "avail")
+                   "done_mid", "next_mid", "avail", "blocking")
 
 
 class MapfStepOut(ctypes.Structure):

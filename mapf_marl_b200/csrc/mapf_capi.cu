@@ -167,6 +167,8 @@ void mapf_default_cfg(mapf_cfg* c) {
   c->reward_sum_mode = 0;
   c->step_reward_is_int = 0;
   c->collide_reward_is_int = 1;
+  c->blocking_reward = 0;
+  c->blocking_cost = -1.0;  /* PRIMAL:25 */
 }
 
 int mapf_destroy(mapf_handle* h) {
@@ -182,6 +184,9 @@ int mapf_destroy(mapf_handle* h) {
   cudaFree((void*)h->S.mag_lut);
   cudaFree(h->S.stats);
   cudaFree(h->S.err_flags);
+  cudaFree(h->S.pos_prev);
+  cudaFree(h->S.last_status);
+  cudaFree(h->S.last_reward);
   cudaFree(h->S.at_goal);
   cudaFree(h->S.goal_cost);
   cudaFree(h->S.agent_steps);
@@ -218,6 +223,12 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
     return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: unknown obs_mode %d", c->obs_mode);
   if (c->obs_mode == MAPF_OBS_PARTIAL_WINDOW && c->mode != MAPF_MODE_PARTIAL)
     return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_create: the PARTIAL window observation needs mode PARTIAL");
+  if (c->blocking_reward) {
+    if (c->mode != MAPF_MODE_PRIMAL || c->obs_mode != MAPF_OBS_PRIMAL_FOV)
+      return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_create: blocking_reward needs mode PRIMAL with the FOV observation");
+    if (c->height > 64 || c->width > 64)
+      return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_create: blocking_reward supports maps up to 64 x 64");
+  }
   if (c->mode == MAPF_MODE_PARTIAL) {
     if (c->obs_window < 1 || c->obs_window > 255 || c->obs_knn_agents < 1 || c->obs_knn_agents > 254)
       return fail(h, MAPF_ERR_INVALID_ARG, "mapf_create: obs_window %d / obs_knn_agents %d out of range",
@@ -268,6 +279,8 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   d.step_is_int = c->step_reward_is_int;
   d.collide_is_int = c->collide_reward_is_int;
   d.collect_stats = c->collect_stats;
+  d.blocking = c->blocking_reward ? 1 : 0;
+  d.blocking_cost = c->blocking_cost;
   d.pW = c->obs_window;
   d.pK = c->obs_knn_agents;
   d.posz = 2 * d.pW * d.pW + 13 * d.pK;
@@ -326,6 +339,11 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   ALLOC(h->S.prev_action, EN);
   ALLOC(h->S.step_count, (size_t)d.E * 4);
   if (c->goal_dist || c->mode == MAPF_MODE_PARTIAL) ALLOC(h->S.goal_dist, EN * d.HW * 2);
+  if (c->blocking_reward) {
+    ALLOC(h->S.pos_prev, EN * 2);
+    ALLOC(h->S.last_status, EN);
+    ALLOC(h->S.last_reward, EN * 8);
+  }
   if (c->mode == MAPF_MODE_PARTIAL) {
     ALLOC(h->S.at_goal, EN);
     ALLOC(h->S.goal_cost, EN * 4);
@@ -451,6 +469,11 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
     const bool need_mid = A.out.done_mid_dev || A.out.next_mid_dev;
     CK((cudaError_t)mapf_launch_tile(d, need_mid ? h->L : h->L_lite, h->S, A, stream));
     h->launches++;
+  }
+  if (A.do_step && h->d.blocking) {   // PRIMAL:579-585: stay-on-goal rewards get the blocking term
+    int n = 0;
+    CK((cudaError_t)mapf_launch_blocking(h->d, h->S, lo, hi, A.out, stream, &n));
+    h->launches += n;
   }
   if (pwin && obs) {
     CK((cudaError_t)mapf_launch_partial_obs(h->d, h->S, (double*)obs, stream));

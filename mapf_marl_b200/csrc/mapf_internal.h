@@ -29,6 +29,8 @@ struct MapfDims {
   int GW;        // words per group string = G * 4*F*F / 32
   int sum_mode, step_is_int, collide_is_int;
   int collect_stats;
+  int blocking;          // PRIMAL blocking reward enabled
+  double blocking_cost;
   uint32_t invN, invW;  // ceil(2^32 / N), ceil(2^32 / W): exact division of values < 65536 by IMAD.HI
   double step_reward, collide_reward;
   double action_cost, idle_cost, goal_reward, collision_reward;
@@ -71,6 +73,10 @@ struct MapfState {
   int16_t* goal_dist;      // [E][N][H][W] or NULL
   const double* mag_lut;   // [mag_lut_len]
   unsigned long long* stats;  // [MAPF_N_STATS]
+  // PRIMAL blocking reward (cfg.blocking_reward): what the follow-up kernel needs from the sweep
+  uint8_t* pos_prev;       // [E][N][2] positions before the last sweep
+  int8_t* last_status;     // [E][N]
+  double* last_reward;     // [E][N]
   // MAPF_MODE_PARTIAL
   uint8_t* at_goal;        // [E][N]
   int32_t* goal_cost;      // [E][N]
@@ -111,6 +117,8 @@ int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, const int16_t* 
                           void* stream);
 int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, const uint8_t* env_mask, int16_t* dist,
                     int primal_costs, void* stream, int* n_launches);
+int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int agent_lo, int agent_hi, const mapf_step_out& out,
+                         void* stream, int* n_launches);
 int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, double* obs, void* stream);
 int mapf_launch_partial_state(const MapfDims& d, const MapfState& S, long long* state, void* stream);
 int mapf_launch_export16(const MapfDims& d, const uint8_t* src_u8x2, int16_t* dst, void* stream);

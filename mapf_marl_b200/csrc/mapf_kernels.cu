@@ -794,6 +794,11 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       copy_out_bytes(S.pnode + a0, s.node, na, tid);
       copy_out_bytes(S.pedge + a0, s.edge, na, tid);
     }
+    if (primal && d.blocking) {   // inputs of the blocking-reward kernel that follows the sweep
+      copy_out_bytes(S.pos_prev + 2 * a0, (const uint8_t*)s.posold, 2 * na, tid);
+      copy_out_bytes((uint8_t*)S.last_status + a0, (const uint8_t*)s.status, na, tid);
+      for (int j = tid; j < na; j += kThreads) S.last_reward[a0 + j] = s.rew[j];
+    }
     copy_out_bytes(S.pos + 2 * a0, (const uint8_t*)s.posnew, 2 * na, tid);
     copy_out_bytes(S.done + a0, s.done, na, tid);
     copy_out_bytes(S.prev_action + a0, s.act, na, tid);
@@ -1306,6 +1311,155 @@ __global__ void mapf_bfs_warp_kernel(const MapfDims d, const MapfState S, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// PRIMAL blocking reward (get_blocking_reward, PRIMAL:513-546), evaluated after the sweep for every agent that
+// stayed on its goal (action 0, status 1; PRIMAL:579-585).  One warp per (env, agent).  The reference evaluates it in
+// the middle of the sweep, so positions are taken "at time i": agents below i stand on their new cells, agents above
+// i still on their old ones.  For every visible robot b (ids 1..N-1: the reference's loop skips the last id, :523)
+// two single-robot shortest paths from b to its goal are compared -- the other visible robots are obstacles, with and
+// without this agent (:535-539).  Paths are warp-synchronous BFS runs over register-resident bit rows (64 x 64 max).
+// ------------------------------------------------------------------------------------------------
+template <typename Row, int RPL>
+__device__ __forceinline__ int warp_path_hops(const Row (&freeR)[RPL], int s0, int s1, int g0, int g1, int lane) {
+  // -1: start or goal blocked, or the goal cannot be reached (NoSolutionError, PRIMAL:505-508)
+  Row f[RPL], vis[RPL];
+  bool ok_s = false, ok_g = false;
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) {
+    const int r = lane * RPL + k;
+    f[k] = (r == s0) ? (((Row)1 << s1) & freeR[k]) : 0;
+    vis[k] = f[k];
+    ok_s |= f[k] != 0;
+    ok_g |= (r == g0) && ((freeR[k] >> g1) & 1);
+  }
+  if (!__any_sync(0xffffffffu, ok_s) || !__any_sync(0xffffffffu, ok_g)) return -1;
+  if (s0 == g0 && s1 == g1) return 0;
+  for (int level = 1; level < 8192; ++level) {
+    const Row from_above = __shfl_up_sync(0xffffffffu, f[RPL - 1], 1);
+    const Row from_below = __shfl_down_sync(0xffffffffu, f[0], 1);
+    bool any = false, hit = false;
+    Row nw[RPL];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      const Row up = (k > 0) ? f[k - 1] : (lane > 0 ? from_above : 0);
+      const Row dn = (k < RPL - 1) ? f[k + 1] : (lane < 31 ? from_below : 0);
+      nw[k] = ((f[k] << 1) | (f[k] >> 1) | up | dn) & freeR[k] & ~vis[k];
+      any |= nw[k] != 0;
+      hit |= (lane * RPL + k == g0) && ((nw[k] >> g1) & 1);
+    }
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      vis[k] |= nw[k];
+      f[k] = nw[k];
+    }
+    if (__any_sync(0xffffffffu, hit)) return level;
+    if (!__any_sync(0xffffffffu, any)) return -1;
+  }
+  return -1;
+}
+
+template <typename Row, int RPL>
+__global__ void mapf_blocking_kernel(const MapfDims d, const MapfState S, int agent_lo, int agent_hi,
+                                     uint8_t* blocking_out, int warps_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long m = (long long)blockIdx.x * warps_per_block + warp;
+  if (m >= (long long)d.E * d.N) return;
+  const int e = (int)(m / d.N), i = (int)(m - (long long)e * d.N);
+  if (lane == 0 && blocking_out) blocking_out[m] = 0;
+  if (i < agent_lo || i >= agent_hi) return;
+  if (S.prev_action[m] != 0 || S.last_status[m] != 1) return;          // only "stayed on goal", PRIMAL:579-580
+  const int H = d.H, W = d.W, N = d.N, F = d.F;
+  constexpr int RB = sizeof(Row) * 8;
+  Row* rows = (Row*)(smem_raw + (size_t)warp * 64 * sizeof(Row));      // robots bit rows of this warp
+  const uchar2* pnew = (const uchar2*)S.pos + (size_t)e * N;
+  const uchar2* pold = (const uchar2*)S.pos_prev + (size_t)e * N;
+  const uchar2* goal = (const uchar2*)S.goal + (size_t)e * N;
+  const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
+  const uchar2 me = pnew[i];
+  const int tl0 = (int)me.x - F / 2, tl1 = (int)me.y - F / 2;
+  const Row valid = (W >= RB) ? ~(Row)0 : (((Row)1 << W) - 1);
+  Row freeW[RPL];
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) {
+    const int r = lane * RPL + k;
+    Row fr = 0;
+    if (r < H) {
+      const uint32_t* prow = ob + (r + d.P) * d.RW + (d.P >> 5);
+      Row wall = __funnelshift_r(prow[0], prow[1], d.P);
+      if (RB == 64) wall |= (Row)__funnelshift_r(prow[1], prow[2], d.P) << (RB / 2);
+      fr = ~wall & valid;
+    }
+    freeW[k] = fr;
+  }
+  for (int r = lane; r < 64; r += 32) rows[r] = 0;
+  __syncwarp();
+  // visible robots at time i (ids 1..N-1 => 0-based 0..N-2), PRIMAL:523-529
+  auto pos_at = [&](int b) { return b < i ? pnew[b] : pold[b]; };
+  for (int b0 = 0; b0 < N - 1; b0 += 32) {
+    const int b = b0 + lane;
+    if (b < N - 1 && b != i) {
+      const uchar2 p = pos_at(b);
+      if ((int)p.x >= tl0 && (int)p.x < tl0 + F && (int)p.y >= tl1 && (int)p.y < tl1 + F)
+        atomicOr((unsigned int*)&rows[p.x] + (sizeof(Row) == 8 ? (p.y >> 5) : 0), 1u << (p.y & 31));
+    }
+  }
+  __syncwarp();
+  Row robots[RPL];
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) robots[k] = (lane * RPL + k < 64) ? rows[lane * RPL + k] : 0;
+  int num_blocking = 0;
+  for (int b0 = 0; b0 < N - 1; b0 += 32) {
+    const int bl = b0 + lane;
+    bool vis = false;
+    if (bl < N - 1 && bl != i) {
+      const uchar2 p = pos_at(bl);
+      vis = (int)p.x >= tl0 && (int)p.x < tl0 + F && (int)p.y >= tl1 && (int)p.y < tl1 + F;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, vis);
+    while (todo) {
+      const int b = b0 + __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uchar2 pb = pos_at(b), gb = goal[b];
+      Row fa[RPL], fbef[RPL];
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) {
+        const int r = lane * RPL + k;
+        Row rb = robots[k];
+        if (r == pb.x) rb &= ~((Row)1 << pb.y);                      // other_locations.remove(pos(agent)), :533
+        fa[k] = freeW[k] & ~rb;                                      // robots = other_locations, :538-539
+        fbef[k] = fa[k];
+        if (r == me.x) fbef[k] &= ~((Row)1 << me.y);                 // ... + [pos(agent_id)], :535-536
+      }
+      const int before = warp_path_hops<Row, RPL>(fbef, pb.x, pb.y, gb.x, gb.y, lane);
+      const int after = warp_path_hops<Row, RPL>(fa, pb.x, pb.y, gb.x, gb.y, lane);
+      if (before < 0 && after < 0) continue;                         // :541
+      if (before >= 0 && after < 0) continue;                        // :542
+      if ((before < 0 && after >= 0) || before > after + 10) ++num_blocking;   // :543-545 (len(path) = hops + 1)
+    }
+  }
+  if (lane == 0) {
+    const double x = __dmul_rn((double)num_blocking, d.blocking_cost);   // num_blocking * BLOCKING_COST, :546
+    S.last_reward[m] = __dadd_rn(d.goal_reward, x);                      // reward = GOAL_REWARD; reward += x, :581-583
+    if (blocking_out) blocking_out[m] = x < 0 ? 1 : 0;                    // :584-585
+  }
+}
+
+// After the blocking kernel: publish the per-agent rewards and refold the team reward.
+__global__ void mapf_blocking_finish_kernel(const MapfDims d, const MapfState S, int agent_lo, int agent_hi,
+                                            double* agent_reward, double* reward) {
+  const long long total = (long long)d.E * d.N;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total;
+       j += (long long)gridDim.x * blockDim.x) {
+    if (agent_reward) agent_reward[j] = S.last_reward[j];
+    if (reward && (j % d.N) == 0) {
+      double tot = 0.0;
+      for (int a = agent_lo; a < agent_hi; ++a) tot = __dadd_rn(tot, S.last_reward[j + a]);
+      reward[j / d.N] = tot;
+    }
+  }
+}
+
 // getAstarCosts quirk (PRIMAL:496-498): `costs = state.copy()`, so cells the search never reached keep
 // `state`: 0 when free, the agent id when an agent stands there.
 __global__ void mapf_primal_costs_agents_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty,
@@ -1537,6 +1691,32 @@ extern "C" int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, cons
                                      const uint8_t* dirty, void* stream) {
   mapf_set_goals_kernel<<<grid_for((long long)d.E * d.N, 256), 256, 0, (cudaStream_t)stream>>>(d, S, goals, dirty);
   return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int agent_lo, int agent_hi,
+                                    const mapf_step_out& out, void* stream, int* n_launches) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long maps = (long long)d.E * d.N;
+  const int w2 = 8;
+  const long long g2 = (maps + w2 - 1) / w2;
+  const bool wide = d.W > 32, tall = d.H > 32;
+#define BLK_LAUNCH(ROW, RPL)                                                                              \
+  mapf_blocking_kernel<ROW, RPL><<<(unsigned)g2, w2 * 32, (size_t)w2 * 64 * sizeof(ROW), st>>>(           \
+      d, S, agent_lo, agent_hi, out.blocking_dev, w2)
+  if (!wide && !tall) BLK_LAUNCH(uint32_t, 1);
+  else if (!wide && tall) BLK_LAUNCH(uint32_t, 2);
+  else if (wide && !tall) BLK_LAUNCH(unsigned long long, 1);
+  else BLK_LAUNCH(unsigned long long, 2);
+#undef BLK_LAUNCH
+  cudaError_t err = cudaGetLastError();
+  *n_launches = 1;
+  if (err == cudaSuccess && (out.agent_reward_dev || out.reward_dev)) {
+    mapf_blocking_finish_kernel<<<grid_for(maps, 256), 256, 0, st>>>(d, S, agent_lo, agent_hi, out.agent_reward_dev,
+                                                                     out.reward_dev);
+    err = cudaGetLastError();
+    *n_launches = 2;
+  }
+  return (int)err;
 }
 
 extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, double* obs, void* stream) {

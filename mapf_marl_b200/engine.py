@@ -36,6 +36,7 @@ _OUT_SPECS = {
     "done_mid": (torch.uint8, lambda N: (N,)),
     "next_mid": (torch.uint8, lambda N: (N, 5)),
     "avail": (torch.uint8, lambda N: (N, 5)),
+    "blocking": (torch.uint8, lambda N: (N,)),
 }
 
 DEFAULT_WANT = ("reward", "terminated", "dones", "avail")
@@ -62,7 +63,7 @@ class MapfEngine:
                  goal_reward=0.0, collision_reward=-2.0, goal_dist=False, collect_stats=True, device=None,
                  reward_sum_mode=None, obs_window=5, obs_knn_agents=5, move_reward=-0.01, stay_reward=-0.02,
                  stay_goal_reward=0, node_collide_reward=-1, edge_collide_reward=-1, env_collide_reward=-1,
-                 complete_reward=1000, complete_fac=1.5, gamma=0.99):
+                 complete_reward=1000, complete_fac=1.5, gamma=0.99, blocking_reward=False, blocking_cost=-1.0):
         if not torch.cuda.is_available():
             raise MapfError("MapfEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -99,6 +100,8 @@ class MapfEngine:
         self._lut = magnitude_lut(self.H, self.W)
         cfg.mag_lut_host = self._lut.ctypes.data
         cfg.mag_lut_len = int(self._lut.size)
+        cfg.blocking_reward = int(bool(blocking_reward))
+        cfg.blocking_cost = float(blocking_cost)
         if self.mode == MODE_PARTIAL:
             cfg.obs_window, cfg.obs_knn_agents = self.obs_window, self.obs_knn_agents
             cfg.move_reward, cfg.stay_reward = float(move_reward), float(stay_reward)

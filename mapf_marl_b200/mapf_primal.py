@@ -10,8 +10,9 @@ getPos/getGoal/done/state/goals.
 Batched surface added (n_envs >= 1, device tensors): step_sweep(actions[E,N]) = one
 `for id in 1..N: _step((id, a))` sweep per environment; observe_all(); astar_costs().
 
-Fenced off, loudly: DIAGONAL_MOVEMENT=True and the blocking reward, which depends on
-the un-vendored od_mstar3 planner (row P7) -- rewards equal the reference's with blocking == 0.
+DIAGONAL_MOVEMENT=True raises.  The blocking reward (row P7) depends on the un-vendored
+od_mstar3 planner in the reference; `blocking_reward=True` computes it with BFS path lengths (what a single-robot
+M* returns), otherwise rewards equal the reference's with blocking == 0.
 """
 
 import numpy as np
@@ -25,7 +26,8 @@ opposite_actions = {0: -1, 1: 3, 2: 4, 3: 1, 4: 2, 5: 7, 6: 8, 7: 5, 8: 6}
 dirDict = {0: (0, 0), 1: (0, 1), 2: (1, 0), 3: (0, -1), 4: (-1, 0)}
 actionDict = {v: k for k, v in dirDict.items()}
 
-_SWEEP_WANT = ("status", "agent_reward", "dones", "valid", "done_mid", "next_mid", "avail", "terminated")
+_SWEEP_WANT = ("status", "agent_reward", "dones", "valid", "done_mid", "next_mid", "avail", "terminated",
+               "blocking")
 
 
 class _WorldView(object):
@@ -84,7 +86,7 @@ class MAPFEnv(object):
 
     def __init__(self, num_agents=1, observation_size=10, world0=None, goals0=None, DIAGONAL_MOVEMENT=False,
                  SIZE=(10, 40), PROB=(0, .5), FULL_HELP=False, blank_world=False, n_envs=1, device=None,
-                 goal_dist=False):
+                 goal_dist=False, blocking_reward=False):
         if DIAGONAL_MOVEMENT:
             raise NotImplementedError("DIAGONAL_MOVEMENT (9 actions) is not implemented by the B200 engine")
         self.num_agents = num_agents
@@ -99,6 +101,9 @@ class MAPFEnv(object):
         self.DIAGONAL_MOVEMENT = DIAGONAL_MOVEMENT
         self._device = device
         self._goal_dist = goal_dist
+        # get_blocking_reward (mapf_primal.py:513-546) with BFS path lengths instead of the un-vendored od_mstar3;
+        # off by default because the fixtures pinned against the reference were recorded with it fenced off
+        self._blocking_reward = bool(blocking_reward)
         self.engine = None
         self.viewer = None
         self.world = _WorldView(self)
@@ -149,7 +154,8 @@ class MAPFEnv(object):
                 self.engine.close()
             self.engine = MapfEngine(E, N, H, W, mode="primal", fov=self.observation_size, device=self._device,
                                      goal_dist=self._goal_dist, action_cost=ACTION_COST, idle_cost=IDLE_COST,
-                                     goal_reward=GOAL_REWARD, collision_reward=COLLISION_REWARD)
+                                     goal_reward=GOAL_REWARD, collision_reward=COLLISION_REWARD,
+                                     blocking_reward=self._blocking_reward, blocking_cost=BLOCKING_COST)
         self._obst0 = obst[0]
         self.initial_world = world0
         self.initial_goals = goals0
@@ -239,7 +245,7 @@ class MAPFEnv(object):
         nextActions = [a for a in range(5) if mask[a]]
         on_goal = bool(out["dones"][0, i].item())
         valid_action = bool(out["valid"][0, i].item())
-        blocking = False
+        blocking = bool(out["blocking"][0, i].item()) if self._blocking_reward else False
         return state, reward, done, nextActions, on_goal, blocking, valid_action
 
     def getAstarCosts(self, start, goal):

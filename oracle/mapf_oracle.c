@@ -47,6 +47,7 @@ typedef struct oracle_env {
   uint8_t* done;     /* [E,N]  GRID _agent_dones */
   int32_t* step_count; /* [E] */
   int threads;
+  int blocking;          /* PRIMAL: compute get_blocking_reward (PRIMAL:513-546) with BFS path lengths */
   /* PARTIAL (marl_partial.py) */
   int pW, pK;                                   /* obs_window, obs_knn_agents */
   double p_move, p_stay, p_stay_goal, p_nc, p_ec, p_envc, p_complete, p_fac, p_gamma;
@@ -368,6 +369,76 @@ static int primal_move_agent(oracle_env* o, int e, int id, int action) {
   return 0;
 }
 
+void oracle_primal_set_blocking(oracle_env* o, int on) { o->blocking = on; }
+
+/* Single-robot shortest path length on the 4-connected grid with `blocked` cells removed: what
+ * od_mstar3.cpp_mstar.find_path(world, [start], [goal], 1, 5) returns for ONE robot is an optimal path, so only its
+ * length matters to get_blocking_reward (len(path) = hops + 1).  -1 = NoSolutionError (PRIMAL:505-508). */
+static int single_robot_path_hops(const oracle_env* o, const int8_t* m, const uint8_t* blocked, int s, int g,
+                                  int32_t* queue, int16_t* dist) {
+  const int H = o->H, W = o->W;
+  if (m[s] || blocked[s] || m[g] || blocked[g]) return -1;
+  for (int c = 0; c < H * W; ++c) dist[c] = -1;
+  int head = 0, tail = 0;
+  dist[s] = 0;
+  queue[tail++] = s;
+  while (head < tail) {
+    int c = queue[head++];
+    if (c == g) return dist[c];
+    int r0 = c / W, c0 = c % W;
+    static const int D[4][2] = {{0, 1}, {1, 0}, {0, -1}, {-1, 0}};
+    for (int q = 0; q < 4; ++q) {
+      int r1 = r0 + D[q][0], c1 = c0 + D[q][1];
+      if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;
+      int n = r1 * W + c1;
+      if (m[n] || blocked[n] || dist[n] >= 0) continue;
+      dist[n] = (int16_t)(dist[c] + 1);
+      queue[tail++] = n;
+    }
+  }
+  return -1;
+}
+
+/* get_blocking_reward, PRIMAL:513-546: how many visible robots (ids 1..N-1 -- the loop skips the last id, :523)
+ * have their path to their goal cut, or lengthened by more than 10, by this robot standing where it stands. */
+static double primal_blocking_reward(const oracle_env* o, int e, int id) {
+  const int H = o->H, W = o->W, N = o->N, F = o->F;
+  const int8_t* m = env_map(o, e);
+  const int16_t* pos = o->pos + (size_t)e * N * 2;
+  const int16_t* goal = o->goal + (size_t)e * N * 2;
+  uint8_t* blocked = (uint8_t*)calloc((size_t)H * W, 1);
+  int32_t* queue = (int32_t*)malloc(sizeof(int32_t) * (size_t)H * W);
+  int16_t* dist = (int16_t*)malloc(sizeof(int16_t) * (size_t)H * W);
+  int others[256], n_others = 0;
+  const int tl0 = pos[2 * (id - 1)] - F / 2, tl1 = pos[2 * (id - 1) + 1] - F / 2;
+  for (int a = 1; a < N; ++a) {                                       /* range(1, num_agents) */
+    if (a == id) continue;
+    int x = pos[2 * (a - 1)], y = pos[2 * (a - 1) + 1];
+    if (x < tl0 || x >= tl0 + F || y >= tl1 + F || y < tl1) continue;
+    others[n_others++] = a;
+    blocked[x * W + y] = 1;
+  }
+  const int me = pos[2 * (id - 1)] * W + pos[2 * (id - 1) + 1];
+  int num_blocking = 0;
+  for (int k = 0; k < n_others; ++k) {
+    const int a = others[k];
+    const int s = pos[2 * (a - 1)] * W + pos[2 * (a - 1) + 1];
+    const int g = goal[2 * (a - 1)] * W + goal[2 * (a - 1) + 1];
+    blocked[s] = 0;                                                   /* other_locations.remove(pos(agent)) */
+    const uint8_t me_was = blocked[me];
+    blocked[me] = 1;
+    const int before = single_robot_path_hops(o, m, blocked, s, g, queue, dist);
+    blocked[me] = me_was;
+    const int after = single_robot_path_hops(o, m, blocked, s, g, queue, dist);
+    blocked[s] = 1;
+    if (before < 0 && after < 0) continue;
+    if (before >= 0 && after < 0) continue;
+    if ((before < 0 && after >= 0) || before > after + 10) num_blocking++;   /* len(path) = hops + 1 on both sides */
+  }
+  free(blocked); free(queue); free(dist);
+  return num_blocking * -1.0;                                         /* BLOCKING_COST, PRIMAL:25 */
+}
+
 /* State.done, PRIMAL:159-165. */
 static int primal_done(const oracle_env* o, int e) {
   const int16_t* gg = o->goals + (size_t)e * o->H * o->W;
@@ -402,7 +473,8 @@ static void primal_valid_actions(const oracle_env* o, int e, int id, int prev_ac
  * (observe_all is separate) and with the blocking reward fenced off (returns 0, see refload.py). */
 int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, int8_t* status_out,
                         double* agent_reward, uint8_t* on_goal_out, uint8_t* valid_out, uint8_t* done_mid,
-                        uint8_t* next_mid, uint8_t* avail, uint8_t* terminated, double* reward) {
+                        uint8_t* next_mid, uint8_t* avail, uint8_t* terminated, double* reward,
+                        uint8_t* blocking_out) {
   int bad = 0;
   const int N = o->N;
 #pragma omp parallel for schedule(static) num_threads(o->threads) reduction(+ : bad)
@@ -416,9 +488,13 @@ int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, i
       if (action > 4) { bad++; action = 0; }
       int status = primal_move_agent(o, e, id, action);            /* world.act, PRIMAL:570 */
       double r;
+      int is_blocking = 0;
       if (action == 0) {                                            /* PRIMAL:579-587 */
-        if (status == 1) r = o->goal_reward + 0.0 * -1.0;          /* GOAL_REWARD + num_blocking(=0) * BLOCKING_COST */
-        else r = o->idle_cost;
+        if (status == 1) {
+          double x = o->blocking ? primal_blocking_reward(o, e, id) : 0.0 * -1.0;   /* num_blocking * BLOCKING_COST */
+          r = o->goal_reward + x;
+          is_blocking = x < 0;
+        } else r = o->idle_cost;
       } else {                                                      /* PRIMAL:588-596 */
         if (status == 1) r = o->goal_reward;
         else if (status < 0) r = o->collision_reward;
@@ -430,6 +506,7 @@ int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, i
       int on_goal = (p[0] == g[0] && p[1] == g[1]);                 /* PRIMAL:633 */
       o->done[k] = (uint8_t)on_goal;
       if (status_out) status_out[k] = (int8_t)status;
+      if (blocking_out) blocking_out[k] = (uint8_t)is_blocking;
       if (agent_reward) agent_reward[k] = r;
       if (on_goal_out) on_goal_out[k] = (uint8_t)on_goal;
       if (valid_out) valid_out[k] = (uint8_t)(status >= 0);         /* PRIMAL:571 */

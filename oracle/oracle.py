@@ -39,7 +39,9 @@ def _lib():
             getattr(lib, name).restype = None
         lib.oracle_grid_step.argtypes = [vp] * 9
         lib.oracle_grid_step.restype = i
-        lib.oracle_primal_sweep.argtypes = [vp, vp, i, i] + [vp] * 9
+        lib.oracle_primal_sweep.argtypes = [vp, vp, i, i] + [vp] * 10
+        lib.oracle_primal_set_blocking.argtypes = [vp, i]
+        lib.oracle_primal_set_blocking.restype = None
         lib.oracle_primal_sweep.restype = i
         lib.oracle_goal_dist.argtypes = [vp, vp, i, vp]
         lib.oracle_goal_dist.restype = None
@@ -160,7 +162,7 @@ class Oracle:
     # ---- PRIMAL
     def primal_sweep(self, actions, lo=0, hi=None,
                      want=("status", "agent_reward", "dones", "valid", "done_mid", "next_mid", "avail",
-                           "terminated", "reward")):
+                           "terminated", "reward", "blocking")):
         a = np.ascontiguousarray(actions, dtype=np.uint8)
         assert a.shape == (self.E, self.N)
         hi = self.N if hi is None else hi
@@ -169,14 +171,19 @@ class Oracle:
                    dones=np.zeros((E, N), np.uint8), valid=np.zeros((E, N), np.uint8),
                    done_mid=np.zeros((E, N), np.uint8), next_mid=np.zeros((E, N, 5), np.uint8),
                    avail=np.zeros((E, N, 5), np.uint8), terminated=np.zeros(E, np.uint8),
-                   reward=np.zeros(E, np.float64))
+                   reward=np.zeros(E, np.float64), blocking=np.zeros((E, N), np.uint8))
         out = {k: v for k, v in out.items() if k in want}
         bad = self._lib.oracle_primal_sweep(self._h, _p(a), int(lo), int(hi), _p(out.get("status")),
                                             _p(out.get("agent_reward")), _p(out.get("dones")),
                                             _p(out.get("valid")), _p(out.get("done_mid")), _p(out.get("next_mid")),
-                                            _p(out.get("avail")), _p(out.get("terminated")), _p(out.get("reward")))
+                                            _p(out.get("avail")), _p(out.get("terminated")), _p(out.get("reward")),
+                                            _p(out.get("blocking")))
         out["bad_actions"] = bad
         return out
+
+    def set_blocking(self, on=True):
+        """PRIMAL blocking reward (mapf_primal.py:513-546) with single-robot BFS path lengths."""
+        self._lib.oracle_primal_set_blocking(self._h, int(bool(on)))
 
     def primal_avail(self, prev_action=None):
         out = np.empty((self.E, self.N, 5), np.uint8)

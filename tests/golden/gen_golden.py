@@ -179,7 +179,7 @@ def mask5(lst):
     return m
 
 
-def run_primal(name, obst, starts, goals, fov, actions, n_costs=3):
+def run_primal(name, obst, starts, goals, fov, actions, n_costs=3, blocking=False, greedy=None):
     n = len(starts)
     T = actions.shape[0]
     world0, goals0 = primal_world(obst, starts, goals)
@@ -210,13 +210,35 @@ def run_primal(name, obst, starts, goals, fov, actions, n_costs=3):
     costs0 = np.array([env.getAstarCosts(env.world.getPos(i), env.world.getGoal(i))
                        for i in range(1, min(n, n_costs) + 1)], dtype=np.int32)
     rec = {k: [] for k in ("status", "reward", "done_mid", "next_mid", "on_goal", "valid",
-                           "pos", "obs", "vec", "avail", "done")}
+                           "pos", "obs", "vec", "avail", "done", "blocking")}
+    if blocking:
+        os.environ["MAPF_REF_BFS_MSTAR"] = "1"
+    else:
+        os.environ.pop("MAPF_REF_BFS_MSTAR", None)
+    actions = actions.copy()
     for t in range(T):
-        row = {k: [] for k in ("reward", "done_mid", "next_mid", "on_goal", "valid")}
+        row = {k: [] for k in ("reward", "done_mid", "next_mid", "on_goal", "valid", "blocking")}
         statuses.clear()
+        if greedy is not None:      # walk down the goal-distance map with probability `greedy`, stay on the goal
+            rsg = np.random.RandomState(1000 + t)
+            for i in range(1, n + 1):
+                if rsg.rand() < greedy:
+                    p = env.world.getPos(i)
+                    if p == env.world.getGoal(i):
+                        actions[t, i - 1] = 0
+                    else:
+                        costs = env.getAstarCosts(p, env.world.getGoal(i))
+                        best, bd = 0, costs[p]
+                        for a_, (dx, dy) in ((1, (0, 1)), (2, (1, 0)), (3, (0, -1)), (4, (-1, 0))):
+                            q = (p[0] + dx, p[1] + dy)
+                            if 0 <= q[0] < obst.shape[0] and 0 <= q[1] < obst.shape[1] and not obst[q] \
+                                    and env.world.state[q] == 0 and costs[q] < bd:
+                                best, bd = a_, costs[q]
+                        actions[t, i - 1] = best
         for i in range(1, n + 1):
-            state, reward, done, nxt, on_goal, blocking, valid = env._step((i, int(actions[t, i - 1])))
-            assert blocking is False
+            state, reward, done, nxt, on_goal, blk, valid = env._step((i, int(actions[t, i - 1])))
+            assert blocking or blk is False
+            row["blocking"].append(bool(blk))
             row["reward"].append(float(reward))
             row["done_mid"].append(bool(done))
             row["next_mid"].append(mask5(nxt))
@@ -228,6 +250,7 @@ def run_primal(name, obst, starts, goals, fov, actions, n_costs=3):
         rec["next_mid"].append(np.array(row["next_mid"], dtype=np.uint8))
         rec["on_goal"].append(np.array(row["on_goal"], dtype=np.uint8))
         rec["valid"].append(np.array(row["valid"], dtype=np.uint8))
+        rec["blocking"].append(np.array(row["blocking"], dtype=np.uint8))
         rec["pos"].append(np.array(env.getPositions(), dtype=np.int16))
         o, v = observe_all()
         rec["obs"].append(o)
@@ -240,12 +263,14 @@ def run_primal(name, obst, starts, goals, fov, actions, n_costs=3):
     out = dict(family="PRIMAL", obst=obst.astype(np.uint8), starts=np.array(starts, dtype=np.int16),
                goals=np.array(goals, dtype=np.int16), fov=np.int64(fov), actions=actions.astype(np.uint8),
                obs0=obs0, vec0=vec0, avail0=avail0, costs0=costs0, costsT=costsT,
+               blocking_enabled=np.int64(bool(blocking)),
                **{k: np.array(v) for k, v in rec.items()})
     out["done"] = out["done"].astype(np.uint8)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    print("wrote", name, "T=%d N=%d HxW=%dx%d F=%d moved_frac=%.2f collisions=%d" % (
+    os.environ.pop("MAPF_REF_BFS_MSTAR", None)
+    print("wrote", name, "T=%d N=%d HxW=%dx%d F=%d moved_frac=%.2f collisions=%d blocking_events=%d" % (
         T, n, obst.shape[0], obst.shape[1], fov, float(np.mean(out["status"] >= 0)),
-        int(np.sum(out["status"] == -3))))
+        int(np.sum(out["status"] == -3)), int(np.sum(out["blocking"]))))
 
 
 def rand_primal_case(seed, h, w, density, n):
@@ -279,6 +304,32 @@ def gen_primal():
     run_primal("primal_rect", obst, s, g, 7, rs.randint(0, 5, [30, 6]))
     rs, obst, s, g = rand_primal_case(7000, 40, 40, 0.25, 7)       # N not a multiple of 4, W > 32
     run_primal("primal_n7w40", obst, s, g, 11, rs.randint(0, 5, [20, 7]))
+
+
+def gen_primal_blocking():
+    """PRIMAL with the blocking reward ON (mapf_primal.py:513-546), od_mstar3 replaced by the BFS stand-in of
+    refload.py: corridor maps where agents parked on their goals lengthen or cut other agents' paths."""
+    rows = ["..........",
+            ".@@@@.@@@.",
+            ".@......@.",
+            ".@.@@@@.@.",
+            "...@..@...",
+            ".@.@..@.@.",
+            ".@.@@.@.@.",
+            ".@......@.",
+            ".@@@.@@@@.",
+            ".........."]
+    obst = np.array([[c == "@" for c in r] for r in rows])
+    fc = free_cells(obst)
+    for k, (seed, n, fov, T) in enumerate(((11, 6, 9, 60), (12, 9, 11, 50), (13, 4, 5, 40))):
+        rs = np.random.RandomState(seed)
+        idx = rs.permutation(len(fc))
+        starts = [fc[i] for i in idx[:n]]
+        goals = [fc[i] for i in rs.permutation(len(fc))[:n]]
+        run_primal("primalb_corridor%d" % k, obst, starts, goals, fov, rs.randint(0, 5, [T, n]),
+                   blocking=True, greedy=0.9)
+    rs, obst, s_, g_ = rand_primal_case(8000, 20, 20, 0.25, 10)
+    run_primal("primalb_rand20", obst, s_, g_, 11, rs.randint(0, 5, [60, 10]), blocking=True, greedy=0.85)
 
 
 # --------------------------------------------------------------------------- PARTIAL distance maps
@@ -399,11 +450,13 @@ def gen_partial():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["grid", "primal", "pdist", "partial"]
+    which = sys.argv[1:] or ["grid", "primal", "primalb", "pdist", "partial"]
     if "grid" in which:
         gen_grid()
     if "primal" in which:
         gen_primal()
+    if "primalb" in which:
+        gen_primal_blocking()
     if "pdist" in which:
         gen_pdist()
     if "partial" in which:

@@ -77,7 +77,35 @@ def _install_stubs():
             pass
 
         def find_path(world, starts, goals, inflation, time_limit):
-            raise NoSolutionError()
+            """Stand-in for od_mstar3.cpp_mstar.find_path (un-vendored).  Default: no solution, which fences the
+            blocking reward off (get_blocking_reward returns 0).  With MAPF_REF_BFS_MSTAR=1 it is a single-agent
+            shortest path (4-connected BFS, what M* with inflation 1 returns for one robot): a list of joint
+            configurations from start to goal inclusive, NoSolutionError when the goal cannot be reached."""
+            if not os.environ.get("MAPF_REF_BFS_MSTAR"):
+                raise NoSolutionError()
+            import collections
+            (sx, sy), (gx, gy) = tuple(starts[0]), tuple(goals[0])
+            H, W = world.shape
+            if world[sx, sy] != 0 or world[gx, gy] != 0:
+                raise NoSolutionError()
+            prev = {(sx, sy): None}
+            dq = collections.deque([(sx, sy)])
+            while dq:
+                cur = dq.popleft()
+                if cur == (gx, gy):
+                    break
+                for dx, dy in ((0, 1), (1, 0), (0, -1), (-1, 0)):
+                    n = (cur[0] + dx, cur[1] + dy)
+                    if 0 <= n[0] < H and 0 <= n[1] < W and world[n] == 0 and n not in prev:
+                        prev[n] = cur
+                        dq.append(n)
+            if (gx, gy) not in prev:
+                raise NoSolutionError()
+            path, cur = [], (gx, gy)
+            while cur is not None:
+                path.append((cur,))
+                cur = prev[cur]
+            return path[::-1]
 
         csa.NoSolutionError = NoSolutionError
         csa.OutOfTimeError = OutOfTimeError

@@ -804,3 +804,83 @@ def test_extreme_sizes_match_oracle(case):
         assert np.array_equal(_np(f32), robs.astype(np.float32)), t
     assert np.array_equal(_np(eng.goal_dist()), orc.goal_dist())
     assert eng.error_flags() == 0
+
+
+# ------------------------------------------------------------------------------------------ PRIMAL blocking reward
+@pytest.mark.parametrize("name", golden_names("PRIMALB"))
+def test_primal_blocking_reward_matches_reference_trace(name):
+    """get_blocking_reward (mapf_primal.py:513-546) through the live reference with od_mstar3 replaced by a
+    single-robot BFS (tests/golden/refload.py): rewards and `blocking` flags of every _step call."""
+    g = load_golden(name)
+    H, W = g["obst"].shape
+    N = g["starts"].shape[0]
+    F = int(g["fov"])
+    eng = _engine(1, N, H, W, mode="primal", fov=F, blocking_reward=True)
+    eng.reset(g["obst"][None], g["starts"][None], g["goals"][None])
+    want = PRIMAL_WANT + ("blocking",)
+    for t in range(g["actions"].shape[0]):
+        out = eng.step_observe(torch.as_tensor(g["actions"][t][None]), want=want)
+        assert np.array_equal(_np(out["status"])[0], g["status"][t]), t
+        assert np.array_equal(_np(out["blocking"])[0], g["blocking"][t]), t
+        assert np.array_equal(_bits(_np(out["agent_reward"])[0]), _bits(g["reward"][t])), t
+        assert np.array_equal(_np(eng.positions())[0], g["pos"][t]), t
+        assert np.array_equal(_np(out["obs"])[0], g["obs"][t]), t
+    assert eng.error_flags() == 0
+    # the per-agent facade returns the same blocking flags and rewards
+    from mapf_marl_b200.mapf_primal import MAPFEnv
+    world0 = -g["obst"].astype(int)
+    goals0 = np.zeros_like(world0)
+    for k in range(N):
+        world0[tuple(g["starts"][k])] = k + 1
+        goals0[tuple(g["goals"][k])] = k + 1
+    env = MAPFEnv(num_agents=N, observation_size=F, world0=world0, goals0=goals0, blocking_reward=True)
+    for t in range(min(12, g["actions"].shape[0])):
+        for i in range(1, N + 1):
+            _, reward, _, _, _, blocking, _ = env._step((i, int(g["actions"][t, i - 1])))
+            assert reward == g["reward"][t, i - 1] and blocking == bool(g["blocking"][t, i - 1])
+
+
+@pytest.mark.parametrize("case", [(48, 9, 10, 10, 11), (16, 20, 24, 40, 7), (8, 40, 64, 64, 11), (6, 12, 40, 20, 9)],
+                         ids=lambda c: "E%d_N%d_%dx%d" % c[:4])
+def test_primal_blocking_reward_batch_matches_oracle(case):
+    from mapf_marl_b200 import maps
+    from oracle.oracle import MODE_PRIMAL
+    E, N, H, W, F = case
+    rs = np.random.RandomState(E + H)
+    obst = np.zeros((E, H, W), np.uint8)
+    starts = np.zeros((E, N, 2), np.int16)
+    goals = np.zeros((E, N, 2), np.int16)
+    for e in range(E):
+        m = (rs.rand(H, W) < 0.3).astype(np.uint8)          # dense: corridors, where blocking happens
+        lab = maps.label_components(m)
+        m[lab != np.argmax(np.bincount(lab[lab >= 0]))] = 1
+        free = np.argwhere(m == 0)
+        obst[e] = m
+        starts[e] = free[rs.permutation(len(free))[:N]]
+        goals[e] = free[rs.permutation(len(free))[:N]]
+        near = rs.rand(N) < 0.6
+        goals[e][near] = starts[e][near]                     # many agents already parked on their goals
+        # goals must stay distinct cells
+        seen = set()
+        for k in range(N):
+            while tuple(goals[e, k]) in seen:
+                goals[e, k] = free[rs.randint(len(free))]
+            seen.add(tuple(goals[e, k]))
+    eng = _engine(E, N, H, W, mode="primal", fov=F, blocking_reward=True)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F)
+    orc.set_blocking(True)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    want = PRIMAL_WANT + ("blocking",)
+    n_events = 0
+    for t in range(6):
+        a = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        a[rs.rand(E, N) < 0.5] = 0                            # lots of "stay"
+        out = eng.step(torch.as_tensor(a, device="cuda"), want=want)
+        ref = orc.primal_sweep(a)
+        for k in ("status", "dones", "valid", "blocking", "avail", "terminated"):
+            assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        assert np.array_equal(_bits(_np(out["agent_reward"])), _bits(ref["agent_reward"])), t
+        assert np.array_equal(_bits(_np(out["reward"])), _bits(ref["reward"])), t
+        n_events += int(ref["blocking"].sum())
+    assert n_events > 0

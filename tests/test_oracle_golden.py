@@ -39,13 +39,14 @@ def test_grid_oracle_matches_reference_trace(name):
         assert out["terminated"][0] == int(g["dones"][t].all())
 
 
-@pytest.mark.parametrize("name", golden_names("PRIMAL"))
+@pytest.mark.parametrize("name", golden_names("PRIMAL") + golden_names("PRIMALB"))
 def test_primal_oracle_matches_reference_trace(name):
     g = load_golden(name)
     H, W = g["obst"].shape
     N = g["starts"].shape[0]
     F = int(g["fov"])
     o = Oracle(1, N, H, W, MODE_PRIMAL, fov=F)
+    o.set_blocking(bool(g.get("blocking_enabled", 0)))
     o.reset(g["obst"][None], g["starts"][None], g["goals"][None])
     obs, vec = o.primal_observe()
     assert np.array_equal(obs[0], g["obs0"])
@@ -62,6 +63,8 @@ def test_primal_oracle_matches_reference_trace(name):
         assert np.array_equal(out["next_mid"][0], g["next_mid"][t]), t
         assert np.array_equal(out["dones"][0], g["on_goal"][t]), t
         assert np.array_equal(out["valid"][0], g["valid"][t]), t
+        if "blocking" in g:
+            assert np.array_equal(out["blocking"][0], g["blocking"][t]), t
         assert np.array_equal(o.positions()[0], g["pos"][t]), t
         assert np.array_equal(out["avail"][0], g["avail"][t]), t
         assert out["terminated"][0] == g["done"][t]
