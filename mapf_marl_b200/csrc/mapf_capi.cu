@@ -465,15 +465,31 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
     A.vec = fov ? vec : nullptr;
   }
   const bool any_out = A.do_step || A.obs || A.vec || A.out.avail_dev;
+  const bool blocking = A.do_step && h->d.blocking;
+  int8_t* user_status = A.out.status_dev;
+  double* user_agent_reward = A.out.agent_reward_dev;
+  if (blocking) {
+    // the blocking-reward kernel that follows the sweep needs the pre-sweep positions, the statuses and the per-agent
+    // rewards: route them into the handle's own buffers (the hot kernel stays free of blocking-specific code)
+    const size_t EN = (size_t)h->d.E * h->d.N;
+    CK(cudaMemcpyAsync(h->S.pos_prev, h->S.pos, EN * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    A.out.status_dev = h->S.last_status;
+    A.out.agent_reward_dev = h->S.last_reward;
+  }
   if (any_out) {
     const bool need_mid = A.out.done_mid_dev || A.out.next_mid_dev;
     CK((cudaError_t)mapf_launch_tile(d, need_mid ? h->L : h->L_lite, h->S, A, stream));
     h->launches++;
   }
-  if (A.do_step && h->d.blocking) {   // PRIMAL:579-585: stay-on-goal rewards get the blocking term
+  if (blocking) {   // PRIMAL:579-585: stay-on-goal rewards get the blocking term
     int n = 0;
-    CK((cudaError_t)mapf_launch_blocking(h->d, h->S, lo, hi, A.out, stream, &n));
+    mapf_step_out o2 = A.out;
+    o2.agent_reward_dev = user_agent_reward;
+    CK((cudaError_t)mapf_launch_blocking(h->d, h->S, lo, hi, o2, stream, &n));
     h->launches += n;
+    if (user_status)
+      CK(cudaMemcpyAsync(user_status, h->S.last_status, (size_t)h->d.E * h->d.N, cudaMemcpyDeviceToDevice,
+                         (cudaStream_t)stream));
   }
   if (pwin && obs) {
     CK((cudaError_t)mapf_launch_partial_obs(h->d, h->S, (double*)obs, stream));

@@ -794,11 +794,6 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       copy_out_bytes(S.pnode + a0, s.node, na, tid);
       copy_out_bytes(S.pedge + a0, s.edge, na, tid);
     }
-    if (primal && d.blocking) {   // inputs of the blocking-reward kernel that follows the sweep
-      copy_out_bytes(S.pos_prev + 2 * a0, (const uint8_t*)s.posold, 2 * na, tid);
-      copy_out_bytes((uint8_t*)S.last_status + a0, (const uint8_t*)s.status, na, tid);
-      for (int j = tid; j < na; j += kThreads) S.last_reward[a0 + j] = s.rew[j];
-    }
     copy_out_bytes(S.pos + 2 * a0, (const uint8_t*)s.posnew, 2 * na, tid);
     copy_out_bytes(S.done + a0, s.done, na, tid);
     copy_out_bytes(S.prev_action + a0, s.act, na, tid);

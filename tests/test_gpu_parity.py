@@ -840,7 +840,7 @@ def test_primal_blocking_reward_matches_reference_trace(name):
             assert reward == g["reward"][t, i - 1] and blocking == bool(g["blocking"][t, i - 1])
 
 
-@pytest.mark.parametrize("case", [(48, 9, 10, 10, 11), (16, 20, 24, 40, 7), (8, 40, 64, 64, 11), (6, 12, 40, 20, 9)],
+@pytest.mark.parametrize("case", [(48, 9, 10, 10, 11), (16, 20, 24, 40, 7), (8, 40, 64, 64, 11), (40, 14, 40, 20, 9)],
                          ids=lambda c: "E%d_N%d_%dx%d" % c[:4])
 def test_primal_blocking_reward_batch_matches_oracle(case):
     from mapf_marl_b200 import maps
