@@ -47,6 +47,8 @@ typedef struct oracle_env {
   uint8_t* done;     /* [E,N]  GRID _agent_dones */
   int32_t* step_count; /* [E] */
   int threads;
+  int diagonal;          /* PRIMAL DIAGONAL_MOVEMENT (PRIMAL:175): 9 actions, diagonalCollision, 8-connected costs */
+  int16_t* past;         /* [E,N,2] State.agents_past (PRIMAL:49, 109, 128) */
   int blocking;          /* PRIMAL: compute get_blocking_reward (PRIMAL:513-546) with BFS path lengths */
   /* PARTIAL (marl_partial.py) */
   int pW, pK;                                   /* obs_window, obs_knn_agents */
@@ -103,6 +105,7 @@ oracle_env* oracle_create(int E, int N, int H, int W, int F, int shared_map, int
   o->total_coll = (int64_t*)calloc((size_t)E, sizeof(int64_t));
   o->terminated = (uint8_t*)calloc((size_t)E, 1);
   o->pdist = NULL;
+  o->past = (int16_t*)calloc((size_t)E * N * 2, sizeof(int16_t));
   return o;
 }
 
@@ -111,7 +114,7 @@ void oracle_destroy(oracle_env* o) {
   free(o->map); free(o->state); free(o->goals); free(o->pos); free(o->goal); free(o->start);
   free(o->done); free(o->step_count);
   free(o->at_goal); free(o->goal_cost); free(o->agent_steps); free(o->pnode); free(o->pedge);
-  free(o->total_coll); free(o->terminated); free(o->pdist); free(o);
+  free(o->total_coll); free(o->terminated); free(o->pdist); free(o->past); free(o);
 }
 
 void oracle_get_positions(const oracle_env* o, int16_t* out) { memcpy(out, o->pos, (size_t)o->E * o->N * 4); }
@@ -306,8 +309,12 @@ int oracle_grid_step(oracle_env* o, const uint8_t* actions, double* reward, uint
  * PRIMAL   (mapf_primal.py)
  * ---------------------------------------------------------------------------------------- */
 
-static const int PRIMAL_DIR[5][2] = {{0, 0}, {0, 1}, {1, 0}, {0, -1}, {-1, 0}}; /* dirDict, PRIMAL:28 */
-static const int PRIMAL_OPPOSITE[5] = {-1, 3, 4, 1, 2};                          /* opposite_actions, PRIMAL:26 */
+static const int PRIMAL_DIR[9][2] = {{0, 0}, {0, 1}, {1, 0}, {0, -1}, {-1, 0},
+                                     {1, 1}, {1, -1}, {-1, -1}, {-1, 1}};           /* dirDict, PRIMAL:28 */
+static const int PRIMAL_OPPOSITE[9] = {-1, 3, 4, 1, 2, 7, 8, 5, 6};                 /* opposite_actions, PRIMAL:26 */
+
+void oracle_primal_set_diagonal(oracle_env* o, int on) { o->diagonal = on; }
+int oracle_n_actions(const oracle_env* o) { return o->diagonal ? 9 : 5; }
 
 /* _setWorld with world0/goals0 + State.__init__/scanForAgents, PRIMAL:278-309, 44-66. */
 void oracle_primal_reset(oracle_env* o, const int8_t* map, const int16_t* starts, const int16_t* goals) {
@@ -316,6 +323,7 @@ void oracle_primal_reset(oracle_env* o, const int8_t* map, const int16_t* starts
   if (starts) memcpy(o->start, starts, (size_t)o->E * o->N * 4);
   if (goals) memcpy(o->goal, goals, (size_t)o->E * o->N * 4);
   memcpy(o->pos, o->start, (size_t)o->E * o->N * 4);
+  memcpy(o->past, o->start, (size_t)o->E * o->N * 4);                /* agents_last == agents, PRIMAL:61-65 */
   memset(o->step_count, 0, (size_t)o->E * 4);
 #pragma omp parallel for schedule(static) num_threads(o->threads)
   for (int e = 0; e < o->E; ++e) {
@@ -349,20 +357,40 @@ void oracle_primal_set_goals(oracle_env* o, const int16_t* goals, const uint8_t*
   }
 }
 
-/* State.moveAgent, PRIMAL:103-135 (DIAGONAL_MOVEMENT off). */
+/* State.diagonalCollision, PRIMAL:77-100: the midpoint of this move equals the midpoint of another agent's last
+ * recorded move (past -> present).  np.isclose on half-integers == equality of the integer sums. */
+static int primal_diagonal_collision(const oracle_env* o, int e, int id, int nx, int ny) {
+  const int16_t* pos = o->pos + (size_t)e * o->N * 2;
+  const int16_t* past = o->past + (size_t)e * o->N * 2;
+  const int lx = pos[2 * (id - 1)], ly = pos[2 * (id - 1) + 1];
+  for (int a = 1; a <= o->N; ++a) {
+    if (a == id) continue;
+    if (past[2 * (a - 1)] + pos[2 * (a - 1)] == lx + nx && past[2 * (a - 1) + 1] + pos[2 * (a - 1) + 1] == ly + ny)
+      return 1;
+  }
+  return 0;
+}
+
+/* State.moveAgent, PRIMAL:103-135. */
 static int primal_move_agent(oracle_env* o, int e, int id, int action) {
   const int W = o->W, H = o->H;
   int16_t* st = o->state + (size_t)e * H * W;
   const int16_t* gg = o->goals + (size_t)e * H * W;
   int16_t* p = o->pos + ((size_t)e * o->N + (id - 1)) * 2;
+  int16_t* pp = o->past + ((size_t)e * o->N + (id - 1)) * 2;
   int ax = p[0], ay = p[1];
   int dx = PRIMAL_DIR[action][0], dy = PRIMAL_DIR[action][1];
-  if (dx == 0 && dy == 0) return gg[ax * W + ay] == id ? 1 : 0;
+  if (dx == 0 && dy == 0) {
+    pp[0] = (int16_t)ax; pp[1] = (int16_t)ay;                        /* :109 */
+    return gg[ax * W + ay] == id ? 1 : 0;
+  }
   if (ax + dx >= H || ax + dx < 0 || ay + dy >= W || ay + dy < 0) return -1;
   if (st[(ax + dx) * W + ay + dy] < 0) return -2;
   if (st[(ax + dx) * W + ay + dy] > 0) return -3;
+  if (o->diagonal && primal_diagonal_collision(o, e, id, ax + dx, ay + dy)) return -3;   /* :122-124 */
   st[ax * W + ay] = 0;
   st[(ax + dx) * W + ay + dy] = (int16_t)id;
+  pp[0] = (int16_t)ax; pp[1] = (int16_t)ay;                          /* :128 */
   p[0] = (int16_t)(ax + dx); p[1] = (int16_t)(ay + dy);
   if (gg[(ax + dx) * W + ay + dy] == id) return 1;
   if (gg[ax * W + ay] == id) return 2;
@@ -450,23 +478,24 @@ static int primal_done(const oracle_env* o, int e) {
   return complete == o->N;
 }
 
-/* _listNextValidActions, PRIMAL:639-667, as a 5-entry mask. */
-static void primal_valid_actions(const oracle_env* o, int e, int id, int prev_action, uint8_t* out5) {
-  const int W = o->W, H = o->H;
+/* _listNextValidActions, PRIMAL:639-667, as an n_actions-entry mask (5, or 9 with DIAGONAL_MOVEMENT). */
+static void primal_valid_actions(const oracle_env* o, int e, int id, int prev_action, uint8_t* out) {
+  const int W = o->W, H = o->H, na = o->diagonal ? 9 : 5;
   const int16_t* st = o->state + (size_t)e * H * W;
   const int16_t* p = o->pos + ((size_t)e * o->N + (id - 1)) * 2;
   int ax = p[0], ay = p[1];
-  out5[0] = 1;
-  for (int a = 1; a < 5; ++a) {
+  out[0] = 1;
+  for (int a = 1; a < na; ++a) {
     int dx = PRIMAL_DIR[a][0], dy = PRIMAL_DIR[a][1];
-    out5[a] = 0;
+    out[a] = 0;
     if (ax + dx >= H || ax + dx < 0 || ay + dy >= W || ay + dy < 0) continue;
     if (st[(ax + dx) * W + ay + dy] < 0) continue;
     if (st[(ax + dx) * W + ay + dy] > 0) continue;
-    out5[a] = 1;
+    if (o->diagonal && primal_diagonal_collision(o, e, id, ax + dx, ay + dy)) continue;   /* :658-660 */
+    out[a] = 1;
   }
   int opp = PRIMAL_OPPOSITE[prev_action];
-  if (opp >= 0) out5[opp] = 0;                                      /* PRIMAL:664-665 */
+  if (opp >= 0) out[opp] = 0;                                       /* PRIMAL:664-665 */
 }
 
 /* One sweep `for id in lo+1..hi: _step((id, a))`, PRIMAL:549-637 without the observation
@@ -485,7 +514,7 @@ int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, i
       size_t k = (size_t)e * N + i;
       int id = i + 1;
       int action = actions[k];
-      if (action > 4) { bad++; action = 0; }
+      if (action > (o->diagonal ? 8 : 4)) { bad++; action = 0; }
       int status = primal_move_agent(o, e, id, action);            /* world.act, PRIMAL:570 */
       double r;
       int is_blocking = 0;
@@ -511,13 +540,13 @@ int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, i
       if (on_goal_out) on_goal_out[k] = (uint8_t)on_goal;
       if (valid_out) valid_out[k] = (uint8_t)(status >= 0);         /* PRIMAL:571 */
       if (done_mid) done_mid[k] = (uint8_t)primal_done(o, e);       /* PRIMAL:626 */
-      if (next_mid) primal_valid_actions(o, e, id, action, next_mid + 5 * k); /* PRIMAL:630 */
+      if (next_mid) primal_valid_actions(o, e, id, action, next_mid + (size_t)(o->diagonal ? 9 : 5) * k); /* PRIMAL:630 */
     }
     if (avail)
       for (int i = 0; i < N; ++i) {
         size_t k = (size_t)e * N + i;
-        int prev = (i >= lo && i < hi) ? (actions[k] > 4 ? 0 : actions[k]) : 0;
-        primal_valid_actions(o, e, i + 1, prev, avail + 5 * k);
+        int prev = (i >= lo && i < hi) ? (actions[k] > (o->diagonal ? 8 : 4) ? 0 : actions[k]) : 0;
+        primal_valid_actions(o, e, i + 1, prev, avail + (size_t)(o->diagonal ? 9 : 5) * k);
       }
     if (terminated) terminated[e] = (uint8_t)primal_done(o, e);
     if (reward) reward[e] = total;
@@ -531,7 +560,7 @@ void oracle_primal_avail(const oracle_env* o, const uint8_t* prev_action, uint8_
   for (int e = 0; e < o->E; ++e)
     for (int i = 0; i < o->N; ++i) {
       size_t k = (size_t)e * o->N + i;
-      primal_valid_actions(o, e, i + 1, prev_action ? prev_action[k] : 0, avail + 5 * k);
+      primal_valid_actions(o, e, i + 1, prev_action ? prev_action[k] : 0, avail + (size_t)(o->diagonal ? 9 : 5) * k);
     }
 }
 
@@ -619,8 +648,9 @@ void oracle_goal_dist(const oracle_env* o, const uint8_t* dirty, int primal_cost
         while (head < tail) {
           int c = queue[head++];
           int r0 = c / W, c0 = c % W;
-          static const int D[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}};
-          for (int q = 0; q < 4; ++q) {
+          static const int D[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {1, 1}, {1, -1}, {-1, -1}, {-1, 1}};
+          const int nd = (primal_costs && o->diagonal) ? 8 : 4;      /* getNeighbors, PRIMAL:421-437 */
+          for (int q = 0; q < nd; ++q) {
             int r1 = r0 + D[q][0], c1 = c0 + D[q][1];
             if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;
             int n = r1 * W + c1;

@@ -42,6 +42,8 @@ def _lib():
         lib.oracle_primal_sweep.argtypes = [vp, vp, i, i] + [vp] * 10
         lib.oracle_primal_set_blocking.argtypes = [vp, i]
         lib.oracle_primal_set_blocking.restype = None
+        lib.oracle_primal_set_diagonal.argtypes = [vp, i]
+        lib.oracle_primal_set_diagonal.restype = None
         lib.oracle_primal_sweep.restype = i
         lib.oracle_goal_dist.argtypes = [vp, vp, i, vp]
         lib.oracle_goal_dist.restype = None
@@ -85,6 +87,7 @@ class Oracle:
             collide_is_int = isinstance(collide_reward, int)
         self.E, self.N, self.H, self.W, self.F = n_envs, n_agents, height, width, fov
         self.mode = mode
+        self.n_actions = 5
         self.shared_map = bool(shared_map)
         self._lib = _lib()
         self._h = self._lib.oracle_create(n_envs, n_agents, height, width, fov, int(self.shared_map),
@@ -169,8 +172,8 @@ class Oracle:
         E, N = self.E, self.N
         out = dict(status=np.zeros((E, N), np.int8), agent_reward=np.zeros((E, N), np.float64),
                    dones=np.zeros((E, N), np.uint8), valid=np.zeros((E, N), np.uint8),
-                   done_mid=np.zeros((E, N), np.uint8), next_mid=np.zeros((E, N, 5), np.uint8),
-                   avail=np.zeros((E, N, 5), np.uint8), terminated=np.zeros(E, np.uint8),
+                   done_mid=np.zeros((E, N), np.uint8), next_mid=np.zeros((E, N, self.n_actions), np.uint8),
+                   avail=np.zeros((E, N, self.n_actions), np.uint8), terminated=np.zeros(E, np.uint8),
                    reward=np.zeros(E, np.float64), blocking=np.zeros((E, N), np.uint8))
         out = {k: v for k, v in out.items() if k in want}
         bad = self._lib.oracle_primal_sweep(self._h, _p(a), int(lo), int(hi), _p(out.get("status")),
@@ -181,12 +184,17 @@ class Oracle:
         out["bad_actions"] = bad
         return out
 
+    def set_diagonal(self, on=True):
+        """PRIMAL DIAGONAL_MOVEMENT (mapf_primal.py:175): 9 actions; call before reset()."""
+        self._lib.oracle_primal_set_diagonal(self._h, int(bool(on)))
+        self.n_actions = 9 if on else 5
+
     def set_blocking(self, on=True):
         """PRIMAL blocking reward (mapf_primal.py:513-546) with single-robot BFS path lengths."""
         self._lib.oracle_primal_set_blocking(self._h, int(bool(on)))
 
     def primal_avail(self, prev_action=None):
-        out = np.empty((self.E, self.N, 5), np.uint8)
+        out = np.empty((self.E, self.N, self.n_actions), np.uint8)
         pa = None if prev_action is None else np.ascontiguousarray(prev_action, dtype=np.uint8)
         self._lib.oracle_primal_avail(self._h, _p(pa), _p(out))
         return out

@@ -32,7 +32,7 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_names(family):
-    pref = {"GRID": "grid_", "PRIMAL": "primal_", "PDIST": "pdist_", "PARTIAL": "partial_", "PRIMALB": "primalb_"}[family]
+    pref = {"GRID": "grid_", "PRIMAL": "primal_", "PDIST": "pdist_", "PARTIAL": "partial_", "PRIMALB": "primalb_", "PRIMALD": "primald_"}[family]
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith(pref) and f.endswith(".npz"))
 
 

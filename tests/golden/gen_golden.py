@@ -172,18 +172,20 @@ def primal_world(obst, starts, goals):
     return world, g
 
 
-def mask5(lst):
-    m = np.zeros(5, np.uint8)
+def mask5(lst, n_act=5):
+    m = np.zeros(n_act, np.uint8)
     for a in lst:
         m[a] = 1
     return m
 
 
-def run_primal(name, obst, starts, goals, fov, actions, n_costs=3, blocking=False, greedy=None):
+def run_primal(name, obst, starts, goals, fov, actions, n_costs=3, blocking=False, greedy=None, diagonal=False):
     n = len(starts)
     T = actions.shape[0]
     world0, goals0 = primal_world(obst, starts, goals)
-    env = PRIMAL.MAPFEnv(num_agents=n, observation_size=fov, world0=world0.copy(), goals0=goals0.copy())
+    env = PRIMAL.MAPFEnv(num_agents=n, observation_size=fov, world0=world0.copy(), goals0=goals0.copy(),
+                         DIAGONAL_MOVEMENT=diagonal)
+    n_act = 9 if diagonal else 5
     statuses = []
     orig_act = env.world.act
 
@@ -206,7 +208,7 @@ def run_primal(name, obst, starts, goals, fov, actions, n_costs=3, blocking=Fals
         return o, v
 
     obs0, vec0 = observe_all()
-    avail0 = np.array([mask5(env._listNextValidActions(i)) for i in range(1, n + 1)])
+    avail0 = np.array([mask5(env._listNextValidActions(i), n_act) for i in range(1, n + 1)])
     costs0 = np.array([env.getAstarCosts(env.world.getPos(i), env.world.getGoal(i))
                        for i in range(1, min(n, n_costs) + 1)], dtype=np.int32)
     rec = {k: [] for k in ("status", "reward", "done_mid", "next_mid", "on_goal", "valid",
@@ -241,7 +243,7 @@ def run_primal(name, obst, starts, goals, fov, actions, n_costs=3, blocking=Fals
             row["blocking"].append(bool(blk))
             row["reward"].append(float(reward))
             row["done_mid"].append(bool(done))
-            row["next_mid"].append(mask5(nxt))
+            row["next_mid"].append(mask5(nxt, n_act))
             row["on_goal"].append(bool(on_goal))
             row["valid"].append(bool(valid))
         rec["status"].append(np.array(statuses, dtype=np.int8))
@@ -255,7 +257,7 @@ def run_primal(name, obst, starts, goals, fov, actions, n_costs=3, blocking=Fals
         o, v = observe_all()
         rec["obs"].append(o)
         rec["vec"].append(v)
-        rec["avail"].append(np.array([mask5(env._listNextValidActions(i, int(actions[t, i - 1])))
+        rec["avail"].append(np.array([mask5(env._listNextValidActions(i, int(actions[t, i - 1])), n_act)
                                       for i in range(1, n + 1)]))
         rec["done"].append(bool(env.world.done()))
     costsT = np.array([env.getAstarCosts(env.world.getPos(i), env.world.getGoal(i))
@@ -263,7 +265,7 @@ def run_primal(name, obst, starts, goals, fov, actions, n_costs=3, blocking=Fals
     out = dict(family="PRIMAL", obst=obst.astype(np.uint8), starts=np.array(starts, dtype=np.int16),
                goals=np.array(goals, dtype=np.int16), fov=np.int64(fov), actions=actions.astype(np.uint8),
                obs0=obs0, vec0=vec0, avail0=avail0, costs0=costs0, costsT=costsT,
-               blocking_enabled=np.int64(bool(blocking)),
+               blocking_enabled=np.int64(bool(blocking)), diagonal=np.int64(bool(diagonal)),
                **{k: np.array(v) for k, v in rec.items()})
     out["done"] = out["done"].astype(np.uint8)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
@@ -304,6 +306,22 @@ def gen_primal():
     run_primal("primal_rect", obst, s, g, 7, rs.randint(0, 5, [30, 6]))
     rs, obst, s, g = rand_primal_case(7000, 40, 40, 0.25, 7)       # N not a multiple of 4, W > 32
     run_primal("primal_n7w40", obst, s, g, 11, rs.randint(0, 5, [20, 7]))
+
+
+def gen_primal_diagonal():
+    """PRIMAL with DIAGONAL_MOVEMENT=True (9 actions, diagonalCollision mapf_primal.py:77-100, 8-connected costs)."""
+    rs, obst, s_, g_ = rand_primal_case(9000, 12, 12, 0.15, 8)
+    run_primal("primald_12", obst, s_, g_, 7, rs.randint(0, 9, [60, 8]), diagonal=True)
+    rs, obst, s_, g_ = rand_primal_case(9100, 7, 7, 0.05, 14)          # crowded: many crossings
+    run_primal("primald_crowd", obst, s_, g_, 5, rs.randint(0, 9, [80, 14]), diagonal=True)
+    rs, obst, s_, g_ = rand_primal_case(9200, 20, 24, 0.2, 12)
+    acts = rs.randint(0, 9, [40, 12])
+    acts[rs.rand(40, 12) < 0.5] = rs.randint(5, 9)                     # mostly diagonal moves
+    run_primal("primald_rect", obst, s_, g_, 11, acts, diagonal=True)
+    obst = np.zeros((6, 6), bool)
+    run_primal("primald_open6", obst, [(r, c) for r in range(3) for c in range(4)],
+               [(5 - r, 5 - c) for r in range(3) for c in range(4)], 3,
+               np.random.RandomState(9300).randint(4, 9, [50, 12]), diagonal=True)
 
 
 def gen_primal_blocking():
@@ -450,13 +468,15 @@ def gen_partial():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["grid", "primal", "primalb", "pdist", "partial"]
+    which = sys.argv[1:] or ["grid", "primal", "primalb", "primald", "pdist", "partial"]
     if "grid" in which:
         gen_grid()
     if "primal" in which:
         gen_primal()
     if "primalb" in which:
         gen_primal_blocking()
+    if "primald" in which:
+        gen_primal_diagonal()
     if "pdist" in which:
         gen_pdist()
     if "partial" in which:

@@ -39,7 +39,7 @@ def test_grid_oracle_matches_reference_trace(name):
         assert out["terminated"][0] == int(g["dones"][t].all())
 
 
-@pytest.mark.parametrize("name", golden_names("PRIMAL") + golden_names("PRIMALB"))
+@pytest.mark.parametrize("name", golden_names("PRIMAL") + golden_names("PRIMALB") + golden_names("PRIMALD"))
 def test_primal_oracle_matches_reference_trace(name):
     g = load_golden(name)
     H, W = g["obst"].shape
@@ -47,6 +47,7 @@ def test_primal_oracle_matches_reference_trace(name):
     F = int(g["fov"])
     o = Oracle(1, N, H, W, MODE_PRIMAL, fov=F)
     o.set_blocking(bool(g.get("blocking_enabled", 0)))
+    o.set_diagonal(bool(g.get("diagonal", 0)))
     o.reset(g["obst"][None], g["starts"][None], g["goals"][None])
     obs, vec = o.primal_observe()
     assert np.array_equal(obs[0], g["obs0"])
