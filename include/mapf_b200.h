@@ -148,6 +148,11 @@ typedef struct mapf_cfg {
    * counts.  Maps up to 64 x 64. */
   int32_t blocking_reward;
   double blocking_cost;      /* BLOCKING_COST, PRIMAL:25 (-1.0) */
+  /* MAPF_MODE_PRIMAL: DIAGONAL_MOVEMENT=True (PRIMAL:175): 9 actions {5:(1,1) 6:(1,-1) 7:(-1,-1) 8:(-1,1)} (dirDict,
+   * PRIMAL:28), State.diagonalCollision (PRIMAL:77-100) against every other agent's last recorded move, 9-wide action
+   * masks ([E,N,9] for avail_dev / next_mid_dev) and 8-connected getAstarCosts (primal_costs in mapf_bfs). */
+  int32_t diagonal_movement;
+  int32_t reserved3;
 } mapf_cfg;
 
 /* Outputs of one step.  Every pointer is a device pointer and may be NULL (not written). */
@@ -172,9 +177,11 @@ typedef struct mapf_step_out {
   uint8_t* valid_dev;
   /* [E, N] PRIMAL `done` as returned by the i-th _step call of the sweep (mid-sweep, PRIMAL:626). */
   uint8_t* done_mid_dev;
-  /* [E, N, 5] PRIMAL `nextActions` as returned by the i-th _step call (mid-sweep, PRIMAL:630). */
+  /* [E, N, A] PRIMAL `nextActions` as returned by the i-th _step call (mid-sweep, PRIMAL:630); A = 5, or 9 with
+   * cfg.diagonal_movement. */
   uint8_t* next_mid_dev;
-  /* [E, N, 5] available-action mask after the step.  GRID: get_avail_actions (GRID:198-224).
+  /* [E, N, A] available-action mask after the step (A = 5, or 9 with cfg.diagonal_movement).
+   * GRID: get_avail_actions (GRID:198-224).
    * PRIMAL: _listNextValidActions(i, action_i) evaluated after the whole sweep (PRIMAL:639-667). */
   uint8_t* avail_dev;
   /* [E, N] PRIMAL `blocking` as returned by _step (PRIMAL:578-585, 637); needs cfg.blocking_reward. */

@@ -46,6 +46,7 @@ class MapfCfg(ctypes.Structure):
         ("env_collide_reward", ctypes.c_double),
         ("complete_lut_host", _vp), ("complete_lut_len", ctypes.c_int32), ("blocking_reward", ctypes.c_int32),
         ("blocking_cost", ctypes.c_double),
+        ("diagonal_movement", ctypes.c_int32), ("reserved3", ctypes.c_int32),
     ]
 
 

@@ -96,6 +96,14 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L, bool s
   L->envcnt_off = take(4 * epb);
   L->envcnt2_off = take(4 * epb);
   L->envstep_off = take(4 * epb);
+  if (d.diag) {   // PRIMAL with DIAGONAL_MOVEMENT only: the common layouts stay as they are
+    L->pastold_off = take(2 * na);
+    L->pastnew_off = take(2 * na);
+    L->mask16_off = take(2 * na);
+    L->nextmid16_off = take(2 * na);
+  } else {
+    L->pastold_off = L->pastnew_off = L->mask16_off = L->nextmid16_off = scratch0;
+  }
   const int scratch1 = off;
   const int str_bytes = fov ? ((na + d.G - 1) / d.G) * d.GW * 4 + 16 : 16;
   L->str_off = scratch0;
@@ -185,6 +193,7 @@ int mapf_destroy(mapf_handle* h) {
   cudaFree(h->S.stats);
   cudaFree(h->S.err_flags);
   cudaFree(h->S.pos_prev);
+  cudaFree(h->S.past);
   cudaFree(h->S.last_status);
   cudaFree(h->S.last_reward);
   cudaFree(h->S.at_goal);
@@ -228,6 +237,12 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
       return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_create: blocking_reward needs mode PRIMAL with the FOV observation");
     if (c->height > 64 || c->width > 64)
       return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_create: blocking_reward supports maps up to 64 x 64");
+  }
+  if (c->diagonal_movement) {
+    if (c->mode != MAPF_MODE_PRIMAL)
+      return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_create: diagonal_movement exists only in mode PRIMAL");
+    if (c->blocking_reward)
+      return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_create: blocking_reward with diagonal_movement is not supported");
   }
   if (c->mode == MAPF_MODE_PARTIAL) {
     if (c->obs_window < 1 || c->obs_window > 255 || c->obs_knn_agents < 1 || c->obs_knn_agents > 254)
@@ -281,6 +296,8 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   d.collect_stats = c->collect_stats;
   d.blocking = c->blocking_reward ? 1 : 0;
   d.blocking_cost = c->blocking_cost;
+  d.diag = c->diagonal_movement ? 1 : 0;
+  d.nact = d.diag ? 9 : 5;
   d.pW = c->obs_window;
   d.pK = c->obs_knn_agents;
   d.posz = 2 * d.pW * d.pW + 13 * d.pK;
@@ -339,6 +356,7 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   ALLOC(h->S.prev_action, EN);
   ALLOC(h->S.step_count, (size_t)d.E * 4);
   if (c->goal_dist || c->mode == MAPF_MODE_PARTIAL) ALLOC(h->S.goal_dist, EN * d.HW * 2);
+  if (d.diag) ALLOC(h->S.past, EN * 2);
   if (c->blocking_reward) {
     ALLOC(h->S.pos_prev, EN * 2);
     ALLOC(h->S.last_status, EN);
@@ -372,6 +390,7 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   if (e == cudaSuccess) e = cudaMemset(h->S.done, 0, EN);
   if (e == cudaSuccess) e = cudaMemset(h->S.prev_action, 0, EN);
   if (e == cudaSuccess) e = cudaMemset(h->S.step_count, 0, (size_t)d.E * 4);
+  if (e == cudaSuccess && d.diag) e = cudaMemset(h->S.past, 0, EN * 2);
   if (e == cudaSuccess) e = cudaMemset(h->S.stats, 0, MAPF_N_STATS * 8);
   if (e == cudaSuccess) e = cudaMemset(h->S.err_flags, 0, 4);
   if (e == cudaSuccess) {
@@ -390,7 +409,7 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
     if (e == cudaSuccess) e = cudaMemset(h->S.terminated, 0, (size_t)d.E);
   }
   if (e == cudaSuccess && h->L.total_bytes > 48 * 1024)
-    e = (cudaError_t)mapf_configure_tile(h->fov_fast ? d.F : 0, d.mode, h->L.total_bytes);
+    e = (cudaError_t)mapf_configure_tile(h->fov_fast ? d.F : 0, d.diag ? MAPF_MODE_PRIMAL_DIAG : d.mode, h->L.total_bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     int rc = cuda_fail(nullptr, e, "mapf_create: initialisation");
@@ -635,7 +654,7 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   if (io->reward_host) LAZY(h->hs_reward, (size_t)d.E * 8);
   if (io->terminated_host) LAZY(h->hs_terminated, (size_t)d.E);
   if (io->dones_host) LAZY(h->hs_dones, EN);
-  if (io->avail_host) LAZY(h->hs_avail, EN * 5);
+  if (io->avail_host) LAZY(h->hs_avail, EN * d.nact);
   if (io->vec_host) LAZY(h->hs_vec, EN * 24);
 #undef LAZY
   if (obs_bytes > h->hs_obs_bytes) {
@@ -659,7 +678,7 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   if (io->terminated_host)
     CK(cudaMemcpyAsync(io->terminated_host, h->hs_terminated, (size_t)d.E, cudaMemcpyDeviceToHost, st));
   if (io->dones_host) CK(cudaMemcpyAsync(io->dones_host, h->hs_dones, EN, cudaMemcpyDeviceToHost, st));
-  if (io->avail_host) CK(cudaMemcpyAsync(io->avail_host, h->hs_avail, EN * 5, cudaMemcpyDeviceToHost, st));
+  if (io->avail_host) CK(cudaMemcpyAsync(io->avail_host, h->hs_avail, EN * d.nact, cudaMemcpyDeviceToHost, st));
   if (io->vec_host) CK(cudaMemcpyAsync(io->vec_host, h->hs_vec, EN * 24, cudaMemcpyDeviceToHost, st));
   if (io->obs_host) CK(cudaMemcpyAsync(io->obs_host, h->hs_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -10,6 +10,7 @@
 #endif
 #define MAPF_MAX_AGENTS 255
 #define MAPF_MAX_SIDE 255
+#define MAPF_MODE_PRIMAL_DIAG 3   // internal: MAPF_MODE_PRIMAL with cfg.diagonal_movement (its own kernel instantiation)
 
 // Problem dimensions and constants, passed by value to every kernel.
 struct MapfDims {
@@ -30,6 +31,8 @@ struct MapfDims {
   int sum_mode, step_is_int, collide_is_int;
   int collect_stats;
   int blocking;          // PRIMAL blocking reward enabled
+  int diag;              // PRIMAL DIAGONAL_MOVEMENT
+  int nact;              // 5, or 9 with diagonal movement
   double blocking_cost;
   uint32_t invN, invW;  // ceil(2^32 / N), ceil(2^32 / W): exact division of values < 65536 by IMAD.HI
   double step_reward, collide_reward;
@@ -57,6 +60,8 @@ struct MapfTileLayout {
   int envcnt2_off;  // int [epb]: PARTIAL: sum of node flags + edge counts
   int envstep_off;  // int [epb]: step counter before this step
   int atgoal_off;   // u8 [epb*N]: PARTIAL _agent_at_goals
+  int pastold_off, pastnew_off;   // uchar2 [epb*N]: PRIMAL diagonal mode, State.agents_past before / after the sweep
+  int mask16_off, nextmid16_off;  // u16 [epb*N]: 9-wide action masks (diagonal mode)
   int str_off;      // bit strings: ceil(epb*N / G) * GW u32
   int total_bytes;
 };
@@ -75,6 +80,7 @@ struct MapfState {
   unsigned long long* stats;  // [MAPF_N_STATS]
   // PRIMAL blocking reward (cfg.blocking_reward): what the follow-up kernel needs from the sweep
   uint8_t* pos_prev;       // [E][N][2] positions before the last sweep
+  uint8_t* past;           // [E][N][2] State.agents_past (diagonal mode)
   int8_t* last_status;     // [E][N]
   double* last_reward;     // [E][N]
   // MAPF_MODE_PARTIAL
@@ -116,7 +122,7 @@ int mapf_launch_reset(const MapfDims& d, const MapfState& S, const int16_t* star
 int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, const int16_t* goals, const uint8_t* dirty,
                           void* stream);
 int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, const uint8_t* env_mask, int16_t* dist,
-                    int primal_costs, void* stream, int* n_launches);
+                    int primal_costs, void* stream, int* n_launches);   // 8-connected when primal_costs && d.diag
 int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int agent_lo, int agent_hi, const mapf_step_out& out,
                          void* stream, int* n_launches);
 int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, double* obs, void* stream);

@@ -55,6 +55,8 @@ struct Smem {
   double* envrew;
   uint8_t* envterm;
   uint8_t* atgoal;
+  uchar2 *pastold, *pastnew;     // diagonal mode: agents_past before / after the sweep
+  uint16_t *mask16, *nextmid16;  // diagonal mode: 9-wide action masks
   uint32_t* str;
 };
 
@@ -83,6 +85,10 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const MapfTileLayout&
   s.envrew = (double*)(base + L.envrew_off);
   s.envterm = base + L.envterm_off;
   s.atgoal = base + L.atgoal_off;
+  s.pastold = (uchar2*)(base + L.pastold_off);
+  s.pastnew = (uchar2*)(base + L.pastnew_off);
+  s.mask16 = (uint16_t*)(base + L.mask16_off);
+  s.nextmid16 = (uint16_t*)(base + L.nextmid16_off);
   s.str = (uint32_t*)(base + L.str_off);
   return s;
 }
@@ -124,6 +130,21 @@ __device__ __noinline__ void copy_out_bytes(uint8_t* dst, const uint8_t* src, in
     for (int i = (nw << 2) + tid; i < n; i += kThreads) dst[i] = src[i];
   } else {
     for (int i = tid; i < n; i += kThreads) dst[i] = src[i];
+  }
+}
+
+// PRIMAL dirDict (PRIMAL:28) for the 9 actions {0:(0,0) 1:(0,1) 2:(1,0) 3:(0,-1) 4:(-1,0) 5:(1,1) 6:(1,-1) 7:(-1,-1)
+// 8:(-1,1)}, two bits per action holding delta + 1; and opposite_actions (PRIMAL:26), four bits per action (0 = none).
+__device__ __forceinline__ int dir9_dx(int a) { return (int)((0x002865u >> (2 * a)) & 3u) - 1; }
+__device__ __forceinline__ int dir9_dy(int a) { return (int)((0x020919u >> (2 * a)) & 3u) - 1; }
+__device__ __forceinline__ int opposite9(int a) { return (int)((0x658721430ull >> (4 * a)) & 15ull); }
+
+// Expands per-agent n-bit masks (uint16) to the [na][nact] uint8 layout (diagonal mode: nact = 9).
+__device__ __noinline__ void write_mask_n(uint8_t* dst, const uint16_t* mask, int na, int nact, int tid) {
+  const int n = nact * na;
+  for (int idx = tid; idx < n; idx += kThreads) {
+    const int ag = idx / nact;
+    dst[idx] = (mask[ag] >> (idx - nact * ag)) & 1u;
   }
 }
 
@@ -206,6 +227,7 @@ constexpr uint8_t RES_UNRESOLVED = 0, RES_MOVED = 1, RES_STAYS = 2;
 
 // PRIMAL phase A for agent j: State.moveAgent's checks that do not involve other robots (PRIMAL:107-118).
 // mv[j] = padded target cell (0xffffffff: no claim to make); status[j] = pre-status.
+template <bool DIAG>
 __device__ __forceinline__ void primal_phase_a(const MapfDims& d, const Smem& s, const MapfTileArgs& A, int j, int el,
                                                int a) {
   const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
@@ -218,8 +240,8 @@ __device__ __forceinline__ void primal_phase_a(const MapfDims& d, const Smem& s,
   } else if (act == 0) {
     st = PRE_STAY;
   } else {
-    const int t0 = (int)p.x + (act == 2 ? 1 : (act == 4 ? -1 : 0));  // dirDict, PRIMAL:28
-    const int t1 = (int)p.y + (act == 1 ? 1 : (act == 3 ? -1 : 0));
+    const int t0 = (int)p.x + (DIAG ? dir9_dx(act) : (act == 2 ? 1 : (act == 4 ? -1 : 0)));  // dirDict, PRIMAL:28
+    const int t1 = (int)p.y + (DIAG ? dir9_dy(act) : (act == 1 ? 1 : (act == 3 ? -1 : 0)));
     if (bm_test(ob, d.RW, d.P, t0, t1)) {
       st = (t0 < 0 || t0 >= d.H || t1 < 0 || t1 >= d.W) ? -1 : -2;   // PRIMAL:114-118
     } else {
@@ -229,6 +251,50 @@ __device__ __forceinline__ void primal_phase_a(const MapfDims& d, const Smem& s,
   }
   s.status[j] = st;
   s.mv[j] = tc;
+}
+
+// Diagonal mode, State.diagonalCollision (PRIMAL:77-100): does the midpoint of the move (lx,ly) -> (nx,ny) of agent a
+// equal the midpoint of another agent's last recorded move?  (np.isclose on half-integers == integer sums equal.)
+__device__ __forceinline__ bool diagonal_collision(const uchar2* past, const uchar2* pos, int N, int a, int lx, int ly,
+                                                   int nx, int ny) {
+  for (int k = 0; k < N; ++k) {
+    if (k == a) continue;
+    const uchar2 q = past[k], r = pos[k];
+    if ((int)q.x + r.x == lx + nx && (int)q.y + r.y == ly + ny) return true;
+  }
+  return false;
+}
+
+// Diagonal mode, phase B: the sweep itself, one lane per environment.  The crossing rule looks at other agents' last
+// RECORDED move (agents_past is only updated when an agent acts, PRIMAL:109, 128), which makes the outcome depend on
+// the running state of the whole sweep; the mode is off by default in the reference, so it simply walks the agents in
+// id order against the live grid, live positions (posnew) and live agents_past (pastnew).
+__device__ __forceinline__ void primal_phase_b_diag(const MapfDims& d, const Smem& s, const MapfTileArgs& A, int el) {
+  const int N = d.N, jb = el * N;
+  uint8_t* grid = s.grida + el * d.grid_bytes;
+  uchar2* pos = s.posnew + jb;
+  uchar2* past = s.pastnew + jb;
+  for (int i = A.agent_lo; i < A.agent_hi; ++i) {
+    const int j = jb + i;
+    const int8_t st = s.status[j];
+    const uchar2 p = pos[i];
+    if (st == PRE_STAY) {
+      past[i] = p;                                                   // PRIMAL:109
+    } else if (st == PRE_MOVE) {
+      const int tc = (int)s.mv[j];
+      const int act = s.act[j];
+      const int nx = (int)p.x + dir9_dx(act), ny = (int)p.y + dir9_dy(act);
+      if (grid[tc] != 0 || diagonal_collision(past, pos, N, i, p.x, p.y, nx, ny)) {
+        s.status[j] = -3;                                            // PRIMAL:119-124
+      } else {
+        grid[gcell(d, p.x, p.y)] = 0;                                // PRIMAL:126-129
+        grid[tc] = (uint8_t)(i + 1);
+        past[i] = p;
+        pos[i] = make_uchar2((unsigned char)nx, (unsigned char)ny);
+        s.status[j] = PRE_MOVED;
+      }
+    }
+  }
 }
 
 // PRIMAL phase B: the outcome of the ordered sweep `for id in 1..N: moveAgent(id)` (PRIMAL:119-129) WITHOUT walking
@@ -265,6 +331,7 @@ __device__ __forceinline__ uint8_t primal_classify(const MapfDims& d, const Smem
 }
 
 // PRIMAL phase C for agent j: final status (PRIMAL:108-110, 130-135), reward table (:579-597), on_goal (:633).
+template <bool DIAG>
 __device__ __forceinline__ bool primal_phase_c(const MapfDims& d, const Smem& s, int j, int el, int a,
                                                unsigned int& c_env, unsigned int& c_rob, unsigned int& c_arr) {
   const uchar2 po = s.posold[j], g = s.goal[j];
@@ -272,7 +339,9 @@ __device__ __forceinline__ bool primal_phase_c(const MapfDims& d, const Smem& s,
   const bool swept = st != PRE_SKIP;
   uchar2 pn = po;
   const int act = s.act[j];
-  if (st == PRE_MOVE) {
+  if (DIAG) {
+    pn = s.posnew[j];                                                // the serial sweep already moved the agent
+  } else if (st == PRE_MOVE) {
     if (s.res[j] == RES_MOVED) {
       pn = make_uchar2((unsigned char)((int)po.x + (act == 2 ? 1 : (act == 4 ? -1 : 0))),
                        (unsigned char)((int)po.y + (act == 1 ? 1 : (act == 3 ? -1 : 0))));
@@ -358,6 +427,51 @@ __device__ void primal_mid_outputs(const MapfDims& d, const Smem& s, const MapfT
       new_prefix += __popc(bn);
       old_prefix += __popc(bo);
     }
+  }
+}
+
+// Diagonal mode: the 9-wide masks.  `ahead` = index of the sweeping agent at the moment the mask is evaluated: agents
+// below it are taken from their post-sweep records (posnew / pastnew), the others from the pre-sweep ones; ahead = N
+// gives the state after the whole sweep.  _listNextValidActions, PRIMAL:639-667 with the crossing test :658-660.
+__device__ __forceinline__ bool diagonal_collision_at(const Smem& s, int jb, int N, int a, int ahead, int sx, int sy) {
+  for (int k = 0; k < N; ++k) {
+    if (k == a) continue;
+    const uchar2 q = (k < ahead) ? s.pastnew[jb + k] : s.pastold[jb + k];
+    const uchar2 r = (k < ahead) ? s.posnew[jb + k] : s.posold[jb + k];
+    if ((int)q.x + r.x == sx && (int)q.y + r.y == sy) return true;
+  }
+  return false;
+}
+
+// Mid-sweep `done` and `nextActions` of the diagonal mode (PRIMAL:626-630), one thread per agent.
+__device__ void primal_mid_outputs_diag(const MapfDims& d, const Smem& s, const MapfTileArgs& A, int ne, int tid) {
+  const int N = d.N, na = ne * N;
+  for (int j = tid; j < na; j += kThreads) {
+    const int el = fast_div(j, d.invN), a = j - el * N, jb = el * N;
+    const uint8_t* grid = s.grida + el * d.grid_bytes;
+    const uint8_t* gold = s.gridb + el * d.grid_bytes;
+    const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+    int cnt = 0;
+    for (int k = 0; k < N; ++k) {
+      const uchar2 q = (k <= a) ? s.posnew[jb + k] : s.posold[jb + k], g = s.goal[jb + k];
+      cnt += (q.x == g.x && q.y == g.y) ? 1 : 0;
+    }
+    if (cnt == N) s.flag[j] |= 4;
+    const uchar2 pn = s.posnew[j];
+    uint32_t m = 1;
+    for (int k = 1; k <= 8; ++k) {
+      const int n0 = (int)pn.x + dir9_dx(k), n1 = (int)pn.y + dir9_dy(k);
+      if (bm_test(ob, d.RW, d.P, n0, n1)) continue;
+      const int c = gcell(d, n0, n1);
+      const int idn = grid[c], ido = gold[c];
+      if ((ido > a + 1) || (idn != 0 && idn < a + 1)) continue;
+      if (diagonal_collision_at(s, jb, N, a, a + 1, (int)pn.x + n0, (int)pn.y + n1)) continue;
+      m |= 1u << k;
+    }
+    const int opp = opposite9(s.act[j]);
+    if (opp > 0) m &= ~(1u << opp);
+    const bool swept = (a >= A.agent_lo && a < A.agent_hi);
+    s.nextmid16[j] = (uint16_t)(swept ? m : 0);
   }
 }
 
@@ -559,8 +673,10 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
   const int ne = min(d.epb, d.E - e0);
   const int na = ne * N;
   const size_t a0 = (size_t)e0 * N;
-  constexpr bool primal = MODE == MAPF_MODE_PRIMAL;     // the mode is a template parameter: the other modes' code is
-  constexpr bool partial = MODE == MAPF_MODE_PARTIAL;   // not even in this kernel's instruction stream
+  // the mode is a template parameter: the other modes' code is not even in this kernel's instruction stream
+  constexpr bool diag = MODE == MAPF_MODE_PRIMAL_DIAG;   // PRIMAL with DIAGONAL_MOVEMENT (9 actions)
+  constexpr bool primal = MODE == MAPF_MODE_PRIMAL || diag;
+  constexpr bool partial = MODE == MAPF_MODE_PARTIAL;
   int* envcnt2 = (int*)(smem_raw + L.envcnt2_off);
   const bool do_step = A.do_step != 0;
   const bool need_mid = primal && do_step && ((A.out.done_mid_dev != nullptr) || (A.out.next_mid_dev != nullptr));
@@ -589,12 +705,17 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     s.goal[j] = ((const uchar2*)S.goal)[a0 + j];
     s.done[j] = S.done[a0 + j];
     if (partial) s.atgoal[j] = S.at_goal[a0 + j];
+    if (diag) {
+      const uchar2 q = ((const uchar2*)S.past)[a0 + j];
+      s.pastold[j] = q;
+      s.pastnew[j] = q;
+    }
     const int el = fast_div(j, d.invN), a = j - el * N;
     int act = S.prev_action[a0 + j];
     if (do_step && a >= A.agent_lo && a < A.agent_hi) {
       long long v = (A.act_dtype == MAPF_I64) ? ((const long long*)A.actions)[a0 + j]
                                               : (long long)((const uint8_t*)A.actions)[a0 + j];
-      if (v < 0 || v > 4) {                                          // GRID:92 / PRIMAL:556 assert
+      if (v < 0 || v > (diag ? 8 : 4)) {                             // GRID:92 / PRIMAL:556 assert
         bad = true;
         v = primal ? 0 : 4;
       }
@@ -627,7 +748,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
     const int cell = gcell(d, p.x, p.y);
     if (primal) {
       grid[cell] = (uint8_t)(a + 1);
-      if (do_step) primal_phase_a(d, s, A, j, el, a);
+      if (do_step) primal_phase_a<diag>(d, s, A, j, el, a);
     } else {
       byte_inc(grid, cell);
       if (do_step) {
@@ -646,6 +767,11 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       if (need_mid)   // keep the pre-sweep id grid for the mid-sweep outputs
         for (int i = tid; i < ((ne * d.grid_bytes) >> 4); i += kThreads)
           ((uint4*)s.gridb)[i] = ((const uint4*)s.grida)[i];
+      if constexpr (diag) {
+        __syncthreads();                       // the copy above reads the grid the sweep is about to change
+        for (int el = tid; el < ne; el += kThreads) primal_phase_b_diag(d, s, A, el);
+        __syncthreads();
+      } else {
       bool pending = false;
       for (int j = tid; j < na; j += kThreads) {
         const int el = fast_div(j, d.invN), a = j - el * N;
@@ -669,6 +795,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
           s.grida[fast_div(j, d.invN) * d.grid_bytes + gcell(d, p.x, p.y)] = 0;
         }
       __syncthreads();
+      }
     }
   PHASE_MARK(3);
     // ---- phase C
@@ -680,7 +807,7 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       if (active) {
         el = fast_div(j, d.invN);
         const int a = j - el * N;
-        flag = primal ? primal_phase_c(d, s, j, el, a, c0, c1, c3)
+        flag = primal ? primal_phase_c<diag>(d, s, j, el, a, c0, c1, c3)
                       : grid_phase_c(d, s, j, el, a, partial, envcnt2, c1, c2);
       }
       // per-environment count of agents on goal (PRIMAL) / done (GRID), one shared-memory atomic per (warp, env)
@@ -701,7 +828,10 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       }
     }
     if (primal) __syncthreads();   // phase C entered the new cells into the id grid
-    if (need_mid) primal_mid_outputs(d, s, A, ne, tid);
+    if (need_mid) {
+      if constexpr (diag) primal_mid_outputs_diag(d, s, A, ne, tid);
+      else primal_mid_outputs(d, s, A, ne, tid);
+    }
   }
 
   PHASE_MARK(4);
@@ -716,7 +846,21 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       const int pc = (int)p.y + d.P;
       atomicOr(&ag[((int)p.x + d.P) * d.RW + (pc >> 5)], 1u << (pc & 31));
     }
-    if (want_avail) {
+    if (diag && want_avail) {                                        // 9-wide _listNextValidActions
+      const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+      const uint8_t* grid = gridcur + el * d.grid_bytes;
+      const int a = j - el * N;
+      uint32_t m = 1;
+      for (int k = 1; k <= 8; ++k) {
+        const int n0 = (int)p.x + dir9_dx(k), n1 = (int)p.y + dir9_dy(k);
+        if (bm_test(ob, d.RW, d.P, n0, n1) || grid[gcell(d, n0, n1)] != 0) continue;
+        if (diagonal_collision_at(s, el * N, N, a, N, (int)p.x + n0, (int)p.y + n1)) continue;
+        m |= 1u << k;
+      }
+      const int opp = opposite9(s.act[j]);
+      if (opp > 0) m &= ~(1u << opp);
+      s.mask16[j] = (uint16_t)m;
+    } else if (want_avail) {
       const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
       uint8_t m;
       if (primal) {                                                  // _listNextValidActions, PRIMAL:639-667
@@ -809,9 +953,17 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       for (int j = tid; j < na; j += kThreads) A.out.valid_dev[a0 + j] = primal ? ((s.flag[j] >> 1) & 1) : 1;
     if (primal && A.out.done_mid_dev)
       for (int j = tid; j < na; j += kThreads) A.out.done_mid_dev[a0 + j] = (s.flag[j] >> 2) & 1;
-    if (primal && A.out.next_mid_dev) write_mask5(A.out.next_mid_dev + 5 * a0, s.nextmid, na, tid);
+    if constexpr (diag) {
+      copy_out_bytes(S.past + 2 * a0, (const uint8_t*)s.pastnew, 2 * na, tid);
+      if (A.out.next_mid_dev) write_mask_n(A.out.next_mid_dev + 9 * a0, s.nextmid16, na, 9, tid);
+    } else {
+      if (primal && A.out.next_mid_dev) write_mask5(A.out.next_mid_dev + 5 * a0, s.nextmid, na, tid);
+    }
   }
-  if (want_avail) write_mask5(A.out.avail_dev + 5 * a0, s.avail, na, tid);
+  if (want_avail) {
+    if constexpr (diag) write_mask_n(A.out.avail_dev + 9 * a0, s.mask16, na, 9, tid);
+    else write_mask5(A.out.avail_dev + 5 * a0, s.avail, na, tid);
+  }
   if (tid == 0 && bad_flag) atomicOr(S.err_flags, MAPF_FLAG_BAD_ACTION);
 
   PHASE_MARK(6);
@@ -1083,6 +1235,7 @@ __global__ void mapf_reset_kernel(const MapfDims d, const MapfState S, const int
     const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
     if (bm_test(ob, d.RW, d.P, st.x, st.y)) flags |= MAPF_FLAG_START_ON_WALL;
     ((uchar2*)S.pos)[j] = st;                                        // GRID:79
+    if (d.diag) ((uchar2*)S.past)[j] = st;                           // agents_past == agents after scanForAgents, PRIMAL:61-65
     S.done[j] = (d.mode == MAPF_MODE_PRIMAL) ? (uint8_t)(st.x == g.x && st.y == g.y) : 0;   // GRID:75
     S.prev_action[j] = (d.mode == MAPF_MODE_PRIMAL) ? 0 : 4;
     if (a == 0) S.step_count[e] = 0;                                 // GRID:73
@@ -1145,7 +1298,7 @@ __global__ void mapf_export16_kernel(long long n, const uint8_t* src, int16_t* d
 // smem per warp: 4 bitmaps [H][RWB] (free, visited, frontier A/B) and, when it fits, the int16 map.
 // ------------------------------------------------------------------------------------------------
 __global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty, const uint8_t* env_mask,
-                                int16_t* dist, int RWB, int warps_per_block, int stage_dist) {
+                                int16_t* dist, int RWB, int warps_per_block, int stage_dist, int conn8) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long m = (long long)blockIdx.x * warps_per_block + warp;   // (env, agent) index
@@ -1191,12 +1344,17 @@ __global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8
     uint32_t any = 0;
     for (int it = lane; it < items; it += 32) {
       const int r = it / RWB, k = it - r * RWB;
-      const uint32_t f = cur[it];
-      uint32_t nb = (f << 1) | (f >> 1);
-      if (k > 0) nb |= cur[it - 1] >> 31;
-      if (k < RWB - 1) nb |= cur[it + 1] << 31;
-      if (r > 0) nb |= cur[it - RWB];
-      if (r < H - 1) nb |= cur[it + RWB];
+      // a row of the frontier spread one cell to the left and right (bits carried across the 32-cell words)
+      auto spread = [&](int idx) {
+        const uint32_t f = cur[idx];
+        uint32_t sp = f | (f << 1) | (f >> 1);
+        if (k > 0) sp |= cur[idx - 1] >> 31;
+        if (k < RWB - 1) sp |= cur[idx + 1] << 31;
+        return sp;
+      };
+      uint32_t nb = spread(it);
+      if (r > 0) nb |= conn8 ? spread(it - RWB) : cur[it - RWB];     // 8 neighbours: getNeighbors with diagonals, PRIMAL:421-437
+      if (r < H - 1) nb |= conn8 ? spread(it + RWB) : cur[it + RWB];
       uint32_t nw = nb & freeb[it] & ~vis[it];
       vis[it] |= nw;
       nxt[it] = nw;
@@ -1230,7 +1388,7 @@ __global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8
 // above and below) and a handful of logic ops per row; no shared-memory traffic except the int16 distance map
 // that is staged for the final coalesced store.
 // ------------------------------------------------------------------------------------------------
-template <typename Row, int RPL>
+template <typename Row, int RPL, bool CONN8>
 __global__ void mapf_bfs_warp_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty,
                                      const uint8_t* env_mask, int16_t* dist, int warps_per_block) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1279,8 +1437,12 @@ __global__ void mapf_bfs_warp_kernel(const MapfDims d, const MapfState S, const 
     bool any = false;
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
-      const Row up = (k > 0) ? f[k - 1] : (lane > 0 ? from_above : 0);
-      const Row dn = (k < RPL - 1) ? f[k + 1] : (lane < 31 ? from_below : 0);
+      Row up = (k > 0) ? f[k - 1] : (lane > 0 ? from_above : 0);
+      Row dn = (k < RPL - 1) ? f[k + 1] : (lane < 31 ? from_below : 0);
+      if (CONN8) {                                                         // diagonal neighbours, PRIMAL:421-437
+        up |= (up << 1) | (up >> 1);
+        dn |= (dn << 1) | (dn >> 1);
+      }
       nw[k] = ((f[k] << 1) | (f[k] >> 1) | up | dn) & freeR[k] & ~vis[k];
       any |= nw[k] != 0;
     }
@@ -1633,7 +1795,15 @@ extern "C" int mapf_configure_tile(int F, int mode, int smem_bytes) {
   const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
   if (mode == MAPF_MODE_GRID) err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_GRID>, attr, smem_bytes);
   else if (mode == MAPF_MODE_PARTIAL) err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_PARTIAL>, attr, smem_bytes);
-  else {
+  else if (mode == MAPF_MODE_PRIMAL_DIAG) {
+    switch (F) {
+      case 0: err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_PRIMAL_DIAG>, attr, smem_bytes); break;
+#define X(f) case f: err = cudaFuncSetAttribute(mapf_tile_kernel<f, MAPF_MODE_PRIMAL_DIAG>, attr, smem_bytes); break;
+      MAPF_FOR_EACH_FOV(X)
+#undef X
+      default: break;
+    }
+  } else {
     switch (F) {
       case 0: err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_PRIMAL>, attr, smem_bytes); break;
 #define X(f) case f: err = cudaFuncSetAttribute(mapf_tile_kernel<f, MAPF_MODE_PRIMAL>, attr, smem_bytes); break;
@@ -1651,6 +1821,16 @@ extern "C" int mapf_launch_tile(const MapfDims& d, const MapfTileLayout& L, cons
   if (d.mode == MAPF_MODE_GRID) return (int)launch_tile_f<0, MAPF_MODE_GRID>(d, L, S, A, st);
   if (d.mode == MAPF_MODE_PARTIAL) return (int)launch_tile_f<0, MAPF_MODE_PARTIAL>(d, L, S, A, st);
   const int F = (d.obs_mode == MAPF_OBS_PRIMAL_FOV) ? d.F : 0;
+  if (d.diag) {
+    switch (F) {
+      case 0: return (int)launch_tile_f<0, MAPF_MODE_PRIMAL_DIAG>(d, L, S, A, st);
+#define X(f) case f: return (int)launch_tile_f<f, MAPF_MODE_PRIMAL_DIAG>(d, L, S, A, st);
+      MAPF_FOR_EACH_FOV(X)
+#undef X
+      default:
+        return (int)cudaErrorInvalidValue;
+    }
+  }
   switch (F) {
     case 0: return (int)launch_tile_f<0, MAPF_MODE_PRIMAL>(d, L, S, A, st);
 #define X(f) case f: return (int)launch_tile_f<f, MAPF_MODE_PRIMAL>(d, L, S, A, st);
@@ -1754,6 +1934,7 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
     if (e != cudaSuccess) return (int)e;
   }
   const long long maps = (long long)d.E * d.N;
+  const int conn8 = (primal_costs && d.diag) ? 1 : 0;   // getAstarCosts with DIAGONAL_MOVEMENT, PRIMAL:421-437
   if (d.W <= 64 && d.H <= 64) {
     // register-resident warp-synchronous kernel; shared memory only stages the int16 map for the coalesced store
     const int w2 = 8;
@@ -1763,11 +1944,17 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
 #define BFS_LAUNCH(ROW, RPL)                                                                                       \
   do {                                                                                                             \
     if (sm2 > 48 * 1024) {                                                                                         \
-      cudaError_t e_ = cudaFuncSetAttribute(mapf_bfs_warp_kernel<ROW, RPL>,                                        \
+      cudaError_t e_ = cudaFuncSetAttribute(mapf_bfs_warp_kernel<ROW, RPL, false>,                                 \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);                \
+      if (e_ == cudaSuccess)                                                                                       \
+        e_ = cudaFuncSetAttribute(mapf_bfs_warp_kernel<ROW, RPL, true>,                                            \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);                          \
       if (e_ != cudaSuccess) return (int)e_;                                                                       \
     }                                                                                                              \
-    mapf_bfs_warp_kernel<ROW, RPL><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, dirty, env_mask, dist, w2);           \
+    if (conn8)                                                                                                     \
+      mapf_bfs_warp_kernel<ROW, RPL, true><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, dirty, env_mask, dist, w2);   \
+    else                                                                                                           \
+      mapf_bfs_warp_kernel<ROW, RPL, false><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, dirty, env_mask, dist, w2);  \
   } while (0)
     if (!wide && !tall) BFS_LAUNCH(uint32_t, 1);
     else if (!wide && tall) BFS_LAUNCH(uint32_t, 2);
@@ -1776,7 +1963,7 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
 #undef BFS_LAUNCH
   } else {
     const long long grid = (maps + warps - 1) / warps;
-    mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, dirty, env_mask, dist, RWB, warps, stage);
+    mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, dirty, env_mask, dist, RWB, warps, stage, conn8);
   }
   cudaError_t err = cudaGetLastError();
   *n_launches = 1;

@@ -34,8 +34,8 @@ _OUT_SPECS = {
     "edge": (torch.int16, lambda N: (N,)),
     "valid": (torch.uint8, lambda N: (N,)),
     "done_mid": (torch.uint8, lambda N: (N,)),
-    "next_mid": (torch.uint8, lambda N: (N, 5)),
-    "avail": (torch.uint8, lambda N: (N, 5)),
+    "next_mid": (torch.uint8, lambda N: (N, -1)),   # -1: the engine's n_actions (5, or 9 with diagonal movement)
+    "avail": (torch.uint8, lambda N: (N, -1)),
     "blocking": (torch.uint8, lambda N: (N,)),
 }
 
@@ -63,7 +63,8 @@ class MapfEngine:
                  goal_reward=0.0, collision_reward=-2.0, goal_dist=False, collect_stats=True, device=None,
                  reward_sum_mode=None, obs_window=5, obs_knn_agents=5, move_reward=-0.01, stay_reward=-0.02,
                  stay_goal_reward=0, node_collide_reward=-1, edge_collide_reward=-1, env_collide_reward=-1,
-                 complete_reward=1000, complete_fac=1.5, gamma=0.99, blocking_reward=False, blocking_cost=-1.0):
+                 complete_reward=1000, complete_fac=1.5, gamma=0.99, blocking_reward=False, blocking_cost=-1.0,
+                 diagonal_movement=False):
         if not torch.cuda.is_available():
             raise MapfError("MapfEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -102,6 +103,8 @@ class MapfEngine:
         cfg.mag_lut_len = int(self._lut.size)
         cfg.blocking_reward = int(bool(blocking_reward))
         cfg.blocking_cost = float(blocking_cost)
+        cfg.diagonal_movement = int(bool(diagonal_movement))   # DIAGONAL_MOVEMENT, mapf_primal.py:175
+        self.n_actions = 9 if diagonal_movement else 5
         if self.mode == MODE_PARTIAL:
             cfg.obs_window, cfg.obs_knn_agents = self.obs_window, self.obs_knn_agents
             cfg.move_reward, cfg.stay_reward = float(move_reward), float(stay_reward)
@@ -181,7 +184,8 @@ class MapfEngine:
             if name not in _OUT_SPECS:
                 raise KeyError("unknown step output %r (choose from %s)" % (name, ", ".join(STEP_OUT_FIELDS)))
             dtype, suffix = _OUT_SPECS[name]
-            t = self._buf("out_" + name, (self.E,) + suffix(self.N), dtype)
+            shape = tuple(self.n_actions if k == -1 else k for k in suffix(self.N))
+            t = self._buf("out_" + name, (self.E,) + shape, dtype)
             setattr(so, name + "_dev", t.data_ptr())
             outs[name] = t
         return so, outs
@@ -288,7 +292,7 @@ class MapfEngine:
         return outs
 
     def avail(self):
-        out = self._buf("out_avail", (self.E, self.N, 5), torch.uint8)
+        out = self._buf("out_avail", (self.E, self.N, self.n_actions), torch.uint8)
         with torch.cuda.device(self.device):
             self._check(self.lib.mapf_avail(self._h, self._ptr(out), self._stream()), "mapf_avail")
         return out
@@ -341,7 +345,7 @@ class MapfEngine:
         if "dones" in want:
             bufs["dones"] = torch.empty((E, N), dtype=torch.uint8).pin_memory()
         if "avail" in want:
-            bufs["avail"] = torch.empty((E, N, 5), dtype=torch.uint8).pin_memory()
+            bufs["avail"] = torch.empty((E, N, self.n_actions), dtype=torch.uint8).pin_memory()
         odt = I8
         if "obs" in want:
             if self.obs_mode == OBS_PRIMAL_FOV:

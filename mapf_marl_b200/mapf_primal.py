@@ -10,9 +10,10 @@ getPos/getGoal/done/state/goals.
 Batched surface added (n_envs >= 1, device tensors): step_sweep(actions[E,N]) = one
 `for id in 1..N: _step((id, a))` sweep per environment; observe_all(); astar_costs().
 
-DIAGONAL_MOVEMENT=True raises.  The blocking reward (row P7) depends on the un-vendored
-od_mstar3 planner in the reference; `blocking_reward=True` computes it with BFS path lengths (what a single-robot
-M* returns), otherwise rewards equal the reference's with blocking == 0.
+DIAGONAL_MOVEMENT=True switches the engine to the 9-action sweep with the crossing test
+(State.diagonalCollision, :77-100) and 8-connected getAstarCosts.  The blocking reward (row P7) depends on the
+un-vendored od_mstar3 planner in the reference; `blocking_reward=True` computes it with BFS path lengths (what a
+single-robot M* returns), otherwise rewards equal the reference's with blocking == 0.
 """
 
 import numpy as np
@@ -23,7 +24,7 @@ from .engine import MapfEngine
 
 ACTION_COST, IDLE_COST, GOAL_REWARD, COLLISION_REWARD, FINISH_REWARD, BLOCKING_COST = -0.3, -.5, 0.0, -2., 20., -1.
 opposite_actions = {0: -1, 1: 3, 2: 4, 3: 1, 4: 2, 5: 7, 6: 8, 7: 5, 8: 6}
-dirDict = {0: (0, 0), 1: (0, 1), 2: (1, 0), 3: (0, -1), 4: (-1, 0)}
+dirDict = {0: (0, 0), 1: (0, 1), 2: (1, 0), 3: (0, -1), 4: (-1, 0), 5: (1, 1), 6: (1, -1), 7: (-1, -1), 8: (-1, 1)}
 actionDict = {v: k for k, v in dirDict.items()}
 
 _SWEEP_WANT = ("status", "agent_reward", "dones", "valid", "done_mid", "next_mid", "avail", "terminated",
@@ -87,8 +88,8 @@ class MAPFEnv(object):
     def __init__(self, num_agents=1, observation_size=10, world0=None, goals0=None, DIAGONAL_MOVEMENT=False,
                  SIZE=(10, 40), PROB=(0, .5), FULL_HELP=False, blank_world=False, n_envs=1, device=None,
                  goal_dist=False, blocking_reward=False):
-        if DIAGONAL_MOVEMENT:
-            raise NotImplementedError("DIAGONAL_MOVEMENT (9 actions) is not implemented by the B200 engine")
+        if DIAGONAL_MOVEMENT and blocking_reward:
+            raise NotImplementedError("blocking_reward with DIAGONAL_MOVEMENT is not implemented by the B200 engine")
         self.num_agents = num_agents
         self.n_envs = int(n_envs)
         self.individual_rewards = [0 for _ in range(num_agents)]
@@ -98,7 +99,8 @@ class MAPFEnv(object):
         self.fresh = True
         self.FULL_HELP = FULL_HELP
         self.finished = False
-        self.DIAGONAL_MOVEMENT = DIAGONAL_MOVEMENT
+        self.DIAGONAL_MOVEMENT = bool(DIAGONAL_MOVEMENT)
+        self.n_actions = 9 if DIAGONAL_MOVEMENT else 5                  # action_space, :198-201
         self._device = device
         self._goal_dist = goal_dist
         # get_blocking_reward (mapf_primal.py:513-546) with BFS path lengths instead of the un-vendored od_mstar3;
@@ -155,7 +157,8 @@ class MAPFEnv(object):
             self.engine = MapfEngine(E, N, H, W, mode="primal", fov=self.observation_size, device=self._device,
                                      goal_dist=self._goal_dist, action_cost=ACTION_COST, idle_cost=IDLE_COST,
                                      goal_reward=GOAL_REWARD, collision_reward=COLLISION_REWARD,
-                                     blocking_reward=self._blocking_reward, blocking_cost=BLOCKING_COST)
+                                     blocking_reward=self._blocking_reward, blocking_cost=BLOCKING_COST,
+                                     diagonal_movement=self.DIAGONAL_MOVEMENT)
         self._obst0 = obst[0]
         self.initial_world = world0
         self.initial_goals = goals0
@@ -223,12 +226,12 @@ class MAPFEnv(object):
         prev[:, agent_id - 1] = int(prev_action)
         self.engine.set_prev_actions(prev)
         mask = self.engine.avail()[0, agent_id - 1].cpu().tolist()
-        return [a for a in range(5) if mask[a]]
+        return [a for a in range(self.n_actions) if mask[a]]
 
     def _step(self, action_input, episode=0):
         self.fresh = False
         assert len(action_input) == 2, 'Action input should be a tuple with the form (agent_id, action)'
-        assert action_input[1] in range(5), 'Invalid action'
+        assert action_input[1] in range(self.n_actions), 'Invalid action'
         assert action_input[0] in range(1, self.num_agents + 1)
         agent_id, action = int(action_input[0]), int(action_input[1])
         acts = torch.zeros((self.n_envs, self.num_agents), dtype=torch.uint8)
@@ -242,7 +245,7 @@ class MAPFEnv(object):
         done = bool(out["done_mid"][0, i].item())
         self.finished |= done
         mask = out["next_mid"][0, i].cpu().tolist()
-        nextActions = [a for a in range(5) if mask[a]]
+        nextActions = [a for a in range(self.n_actions) if mask[a]]
         on_goal = bool(out["dones"][0, i].item())
         valid_action = bool(out["valid"][0, i].item())
         blocking = bool(out["blocking"][0, i].item()) if self._blocking_reward else False

@@ -884,3 +884,130 @@ def test_primal_blocking_reward_batch_matches_oracle(case):
         assert np.array_equal(_bits(_np(out["reward"])), _bits(ref["reward"])), t
         n_events += int(ref["blocking"].sum())
     assert n_events > 0
+
+
+# ------------------------------------------------------------------------------------------ PRIMAL DIAGONAL_MOVEMENT
+@pytest.mark.parametrize("name", golden_names("PRIMALD"))
+def test_primal_diagonal_engine_matches_reference_trace(name):
+    """DIAGONAL_MOVEMENT=True (PRIMAL:175): 9 actions, crossing test, 9-wide masks, 8-connected costs."""
+    g = load_golden(name)
+    H, W = g["obst"].shape
+    N = g["starts"].shape[0]
+    F = int(g["fov"])
+    eng = _engine(1, N, H, W, mode="primal", fov=F, diagonal_movement=True)
+    eng.reset(g["obst"][None], g["starts"][None], g["goals"][None])
+    obs, vec = eng.observe()
+    assert np.array_equal(_np(obs)[0], g["obs0"])
+    assert np.array_equal(_np(eng.avail())[0], g["avail0"]) and g["avail0"].shape[-1] == 9
+    nc = g["costs0"].shape[0]
+    assert np.array_equal(_np(eng.goal_dist(primal_costs=True))[0, :nc], g["costs0"])
+    for t in range(g["actions"].shape[0]):
+        a = torch.as_tensor(g["actions"][t][None])
+        if t % 2 == 0:
+            out = eng.step_observe(a, want=PRIMAL_WANT)
+            obs, vec = out["obs"], out["vec"]
+        else:
+            out = eng.step(a, want=PRIMAL_WANT)
+            obs, vec = eng.observe()
+        assert np.array_equal(_np(out["status"])[0], g["status"][t]), t
+        assert np.array_equal(_bits(_np(out["agent_reward"])[0]), _bits(g["reward"][t])), t
+        assert np.array_equal(_np(out["done_mid"])[0], g["done_mid"][t]), t
+        assert np.array_equal(_np(out["next_mid"])[0], g["next_mid"][t]), t
+        assert np.array_equal(_np(out["dones"])[0], g["on_goal"][t]), t
+        assert np.array_equal(_np(out["valid"])[0], g["valid"][t]), t
+        assert np.array_equal(_np(eng.positions())[0], g["pos"][t]), t
+        assert np.array_equal(_np(out["avail"])[0], g["avail"][t]), t
+        assert _np(out["terminated"])[0] == g["done"][t]
+        assert np.array_equal(_np(obs)[0], g["obs"][t]), t
+        assert np.array_equal(_bits(_np(vec)[0]), _bits(g["vec"][t])), t
+    assert np.array_equal(_np(eng.goal_dist(primal_costs=True))[0, :nc], g["costsT"])
+    assert eng.error_flags() == 0
+
+
+DIAG_CASES = [
+    # E, N, H, W, F, density, T
+    (200, 8, 20, 20, 11, 0.2, 10),
+    (64, 32, 32, 32, 11, 0.3, 6),
+    (37, 7, 40, 40, 9, 0.25, 6),       # ragged, W > 32
+    (64, 12, 8, 8, 5, 0.05, 16),       # crowded: many crossings
+    (8, 140, 70, 70, 7, 0.1, 4),       # N > 128, map > 64 (shared-memory BFS with 8 neighbours)
+    (16, 9, 16, 16, 6, 0.2, 6),        # generic observation kernel
+]
+
+
+@pytest.mark.parametrize("case", DIAG_CASES, ids=lambda c: "E%d_N%d_%dx%d_F%d" % c[:5])
+def test_primal_diagonal_batch_matches_oracle(case):
+    from mapf_marl_b200 import maps
+    from oracle.oracle import MODE_PRIMAL
+    E, N, H, W, F, dens, T = case
+    obst, starts, goals = maps.synthetic_batch(300 + E, E, H, W, dens, N, distinct=0)
+    eng = _engine(E, N, H, W, mode="primal", fov=F, diagonal_movement=True)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F)
+    orc.set_diagonal(True)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    assert np.array_equal(_np(eng.avail()), orc.primal_avail())
+    rs = np.random.RandomState(E + N)
+    for t in range(T):
+        a = rs.randint(0, 9, (E, N)).astype(np.uint8)
+        ad = torch.as_tensor(a.astype(np.int64) if t % 3 == 1 else a, device="cuda")
+        if t % 2 == 0:
+            out = eng.step_observe(ad, want=PRIMAL_WANT)
+            obs, vec = out["obs"], out["vec"]
+        else:
+            out = eng.step(ad, want=("status", "agent_reward", "reward", "dones", "valid", "avail", "terminated"))
+            obs, vec = eng.observe()
+        ref = orc.primal_sweep(a)
+        robs, rvec = orc.primal_observe()
+        for k in ("status", "dones", "valid", "done_mid", "next_mid", "avail", "terminated"):
+            if k in out:
+                assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        assert np.array_equal(_bits(_np(out["agent_reward"])), _bits(ref["agent_reward"])), t
+        assert np.array_equal(_bits(_np(out["reward"])), _bits(ref["reward"])), t
+        assert np.array_equal(_np(eng.positions()), orc.positions()), t
+        assert np.array_equal(_np(obs), robs), t
+        assert np.array_equal(_bits(_np(vec)), _bits(rvec)), t
+    # partial sweeps (one _step call at a time) against the same oracle
+    a = rs.randint(0, 9, (E, N)).astype(np.uint8)
+    for lo in range(0, N, max(1, N // 3)):
+        hi = min(N, lo + max(1, N // 3))
+        out = eng.step(torch.as_tensor(a, device="cuda"), want=PRIMAL_WANT, agent_range=(lo, hi))
+        ref = orc.primal_sweep(a, lo=lo, hi=hi)
+        for k in ("status", "dones", "valid", "done_mid", "next_mid", "terminated"):
+            assert np.array_equal(_np(out[k])[:, lo:hi] if _np(out[k]).ndim > 1 else _np(out[k]),
+                                  ref[k][:, lo:hi] if ref[k].ndim > 1 else ref[k]), (k, lo)
+        assert np.array_equal(_np(eng.positions()), orc.positions()), lo
+    assert np.array_equal(_np(eng.goal_dist(primal_costs=True)), orc.goal_dist(primal_costs=True))
+    assert np.array_equal(_np(eng.goal_dist()), orc.goal_dist())
+    assert eng.error_flags() == 0
+    bad = a.copy()
+    bad[0, 0] = 9
+    eng.step(torch.as_tensor(bad, device="cuda"))
+    from mapf_marl_b200 import _lib
+    assert eng.error_flags() == _lib.FLAG_BAD_ACTION
+
+
+def test_mapfenv_dropin_class_diagonal_movement():
+    from mapf_marl_b200.mapf_primal import MAPFEnv
+    g = load_golden("primald_crowd")
+    N = g["starts"].shape[0]
+    F = int(g["fov"])
+    world0 = -g["obst"].astype(int)
+    goals0 = np.zeros_like(world0)
+    for k in range(N):
+        world0[tuple(g["starts"][k])] = k + 1
+        goals0[tuple(g["goals"][k])] = k + 1
+    env = MAPFEnv(num_agents=N, observation_size=F, world0=world0, goals0=goals0, DIAGONAL_MOVEMENT=True)
+    for i in range(1, N + 1):
+        assert env._listNextValidActions(i) == [a for a in range(9) if g["avail0"][i - 1, a]]
+    for t in range(10):
+        for i in range(1, N + 1):
+            a = int(g["actions"][t, i - 1])
+            state, reward, done, nxt, on_goal, blocking, valid = env._step((i, a))
+            assert reward == g["reward"][t, i - 1]
+            assert done == bool(g["done_mid"][t, i - 1])
+            assert nxt == [k for k in range(9) if g["next_mid"][t, i - 1, k]]
+            assert on_goal == bool(g["on_goal"][t, i - 1]) and valid == bool(g["valid"][t, i - 1])
+        assert env.getPositions() == [tuple(p) for p in g["pos"][t].tolist()]
+    with pytest.raises(AssertionError):
+        env._step((1, 9))
