@@ -190,6 +190,7 @@ int mapf_destroy(mapf_handle* h) {
   cudaFree(h->S.step_count);
   cudaFree(h->S.goal_dist);
   cudaFree((void*)h->S.mag_lut);
+  cudaFree((void*)h->S.vec_lut);
   cudaFree(h->S.stats);
   cudaFree(h->S.err_flags);
   cudaFree(h->S.pos_prev);
@@ -396,6 +397,30 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   if (e == cudaSuccess) {
     if (c->mag_lut_host) e = cudaMemcpy(lut, c->mag_lut_host, (size_t)lut_len * 8, cudaMemcpyHostToDevice);
     else e = cudaMemset(lut, 0, 8);
+  }
+  if (e == cudaSuccess && c->obs_mode == MAPF_OBS_PRIMAL_FOV) {
+    // goal unit vectors for every (|dx|, |dy|): the same correctly rounded IEEE division CPython performs for
+    // `dx / mag` (PRIMAL:383-384), done once on the host instead of two DDIVs per agent per step
+    const size_t n = (size_t)d.H * d.W;
+    double* tab = (double*)malloc(n * 32);
+    double* dv = nullptr;
+    if (!tab) e = cudaErrorMemoryAllocation;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dv, n * 32);
+    if (e == cudaSuccess) {
+      const double* ml = (const double*)c->mag_lut_host;
+      for (int a = 0; a < d.H; ++a)
+        for (int b = 0; b < d.W; ++b) {
+          const double mag = ml[a * a + b * b];
+          double* t = tab + ((size_t)a * d.W + b) * 4;
+          t[0] = mag != 0.0 ? (double)a / mag : (double)a;
+          t[1] = mag != 0.0 ? (double)b / mag : (double)b;
+          t[2] = mag;
+          t[3] = 0.0;
+        }
+      e = cudaMemcpy(dv, tab, n * 32, cudaMemcpyHostToDevice);
+      h->S.vec_lut = dv;
+    }
+    free(tab);
   }
   if (e == cudaSuccess && c->mode == MAPF_MODE_PARTIAL) {
     e = cudaMemcpy((void*)h->S.complete_lut, c->complete_lut_host, (size_t)c->complete_lut_len * 8,

@@ -77,6 +77,7 @@ struct MapfState {
   int32_t* step_count;     // [E]
   int16_t* goal_dist;      // [E][N][H][W] or NULL
   const double* mag_lut;   // [mag_lut_len]
+  const double* vec_lut;   // [H][W][4]: {a / mag, b / mag, mag, 0} for |dx| = a, |dy| = b (PRIMAL:380-385), host-built
   unsigned long long* stats;  // [MAPF_N_STATS]
   // PRIMAL blocking reward (cfg.blocking_reward): what the follow-up kernel needs from the sweep
   uint8_t* pos_prev;       // [E][N][2] positions before the last sweep

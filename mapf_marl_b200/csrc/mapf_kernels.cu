@@ -627,7 +627,7 @@ __device__ __forceinline__ void fov_window_planes(uint32_t (&w)[Fov<F>::NW], con
 // goal_map (own goal cell, :366-368) and goals_map (goals of the visible other agents clamped into the window,
 // :374-378): single bits OR-ed into the agent's string in shared memory.  `vis` = poss_map without the agent itself.
 template <int F, bool ATOMIC>
-__device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, const uint32_t (&vis)[Fov<F>::CW], int GS,
+__device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, uint32_t (&vis)[Fov<F>::CW], int GS,
                                               const uint8_t* idgrid, const uchar2* goals_env, uchar2 p, uchar2 g) {
   using T = Fov<F>;
   constexpr int P = F / 2;
@@ -640,19 +640,29 @@ __device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, const uin
   const int gi = (int)g.x - t0, gj = (int)g.y - t1;
   if ((unsigned)gi < (unsigned)F && (unsigned)gj < (unsigned)F) set(T::FF + gi * F + gj);
   const uint8_t* gbase = idgrid + (t0 + 1) * GS + t1 + 1;
+  // One loop over ALL window words: a warp runs max-over-lanes(visible agents) iterations instead of the sum of the
+  // per-word maxima (the visible set is sparse: ~3 agents spread over CW words).
+  for (;;) {
+    uint32_t v = vis[0];
+    int q = 0;
 #pragma unroll
-  for (int q = 0; q < T::CW; ++q) {
-    uint32_t v = vis[q];
-    while (v) {
-      const int idx = 32 * q + __ffs(v) - 1;
-      v &= v - 1;
-      const int wi = idx / F, wj = idx - wi * F;
-      const int id = gbase[wi * GS + wj];          // the agent bit map says somebody stands here: id >= 1
-      const uchar2 og = goals_env[max(id, 1) - 1];
-      const int ci = min(max((int)og.x - t0, 0), F - 1);
-      const int cj = min(max((int)og.y - t1, 0), F - 1);
-      set(2 * T::FF + ci * F + cj);
+    for (int k = 1; k < T::CW; ++k) {
+      const bool next = (v == 0);
+      v = next ? vis[k] : v;
+      q = next ? k : q;
     }
+    if (v == 0) break;
+    const int idx = 32 * q + __ffs(v) - 1;
+    v &= v - 1;
+#pragma unroll
+    for (int k = 0; k < T::CW; ++k)
+      if (q == k) vis[k] = v;
+    const int wi = idx / F, wj = idx - wi * F;
+    const int id = gbase[wi * GS + wj];            // the agent bit map says somebody stands here: id >= 1
+    const uchar2 og = goals_env[id - 1];
+    const int ci = min(max((int)og.x - t0, 0), F - 1);
+    const int cj = min(max((int)og.y - t1, 0), F - 1);
+    set(2 * T::FF + ci * F + cj);
   }
 }
 
@@ -1028,16 +1038,13 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
       }
       if (j < na && A.vec != nullptr) {                              // PRIMAL:380-385
         const int dx = (int)g.x - (int)p.x, dy = (int)g.y - (int)p.y;
-        const double mag = __ldg(S.mag_lut + (dx * dx + dy * dy));
-        double fx = (double)dx, fy = (double)dy;
-        if (mag != 0.0) {
-          fx = __ddiv_rn(fx, mag);
-          fy = __ddiv_rn(fy, mag);
-        }
+        const double2* t = (const double2*)S.vec_lut + 2 * (abs(dx) * d.W + abs(dy));
+        const double2 u = __ldg(t);                                  // |dx| / mag, |dy| / mag (IEEE division is
+        const double2 m = __ldg(t + 1);                              // sign-symmetric; 0 / mag = +0.0 either way)
         double* v = A.vec + 3 * (a0 + j);
-        v[0] = fx;
-        v[1] = fy;
-        v[2] = mag;
+        v[0] = dx < 0 ? -u.x : u.x;
+        v[1] = dy < 0 ? -u.y : u.y;
+        v[2] = m.x;
       }
       __syncthreads();
       if (valid) {

@@ -17,9 +17,11 @@ def line_map(sass_path, kernel):
             active = kernel in ln
         if not active:
             continue
-        mm = re.search(r'//## File "[^"]*", line (\d+)(.*)', ln)
+        mm = re.search(r'//## File "([^"]*)", line (\d+)(.*)', ln)
         if mm:
-            cur = int(mm.group(1))
+            # lines of other files (CUDA headers with inlined intrinsics) are reported as "<header>:<line>"
+            f = mm.group(1).rsplit("/", 1)[-1]
+            cur = int(mm.group(2)) if f.endswith(".cu") else "%s:%s" % (f, mm.group(2))
             continue
         mm = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(\S.*);", ln)
         if mm:
