@@ -123,16 +123,6 @@ __device__ __forceinline__ void st_stream16(void* p, uint4 v) {
 // 4 bits -> 4 bytes of 0/1 (bit k lands in byte k).
 __device__ __forceinline__ uint32_t expand4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
-__device__ __noinline__ void copy_out_bytes(uint8_t* dst, const uint8_t* src, int n, int tid) {
-  if (((((uintptr_t)dst) | ((uintptr_t)src)) & 3) == 0) {
-    const int nw = n >> 2;
-    for (int i = tid; i < nw; i += kThreads) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
-    for (int i = (nw << 2) + tid; i < n; i += kThreads) dst[i] = src[i];
-  } else {
-    for (int i = tid; i < n; i += kThreads) dst[i] = src[i];
-  }
-}
-
 // PRIMAL dirDict (PRIMAL:28) for the 9 actions {0:(0,0) 1:(0,1) 2:(1,0) 3:(0,-1) 4:(-1,0) 5:(1,1) 6:(1,-1) 7:(-1,-1)
 // 8:(-1,1)}, two bits per action holding delta + 1; and opposite_actions (PRIMAL:26), four bits per action (0 = none).
 __device__ __forceinline__ int dir9_dx(int a) { return (int)((0x002865u >> (2 * a)) & 3u) - 1; }
@@ -892,7 +882,13 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
         m |= bm_test(ob, d.RW, d.P, (int)p.x, (int)p.y - 1) ? 0 : 4;
         m |= bm_test(ob, d.RW, d.P, (int)p.x, (int)p.y + 1) ? 0 : 8;
       }
-      s.avail[j] = m;
+      // [E,N,5] mask straight from the register: 5 byte stores per agent (the L2 merges the partial sectors)
+      uint8_t* o = A.out.avail_dev + 5 * (a0 + j);
+      o[0] = m & 1;
+      o[1] = (m >> 1) & 1;
+      o[2] = (m >> 2) & 1;
+      o[3] = (m >> 3) & 1;
+      o[4] = (m >> 4) & 1;
     }
   }
   __syncthreads();
@@ -942,37 +938,37 @@ __global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, c
         atomicAdd(&S.stats[tid], (unsigned long long)stat[tid]);
       }
     }
-    if (partial) {   // phase D changed done / rewards of whole environments
-      __syncthreads();
-      copy_out_bytes(S.at_goal + a0, s.atgoal, na, tid);
-      copy_out_bytes(S.pnode + a0, s.node, na, tid);
-      copy_out_bytes(S.pedge + a0, s.edge, na, tid);
+    if (partial) __syncthreads();   // phase D changed done / rewards of whole environments
+    // state write-back and the per-agent outputs: thread j stores agent j's records (byte stores of a warp cover
+    // whole 32-byte sectors; a shared-memory staging pass costs more instructions than it saves transactions)
+    for (int j = tid; j < na; j += kThreads) {
+      const size_t gj = a0 + j;
+      const uint8_t dn = s.done[j];
+      ((uchar2*)S.pos)[gj] = s.posnew[j];
+      S.done[gj] = dn;
+      S.prev_action[gj] = s.act[j];
+      if (partial) {
+        S.at_goal[gj] = s.atgoal[j];
+        S.pnode[gj] = s.node[j];
+        S.pedge[gj] = s.edge[j];
+      }
+      if (diag) ((uchar2*)S.past)[gj] = s.pastnew[j];
+      if (A.out.dones_dev) A.out.dones_dev[gj] = dn;
+      if (A.out.status_dev) A.out.status_dev[gj] = s.status[j];
+      if (A.out.agent_reward_dev) A.out.agent_reward_dev[gj] = s.rew[j];
+      if (A.out.node_dev) A.out.node_dev[gj] = primal ? 0 : (int16_t)s.node[j];
+      if (A.out.edge_dev) A.out.edge_dev[gj] = primal ? 0 : (int16_t)s.edge[j];
+      if (A.out.valid_dev) A.out.valid_dev[gj] = primal ? ((s.flag[j] >> 1) & 1) : 1;
+      if (primal && A.out.done_mid_dev) A.out.done_mid_dev[gj] = (s.flag[j] >> 2) & 1;
     }
-    copy_out_bytes(S.pos + 2 * a0, (const uint8_t*)s.posnew, 2 * na, tid);
-    copy_out_bytes(S.done + a0, s.done, na, tid);
-    copy_out_bytes(S.prev_action + a0, s.act, na, tid);
-    if (A.out.dones_dev) copy_out_bytes(A.out.dones_dev + a0, s.done, na, tid);
-    if (A.out.status_dev) copy_out_bytes((uint8_t*)A.out.status_dev + a0, (const uint8_t*)s.status, na, tid);
-    if (A.out.agent_reward_dev)
-      for (int j = tid; j < na; j += kThreads) A.out.agent_reward_dev[a0 + j] = s.rew[j];
-    if (A.out.node_dev)
-      for (int j = tid; j < na; j += kThreads) A.out.node_dev[a0 + j] = primal ? 0 : (int16_t)s.node[j];
-    if (A.out.edge_dev)
-      for (int j = tid; j < na; j += kThreads) A.out.edge_dev[a0 + j] = primal ? 0 : (int16_t)s.edge[j];
-    if (A.out.valid_dev)
-      for (int j = tid; j < na; j += kThreads) A.out.valid_dev[a0 + j] = primal ? ((s.flag[j] >> 1) & 1) : 1;
-    if (primal && A.out.done_mid_dev)
-      for (int j = tid; j < na; j += kThreads) A.out.done_mid_dev[a0 + j] = (s.flag[j] >> 2) & 1;
     if constexpr (diag) {
-      copy_out_bytes(S.past + 2 * a0, (const uint8_t*)s.pastnew, 2 * na, tid);
       if (A.out.next_mid_dev) write_mask_n(A.out.next_mid_dev + 9 * a0, s.nextmid16, na, 9, tid);
     } else {
       if (primal && A.out.next_mid_dev) write_mask5(A.out.next_mid_dev + 5 * a0, s.nextmid, na, tid);
     }
   }
-  if (want_avail) {
-    if constexpr (diag) write_mask_n(A.out.avail_dev + 9 * a0, s.mask16, na, 9, tid);
-    else write_mask5(A.out.avail_dev + 5 * a0, s.avail, na, tid);
+  if constexpr (diag) {
+    if (want_avail) write_mask_n(A.out.avail_dev + 9 * a0, s.mask16, na, 9, tid);
   }
   if (tid == 0 && bad_flag) atomicOr(S.err_flags, MAPF_FLAG_BAD_ACTION);
 
