@@ -660,7 +660,7 @@ __device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, uint32_t 
 // The tile kernel: stage -> [step] -> state write-back + small outputs -> [observation].
 // ------------------------------------------------------------------------------------------------
 template <int F, int MODE>
-__global__ void __launch_bounds__(kThreads) mapf_tile_kernel(const MapfDims d, const MapfTileLayout L,
+__global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims d, const MapfTileLayout L,
                                                              const MapfState S, const MapfTileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned int stat[MAPF_N_STATS];
