@@ -659,7 +659,9 @@ __device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, uint32_t 
 // ------------------------------------------------------------------------------------------------
 // The tile kernel: stage -> [step] -> state write-back + small outputs -> [observation].
 // ------------------------------------------------------------------------------------------------
-template <int F, int MODE>
+// SINGLE: the tile holds at most kThreads agents (the host guarantees it), so every per-agent / per-environment loop is
+// one guarded pass -- no loop counters, compares and back edges around each phase (worth 7 % of the c3 step).
+template <int F, int MODE, bool SINGLE>
 __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims d, const MapfTileLayout L,
                                                              const MapfState S, const MapfTileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -686,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
   if (tid < MAPF_N_STATS) stat[tid] = 0;
   if (tid == 0) bad_flag = 0;
   int* envstep = (int*)(smem_raw + L.envstep_off);
-  for (int el = tid; el < ne; el += kThreads) {
+  for (int el = tid, it_ = 0; el < ne && (!SINGLE || it_ == 0); el += kThreads, ++it_) {
     envcnt[el] = 0;
     envcnt2[el] = 0;
     envstep[el] = S.step_count[e0 + el];   // staged with the other global loads: no mid-kernel round trip
@@ -698,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     for (int i = tid; i < nvec; i += kThreads) dst[i] = __ldg(src + i);
   }
   bool bad = false;
-  for (int j = tid; j < na; j += kThreads) {
+  for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
     const uchar2 p = ((const uchar2*)S.pos)[a0 + j];
     s.posold[j] = p;
     s.posnew[j] = p;
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
   // ---- phase A: occupancy of the current positions (PRIMAL State.state ids, PRIMAL:32-47; GRID agent counts,
   //      GRID:299) and the agent-independent part of the step
   unsigned int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-  for (int j = tid; j < na; j += kThreads) {
+  for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
     const int el = fast_div(j, d.invN), a = j - el * N;
     const uchar2 p = s.posold[j];
     uint8_t* grid = s.grida + el * d.grid_bytes;
@@ -769,11 +771,11 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
           ((uint4*)s.gridb)[i] = ((const uint4*)s.grida)[i];
       if constexpr (diag) {
         __syncthreads();                       // the copy above reads the grid the sweep is about to change
-        for (int el = tid; el < ne; el += kThreads) primal_phase_b_diag(d, s, A, el);
+        for (int el = tid, it_ = 0; el < ne && (!SINGLE || it_ == 0); el += kThreads, ++it_) primal_phase_b_diag(d, s, A, el);
         __syncthreads();
       } else {
       bool pending = false;
-      for (int j = tid; j < na; j += kThreads) {
+      for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
         const int el = fast_div(j, d.invN), a = j - el * N;
         const uint8_t r = primal_classify(d, s, j, el, a);
         s.res[j] = r;
@@ -781,7 +783,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
       }
       while (__syncthreads_or(pending)) {      // an agent waits only for a LOWER id: every round makes progress
         pending = false;
-        for (int j = tid; j < na; j += kThreads) {
+        for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
           if (s.res[j] != RES_UNRESOLVED) continue;
           const int el = fast_div(j, d.invN);
           const uint8_t rk = s.res[el * N + s.dep[j]];
@@ -789,7 +791,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
           else s.res[j] = rk;                  // moves iff the agent ahead of it moved away
         }
       }
-      for (int j = tid; j < na; j += kThreads)   // vacate the old cells; phase C enters the new ones
+      for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_)   // vacate the old cells; phase C enters the new ones
         if (s.res[j] == RES_MOVED) {
           const uchar2 p = s.posold[j];
           s.grida[fast_div(j, d.invN) * d.grid_bytes + gcell(d, p.x, p.y)] = 0;
@@ -799,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     }
   PHASE_MARK(3);
     // ---- phase C
-    for (int j0 = 0; j0 < na; j0 += kThreads) {
+    for (int j0 = 0; j0 < na && (!SINGLE || j0 == 0); j0 += kThreads) {
       const int j = j0 + tid;
       const bool active = j < na;
       int el = -1;
@@ -838,7 +840,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
   // ---- agent bitmap of the post-step positions + available-action masks
   const uint8_t* gridcur = (!primal && do_step) ? s.gridb : s.grida;
   const bool want_avail = A.out.avail_dev != nullptr;
-  for (int j = tid; j < na; j += kThreads) {
+  for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
     const int el = fast_div(j, d.invN);
     const uchar2 p = s.posnew[j];
     if (F > 0) {
@@ -896,7 +898,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
   PHASE_MARK(5);
   // ---- phase D + state write-back + the small per-agent / per-env outputs (coalesced over the tile)
   if (do_step) {
-    for (int el = tid; el < ne; el += kThreads) {
+    for (int el = tid, it_ = 0; el < ne && (!SINGLE || it_ == 0); el += kThreads, ++it_) {
       const bool all = envcnt[el] == N;        // PRIMAL State.done (:159-165) / GRID episode_done (:267)
       if (A.out.terminated_dev) A.out.terminated_dev[e0 + el] = all ? 1 : 0;
       if (primal) {
@@ -941,7 +943,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     if (partial) __syncthreads();   // phase D changed done / rewards of whole environments
     // state write-back and the per-agent outputs: thread j stores agent j's records (byte stores of a warp cover
     // whole 32-byte sectors; a shared-memory staging pass costs more instructions than it saves transactions)
-    for (int j = tid; j < na; j += kThreads) {
+    for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
       const size_t gj = a0 + j;
       const uint8_t dn = s.done[j];
       ((uchar2*)S.pos)[gj] = s.posnew[j];
@@ -996,7 +998,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     __syncthreads();   // the bit strings reuse the step-phase scratch: everybody has finished the write-back
     // phase 1: one thread per agent builds its 4*F*F bits and the goal vector; G agents share a
     // word-aligned group string.
-    for (int base = 0; base < na; base += kThreads) {
+    for (int base = 0; base < na && (!SINGLE || base == 0); base += kThreads) {
       const int j = base + tid;
       const bool valid = (j < na) && (A.obs != nullptr);
       uint32_t first = 0;
@@ -1757,8 +1759,21 @@ template <int F, int MODE>
 cudaError_t launch_tile_f(const MapfDims& d, const MapfTileLayout& L, const MapfState& S, const MapfTileArgs& A,
                           cudaStream_t st) {
   const int grid = (d.E + d.epb - 1) / d.epb;
-  mapf_tile_kernel<F, MODE><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
+  // the diagonal mode is off the hot path: it only has the looped instantiation
+  if (MODE != MAPF_MODE_PRIMAL_DIAG && d.epb * d.N <= kThreads)
+    mapf_tile_kernel<F, MODE, (MODE != MAPF_MODE_PRIMAL_DIAG)><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
+  else
+    mapf_tile_kernel<F, MODE, false><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
   return cudaGetLastError();
+}
+
+template <int F, int MODE>
+cudaError_t configure_tile_f(int smem_bytes) {
+  const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  cudaError_t e = cudaFuncSetAttribute(mapf_tile_kernel<F, MODE, false>, attr, smem_bytes);
+  if (e == cudaSuccess && MODE != MAPF_MODE_PRIMAL_DIAG)
+    e = cudaFuncSetAttribute(mapf_tile_kernel<F, MODE, (MODE != MAPF_MODE_PRIMAL_DIAG)>, attr, smem_bytes);
+  return e;
 }
 
 int grid_for(long long total, int block) {
@@ -1795,21 +1810,20 @@ extern "C" int mapf_tile_has_fov(int F) {
 
 extern "C" int mapf_configure_tile(int F, int mode, int smem_bytes) {
   cudaError_t err = cudaErrorInvalidValue;
-  const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-  if (mode == MAPF_MODE_GRID) err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_GRID>, attr, smem_bytes);
-  else if (mode == MAPF_MODE_PARTIAL) err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_PARTIAL>, attr, smem_bytes);
+  if (mode == MAPF_MODE_GRID) err = configure_tile_f<0, MAPF_MODE_GRID>(smem_bytes);
+  else if (mode == MAPF_MODE_PARTIAL) err = configure_tile_f<0, MAPF_MODE_PARTIAL>(smem_bytes);
   else if (mode == MAPF_MODE_PRIMAL_DIAG) {
     switch (F) {
-      case 0: err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_PRIMAL_DIAG>, attr, smem_bytes); break;
-#define X(f) case f: err = cudaFuncSetAttribute(mapf_tile_kernel<f, MAPF_MODE_PRIMAL_DIAG>, attr, smem_bytes); break;
+      case 0: err = configure_tile_f<0, MAPF_MODE_PRIMAL_DIAG>(smem_bytes); break;
+#define X(f) case f: err = configure_tile_f<f, MAPF_MODE_PRIMAL_DIAG>(smem_bytes); break;
       MAPF_FOR_EACH_FOV(X)
 #undef X
       default: break;
     }
   } else {
     switch (F) {
-      case 0: err = cudaFuncSetAttribute(mapf_tile_kernel<0, MAPF_MODE_PRIMAL>, attr, smem_bytes); break;
-#define X(f) case f: err = cudaFuncSetAttribute(mapf_tile_kernel<f, MAPF_MODE_PRIMAL>, attr, smem_bytes); break;
+      case 0: err = configure_tile_f<0, MAPF_MODE_PRIMAL>(smem_bytes); break;
+#define X(f) case f: err = configure_tile_f<f, MAPF_MODE_PRIMAL>(smem_bytes); break;
       MAPF_FOR_EACH_FOV(X)
 #undef X
       default: break;
