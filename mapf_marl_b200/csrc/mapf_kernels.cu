@@ -647,7 +647,7 @@ __device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, uint32_t 
 #pragma unroll
     for (int k = 0; k < T::CW; ++k)
       if (q == k) vis[k] = v;
-    const int wi = idx / F, wj = idx - wi * F;
+    const int wi = (int)((unsigned)idx / (unsigned)F), wj = idx - wi * F;
     const int id = gbase[wi * GS + wj];            // the agent bit map says somebody stands here: id >= 1
     const uchar2 og = goals_env[id - 1];
     const int ci = min(max((int)og.x - t0, 0), F - 1);
@@ -688,52 +688,91 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
   if (tid < MAPF_N_STATS) stat[tid] = 0;
   if (tid == 0) bad_flag = 0;
   int* envstep = (int*)(smem_raw + L.envstep_off);
-  for (int el = tid, it_ = 0; el < ne && (!SINGLE || it_ == 0); el += kThreads, ++it_) {
-    envcnt[el] = 0;
-    envcnt2[el] = 0;
-    envstep[el] = S.step_count[e0 + el];   // staged with the other global loads: no mid-kernel round trip
-  }
-  {
-    const int nvec = ((d.shared_map ? 1 : ne) * d.bm_words) >> 2;
-    const uint4* src = (const uint4*)(S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e0 * d.bm_words));
-    uint4* dst = (uint4*)s.obst;
-    for (int i = tid; i < nvec; i += kThreads) dst[i] = __ldg(src + i);
-  }
-  bool bad = false;
-  for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
-    const uchar2 p = ((const uchar2*)S.pos)[a0 + j];
-    s.posold[j] = p;
-    s.posnew[j] = p;
-    s.goal[j] = ((const uchar2*)S.goal)[a0 + j];
-    s.done[j] = S.done[a0 + j];
-    if (partial) s.atgoal[j] = S.at_goal[a0 + j];
-    if (diag) {
-      const uchar2 q = ((const uchar2*)S.past)[a0 + j];
-      s.pastold[j] = q;
-      s.pastnew[j] = q;
+  // Every global load of the tile is issued before anything waits on one, and the zero fill runs while they are in
+  // flight: ONE exposed memory latency per tile (load -> store -> load -> store chains cost two or three).
+  struct AgentRec {
+    uchar2 p, g, past;
+    uint8_t dn, pv, atg;
+    long long av;
+  };
+  auto load_rec = [&](int j, AgentRec& r) {
+    r.p = ((const uchar2*)S.pos)[a0 + j];
+    r.g = ((const uchar2*)S.goal)[a0 + j];
+    r.dn = S.done[a0 + j];
+    r.pv = S.prev_action[a0 + j];
+    r.atg = 0;
+    if (partial) r.atg = S.at_goal[a0 + j];
+    r.past = make_uchar2(0, 0);
+    if (diag) r.past = ((const uchar2*)S.past)[a0 + j];
+    r.av = -1;
+    if (do_step) {
+      const int el = fast_div(j, d.invN), a = j - el * N;
+      if (a >= A.agent_lo && a < A.agent_hi)
+        r.av = (A.act_dtype == MAPF_I64) ? ((const long long*)A.actions)[a0 + j]
+                                         : (long long)((const uint8_t*)A.actions)[a0 + j];
     }
-    const int el = fast_div(j, d.invN), a = j - el * N;
-    int act = S.prev_action[a0 + j];
-    if (do_step && a >= A.agent_lo && a < A.agent_hi) {
-      long long v = (A.act_dtype == MAPF_I64) ? ((const long long*)A.actions)[a0 + j]
-                                              : (long long)((const uint8_t*)A.actions)[a0 + j];
-      if (v < 0 || v > (diag ? 8 : 4)) {                             // GRID:92 / PRIMAL:556 assert
-        bad = true;
-        v = primal ? 0 : 4;
+  };
+  bool bad = false;
+  auto store_rec = [&](int j, const AgentRec& r) {
+    s.posold[j] = r.p;
+    s.posnew[j] = r.p;
+    s.goal[j] = r.g;
+    s.done[j] = r.dn;
+    if (partial) s.atgoal[j] = r.atg;
+    if (diag) {
+      s.pastold[j] = r.past;
+      s.pastnew[j] = r.past;
+    }
+    int act = r.pv;
+    if (do_step) {
+      const int el = fast_div(j, d.invN), a = j - el * N;
+      if (a >= A.agent_lo && a < A.agent_hi) {
+        long long v = r.av;
+        if (v < 0 || v > (diag ? 8 : 4)) {                           // GRID:92 / PRIMAL:556 assert
+          bad = true;
+          v = primal ? 0 : 4;
+        }
+        act = (int)v;
       }
-      act = (int)v;
     }
     s.act[j] = (uint8_t)act;
-  }
+  };
+  const int nvec = ((d.shared_map ? 1 : ne) * d.bm_words) >> 2;
+  const uint4* osrc = (const uint4*)(S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e0 * d.bm_words));
+  uint4* odst = (uint4*)s.obst;
+  uint4 ob0 = make_uint4(0, 0, 0, 0);
+  if (tid < nvec) ob0 = __ldg(osrc + tid);
+  AgentRec r0;
+  if (tid < na) load_rec(tid, r0);
+  int sc0 = 0;
+  if (tid < ne) sc0 = S.step_count[e0 + tid];
   {
+    // zero the agent bit rows and the occupancy grid(s): they are adjacent in the tile layout, one loop clears them
     const uint4 z = make_uint4(0, 0, 0, 0);
-    const int ngrid = (ne * d.grid_bytes) >> 4;
-    for (int i = tid; i < ngrid; i += kThreads) ((uint4*)s.grida)[i] = z;
-    if (!primal && do_step)
-      for (int i = tid; i < ngrid; i += kThreads) ((uint4*)s.gridb)[i] = z;
-    if (F > 0) {
-      const int nag = (ne * d.bm_words) >> 2;
-      for (int i = tid; i < nag; i += kThreads) ((uint4*)s.agt)[i] = z;
+    const int nz = (L.grida_off - L.agt_off + d.epb * d.grid_bytes * ((!primal && do_step) ? 2 : 1)) >> 4;
+    uint4* zp = (uint4*)(smem_raw + L.agt_off);
+#pragma unroll 1
+    for (int i = tid; i < nz; i += kThreads) zp[i] = z;
+  }
+  if (tid < nvec) odst[tid] = ob0;
+#pragma unroll 1
+  for (int i = tid + kThreads; i < nvec; i += kThreads) odst[i] = __ldg(osrc + i);
+  if (tid < ne) {
+    envcnt[tid] = 0;
+    envcnt2[tid] = 0;
+    envstep[tid] = sc0;
+  }
+  if (tid < na) store_rec(tid, r0);
+  if (!SINGLE) {
+    for (int el = tid + kThreads; el < ne; el += kThreads) {
+      envcnt[el] = 0;
+      envcnt2[el] = 0;
+      envstep[el] = S.step_count[e0 + el];
+    }
+    for (int j = tid + kThreads; j < na; j += kThreads) {
+      AgentRec r;
+      load_rec(j, r);
+      store_rec(j, r);
     }
   }
   __syncthreads();
@@ -904,6 +943,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
       if (primal) {
         if (A.out.reward_dev) {
           double tot = 0.0;
+#pragma unroll 8   // the adds are one dependent chain (the reference's order); unrolling lets the loads run ahead
           for (int i = A.agent_lo; i < A.agent_hi; ++i) tot = __dadd_rn(tot, s.rew[el * N + i]);
           A.out.reward_dev[e0 + el] = tot;
         }
@@ -1005,10 +1045,15 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
       uint32_t vis[T::CW];
       int w0 = 0, sh = 0, el = 0;
       uchar2 p = make_uchar2(0, 0), g = make_uchar2(0, 0);
+      const double2* vt = nullptr;
       if (j < na) {
         el = fast_div(j, d.invN);
         p = s.posnew[j];
         g = s.goal[j];
+        if (A.vec != nullptr) {   // the goal-vector table entry is needed at the END of this pass: start fetching it now
+          vt = (const double2*)S.vec_lut + 2 * (abs((int)g.x - (int)p.x) * d.W + abs((int)g.y - (int)p.y));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(vt));
+        }
       }
       if (valid) {
         uint32_t w[T::NW];
@@ -1036,9 +1081,8 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
       }
       if (j < na && A.vec != nullptr) {                              // PRIMAL:380-385
         const int dx = (int)g.x - (int)p.x, dy = (int)g.y - (int)p.y;
-        const double2* t = (const double2*)S.vec_lut + 2 * (abs(dx) * d.W + abs(dy));
-        const double2 u = __ldg(t);                                  // |dx| / mag, |dy| / mag (IEEE division is
-        const double2 m = __ldg(t + 1);                              // sign-symmetric; 0 / mag = +0.0 either way)
+        const double2 u = __ldg(vt);                                 // |dx| / mag, |dy| / mag (IEEE division is
+        const double2 m = __ldg(vt + 1);                             // sign-symmetric; 0 / mag = +0.0 either way)
         double* v = A.vec + 3 * (a0 + j);
         v[0] = dx < 0 ? -u.x : u.x;
         v[1] = dy < 0 ? -u.y : u.y;
