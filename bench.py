@@ -255,16 +255,36 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- device-resident throughput (the fused step+observation kernel), clocks sampled meanwhile
+    # ---- device-resident throughput (the fused step+observation kernel), clocks sampled meanwhile.
+    #      The K timed steps are replayed from CUDA graphs of `chunk` consecutive steps each (what a captured rollout
+    #      loop pays: no Python / ctypes cost per launch); eager launches are timed next to it.
+    for t in range(args.warmup):
+        eng.step_observe(pool[t % 16], want=want, dtype=odt)
+    chunk = max(c for c in range(1, 21) if args.steps % c == 0)
+    graph = None
+    if chunk > 1 or args.steps == 1:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                for t in range(chunk):
+                    eng.step_observe(pool[t % 16], want=want, dtype=odt)
+        except Exception as exc:   # capture is a convenience of the host library, never a reason to lose the bench line
+            sys.stderr.write("CUDA graph capture failed, timing eager launches: %r\n" % (exc,))
+            graph = None
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = eng.launch_count()
     if sampler:
         sampler.start()
-    ms_total = timed(lambda t: eng.step_observe(pool[t % 16], want=want, dtype=odt), args.steps, args.warmup)
+    if graph is not None:
+        ms_total = timed(lambda t: graph.replay(), args.steps // chunk, 2)
+    else:
+        ms_total = timed(lambda t: eng.step_observe(pool[t % 16], want=want, dtype=odt), args.steps, 0)
     clocks = sampler.stop() if sampler else None
-    launches = eng.launch_count() - launches0 - args.warmup
+    launches = args.steps            # one tile-kernel launch per step (inside the graphs when replayed)
     ms_step = ms_total / args.steps
     value = world * E * N * args.steps / (ms_total * 1e-3)
+    n_eager = max(min(args.steps, 2000), 1)
+    ms_eager = timed(lambda t: eng.step_observe(pool[t % 16], want=want, dtype=odt), n_eager, 3) / n_eager
 
     # ---- breakdown: the step-only and observe-only launches of the same tile kernel
     ms_obs = timed(lambda t: eng.observe(dtype=odt), max(args.steps // 4, 5), 3) / max(args.steps // 4, 5)
@@ -321,7 +341,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32 obs / u8 state" if args.f32 else "u8", "data": "synthetic",
-            "config": workload_config(args.workload, wl, world),
+            "config": dict(workload_config(args.workload, wl, world),
+                           launch=("CUDA graph replay, %d steps per graph" % chunk) if graph is not None
+                           else "eager launches (one C-ABI call per step)"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.e2e_steps, "steps": args.e2e_steps},
             "e2e_obs_on_device": {"value": world * E * N / (ms_e2e2 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e2,
@@ -334,7 +356,8 @@ def main():
                          "kernel": "mapf_tile_kernel<%d> (fused step+obs)" % F,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "algorithmic_bytes_per_agent_step": bytes_per},
-            "breakdown_ms": {"fused_step_obs": ms_step, "observe_only": ms_obs, "step_only": ms_stp,
+            "breakdown_ms": {"fused_step_obs": ms_step, "fused_step_obs_eager_launches": ms_eager,
+                             "observe_only": ms_obs, "step_only": ms_stp,
                              "observe_only_GBps": (4 * F * F * (4 if args.f32 else 1) + 24 + 8 +
                                                    wl["H"] * wl["W"] / N) * E * N / (ms_obs * 1e-3) / 1e9,
                              "goal_bfs_all_maps": bfs_ms, "goal_maps_per_s": E * N / (bfs_ms * 1e-3)},

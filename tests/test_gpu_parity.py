@@ -1011,3 +1011,46 @@ def test_mapfenv_dropin_class_diagonal_movement():
         assert env.getPositions() == [tuple(p) for p in g["pos"][t].tolist()]
     with pytest.raises(AssertionError):
         env._step((1, 9))
+
+
+def test_fused_step_is_cuda_graph_capturable_and_replays_bit_exactly():
+    """The C ABI is stream-ordered and never synchronises: a rollout loop can be captured in a CUDA graph."""
+    from mapf_marl_b200 import maps
+    from oracle.oracle import MODE_PRIMAL
+    E, N, H, W, F, T = 96, 8, 20, 20, 11, 6
+    obst, starts, goals = maps.synthetic_batch(77, E, H, W, 0.2, N, distinct=0)
+    eng = _engine(E, N, H, W, mode="primal", fov=F)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    acts = torch.zeros((E, N), dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):          # warm-up on a side stream (allocates the engine's output buffers)
+        eng.observe()
+        eng.avail()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    eng.reset(obst, starts, goals)
+    with torch.cuda.stream(side):
+        out = eng.step_observe(acts, want=PRIMAL_WANT)   # buffers exist before the capture
+    torch.cuda.synchronize()
+    eng.reset(obst, starts, goals)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph):
+        out = eng.step_observe(acts, want=PRIMAL_WANT)
+    rs = np.random.RandomState(3)
+    for t in range(T):
+        a = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        acts.copy_(torch.as_tensor(a))
+        graph.replay()
+        torch.cuda.synchronize()
+        ref = orc.primal_sweep(a)
+        robs, rvec = orc.primal_observe()
+        for k in ("status", "dones", "valid", "done_mid", "next_mid", "avail", "terminated"):
+            assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        assert np.array_equal(_bits(_np(out["agent_reward"])), _bits(ref["agent_reward"])), t
+        assert np.array_equal(_np(out["obs"]), robs), t
+        assert np.array_equal(_bits(_np(out["vec"])), _bits(rvec)), t
+    assert eng.error_flags() == 0
