@@ -162,7 +162,7 @@ def run_reference_arm(args, wl, rank):
         "note": "the reference is pure Python and cannot travel to the GPU box; this is the C oracle port, "
                 "pinned bit-exact to the live reference by tests/test_oracle_golden.py",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(name, wl, gpus):
@@ -174,6 +174,15 @@ def workload_config(name, wl, gpus):
         "l2": "per-step working set (obs output %.0f MB) exceeds the 126 MB L2" % (
             wl["E"] * wl["N"] * 4 * wl["F"] ** 2 / 1e6),
         "parallelism": "envs sharded by index over %d GPU(s), no data-path collective" % gpus}
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -188,6 +197,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--f32", action="store_true", help="emit float32 observations instead of uint8")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: library banners (NCCL prints its version to stdout) are sent to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     wl = dict(WORKLOADS[args.workload])
     if args.envs:
         wl["E"] = args.envs
@@ -374,7 +388,7 @@ def main():
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "%d envs x %d agents x %d steps of %s (step+obs), C oracle port, OpenMP over envs on "
                           "%d threads, %.1f s" % (n_cpu, N, n_steps, args.workload, cores, dt)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
