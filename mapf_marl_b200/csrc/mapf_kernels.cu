@@ -825,9 +825,16 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
         for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
           if (s.res[j] != RES_UNRESOLVED) continue;
           const int el = fast_div(j, d.invN);
-          const uint8_t rk = s.res[el * N + s.dep[j]];
-          if (rk == RES_UNRESOLVED) pending = true;
-          else s.res[j] = rk;                  // moves iff the agent ahead of it moved away
+          const int k = el * N + s.dep[j];
+          const uint8_t rk = s.res[k];
+          if (rk == RES_UNRESOLVED) {
+            // pointer jumping: k's outcome is its own predecessor's, so wait for that one directly -- a convoy of
+            // length L resolves in log2(L) rounds (any value read here is an agent further up the same chain)
+            s.dep[j] = s.dep[k];
+            pending = true;
+          } else {
+            s.res[j] = rk;                     // moves iff the agent ahead of it moved away
+          }
         }
       }
       for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_)   // vacate the old cells; phase C enters the new ones
