@@ -307,12 +307,25 @@ def main():
     # ---- end to end: pinned host actions in, every output back on the host, through the C-ABI host entry point
     io, bufs, h2d, d2h = eng.make_host_io(obs_dtype=odt)
     host_pool = pool[:4].cpu()
+    host_pool_np = host_pool.numpy()
+    act_np = bufs["actions"].numpy()          # view of the pinned action buffer
 
     def e2e_step(t):
-        bufs["actions"].copy_(host_pool[t % 4])
+        # a plain memcpy into the pinned buffer (torch's CPU copy_ would fan out to its OpenMP pool, whose threads then
+        # spin on every core for milliseconds and compete with the library's unpack threads)
+        np.copyto(act_np, host_pool_np[t % 4])
         eng.step_observe_host(io)
     ms_e2e = timed(e2e_step, args.e2e_steps, 3)
     e2e_value = world * E * N * args.e2e_steps / (ms_e2e * 1e-3)
+    e2e_transport = "bit-packed observation over PCIe, expanded to uint8 by the library's host threads" \
+        if (odt == torch.uint8 and eng.host_transport() == 1) else "dense copies"
+    # the same call with dense copies of the uint8 observation (informational)
+    ms_e2e_dense = None
+    if odt == torch.uint8 and eng.host_transport() == 1:
+        eng.host_transport(False)
+        _, _, _, d2h_dense = eng.make_host_io(obs_dtype=odt)
+        ms_e2e_dense = timed(e2e_step, args.e2e_steps, 2) / args.e2e_steps
+        eng.host_transport(True)
 
     # ---- the same host entry point when the policy lives on the GPU (pymarl's controller does): actions come from
     #      the host, reward / terminated go back, the observation stays in device memory for the agent network
@@ -359,7 +372,11 @@ def main():
                            launch=("CUDA graph replay, %d steps per graph" % chunk) if graph is not None
                            else "eager launches (one C-ABI call per step)"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.e2e_steps, "steps": args.e2e_steps},
+                    "ms_per_step": ms_e2e / args.e2e_steps, "steps": args.e2e_steps, "transport": e2e_transport},
+            "e2e_dense_transport": None if ms_e2e_dense is None else {
+                "value": world * E * N / (ms_e2e_dense * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_dense,
+                "d2h_bytes_per_step": d2h_dense,
+                "note": "informational: the same host call with the uint8 observation copied densely over PCIe"},
             "e2e_obs_on_device": {"value": world * E * N / (ms_e2e2 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e2,
                                   "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2,
                                   "note": "informational: host actions in, reward/terminated out, observation left "

@@ -73,7 +73,12 @@ typedef enum mapf_dtype {
   MAPF_I64 = 1,
   MAPF_F32 = 2,
   MAPF_I8 = 3,
-  MAPF_F64 = 4
+  MAPF_F64 = 4,
+  /* FOV observations only: the 0/1 cells packed one bit per cell, bit i of the stream == byte i of the MAPF_U8
+   * tensor [E,N,4,F,F] (little-endian bit order inside 32-bit words), ceil(E*N*4*F*F / 32) words.  8x fewer bytes
+   * for a consumer that takes bits (and the transport format of mapf_step_observe_host).  Needs a specialised
+   * field-of-view kernel and whole observation groups per tile: mapf_obs_bits_supported(). */
+  MAPF_BITS = 5
 } mapf_dtype;
 
 /* Device-side error flag bits (mapf_error_flags). */
@@ -238,8 +243,8 @@ int mapf_step_agents(mapf_handle* h, const void* actions_dev, int act_dtype, int
 
 /* Replaces get_obs/get_state (GRID:143-196) or `_observe(id)` for every id (PRIMAL:343-386).
  *   MAPF_OBS_FULLMAP:    obs_dev int8[E, H*W] (MAPF_I8); vec_dev ignored.
- *   MAPF_OBS_PRIMAL_FOV: obs_dev [E,N,4,F,F] of obs_dtype (MAPF_U8 or MAPF_F32), channel order
- *                        [poss_map, goal_map, goals_map, obs_map] (PRIMAL:386);
+ *   MAPF_OBS_PRIMAL_FOV: obs_dev [E,N,4,F,F] of obs_dtype (MAPF_U8 or MAPF_F32; MAPF_BITS: the same cells as a
+ *                        bit stream), channel order [poss_map, goal_map, goals_map, obs_map] (PRIMAL:386);
  *                        vec_dev double[E,N,3] = [dx/mag, dy/mag, mag] or NULL. */
 int mapf_observe(mapf_handle* h, void* obs_dev, int obs_dtype, double* vec_dev, void* stream);
 
@@ -249,8 +254,17 @@ int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, co
 
 /* Host-buffer form of mapf_step_observe: copies io->actions_host to the device, runs the fused
  * kernel, copies the requested outputs back and waits for them.  This is the call the e2e
- * benchmark times. */
+ * benchmark times.
+ * MAPF_U8 field-of-view observations cross PCIe as packed bits (MAPF_BITS, 8x fewer bytes) in chunks and are
+ * expanded to the 0/1 bytes of obs_host by the library's host threads while the next chunk is in flight; the
+ * result is byte-identical to the dense copy.  mapf_host_transport(h, 0) switches back to the dense copy. */
 int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream);
+
+/* 1 when observations of this handle can be produced as MAPF_BITS. */
+int mapf_obs_bits_supported(const mapf_handle* h);
+/* packed != 0 (default): bit-packed PCIe transport in mapf_step_observe_host when supported; 0: dense copies.
+ * Returns the mode now in effect (1 packed, 0 dense). */
+int mapf_host_transport(mapf_handle* h, int packed);
 
 /* Replaces get_avail_actions (GRID:198-224) / _listNextValidActions(id, prev_action) (PRIMAL:639-667)
  * for the current state.  avail_dev uint8[E,N,5]. */

@@ -19,7 +19,7 @@ ABI_VERSION = 1
 MAPF_OK = 0
 MODE_GRID, MODE_PRIMAL, MODE_PARTIAL = 0, 1, 2
 OBS_FULLMAP, OBS_PRIMAL_FOV, OBS_PARTIAL_WINDOW = 0, 1, 2
-U8, I64, F32, I8, F64 = 0, 1, 2, 3, 4
+U8, I64, F32, I8, F64, BITS = 0, 1, 2, 3, 4, 5
 FLAG_BAD_ACTION, FLAG_BAD_POSITION, FLAG_START_ON_WALL, FLAG_START_OVERLAP, FLAG_GOAL_OVERLAP = 1, 2, 4, 8, 16
 N_STATS = 8
 STAT_NAMES = ("env_steps", "agent_steps", "env_collisions", "node_collisions", "edge_collisions",
@@ -80,6 +80,8 @@ PROTOTYPES = {
     "mapf_observe": (_i, [_vp, _vp, _i, _vp, _vp]),
     "mapf_step_observe": (_i, [_vp, _vp, _i, ctypes.POINTER(MapfStepOut), _vp, _i, _vp, _vp]),
     "mapf_step_observe_host": (_i, [_vp, ctypes.POINTER(MapfHostIO), _vp]),
+    "mapf_obs_bits_supported": (_i, [_vp]),
+    "mapf_host_transport": (_i, [_vp, _i]),
     "mapf_avail": (_i, [_vp, _vp, _vp]),
     "mapf_bfs": (_i, [_vp, _vp, _vp, _i, _vp]),
     "mapf_set_prev_actions": (_i, [_vp, _vp, _vp]),
@@ -96,8 +98,8 @@ PROTOTYPES = {
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["mapf_kernels.cu", "mapf_capi.cu"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
+SOURCES = ["mapf_kernels.cu", "mapf_capi.cu", "mapf_host_unpack.cpp"]
 
 
 def _nvcc():

@@ -10,6 +10,8 @@
 
 #include "mapf_internal.h"
 
+#define MAPF_HOST_CHUNKS 8
+
 struct mapf_handle {
   mapf_cfg cfg;
   MapfDims d;
@@ -29,8 +31,22 @@ struct mapf_handle {
   void* hs_obs;
   size_t hs_obs_bytes;
   double* hs_vec;
+  // bit-packed PCIe transport of the host entry point (mapf_host_unpack.cpp)
+  int packed_transport;        // 1 (default): ship MAPF_BITS and expand on the host when supported
+  uint32_t* hs_bits;           // device: the packed observation
+  uint32_t* hp_bits;           // pinned host staging of the same size
+  size_t bits_words;
+  struct MapfUnpackPool* pool;
+  cudaEvent_t chunk_ev[MAPF_HOST_CHUNKS];
+  int chunk_ev_ready;
   char err[512];
 };
+
+extern "C" {
+struct MapfUnpackPool* mapf_unpack_pool_create(int threads);
+void mapf_unpack_pool_destroy(struct MapfUnpackPool* p);
+void mapf_unpack_pool_run(struct MapfUnpackPool* p, const uint32_t* bits, uint8_t* out, size_t out_bytes);
+}
 
 static thread_local char g_create_err[512] = "";
 
@@ -212,6 +228,11 @@ int mapf_destroy(mapf_handle* h) {
   cudaFree(h->hs_avail);
   cudaFree(h->hs_obs);
   cudaFree(h->hs_vec);
+  cudaFree(h->hs_bits);
+  if (h->hp_bits) cudaFreeHost(h->hp_bits);
+  if (h->chunk_ev_ready)
+    for (int c = 0; c < MAPF_HOST_CHUNKS; ++c) cudaEventDestroy(h->chunk_ev[c]);
+  if (h->pool) mapf_unpack_pool_destroy(h->pool);
   delete h;
   return MAPF_OK;
 }
@@ -268,6 +289,7 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   memset(h, 0, sizeof(*h));
   h->cfg = *c;
   h->cfg.mag_lut_host = nullptr;
+  h->packed_transport = 1;
   cudaError_t e = cudaGetDevice(&h->device);
   if (e != cudaSuccess) {
     int rc = cuda_fail(nullptr, e, "cudaGetDevice");
@@ -477,6 +499,12 @@ int mapf_set_goals(mapf_handle* h, const int16_t* goals_dev, const uint8_t* dirt
   return MAPF_OK;
 }
 
+// MAPF_BITS output: a specialised field-of-view kernel, and every tile holds whole observation groups (tile strings
+// start on word boundaries).
+static bool bits_supported(const mapf_handle* h) {
+  return h->d.obs_mode == MAPF_OBS_PRIMAL_FOV && h->fov_fast && (h->d.epb * h->d.N) % h->d.G == 0;
+}
+
 static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, int hi, const mapf_step_out* out,
                     void* obs, int obs_dtype, double* vec, void* stream) {
   MapfTileArgs A;
@@ -496,8 +524,11 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
   const bool fov = h->d.obs_mode == MAPF_OBS_PRIMAL_FOV;
   const bool pwin = h->d.obs_mode == MAPF_OBS_PARTIAL_WINDOW;
   if (obs) {
-    if (fov && obs_dtype != MAPF_U8 && obs_dtype != MAPF_F32)
-      return fail(h, MAPF_ERR_INVALID_ARG, "FOV observations are MAPF_U8 or MAPF_F32");
+    if (fov && obs_dtype == MAPF_BITS && !bits_supported(h))
+      return fail(h, MAPF_ERR_UNSUPPORTED, "MAPF_BITS observations are not available for this configuration "
+                                           "(mapf_obs_bits_supported)");
+    if (fov && obs_dtype != MAPF_U8 && obs_dtype != MAPF_F32 && obs_dtype != MAPF_BITS)
+      return fail(h, MAPF_ERR_INVALID_ARG, "FOV observations are MAPF_U8, MAPF_F32 or MAPF_BITS");
     if (pwin && obs_dtype != MAPF_F64) return fail(h, MAPF_ERR_INVALID_ARG, "PARTIAL window observations are MAPF_F64");
     if (!fov && !pwin && obs_dtype != MAPF_I8)
       return fail(h, MAPF_ERR_INVALID_ARG, "full-map observations are MAPF_I8");
@@ -660,12 +691,22 @@ int mapf_error_flags(mapf_handle* h, uint32_t* flags_host, void* stream) {
   return MAPF_OK;
 }
 
+int mapf_obs_bits_supported(const mapf_handle* h) { return (h && bits_supported(h)) ? 1 : 0; }
+
+int mapf_host_transport(mapf_handle* h, int packed) {
+  if (!h) return 0;
+  h->packed_transport = packed ? 1 : 0;
+  return (h->packed_transport && bits_supported(h)) ? 1 : 0;
+}
+
 int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream) {
   if (!h || !io || !io->actions_host) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_step_observe_host: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
   const MapfDims& d = h->d;
   const size_t EN = (size_t)d.E * d.N;
   const bool fov = d.obs_mode == MAPF_OBS_PRIMAL_FOV;
+  // uint8 field-of-view observations cross PCIe as bits and are expanded by the host pool (byte-identical result)
+  const bool packed = io->obs_host && fov && io->obs_dtype == MAPF_U8 && h->packed_transport && bits_supported(h);
   size_t obs_bytes = 0;
   if (io->obs_host) {
     if (fov) obs_bytes = EN * 4 * d.F * d.F * (io->obs_dtype == MAPF_F32 ? 4 : 1);
@@ -683,14 +724,28 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   if (io->dones_host) LAZY(h->hs_dones, EN);
   if (io->avail_host) LAZY(h->hs_avail, EN * d.nact);
   if (io->vec_host) LAZY(h->hs_vec, EN * 24);
-#undef LAZY
-  if (obs_bytes > h->hs_obs_bytes) {
+  const size_t tile_words = packed ? ((size_t)d.epb * d.N * 4 * d.F * d.F) >> 5 : 0;
+  const size_t ntiles = ((size_t)d.E + d.epb - 1) / d.epb;
+  if (packed) {
+    h->bits_words = ntiles * tile_words;
+    LAZY(h->hs_bits, h->bits_words * 4);
+    if (!h->hp_bits) CK(cudaHostAlloc((void**)&h->hp_bits, h->bits_words * 4, cudaHostAllocDefault));
+    if (!h->pool) {
+      h->pool = mapf_unpack_pool_create(0);
+      if (!h->pool) return fail(h, MAPF_ERR_ALLOC, "mapf_step_observe_host: cannot start the host unpack threads");
+    }
+    if (!h->chunk_ev_ready) {
+      for (int c = 0; c < MAPF_HOST_CHUNKS; ++c) CK(cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
+      h->chunk_ev_ready = 1;
+    }
+  } else if (obs_bytes > h->hs_obs_bytes) {
     cudaFree(h->hs_obs);
     h->hs_obs = nullptr;
     h->hs_obs_bytes = 0;
     CK(cudaMalloc(&h->hs_obs, obs_bytes));
     h->hs_obs_bytes = obs_bytes;
   }
+#undef LAZY
   CK(cudaMemcpyAsync(h->hs_actions, io->actions_host, EN, cudaMemcpyHostToDevice, st));
   mapf_step_out out;
   memset(&out, 0, sizeof(out));
@@ -698,16 +753,43 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   out.terminated_dev = io->terminated_host ? h->hs_terminated : nullptr;
   out.dones_dev = io->dones_host ? h->hs_dones : nullptr;
   out.avail_dev = io->avail_host ? h->hs_avail : nullptr;
-  int rc = run_tile(h, h->hs_actions, MAPF_U8, 0, d.N, &out, io->obs_host ? h->hs_obs : nullptr, io->obs_dtype,
+  void* obs_dev = !io->obs_host ? nullptr : (packed ? (void*)h->hs_bits : h->hs_obs);
+  int rc = run_tile(h, h->hs_actions, MAPF_U8, 0, d.N, &out, obs_dev, packed ? (int)MAPF_BITS : io->obs_dtype,
                     io->vec_host ? h->hs_vec : nullptr, stream);
   if (rc != MAPF_OK) return rc;
-  if (io->reward_host) CK(cudaMemcpyAsync(io->reward_host, h->hs_reward, (size_t)d.E * 8, cudaMemcpyDeviceToHost, st));
-  if (io->terminated_host)
-    CK(cudaMemcpyAsync(io->terminated_host, h->hs_terminated, (size_t)d.E, cudaMemcpyDeviceToHost, st));
-  if (io->dones_host) CK(cudaMemcpyAsync(io->dones_host, h->hs_dones, EN, cudaMemcpyDeviceToHost, st));
-  if (io->avail_host) CK(cudaMemcpyAsync(io->avail_host, h->hs_avail, EN * d.nact, cudaMemcpyDeviceToHost, st));
-  if (io->vec_host) CK(cudaMemcpyAsync(io->vec_host, h->hs_vec, EN * 24, cudaMemcpyDeviceToHost, st));
-  if (io->obs_host) CK(cudaMemcpyAsync(io->obs_host, h->hs_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+  auto copy_small_outputs = [&]() -> int {
+    if (io->reward_host) CK(cudaMemcpyAsync(io->reward_host, h->hs_reward, (size_t)d.E * 8, cudaMemcpyDeviceToHost, st));
+    if (io->terminated_host)
+      CK(cudaMemcpyAsync(io->terminated_host, h->hs_terminated, (size_t)d.E, cudaMemcpyDeviceToHost, st));
+    if (io->dones_host) CK(cudaMemcpyAsync(io->dones_host, h->hs_dones, EN, cudaMemcpyDeviceToHost, st));
+    if (io->avail_host) CK(cudaMemcpyAsync(io->avail_host, h->hs_avail, EN * d.nact, cudaMemcpyDeviceToHost, st));
+    if (io->vec_host) CK(cudaMemcpyAsync(io->vec_host, h->hs_vec, EN * 24, cudaMemcpyDeviceToHost, st));
+    return MAPF_OK;
+  };
+  if (packed) {
+    // chunks of whole tiles: the copy of chunk c+1 (and of the small outputs, queued last) runs while the pool
+    // expands chunk c
+    const size_t per = (ntiles + MAPF_HOST_CHUNKS - 1) / MAPF_HOST_CHUNKS;
+    int nchunks = 0;
+    for (size_t t0 = 0; t0 < ntiles; t0 += per, ++nchunks) {
+      const size_t t1 = t0 + per < ntiles ? t0 + per : ntiles;
+      CK(cudaMemcpyAsync(h->hp_bits + t0 * tile_words, h->hs_bits + t0 * tile_words, (t1 - t0) * tile_words * 4,
+                         cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(h->chunk_ev[nchunks], st));
+    }
+    if ((rc = copy_small_outputs()) != MAPF_OK) return rc;
+    int c = 0;
+    for (size_t t0 = 0; t0 < ntiles; t0 += per, ++c) {
+      const size_t t1 = t0 + per < ntiles ? t0 + per : ntiles;
+      const size_t byte0 = t0 * tile_words * 32;
+      const size_t byte1 = t1 * tile_words * 32 < obs_bytes ? t1 * tile_words * 32 : obs_bytes;   // last tile may be short
+      CK(cudaEventSynchronize(h->chunk_ev[c]));
+      mapf_unpack_pool_run(h->pool, h->hp_bits + t0 * tile_words, (uint8_t*)io->obs_host + byte0, byte1 - byte0);
+    }
+  } else {
+    if ((rc = copy_small_outputs()) != MAPF_OK) return rc;
+    if (io->obs_host) CK(cudaMemcpyAsync(io->obs_host, h->hs_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+  }
   CK(cudaStreamSynchronize(st));
   return MAPF_OK;
 }

@@ -1111,7 +1111,13 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
   PHASE_MARK(8);
     // phase 2: expand the tile's bit string; thread q writes output bytes [16q, 16q+16)
     const size_t nbits = (size_t)na * T::NB;
-    if (A.obs_dtype == MAPF_U8) {
+    if (A.obs_dtype == MAPF_BITS) {
+      // the strings as they are: tile t starts at word a0 * NB / 32 (the host only selects this output when every
+      // tile holds whole groups, so the tile's first bit sits on a word boundary)
+      uint32_t* out = (uint32_t*)A.obs + ((a0 * T::NB) >> 5);
+      const int nw = (int)((nbits + 31) >> 5);
+      for (int q = tid; q < nw; q += kThreads) out[q] = s.str[q];
+    } else if (A.obs_dtype == MAPF_U8) {
       uint8_t* out = (uint8_t*)A.obs + a0 * T::NB;
       const int lead = (int)((16 - ((uintptr_t)out & 15)) & 15);   // 0 unless the tile holds an odd number of groups
       if (lead == 0) {

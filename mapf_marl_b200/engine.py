@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (F32, F64, I8, I64, MODE_GRID, MODE_PARTIAL, MODE_PRIMAL, OBS_FULLMAP, OBS_PARTIAL_WINDOW,
+from ._lib import (BITS, F32, F64, I8, I64, MODE_GRID, MODE_PARTIAL, MODE_PRIMAL, OBS_FULLMAP, OBS_PARTIAL_WINDOW,
                    OBS_PRIMAL_FOV, STAT_NAMES, STEP_OUT_FIELDS, U8, MapfCfg, MapfHostIO, MapfStepOut)
 
 _OUT_SPECS = {
@@ -259,8 +259,15 @@ class MapfEngine:
 
     def _obs_buffers(self, dtype, want_vec):
         if self.obs_mode == OBS_PRIMAL_FOV:
+            if dtype == "bits":
+                # one bit per cell, bit i of the stream == element i of the uint8 tensor (little-endian bit order):
+                # np.unpackbits(obs.cpu().numpy(), bitorder="little")[:E*N*4*F*F] gives the cells back
+                nwords = (self.E * self.N * 4 * self.F * self.F + 31) // 32
+                obs = self._buf("obs_bits", (nwords * 4,), torch.uint8)
+                vec = self._buf("vec", (self.E, self.N, 3), torch.float64) if want_vec else None
+                return obs, vec, BITS
             if dtype not in (torch.uint8, torch.float32):
-                raise ValueError("FOV observations are uint8 or float32")
+                raise ValueError("FOV observations are uint8, float32 or 'bits'")
             obs = self._buf("obs_%s" % dtype, (self.E, self.N, 4, self.F, self.F), dtype)
             vec = self._buf("vec", (self.E, self.N, 3), torch.float64) if want_vec else None
             return obs, vec, (U8 if dtype == torch.uint8 else F32)
@@ -362,7 +369,25 @@ class MapfEngine:
         io.obs_dtype = odt
         h2d = bufs["actions"].numel()
         d2h = sum(t.numel() * t.element_size() for k, t in bufs.items() if k != "actions")
+        if "obs" in bufs and odt == U8 and self.host_transport() == 1:
+            # uint8 FOV observations cross PCIe as packed bits (whole tiles) and are expanded by the library's host threads
+            d2h += self.packed_obs_bytes() - bufs["obs"].numel()
         return io, bufs, h2d, d2h
+
+    def bits_supported(self):
+        return bool(self.lib.mapf_obs_bits_supported(self._h))
+
+    def host_transport(self, packed=None):
+        """Query (packed=None) or set the PCIe transport of step_observe_host: 1 = bit-packed + host expansion,
+        0 = dense copies.  Returns the mode in effect."""
+        if packed is None:
+            packed = getattr(self, "_packed_transport", True)
+        self._packed_transport = bool(packed)
+        return int(self.lib.mapf_host_transport(self._h, int(bool(packed))))
+
+    def packed_obs_bytes(self):
+        """Bytes of one bit-packed FOV observation as the host entry point copies it (whole tiles)."""
+        return (self.E * self.N * 4 * self.F * self.F + 31) // 32 * 4
 
     def step_observe_host(self, io):
         """Host buffers in, host buffers out; returns when the outputs are on the host."""

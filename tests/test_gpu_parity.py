@@ -387,24 +387,81 @@ def test_bad_action_sets_device_flag_and_bad_args_are_rejected():
     assert f & _lib.FLAG_START_ON_WALL and f & _lib.FLAG_BAD_POSITION and f & _lib.FLAG_START_OVERLAP
 
 
-def test_host_buffer_entry_point_matches_device_path():
+HOST_CASES = [
+    # E, N, H, W, F, packed transport requested
+    (96, 8, 20, 20, 11, True),
+    (96, 8, 20, 20, 11, False),
+    (37, 32, 32, 32, 11, True),     # last tile partial (37 envs, 4 per tile)
+    (50, 7, 18, 18, 9, True),       # N not a multiple of the group size: tiles of 8 envs, last one short
+    (33, 128, 64, 64, 11, True),    # one environment per tile
+    (16, 9, 16, 16, 6, True),       # FOV without a specialised kernel: bits unsupported, dense copy
+    (20, 5, 9, 13, 3, True),        # tiny FOV (G = 8, N = 5)
+]
+
+
+@pytest.mark.parametrize("case", HOST_CASES, ids=lambda c: "E%d_N%d_%dx%d_F%d_%s" % (c[:5] + ("packed" if c[5] else "dense",)))
+def test_host_buffer_entry_point_matches_device_path(case):
+    """mapf_step_observe_host: dense copies and the bit-packed PCIe transport (bits expanded by the library's host
+    threads) deliver byte-identical host buffers, equal to the device path."""
     from mapf_marl_b200 import maps
-    E, N, H, W, F = 96, 8, 20, 20, 11
-    obst, starts, goals = maps.synthetic_batch(11, E, H, W, 0.2, N, distinct=0)
+    E, N, H, W, F, packed = case
+    obst, starts, goals = maps.synthetic_batch(11, E, H, W, 0.2 if H < 64 else 0.1, N, distinct=0)
     a = _engine(E, N, H, W, mode="primal", fov=F)
     b = _engine(E, N, H, W, mode="primal", fov=F)
     a.reset(obst, starts, goals)
     b.reset(obst, starts, goals)
+    mode = b.host_transport(packed)
+    assert mode == int(packed and b.bits_supported())
     io, bufs, h2d, d2h = b.make_host_io()
-    assert h2d == E * N and d2h == E * 8 + E + E * N + E * N * 5 + E * N * 4 * F * F + E * N * 24
+    obs_bytes = b.packed_obs_bytes() if mode else E * N * 4 * F * F
+    assert h2d == E * N and d2h == E * 8 + E + E * N + E * N * 5 + obs_bytes + E * N * 24
+    bufs["obs"].fill_(7)
     rs = np.random.RandomState(1)
-    for t in range(5):
+    for t in range(4):
         act = rs.randint(0, 5, (E, N)).astype(np.uint8)
         out = a.step_observe(torch.as_tensor(act, device="cuda"))
         bufs["actions"].copy_(torch.as_tensor(act))
         b.step_observe_host(io)
         for k in ("reward", "terminated", "dones", "avail", "obs", "vec"):
             assert torch.equal(out[k].cpu(), bufs[k]), (k, t)
+    # an unaligned, unpinned destination buffer works as well
+    raw = np.empty(E * N * 4 * F * F + 3, np.uint8)
+    io.obs_host = raw[3:].ctypes.data
+    act = rs.randint(0, 5, (E, N)).astype(np.uint8)
+    out = a.step_observe(torch.as_tensor(act, device="cuda"))
+    bufs["actions"].copy_(torch.as_tensor(act))
+    b.step_observe_host(io)
+    assert np.array_equal(raw[3:].reshape(E, N, 4, F, F), _np(out["obs"]))
+
+
+@pytest.mark.parametrize("case", [(64, 8, 20, 20, 11), (37, 32, 32, 32, 11), (9, 128, 64, 64, 11), (40, 6, 12, 12, 10),
+                                  (24, 16, 16, 16, 5)], ids=lambda c: "E%d_N%d_%dx%d_F%d" % c)
+def test_bit_packed_observation_equals_the_uint8_tensor(case):
+    """obs dtype MAPF_BITS: bit i of the stream == byte i of the uint8 observation."""
+    from mapf_marl_b200 import maps
+    E, N, H, W, F = case
+    obst, starts, goals = maps.synthetic_batch(5, E, H, W, 0.15, N, distinct=0)
+    eng = _engine(E, N, H, W, mode="primal", fov=F)
+    eng.reset(obst, starts, goals)
+    assert eng.bits_supported()
+    rs = np.random.RandomState(2)
+    n = E * N * 4 * F * F
+    for t in range(3):
+        dense, vec = eng.observe()
+        dense = _np(dense).copy()
+        bits, vec2 = eng.observe(dtype="bits")
+        assert np.array_equal(np.unpackbits(_np(bits), bitorder="little")[:n], dense.reshape(-1)), t
+        assert torch.equal(vec, vec2)
+        act = torch.as_tensor(rs.randint(0, 5, (E, N)).astype(np.uint8), device="cuda")
+        out = eng.step_observe(act, dtype="bits")
+        dense2, _ = eng.observe()
+        assert np.array_equal(np.unpackbits(_np(out["obs"]), bitorder="little")[:n], _np(dense2).reshape(-1)), t
+    gen = _engine(16, 9, 16, 16, mode="primal", fov=6)     # no specialised kernel for F = 6
+    assert not gen.bits_supported()
+    gen.reset(*maps.synthetic_batch(5, 16, 16, 16, 0.1, 9, distinct=0))
+    from mapf_marl_b200.engine import MapfError
+    with pytest.raises(MapfError):
+        gen.observe(dtype="bits")
 
 
 def test_set_goals_and_dirty_bfs():
