@@ -317,11 +317,11 @@ def main():
         eng.step_observe_host(io)
     ms_e2e = timed(e2e_step, args.e2e_steps, 3)
     e2e_value = world * E * N * args.e2e_steps / (ms_e2e * 1e-3)
-    e2e_transport = "bit-packed observation over PCIe, expanded to uint8 by the library's host threads" \
-        if (odt == torch.uint8 and eng.host_transport() == 1) else "dense copies"
+    e2e_transport = "bit-packed observation over PCIe, expanded to the requested dtype by the library's host threads" \
+        if eng.host_transport() == 1 else "dense copies"
     # the same call with dense copies of the uint8 observation (informational)
     ms_e2e_dense = None
-    if odt == torch.uint8 and eng.host_transport() == 1:
+    if eng.host_transport() == 1:
         eng.host_transport(False)
         _, _, _, d2h_dense = eng.make_host_io(obs_dtype=odt)
         ms_e2e_dense = timed(e2e_step, args.e2e_steps, 2) / args.e2e_steps
@@ -376,7 +376,7 @@ def main():
             "e2e_dense_transport": None if ms_e2e_dense is None else {
                 "value": world * E * N / (ms_e2e_dense * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_dense,
                 "d2h_bytes_per_step": d2h_dense,
-                "note": "informational: the same host call with the uint8 observation copied densely over PCIe"},
+                "note": "informational: the same host call with the observation tensor copied densely over PCIe"},
             "e2e_obs_on_device": {"value": world * E * N / (ms_e2e2 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e2,
                                   "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2,
                                   "note": "informational: host actions in, reward/terminated out, observation left "

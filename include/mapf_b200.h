@@ -255,8 +255,8 @@ int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, co
 /* Host-buffer form of mapf_step_observe: copies io->actions_host to the device, runs the fused
  * kernel, copies the requested outputs back and waits for them.  This is the call the e2e
  * benchmark times.
- * MAPF_U8 field-of-view observations cross PCIe as packed bits (MAPF_BITS, 8x fewer bytes) in chunks and are
- * expanded to the 0/1 bytes of obs_host by the library's host threads while the next chunk is in flight; the
+ * MAPF_U8 / MAPF_F32 field-of-view observations cross PCIe as packed bits (MAPF_BITS, 8x / 32x fewer bytes) in
+ * chunks and are expanded to the 0/1 cells of obs_host by the library's host threads while the next chunk is in flight; the
  * result is byte-identical to the dense copy.  mapf_host_transport(h, 0) switches back to the dense copy. */
 int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream);
 

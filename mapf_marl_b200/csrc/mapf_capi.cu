@@ -45,7 +45,7 @@ struct mapf_handle {
 extern "C" {
 struct MapfUnpackPool* mapf_unpack_pool_create(int threads);
 void mapf_unpack_pool_destroy(struct MapfUnpackPool* p);
-void mapf_unpack_pool_run(struct MapfUnpackPool* p, const uint32_t* bits, uint8_t* out, size_t out_bytes);
+void mapf_unpack_pool_run(struct MapfUnpackPool* p, const uint32_t* bits, void* out, size_t cells, int elem_bytes);
 }
 
 static thread_local char g_create_err[512] = "";
@@ -706,7 +706,9 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   const size_t EN = (size_t)d.E * d.N;
   const bool fov = d.obs_mode == MAPF_OBS_PRIMAL_FOV;
   // uint8 field-of-view observations cross PCIe as bits and are expanded by the host pool (byte-identical result)
-  const bool packed = io->obs_host && fov && io->obs_dtype == MAPF_U8 && h->packed_transport && bits_supported(h);
+  const bool packed = io->obs_host && fov && (io->obs_dtype == MAPF_U8 || io->obs_dtype == MAPF_F32) &&
+                      h->packed_transport && bits_supported(h);
+  const int elem = io->obs_dtype == MAPF_F32 ? 4 : 1;
   size_t obs_bytes = 0;
   if (io->obs_host) {
     if (fov) obs_bytes = EN * 4 * d.F * d.F * (io->obs_dtype == MAPF_F32 ? 4 : 1);
@@ -781,10 +783,12 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
     int c = 0;
     for (size_t t0 = 0; t0 < ntiles; t0 += per, ++c) {
       const size_t t1 = t0 + per < ntiles ? t0 + per : ntiles;
-      const size_t byte0 = t0 * tile_words * 32;
-      const size_t byte1 = t1 * tile_words * 32 < obs_bytes ? t1 * tile_words * 32 : obs_bytes;   // last tile may be short
+      const size_t ncells = obs_bytes / elem;
+      const size_t cell0 = t0 * tile_words * 32;
+      const size_t cell1 = t1 * tile_words * 32 < ncells ? t1 * tile_words * 32 : ncells;   // last tile may be short
       CK(cudaEventSynchronize(h->chunk_ev[c]));
-      mapf_unpack_pool_run(h->pool, h->hp_bits + t0 * tile_words, (uint8_t*)io->obs_host + byte0, byte1 - byte0);
+      mapf_unpack_pool_run(h->pool, h->hp_bits + t0 * tile_words, (uint8_t*)io->obs_host + cell0 * elem, cell1 - cell0,
+                           elem);
     }
   } else {
     if ((rc = copy_small_outputs()) != MAPF_OK) return rc;

@@ -5,7 +5,8 @@
 // them into the caller's buffer while the next chunk is still crossing PCIe.  This is a transport decode of values the
 // GPU computed, not a computation of the path: there is no CPU implementation of step / observe in this library.
 //
-// Bit i of the stream == byte i of the output (little-endian bit order inside 32-bit words).
+// Bit i of the stream == element i of the output (uint8 0/1 or float32 0.0/1.0; little-endian bit order inside
+// 32-bit words).
 #include <stdint.h>
 #include <string.h>
 
@@ -58,13 +59,42 @@ __attribute__((target("avx2"))) void unpack_avx2(const uint32_t* bits, uint8_t* 
 }
 #endif
 
+// The same for float32 cells (0.0f / 1.0f): 32 bits -> 128 bytes per word.
+void unpack_scalar_f32(const uint32_t* bits, uint8_t* dst8, size_t nwords) {
+  float* dst = (float*)dst8;
+  for (size_t i = 0; i < nwords; ++i) {
+    const uint32_t w = bits[i];
+    for (int b = 0; b < 32; ++b) dst[32 * i + b] = (float)((w >> b) & 1u);
+  }
+}
+
+#if MAPF_X86
+__attribute__((target("avx2"))) void unpack_avx2_f32(const uint32_t* bits, uint8_t* dst8, size_t nwords) {
+  float* dst = (float*)dst8;
+  const __m256i bitm = _mm256_setr_epi32(1, 2, 4, 8, 16, 32, 64, 128);
+  const __m256i onef = _mm256_set1_epi32(0x3f800000);
+  const bool aligned = (((uintptr_t)dst) & 31) == 0;
+  for (size_t i = 0; i < nwords; ++i) {
+    const uint32_t w = bits[i];
+#pragma GCC unroll 4
+    for (int k = 0; k < 4; ++k) {
+      __m256i v = _mm256_set1_epi32((int)((w >> (8 * k)) & 0xffu));
+      v = _mm256_and_si256(_mm256_cmpeq_epi32(_mm256_and_si256(v, bitm), bitm), onef);
+      if (aligned) _mm256_stream_si256((__m256i*)(dst + 32 * i + 8 * k), v);
+      else _mm256_storeu_si256((__m256i*)(dst + 32 * i + 8 * k), v);
+    }
+  }
+  if (aligned) _mm_sfence();
+}
+#endif
+
 typedef void (*unpack_fn)(const uint32_t*, uint8_t*, size_t);
 
-unpack_fn pick_unpack() {
+unpack_fn pick_unpack(int elem) {
 #if MAPF_X86
-  if (__builtin_cpu_supports("avx2")) return unpack_avx2;
+  if (__builtin_cpu_supports("avx2")) return elem == 4 ? unpack_avx2_f32 : unpack_avx2;
 #endif
-  return unpack_scalar;
+  return elem == 4 ? unpack_scalar_f32 : unpack_scalar;
 }
 
 }  // namespace
@@ -76,13 +106,13 @@ struct MapfUnpackPool {
   std::condition_variable cv_work, cv_done;
   const uint32_t* src = nullptr;
   uint8_t* dst = nullptr;
-  size_t nwords = 0, nbytes = 0;
+  size_t nwords = 0, ncells = 0;
+  int elem = 1;                     // bytes per output cell: 1 (uint8) or 4 (float32)
   uint64_t generation = 0;
   int pending = 0;
   bool stop = false;
-  unpack_fn fn = nullptr;
 
-  explicit MapfUnpackPool(int n) : fn(pick_unpack()) {
+  explicit MapfUnpackPool(int n) {
     for (int t = 0; t < n; ++t) workers.emplace_back([this, t, n]() { loop(t, n); });
   }
 
@@ -100,7 +130,8 @@ struct MapfUnpackPool {
     for (;;) {
       const uint32_t* s;
       uint8_t* d;
-      size_t lo, hi, nb;
+      size_t lo, hi, nc;
+      int el;
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_work.wait(lk, [&]() { return stop || generation != seen; });
@@ -108,19 +139,21 @@ struct MapfUnpackPool {
         seen = generation;
         s = src;
         d = dst;
-        nb = nbytes;
+        nc = ncells;
+        el = elem;
         // parts are multiples of 2 words so that every part but the first keeps the 64-byte phase of dst
         const size_t per = ((nwords + n - 1) / n + 1) & ~(size_t)1;
         lo = per * t < nwords ? per * t : nwords;
         hi = lo + per < nwords ? lo + per : nwords;
       }
       if (hi > lo) {
-        const size_t full = (hi == nwords && (nb & 31)) ? hi - lo - 1 : hi - lo;   // the very last word may be partial
-        fn(s + lo, d + 32 * lo, full);
+        const unpack_fn fn = pick_unpack(el);
+        const size_t full = (hi == nwords && (nc & 31)) ? hi - lo - 1 : hi - lo;   // the very last word may be partial
+        fn(s + lo, d + 32 * lo * el, full);
         if (full != hi - lo) {
-          uint8_t tail[32];
-          unpack_scalar(s + hi - 1, tail, 1);
-          memcpy(d + 32 * (hi - 1), tail, nb & 31);
+          uint8_t tail[128];
+          (el == 4 ? unpack_scalar_f32 : unpack_scalar)(s + hi - 1, tail, 1);
+          memcpy(d + 32 * (hi - 1) * el, tail, (nc & 31) * el);
         }
       }
       {
@@ -130,13 +163,14 @@ struct MapfUnpackPool {
     }
   }
 
-  // Expands `out_bytes` cells (= bits) starting at bits[0] into dst[0 .. out_bytes).
-  void run(const uint32_t* bits, uint8_t* out, size_t out_bytes) {
+  // Expands `cells` bits starting at bits[0] into `cells` output elements of `elem_bytes` bytes each.
+  void run(const uint32_t* bits, uint8_t* out, size_t cells, int elem_bytes) {
     std::unique_lock<std::mutex> lk(mu);
     src = bits;
     dst = out;
-    nbytes = out_bytes;
-    nwords = (out_bytes + 31) / 32;
+    ncells = cells;
+    elem = elem_bytes;
+    nwords = (cells + 31) / 32;
     pending = (int)workers.size();
     ++generation;
     cv_work.notify_all();
@@ -161,8 +195,8 @@ MapfUnpackPool* mapf_unpack_pool_create(int threads) {
 
 void mapf_unpack_pool_destroy(MapfUnpackPool* p) { delete p; }
 
-void mapf_unpack_pool_run(MapfUnpackPool* p, const uint32_t* bits, uint8_t* out, size_t out_bytes) {
-  p->run(bits, out, out_bytes);
+void mapf_unpack_pool_run(MapfUnpackPool* p, const uint32_t* bits, void* out, size_t cells, int elem_bytes) {
+  p->run(bits, (uint8_t*)out, cells, elem_bytes);
 }
 
 int mapf_unpack_pool_threads(const MapfUnpackPool* p) { return p ? (int)p->workers.size() : 0; }

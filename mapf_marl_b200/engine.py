@@ -369,9 +369,9 @@ class MapfEngine:
         io.obs_dtype = odt
         h2d = bufs["actions"].numel()
         d2h = sum(t.numel() * t.element_size() for k, t in bufs.items() if k != "actions")
-        if "obs" in bufs and odt == U8 and self.host_transport() == 1:
-            # uint8 FOV observations cross PCIe as packed bits (whole tiles) and are expanded by the library's host threads
-            d2h += self.packed_obs_bytes() - bufs["obs"].numel()
+        if "obs" in bufs and odt in (U8, F32) and self.obs_mode == OBS_PRIMAL_FOV and self.host_transport() == 1:
+            # FOV observations cross PCIe as packed bits and are expanded by the library's host threads
+            d2h += self.packed_obs_bytes() - bufs["obs"].numel() * bufs["obs"].element_size()
         return io, bufs, h2d, d2h
 
     def bits_supported(self):

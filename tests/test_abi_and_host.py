@@ -166,3 +166,35 @@ def test_multiagentenv_contract_is_enforced():
                 return None
     with pytest.raises(NotImplementedError):
         MultiAgentEnv().step(None)
+
+
+def test_host_unpack_pool_expands_bits_exactly():
+    """The host half of the bit-packed PCIe transport (csrc/mapf_host_unpack.cpp) needs no GPU: bit i of the stream
+    becomes element i of the output, for uint8 and float32 cells, any alignment, partial last word."""
+    import ctypes
+    import numpy as np
+    from mapf_marl_b200 import _lib
+    _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.mapf_unpack_pool_create.restype = ctypes.c_void_p
+    lib.mapf_unpack_pool_create.argtypes = [ctypes.c_int]
+    lib.mapf_unpack_pool_destroy.argtypes = [ctypes.c_void_p]
+    lib.mapf_unpack_pool_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    rs = np.random.RandomState(0)
+    for threads in (1, 3, 8):
+        pool = lib.mapf_unpack_pool_create(threads)
+        assert pool
+        for cells in (1, 31, 32, 33, 1000, 4 * 121 * 8 * 37, 100003):
+            words = rs.randint(0, 2 ** 32, (cells + 31) // 32, dtype=np.uint64).astype(np.uint32)
+            want = np.unpackbits(words.view(np.uint8), bitorder="little")[:cells]
+            for off in (0, 1, 32):
+                raw = np.full(cells + off + 64, 9, np.uint8)
+                lib.mapf_unpack_pool_run(pool, words.ctypes.data, raw[off:].ctypes.data, cells, 1)
+                assert np.array_equal(raw[off:off + cells], want), (threads, cells, off)
+                assert (raw[:off] == 9).all() and (raw[off + cells:] == 9).all()     # nothing outside the range
+            for off in (0, 1):
+                rawf = np.full(cells + off + 16, 9.0, np.float32)
+                lib.mapf_unpack_pool_run(pool, words.ctypes.data, rawf[off:].ctypes.data, cells, 4)
+                assert np.array_equal(rawf[off:off + cells], want.astype(np.float32)), (threads, cells, off)
+                assert (rawf[:off] == 9).all() and (rawf[off + cells:] == 9).all()
+        lib.mapf_unpack_pool_destroy(pool)

@@ -424,6 +424,14 @@ def test_host_buffer_entry_point_matches_device_path(case):
         b.step_observe_host(io)
         for k in ("reward", "terminated", "dones", "avail", "obs", "vec"):
             assert torch.equal(out[k].cpu(), bufs[k]), (k, t)
+    # float32 observations through the same transport
+    io32, bufs32, _, d2h32 = b.make_host_io(obs_dtype=torch.float32)
+    assert d2h32 == d2h - obs_bytes + (b.packed_obs_bytes() if mode else E * N * 4 * F * F * 4)
+    act = rs.randint(0, 5, (E, N)).astype(np.uint8)
+    out = a.step_observe(torch.as_tensor(act, device="cuda"), dtype=torch.float32)
+    bufs32["actions"].copy_(torch.as_tensor(act))
+    b.step_observe_host(io32)
+    assert torch.equal(out["obs"].cpu(), bufs32["obs"])
     # an unaligned, unpinned destination buffer works as well
     raw = np.empty(E * N * 4 * F * F + 3, np.uint8)
     io.obs_host = raw[3:].ctypes.data
