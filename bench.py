@@ -300,6 +300,11 @@ def main():
     n_eager = max(min(args.steps, 2000), 1)
     ms_eager = timed(lambda t: eng.step_observe(pool[t % 16], want=want, dtype=odt), n_eager, 3) / n_eager
 
+    # ---- the fused launch with the observation left bit-packed (MAPF_BITS, for consumers that take bits; informational)
+    ms_bits = None
+    if eng.bits_supported():
+        ms_bits = timed(lambda t: eng.step_observe(pool[t % 16], want=want, dtype="bits"), n_eager, 3) / n_eager
+
     # ---- breakdown: the step-only and observe-only launches of the same tile kernel
     ms_obs = timed(lambda t: eng.observe(dtype=odt), max(args.steps // 4, 5), 3) / max(args.steps // 4, 5)
     ms_stp = timed(lambda t: eng.step(pool[t % 16], want=want), max(args.steps // 4, 5), 3) / max(args.steps // 4, 5)
@@ -388,6 +393,7 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "algorithmic_bytes_per_agent_step": bytes_per},
             "breakdown_ms": {"fused_step_obs": ms_step, "fused_step_obs_eager_launches": ms_eager,
+                             "fused_step_obs_bit_packed_output": ms_bits,
                              "observe_only": ms_obs, "step_only": ms_stp,
                              "observe_only_GBps": (4 * F * F * (4 if args.f32 else 1) + 24 + 8 +
                                                    wl["H"] * wl["W"] / N) * E * N / (ms_obs * 1e-3) / 1e9,

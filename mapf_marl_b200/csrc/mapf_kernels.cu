@@ -656,6 +656,62 @@ __device__ __forceinline__ void fov_goal_bits(uint32_t* str, int bit0, uint32_t 
   }
 }
 
+// goal_map and goals_map for ODD F in a single-pass tile: the windows are symmetric (j sees b iff b sees j), so every
+// visible pair is enumerated ONCE -- by the agent that finds the other one in the FORWARD half of its window (cells
+// after the centre in row-major order) -- and both agents' bits are set.  Half the cells to scan, half the divergent
+// iterations per warp.  All sets are shared-memory atomics on the tile's flat bit string (agent j's bit i is bit
+// j * 4F^2 + i), issued after every thread has stored its window planes.
+template <int F>
+__device__ __forceinline__ void fov_goal_bits_half(uint32_t* str, int j, int jenv0, const uint32_t (&vis)[Fov<F>::CW],
+                                                   int GS, const uint8_t* idgrid, const uchar2* goals_tile, uchar2 p,
+                                                   uchar2 g) {
+  using T = Fov<F>;
+  constexpr int P = F / 2;
+  constexpr int START = P * F + P + 1;          // first cell after the centre
+  constexpr int NFWD = T::FF - START;           // cells of the forward half
+  constexpr int Q0 = START >> 5, SH = START & 31, CWF = (NFWD + 31) / 32;
+  auto set = [&](int flat) { atomicOr(&str[flat >> 5], 1u << (flat & 31)); };
+  const int t0 = (int)p.x - P, t1 = (int)p.y - P;
+  const int gi = (int)g.x - t0, gj = (int)g.y - t1;
+  if ((unsigned)gi < (unsigned)F && (unsigned)gj < (unsigned)F) set(j * T::NB + T::FF + gi * F + gj);
+  uint32_t f[CWF];
+#pragma unroll
+  for (int k = 0; k < CWF; ++k) {
+    const uint32_t lo = vis[Q0 + k];
+    const uint32_t hi = (Q0 + k + 1 < T::CW) ? vis[Q0 + k + 1] : 0u;
+    f[k] = SH ? __funnelshift_r(lo, hi, SH) : lo;
+  }
+  const uint8_t* gbase = idgrid + (t0 + 1) * GS + t1 + 1;
+  for (;;) {
+    uint32_t v = f[0];
+    int q = 0;
+#pragma unroll
+    for (int k = 1; k < CWF; ++k) {
+      const bool next = (v == 0);
+      v = next ? f[k] : v;
+      q = next ? k : q;
+    }
+    if (v == 0) break;
+    const int idx = START + 32 * q + __ffs(v) - 1;
+    v &= v - 1;
+#pragma unroll
+    for (int k = 0; k < CWF; ++k)
+      if (q == k) f[k] = v;
+    const int wi = (int)((unsigned)idx / (unsigned)F), wj = idx - wi * F;
+    const int jb = jenv0 + gbase[wi * GS + wj] - 1;        // the agent standing there (its index in the tile)
+    const uchar2 og = goals_tile[jb];
+    // its goal, clamped into my window (PRIMAL:374-378)
+    const int ci = min(max((int)og.x - t0, 0), F - 1);
+    const int cj = min(max((int)og.y - t1, 0), F - 1);
+    set(j * T::NB + 2 * T::FF + ci * F + cj);
+    // my goal, clamped into its window (origin = its position - P)
+    const int u0 = t0 + wi - P, u1 = t1 + wj - P;
+    const int di = min(max((int)g.x - u0, 0), F - 1);
+    const int dj = min(max((int)g.y - u1, 0), F - 1);
+    set(jb * T::NB + 2 * T::FF + di * F + dj);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // The tile kernel: stage -> [step] -> state write-back + small outputs -> [observation].
 // ------------------------------------------------------------------------------------------------
@@ -1045,6 +1101,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     __syncthreads();   // the bit strings reuse the step-phase scratch: everybody has finished the write-back
     // phase 1: one thread per agent builds its 4*F*F bits and the goal vector; G agents share a
     // word-aligned group string.
+    constexpr bool kHalf = SINGLE && (F & 1) != 0;   // symmetric windows + one pass: each visible pair is walked once
     for (int base = 0; base < na && (!SINGLE || base == 0); base += kThreads) {
       const int j = base + tid;
       const bool valid = (j < na) && (A.obs != nullptr);
@@ -1083,7 +1140,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
           if (q == 0) first = o;                                 // word shared with the previous agent: OR-ed below
           if (q < nwords && !(q == 0 && sh > 0)) s.str[w0 + q] = o;
         }
-        if (T::kInterior)
+        if (!kHalf && T::kInterior)
           fov_goal_bits<F, false>(s.str + w0, sh, vis, d.GS, gridcur + el * d.grid_bytes, s.goal + el * N, p, g);
       }
       if (j < na && A.vec != nullptr) {                              // PRIMAL:380-385
@@ -1097,7 +1154,10 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
       }
       __syncthreads();
       if (valid) {
-        if (T::kInterior) {
+        if (kHalf) {
+          if (sh > 0) atomicOr(&s.str[w0], first);
+          fov_goal_bits_half<F>(s.str, j, el * N, vis, d.GS, gridcur + el * d.grid_bytes, s.goal, p, g);
+        } else if (T::kInterior) {
           if (sh > 0) s.str[w0] |= first;
         } else {
           if (sh > 0) atomicOr(&s.str[w0], first);
