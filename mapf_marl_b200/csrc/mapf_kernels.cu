@@ -1085,6 +1085,24 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     // get_obs / get_state, GRID:143-196: -1 on walls, else the number of agents on the cell.
     if (A.obs == nullptr) return;
     int8_t* out = (int8_t*)A.obs + (size_t)e0 * d.HW;
+    if ((d.W & 3) == 0) {
+      // four cells of a row per thread: one funnel shift for the wall bits, four count bytes, one packed 32-bit store
+      const int q4 = d.HW >> 2;
+      for (int el = 0; el < ne; ++el) {
+        const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+        const uint8_t* grid = gridcur + el * d.grid_bytes;
+        uint32_t* o32 = (uint32_t*)(out + (size_t)el * d.HW);
+        for (int q = tid; q < q4; q += kThreads) {
+          const int cell = q << 2;
+          const int r = fast_div(cell, d.invW), c = cell - r * d.W;
+          const uint8_t* gp = grid + gcell(d, r, c);
+          const uint32_t cnt = (uint32_t)gp[0] | ((uint32_t)gp[1] << 8) | ((uint32_t)gp[2] << 16) | ((uint32_t)gp[3] << 24);
+          const uint32_t wall = expand4(row_field(ob, d.RW, r + d.P, c + d.P, 0xFu));
+          o32[q] = __vsub4(cnt, wall);                               // `+= 1` on a -1 cell per agent, GRID:299
+        }
+      }
+      return;
+    }
     for (int i = tid; i < ne * d.HW; i += kThreads) {
       const int el = i / d.HW, cell = i - el * d.HW;
       const int r = cell / d.W, c = cell - r * d.W;
@@ -1773,91 +1791,127 @@ __global__ void mapf_primal_costs_free_kernel(const MapfDims d, const uint8_t* d
 __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, double* obs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int e = blockIdx.x, N = d.N, W = d.W, H = d.H, Wn = d.pW, K = d.pK;
-  uint8_t* cnt = smem_raw;                                   // [H*W] agents per cell
-  uint8_t* knn = cnt + ((d.HW + 15) & ~15);                  // [N][K] ids, 255 = empty row
-  const uchar2* pos = (const uchar2*)S.pos + (size_t)e * N;
+  // shared memory: per-cell code (bit 15 = wall, low bits = agents on the cell), positions, the K selected agents of
+  // every agent with their distances, the observer-independent features
+  size_t off = 0;
+  uint16_t* code = (uint16_t*)(smem_raw + off);              // [H*W]
+  off += ((size_t)d.HW * 2 + 15) & ~(size_t)15;
+  double* kdist = (double*)(smem_raw + off);                 // [N][K]
+  off += (size_t)N * K * 8;
+  double* feat = (double*)(smem_raw + off);                  // [N][13]
+  off += (size_t)N * 13 * 8;
+  uchar2* spos = (uchar2*)(smem_raw + off);                  // [N]
+  off += ((size_t)N * 2 + 15) & ~(size_t)15;
+  uint8_t* knn = smem_raw + off;                             // [N][K] ids, 255 = empty row
   const uchar2* goal = (const uchar2*)S.goal + (size_t)e * N;
   const uchar2* start = (const uchar2*)S.start + (size_t)e * N;
   const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
-  for (int i = threadIdx.x; i < ((d.HW + 15) >> 4); i += blockDim.x) ((uint4*)cnt)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  for (int a = threadIdx.x; a < N; a += blockDim.x) byte_inc(cnt, (int)pos[a].x * W + pos[a].y);
-  const int k_m1 = min(N, K) - 1;
-  const long long self_key = (long long)d.HW * d.HW;
-  for (int a = threadIdx.x; a < N; a += blockDim.x) {
-    const uchar2 p = pos[a];
-    long long last_key = -1;
-    int last_idx = -1;
-    knn[a * K] = (uint8_t)a;                                 // knn_agents.insert(0, agent_id), :352
-    for (int r = 0; r < K - 1; ++r) {
-      int best = -1;
-      long long best_key = 0;
-      if (r < k_m1) {
-        for (int b = 0; b < N; ++b) {
-          const int dx = (int)p.x - (int)pos[b].x, dy = (int)p.y - (int)pos[b].y;
-          const long long key = (b == a) ? self_key : (long long)(dx * dx + dy * dy);
-          const bool after_last = key > last_key || (key == last_key && b > last_idx);
-          if (after_last && (best < 0 || key < best_key)) {
-            best = b;
-            best_key = key;
-          }
-        }
-        last_key = best_key;
-        last_idx = best;
-      }
-      knn[a * K + 1 + r] = best < 0 ? (uint8_t)255 : (uint8_t)best;
-    }
+  for (int a = threadIdx.x; a < N; a += blockDim.x) spos[a] = ((const uchar2*)S.pos)[(size_t)e * N + a];
+  for (int c = threadIdx.x; c < d.HW; c += blockDim.x) {
+    const int r = fast_div(c, d.invW), cc = c - r * W;
+    code[c] = bm_test(ob, d.RW, d.P, r, cc) ? (uint16_t)0x8000u : (uint16_t)0;
   }
   __syncthreads();
-  const int osz = d.posz, ww = Wn * Wn;
-  double* out = obs + (size_t)e * N * osz;
-  for (int q = threadIdx.x; q < N * osz; q += blockDim.x) {
-    const int a = q / osz, idx = q - a * osz;
-    const uchar2 p = pos[a];
+  for (int a = threadIdx.x; a < N; a += blockDim.x) {
+    const int cell = (int)spos[a].x * W + spos[a].y;
+    atomicAdd((unsigned int*)(code + (cell & ~1)), 1u << (16 * (cell & 1)));
+  }
+  // K - 1 nearest agents of every agent: stable order by L2 distance == order by (squared integer distance, index),
+  // i.e. by the packed key (distance^2 << 8 | index); the agent itself sorts last (its distance is H*W, larger than
+  // any real one, :560-567).  `tpa` lanes share one agent: each scans a slice of the candidates, a shuffle-min
+  // combines them -- every warp of the block takes part.
+  const int k_m1 = min(N, K) - 1;
+  int tpa = 1;
+  while (tpa < 32 && tpa * 2 * N <= (int)blockDim.x) tpa *= 2;
+  const int per_pass = blockDim.x / tpa, part = threadIdx.x & (tpa - 1);
+  constexpr int kSelf = 1 << 22, kNone = 0x7fffffff;         // kSelf > 2 * 254^2
+  for (int a0 = 0; a0 < N; a0 += per_pass) {
+    const int a = a0 + (int)(threadIdx.x / tpa);
+    const bool live = a < N;
+    const uchar2 p = live ? spos[a] : make_uchar2(0, 0);
+    int last_pk = -1;
+    if (live && part == 0) {
+      knn[a * K] = (uint8_t)a;                               // knn_agents.insert(0, agent_id), :352
+      kdist[a * K] = (double)d.HW;
+    }
+    for (int r = 0; r < K - 1; ++r) {
+      int best = kNone;
+      if (live && r < k_m1) {
+        for (int b = part; b < N; b += tpa) {
+          const uchar2 q = spos[b];
+          const int dx = (int)p.x - (int)q.x, dy = (int)p.y - (int)q.y;
+          const int pk = (((b == a) ? kSelf : dx * dx + dy * dy) << 8) | b;
+          if (pk > last_pk && pk < best) best = pk;
+        }
+      }
+      for (int o = tpa >> 1; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (best != kNone) last_pk = best;
+      if (live && part == 0) {
+        const int b = best & 255, key = best >> 8;
+        knn[a * K + 1 + r] = best == kNone ? (uint8_t)255 : (uint8_t)b;
+        kdist[a * K + 1 + r] = best == kNone ? -1.0 : (b == a ? (double)d.HW : __dsqrt_rn((double)key));
+      }
+    }
+  }
+  // the 13 features of every agent that do not depend on the observer (:353-371; column 11 = kdist)
+  for (int q = threadIdx.x; q < N * 13; q += blockDim.x) {
+    const int na = q / 13, f = q - 13 * na;
+    const uchar2 q0 = spos[na], g = goal[na], st = start[na];
+    const int dx = (int)g.x - (int)q0.x, dy = (int)g.y - (int)q0.y;
     double v;
+    switch (f) {
+      case 0: v = q0.x; break;
+      case 1: v = q0.y; break;
+      case 2: v = st.x; break;
+      case 3: v = st.y; break;
+      case 4: v = g.x; break;
+      case 5: v = g.y; break;
+      case 6:
+      case 7: {                                            // __update_goal_vectors, :957-972
+        const double norm = __dsqrt_rn((double)(dx * dx + dy * dy));
+        v = norm != 0.0 ? __ddiv_rn((double)(f == 6 ? dx : dy), norm) : 0.0;
+        break;
+      }
+      case 8: v = __dsqrt_rn((double)(dx * dx + dy * dy)); break;
+      case 9: v = S.pnode[(size_t)e * N + na]; break;
+      case 10: v = S.pedge[(size_t)e * N + na]; break;
+      case 11: v = 0.0; break;
+      default: v = S.agent_steps[(size_t)e * N + na]; break;
+    }
+    feat[q] = v;
+  }
+  __syncthreads();
+  // output: thread t owns the element indices t, t + blockDim, ... of EVERY agent's block -- the index is decoded once
+  // (window cell or feature slot), then the agents are walked; for one agent consecutive lanes write consecutive
+  // doubles (coalesced streaming stores).
+  const int osz = d.posz, ww = Wn * Wn, half = Wn / 2;
+  double* out = obs + (size_t)e * N * osz;
+  for (int idx = threadIdx.x; idx < osz; idx += blockDim.x) {
+    double* o = out + idx;
     if (idx < 2 * ww) {                                      // the two W x W maps, :326-342
-      const int c = idx < ww ? idx : idx - ww;
+      const bool agents_map = idx >= ww;
+      const int c = agents_map ? idx - ww : idx;
       const int wi = c / Wn, wj = c - wi * Wn;
-      const int i = (int)p.x - Wn / 2 + wi, jx = (int)p.y - Wn / 2 + wj;
-      const bool oob = (i < 0 || i >= H || jx < 0 || jx >= W);
-      const bool wall = oob || bm_test(ob, d.RW, d.P, i, jx);
-      if (idx < ww) v = wall ? 1.0 : 0.0;
-      else v = wall ? 0.0 : (double)cnt[i * W + jx];
+      const int di = wi - half, dj = wj - half;
+      for (int a = 0; a < N; ++a, o += osz) {
+        const uchar2 p = spos[a];
+        const int i = (int)p.x + di, jx = (int)p.y + dj;
+        unsigned int cd = 0x8000u;                           // outside the map counts as a wall
+        if ((unsigned)i < (unsigned)H && (unsigned)jx < (unsigned)W) cd = code[i * W + jx];
+        const bool wall = (cd & 0x8000u) != 0;
+        const double v = agents_map ? (wall ? 0.0 : (double)(cd & 0x7fffu)) : (wall ? 1.0 : 0.0);
+        __stcs(o, v);
+      }
     } else {                                                 // K x 13 features, :344-371
       const int f0 = idx - 2 * ww;
       const int row = f0 / 13, f = f0 - 13 * row;
-      const int na = knn[a * K + row];
-      if (na == 255) {
-        v = -1.0;
-      } else {
-        const uchar2 q0 = pos[na], g = goal[na], st = start[na];
-        const int dx = (int)g.x - (int)q0.x, dy = (int)g.y - (int)q0.y;
-        switch (f) {
-          case 0: v = q0.x; break;
-          case 1: v = q0.y; break;
-          case 2: v = st.x; break;
-          case 3: v = st.y; break;
-          case 4: v = g.x; break;
-          case 5: v = g.y; break;
-          case 6:
-          case 7: {                                          // __update_goal_vectors, :957-972
-            const double norm = __dsqrt_rn((double)(dx * dx + dy * dy));
-            v = norm != 0.0 ? __ddiv_rn((double)(f == 6 ? dx : dy), norm) : 0.0;
-            break;
-          }
-          case 8: v = __dsqrt_rn((double)(dx * dx + dy * dy)); break;
-          case 9: v = S.pnode[(size_t)e * N + na]; break;
-          case 10: v = S.pedge[(size_t)e * N + na]; break;
-          case 11: {
-            const int ex = (int)p.x - (int)q0.x, ey = (int)p.y - (int)q0.y;
-            v = (na == a) ? (double)d.HW : __dsqrt_rn((double)(ex * ex + ey * ey));
-            break;
-          }
-          default: v = S.agent_steps[(size_t)e * N + na]; break;
-        }
+      for (int a = 0; a < N; ++a, o += osz) {
+        const int na = knn[a * K + row];
+        double v = -1.0;
+        if (na != 255) v = (f == 11) ? kdist[a * K + row] : feat[na * 13 + f];
+        __stcs(o, v);
       }
     }
-    out[q] = v;
   }
 }
 
@@ -2029,7 +2083,8 @@ extern "C" int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int a
 }
 
 extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, double* obs, void* stream) {
-  const size_t smem = ((size_t)(d.HW + 15) & ~(size_t)15) + (size_t)d.N * d.pK + 16;
+  const size_t smem = (((size_t)d.HW * 2 + 15) & ~(size_t)15) + (size_t)d.N * d.pK * 8 + (size_t)d.N * 13 * 8 +
+                      (((size_t)d.N * 2 + 15) & ~(size_t)15) + (size_t)d.N * d.pK + 16;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mapf_partial_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -113,8 +113,13 @@ class MapfEngine:
             cfg.env_collide_reward = float(env_collide_reward)
             # the completion bonus per step index, with the reference's own expression (marl_partial.py:296)
             limit = int(episode_limit)
-            self._clut = np.array([(complete_reward / (gamma ** (limit - t))) * complete_fac
-                                   for t in range(limit + 65)], dtype=np.float64)
+            def bonus(t):
+                try:
+                    return (complete_reward / (gamma ** (limit - t))) * complete_fac
+                except (ZeroDivisionError, OverflowError):
+                    # gamma ** (limit - t) underflowed / overflowed: the reference raises at this step count
+                    return float("inf")
+            self._clut = np.array([bonus(t) for t in range(limit + 65)], dtype=np.float64)
             cfg.complete_lut_host = self._clut.ctypes.data
             cfg.complete_lut_len = int(self._clut.size)
         self._h = ctypes.c_void_p()
