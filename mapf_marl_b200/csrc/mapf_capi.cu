@@ -10,7 +10,8 @@
 
 #include "mapf_internal.h"
 
-#define MAPF_HOST_CHUNKS 8
+#include <chrono>
+#define MAPF_HOST_CHUNKS 16
 
 struct mapf_handle {
   mapf_cfg cfg;
@@ -37,15 +38,17 @@ struct mapf_handle {
   uint32_t* hp_bits;           // pinned host staging of the same size
   size_t bits_words;
   struct MapfUnpackPool* pool;
-  cudaEvent_t chunk_ev[MAPF_HOST_CHUNKS];
-  int chunk_ev_ready;
+  uint32_t* hs_prog;           // device: cumulative word count after each chunk (constant per handle)
+  volatile uint32_t* hp_prog;  // pinned host word: the device copies hs_prog[c] here behind chunk c
   char err[512];
 };
 
 extern "C" {
 struct MapfUnpackPool* mapf_unpack_pool_create(int threads);
 void mapf_unpack_pool_destroy(struct MapfUnpackPool* p);
-void mapf_unpack_pool_run(struct MapfUnpackPool* p, const uint32_t* bits, void* out, size_t cells, int elem_bytes);
+int mapf_unpack_pool_expand_streamed(struct MapfUnpackPool* p, const uint32_t* bits, void* out, size_t cells,
+                                     int elem_bytes, const volatile uint32_t* ready_words, int (*poll)(void*),
+                                     void* poll_arg);
 }
 
 static thread_local char g_create_err[512] = "";
@@ -230,8 +233,8 @@ int mapf_destroy(mapf_handle* h) {
   cudaFree(h->hs_vec);
   cudaFree(h->hs_bits);
   if (h->hp_bits) cudaFreeHost(h->hp_bits);
-  if (h->chunk_ev_ready)
-    for (int c = 0; c < MAPF_HOST_CHUNKS; ++c) cudaEventDestroy(h->chunk_ev[c]);
+  cudaFree(h->hs_prog);
+  if (h->hp_prog) cudaFreeHost((void*)h->hp_prog);
   if (h->pool) mapf_unpack_pool_destroy(h->pool);
   delete h;
   return MAPF_OK;
@@ -701,6 +704,11 @@ int mapf_host_transport(mapf_handle* h, int packed) {
 
 int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream) {
   if (!h || !io || !io->actions_host) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_step_observe_host: NULL argument");
+  // MAPF_HOST_TRACE=1: host-side timestamps (microseconds since entry) of this call on stderr, for profiles/
+  static const bool trace = getenv("MAPF_HOST_TRACE") != nullptr;
+  const auto t_entry = std::chrono::steady_clock::now();
+  auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_entry).count(); };
+  double t_queued = 0, t_unpacked = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const MapfDims& d = h->d;
   const size_t EN = (size_t)d.E * d.N;
@@ -736,9 +744,16 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
       h->pool = mapf_unpack_pool_create(0);
       if (!h->pool) return fail(h, MAPF_ERR_ALLOC, "mapf_step_observe_host: cannot start the host unpack threads");
     }
-    if (!h->chunk_ev_ready) {
-      for (int c = 0; c < MAPF_HOST_CHUNKS; ++c) CK(cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
-      h->chunk_ev_ready = 1;
+    if (!h->hp_prog) CK(cudaHostAlloc((void**)&h->hp_prog, 64, cudaHostAllocDefault));
+    if (!h->hs_prog) {
+      uint32_t prog[MAPF_HOST_CHUNKS];
+      const size_t per = (ntiles + MAPF_HOST_CHUNKS - 1) / MAPF_HOST_CHUNKS;
+      for (int c = 0; c < MAPF_HOST_CHUNKS; ++c) {
+        const size_t t1 = (c + 1) * per < ntiles ? (c + 1) * per : ntiles;
+        prog[c] = (uint32_t)(t1 * tile_words);
+      }
+      LAZY(h->hs_prog, sizeof(prog));
+      CK(cudaMemcpyAsync(h->hs_prog, prog, sizeof(prog), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
     }
   } else if (obs_bytes > h->hs_obs_bytes) {
     cudaFree(h->hs_obs);
@@ -769,32 +784,40 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
     return MAPF_OK;
   };
   if (packed) {
-    // chunks of whole tiles: the copy of chunk c+1 (and of the small outputs, queued last) runs while the pool
-    // expands chunk c
+    // Chunks of whole tiles, each followed on the stream by a 4-byte copy of "words in host memory so far" into a
+    // pinned word.  The pool (one job for the whole call, blocks claimed in order, the calling thread works too)
+    // expands chunk c while chunk c+1 and then the small outputs, queued last, are still crossing PCIe.
     const size_t per = (ntiles + MAPF_HOST_CHUNKS - 1) / MAPF_HOST_CHUNKS;
-    int nchunks = 0;
-    for (size_t t0 = 0; t0 < ntiles; t0 += per, ++nchunks) {
-      const size_t t1 = t0 + per < ntiles ? t0 + per : ntiles;
-      CK(cudaMemcpyAsync(h->hp_bits + t0 * tile_words, h->hs_bits + t0 * tile_words, (t1 - t0) * tile_words * 4,
-                         cudaMemcpyDeviceToHost, st));
-      CK(cudaEventRecord(h->chunk_ev[nchunks], st));
-    }
-    if ((rc = copy_small_outputs()) != MAPF_OK) return rc;
+    const size_t ncells = obs_bytes / elem;
+    *h->hp_prog = 0;                                  // the stream has nothing of this handle's host path in flight
     int c = 0;
     for (size_t t0 = 0; t0 < ntiles; t0 += per, ++c) {
       const size_t t1 = t0 + per < ntiles ? t0 + per : ntiles;
-      const size_t ncells = obs_bytes / elem;
-      const size_t cell0 = t0 * tile_words * 32;
-      const size_t cell1 = t1 * tile_words * 32 < ncells ? t1 * tile_words * 32 : ncells;   // last tile may be short
-      CK(cudaEventSynchronize(h->chunk_ev[c]));
-      mapf_unpack_pool_run(h->pool, h->hp_bits + t0 * tile_words, (uint8_t*)io->obs_host + cell0 * elem, cell1 - cell0,
-                           elem);
+      CK(cudaMemcpyAsync(h->hp_bits + t0 * tile_words, h->hs_bits + t0 * tile_words, (t1 - t0) * tile_words * 4,
+                         cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync((void*)h->hp_prog, h->hs_prog + c, 4, cudaMemcpyDeviceToHost, st));
     }
+    if ((rc = copy_small_outputs()) != MAPF_OK) return rc;
+    t_queued = us();
+    struct PollCtx { cudaStream_t st; cudaError_t err; } pc = {st, cudaSuccess};
+    auto poll = [](void* a) -> int {                  // a stream that failed will never publish the words
+      PollCtx* p = (PollCtx*)a;
+      const cudaError_t e = cudaStreamQuery(p->st);
+      if (e == cudaSuccess || e == cudaErrorNotReady) return 0;
+      p->err = e;
+      return 1;
+    };
+    const int ok = mapf_unpack_pool_expand_streamed(h->pool, h->hp_bits, io->obs_host, ncells, elem, h->hp_prog, poll, &pc);
+    t_unpacked = us();
+    if (!ok) return cuda_fail(h, pc.err, "mapf_step_observe_host: device-to-host transfer");
   } else {
     if ((rc = copy_small_outputs()) != MAPF_OK) return rc;
     if (io->obs_host) CK(cudaMemcpyAsync(io->obs_host, h->hs_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
+  if (trace)
+    fprintf(stderr, "mapf_step_observe_host trace (us): queued %.0f, expanded %.0f, stream idle %.0f\n", t_queued,
+            t_unpacked, us());
   return MAPF_OK;
 }
 

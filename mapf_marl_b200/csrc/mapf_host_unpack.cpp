@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -88,32 +89,105 @@ __attribute__((target("avx2"))) void unpack_avx2_f32(const uint32_t* bits, uint8
 }
 #endif
 
+#if MAPF_X86
+// AVX-512BW: one mask move expands 64 bits into a full cache line, written with one non-temporal store.
+__attribute__((target("avx512f,avx512bw"))) void unpack_avx512(const uint32_t* bits, uint8_t* dst, size_t nwords) {
+  const __m512i one = _mm512_set1_epi8(1);
+  size_t i = 0;
+  if ((((uintptr_t)dst) & 31) == 0) {
+    if ((((uintptr_t)dst) & 63) != 0 && nwords) {            // 32-byte phase: one half line first
+      _mm256_stream_si256((__m256i*)dst, _mm512_castsi512_si256(_mm512_maskz_mov_epi8((__mmask64)bits[0], one)));
+      i = 1;
+    }
+    for (; i + 2 <= nwords; i += 2) {
+      uint64_t m;
+      memcpy(&m, bits + i, 8);
+      _mm512_stream_si512((__m512i*)(dst + 32 * i), _mm512_maskz_mov_epi8((__mmask64)m, one));
+    }
+    if (i < nwords)
+      _mm256_stream_si256((__m256i*)(dst + 32 * i),
+                          _mm512_castsi512_si256(_mm512_maskz_mov_epi8((__mmask64)bits[i], one)));
+    _mm_sfence();
+    return;
+  }
+  for (; i + 2 <= nwords; i += 2) {
+    uint64_t m;
+    memcpy(&m, bits + i, 8);
+    _mm512_storeu_si512((void*)(dst + 32 * i), _mm512_maskz_mov_epi8((__mmask64)m, one));
+  }
+  if (i < nwords)
+    _mm256_storeu_si256((__m256i*)(dst + 32 * i), _mm512_castsi512_si256(_mm512_maskz_mov_epi8((__mmask64)bits[i], one)));
+}
+
+__attribute__((target("avx512f,avx512bw"))) void unpack_avx512_f32(const uint32_t* bits, uint8_t* dst8, size_t nwords) {
+  float* dst = (float*)dst8;
+  const __m512 onef = _mm512_set1_ps(1.0f);
+  const bool aligned = (((uintptr_t)dst) & 63) == 0;       // 32 floats per word = 128 bytes: the phase never changes
+  for (size_t i = 0; i < nwords; ++i) {
+    const uint32_t w = bits[i];
+    const __m512 lo = _mm512_maskz_mov_ps((__mmask16)(w & 0xffffu), onef);
+    const __m512 hi = _mm512_maskz_mov_ps((__mmask16)(w >> 16), onef);
+    if (aligned) {
+      _mm512_stream_ps(dst + 32 * i, lo);
+      _mm512_stream_ps(dst + 32 * i + 16, hi);
+    } else {
+      _mm512_storeu_ps(dst + 32 * i, lo);
+      _mm512_storeu_ps(dst + 32 * i + 16, hi);
+    }
+  }
+  if (aligned) _mm_sfence();
+}
+#endif
+
 typedef void (*unpack_fn)(const uint32_t*, uint8_t*, size_t);
 
 unpack_fn pick_unpack(int elem) {
 #if MAPF_X86
+  if (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f"))
+    return elem == 4 ? unpack_avx512_f32 : unpack_avx512;
   if (__builtin_cpu_supports("avx2")) return elem == 4 ? unpack_avx2_f32 : unpack_avx2;
 #endif
   return elem == 4 ? unpack_scalar_f32 : unpack_scalar;
 }
 
+inline void cpu_relax() {
+#if MAPF_X86
+  _mm_pause();
+#else
+  std::this_thread::yield();
+#endif
+}
+
 }  // namespace
 
-// A fixed pool of worker threads; run() splits [0, nwords) statically and returns when every part is done.
+// A fixed pool of worker threads around ONE job at a time.  A job is the expansion of `cells` bits; it is cut into
+// blocks of kBlockWords words that the workers (and the calling thread, inside finish()) claim in order from an atomic
+// counter, so a worker that shares its core with somebody else delays nobody.  The words of a job become readable
+// progressively (they are still crossing PCIe when the job begins): publish(n) says "the first n words are in
+// memory"; a worker that claimed a block beyond that spins until it is.  The count can also live in a word the DEVICE
+// writes (begin(..., ext_ready): a 4-byte copy queued behind every chunk on the same stream), so that no host thread
+// has to wait on CUDA events and forward them: on a box with as many workers as cores that forwarding thread would
+// share a core with a spinning worker.  The workers sleep on a condition variable only BETWEEN jobs, so a job costs
+// one wake-up, not one per PCIe chunk.
 struct MapfUnpackPool {
+  static constexpr size_t kBlockWords = 1024;        // 4 KB of bits -> 32 KB of uint8 / 128 KB of float32
   std::vector<std::thread> workers;
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   const uint32_t* src = nullptr;
   uint8_t* dst = nullptr;
-  size_t nwords = 0, ncells = 0;
+  size_t nwords = 0, ncells = 0, nblocks = 0;
   int elem = 1;                     // bytes per output cell: 1 (uint8) or 4 (float32)
+  unpack_fn fn = nullptr;
   uint64_t generation = 0;
-  int pending = 0;
+  int active = 0;                   // workers that have not yet left the current job
   bool stop = false;
+  std::atomic<size_t> next_block{0}, ready_words{0}, done_blocks{0};
+  const volatile uint32_t* ext_ready = nullptr;   // words in memory, written by the device (pinned host word)
+  std::atomic<bool> aborted{false};               // the caller gave up on the transfer: drain without expanding
 
   explicit MapfUnpackPool(int n) {
-    for (int t = 0; t < n; ++t) workers.emplace_back([this, t, n]() { loop(t, n); });
+    for (int t = 0; t < n; ++t) workers.emplace_back([this]() { loop(); });
   }
 
   ~MapfUnpackPool() {
@@ -125,56 +199,96 @@ struct MapfUnpackPool {
     for (auto& w : workers) w.join();
   }
 
-  void loop(int t, int n) {
+  size_t words_ready() const {
+    if (ext_ready) {
+      const size_t w = *ext_ready;
+      std::atomic_thread_fence(std::memory_order_acquire);
+      return w;
+    }
+    return ready_words.load(std::memory_order_acquire);
+  }
+
+  // Claims and expands blocks until none is left.  `poll` (caller thread only) is asked now and then while waiting
+  // for words; a non-zero answer aborts the job.
+  void work(int (*poll)(void*) = nullptr, void* poll_arg = nullptr) {
+    for (;;) {
+      const size_t b = next_block.fetch_add(1, std::memory_order_relaxed);
+      if (b >= nblocks) return;
+      const size_t lo = b * kBlockWords;
+      const size_t hi = lo + kBlockWords < nwords ? lo + kBlockWords : nwords;
+      for (unsigned spins = 0; words_ready() < hi && !aborted.load(std::memory_order_relaxed); ++spins) {
+        cpu_relax();
+        if ((spins & 63) == 63) {
+          if (poll && poll(poll_arg)) aborted.store(true, std::memory_order_relaxed);
+          std::this_thread::yield();             // oversubscribed boxes (several ranks per host): let the others run
+        }
+      }
+      if (aborted.load(std::memory_order_relaxed)) {
+        done_blocks.fetch_add(1, std::memory_order_release);
+        continue;
+      }
+      const size_t full = (hi == nwords && (ncells & 31)) ? hi - lo - 1 : hi - lo;   // the very last word may be partial
+      fn(src + lo, dst + 32 * lo * elem, full);
+      if (full != hi - lo) {
+        uint8_t tail[128];
+        (elem == 4 ? unpack_scalar_f32 : unpack_scalar)(src + hi - 1, tail, 1);
+        memcpy(dst + 32 * (hi - 1) * elem, tail, (ncells & 31) * elem);
+      }
+      done_blocks.fetch_add(1, std::memory_order_release);
+    }
+  }
+
+  void loop() {
     uint64_t seen = 0;
     for (;;) {
-      const uint32_t* s;
-      uint8_t* d;
-      size_t lo, hi, nc;
-      int el;
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_work.wait(lk, [&]() { return stop || generation != seen; });
         if (stop) return;
         seen = generation;
-        s = src;
-        d = dst;
-        nc = ncells;
-        el = elem;
-        // parts are multiples of 2 words so that every part but the first keeps the 64-byte phase of dst
-        const size_t per = ((nwords + n - 1) / n + 1) & ~(size_t)1;
-        lo = per * t < nwords ? per * t : nwords;
-        hi = lo + per < nwords ? lo + per : nwords;
       }
-      if (hi > lo) {
-        const unpack_fn fn = pick_unpack(el);
-        const size_t full = (hi == nwords && (nc & 31)) ? hi - lo - 1 : hi - lo;   // the very last word may be partial
-        fn(s + lo, d + 32 * lo * el, full);
-        if (full != hi - lo) {
-          uint8_t tail[128];
-          (el == 4 ? unpack_scalar_f32 : unpack_scalar)(s + hi - 1, tail, 1);
-          memcpy(d + 32 * (hi - 1) * el, tail, (nc & 31) * el);
-        }
-      }
+      work();
       {
         std::lock_guard<std::mutex> lk(mu);
-        if (--pending == 0) cv_done.notify_one();
+        if (--active == 0) cv_done.notify_one();
       }
     }
   }
 
-  // Expands `cells` bits starting at bits[0] into `cells` output elements of `elem_bytes` bytes each.
-  void run(const uint32_t* bits, uint8_t* out, size_t cells, int elem_bytes) {
-    std::unique_lock<std::mutex> lk(mu);
+  // Starts the expansion of `cells` bits at bits[0] into `cells` output elements of `elem_bytes` bytes each; no word
+  // is readable yet.
+  void begin(const uint32_t* bits, uint8_t* out, size_t cells, int elem_bytes, const volatile uint32_t* ext = nullptr) {
+    std::lock_guard<std::mutex> lk(mu);
+    ext_ready = ext;
+    aborted.store(false, std::memory_order_relaxed);
     src = bits;
     dst = out;
     ncells = cells;
     elem = elem_bytes;
+    fn = pick_unpack(elem_bytes);
     nwords = (cells + 31) / 32;
-    pending = (int)workers.size();
+    nblocks = (nwords + kBlockWords - 1) / kBlockWords;
+    next_block.store(0, std::memory_order_relaxed);
+    done_blocks.store(0, std::memory_order_relaxed);
+    ready_words.store(0, std::memory_order_relaxed);
+    active = (int)workers.size();
     ++generation;
     cv_work.notify_all();
-    cv_done.wait(lk, [&]() { return pending == 0; });
+  }
+
+  // The first `cells_ready` bits of the job are in memory (monotonic).
+  void publish(size_t cells_ready) {
+    const size_t w = cells_ready >= ncells ? nwords : cells_ready / 32;
+    ready_words.store(w, std::memory_order_release);
+  }
+
+  // The caller helps with the remaining blocks, then waits until every block is written and every worker has left the
+  // job (so that the next begin() cannot race with a late worker).
+  bool finish(int (*poll)(void*) = nullptr, void* poll_arg = nullptr) {
+    work(poll, poll_arg);
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&]() { return active == 0; });
+    return !aborted.load(std::memory_order_relaxed);
   }
 };
 
@@ -184,7 +298,7 @@ MapfUnpackPool* mapf_unpack_pool_create(int threads) {
   if (threads <= 0) {
     threads = (int)std::thread::hardware_concurrency();
     if (threads <= 0) threads = 4;
-    if (threads > 32) threads = 32;
+    if (threads > 64) threads = 64;
   }
   try {
     return new MapfUnpackPool(threads);
@@ -195,8 +309,26 @@ MapfUnpackPool* mapf_unpack_pool_create(int threads) {
 
 void mapf_unpack_pool_destroy(MapfUnpackPool* p) { delete p; }
 
+void mapf_unpack_pool_begin(MapfUnpackPool* p, const uint32_t* bits, void* out, size_t cells, int elem_bytes) {
+  p->begin(bits, (uint8_t*)out, cells, elem_bytes);
+}
+
+void mapf_unpack_pool_publish(MapfUnpackPool* p, size_t cells_ready) { p->publish(cells_ready); }
+
+void mapf_unpack_pool_finish(MapfUnpackPool* p) { p->finish(); }
+
+// The job of one mapf_step_observe_host call: `ready_words` is a pinned host word the device updates behind every
+// chunk; `poll` lets the calling thread notice a failed stream.  Returns 0 when the job was aborted.
+int mapf_unpack_pool_expand_streamed(MapfUnpackPool* p, const uint32_t* bits, void* out, size_t cells, int elem_bytes,
+                                     const volatile uint32_t* ready_words, int (*poll)(void*), void* poll_arg) {
+  p->begin(bits, (uint8_t*)out, cells, elem_bytes, ready_words);
+  return p->finish(poll, poll_arg) ? 1 : 0;
+}
+
 void mapf_unpack_pool_run(MapfUnpackPool* p, const uint32_t* bits, void* out, size_t cells, int elem_bytes) {
-  p->run(bits, (uint8_t*)out, cells, elem_bytes);
+  p->begin(bits, (uint8_t*)out, cells, elem_bytes);
+  p->publish(cells);
+  p->finish();
 }
 
 int mapf_unpack_pool_threads(const MapfUnpackPool* p) { return p ? (int)p->workers.size() : 0; }

@@ -198,3 +198,41 @@ def test_host_unpack_pool_expands_bits_exactly():
                 assert np.array_equal(rawf[off:off + cells], want.astype(np.float32)), (threads, cells, off)
                 assert (rawf[:off] == 9).all() and (rawf[off + cells:] == 9).all()
         lib.mapf_unpack_pool_destroy(pool)
+
+
+def test_host_unpack_pool_progressive_publish():
+    """One job per host call: the words are published chunk by chunk (as they arrive over PCIe) while the workers are
+    already claiming blocks; the result is the same as a one-shot expansion."""
+    import ctypes
+    import threading
+    import time
+    import numpy as np
+    from mapf_marl_b200 import _lib
+    _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.mapf_unpack_pool_create.restype = ctypes.c_void_p
+    lib.mapf_unpack_pool_create.argtypes = [ctypes.c_int]
+    lib.mapf_unpack_pool_destroy.argtypes = [ctypes.c_void_p]
+    lib.mapf_unpack_pool_begin.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    lib.mapf_unpack_pool_publish.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    lib.mapf_unpack_pool_finish.argtypes = [ctypes.c_void_p]
+    rs = np.random.RandomState(1)
+    cells = 1000003
+    nwords = (cells + 31) // 32
+    final = rs.randint(0, 2 ** 32, nwords, dtype=np.uint64).astype(np.uint32)
+    want = np.unpackbits(final.view(np.uint8), bitorder="little")[:cells]
+    pool = lib.mapf_unpack_pool_create(4)
+    for rep in range(3):
+        words = np.zeros(nwords, np.uint32)           # the staging buffer: garbage until a chunk "arrives"
+        out = np.full(cells + 64, 7, np.uint8)
+        lib.mapf_unpack_pool_begin(pool, words.ctypes.data, out.ctypes.data, cells, 1)
+        step = nwords // 7 + 1
+        for lo in range(0, nwords, step):
+            time.sleep(0.002)
+            hi = min(nwords, lo + step)
+            words[lo:hi] = final[lo:hi]
+            lib.mapf_unpack_pool_publish(pool, min(cells, hi * 32))
+        lib.mapf_unpack_pool_finish(pool)
+        assert np.array_equal(out[:cells], want)
+        assert (out[cells:] == 7).all()
+    lib.mapf_unpack_pool_destroy(pool)
