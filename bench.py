@@ -309,6 +309,41 @@ def main():
     ms_obs = timed(lambda t: eng.observe(dtype=odt), max(args.steps // 4, 5), 3) / max(args.steps // 4, 5)
     ms_stp = timed(lambda t: eng.step(pool[t % 16], want=want), max(args.steps // 4, 5), 3) / max(args.steps // 4, 5)
 
+    # ---- c4 only: the lifelong variant of the step (BASELINE config 4): after every fused launch, agents standing on
+    #      their goal pop the next one from their queue (mapf_pop_goals) and the distance maps of exactly those goals are
+    #      recomputed (mapf_bfs with the dirty mask): three launches per step, nothing leaves the device.
+    lifelong = None
+    if wl["warehouse"]:
+        from mapf_marl_b200.lifelong import LifelongGoals
+        Q = 8
+        free = np.argwhere(obst == 0)
+        qbase = {}
+        queue = np.zeros((E, N, Q, 2), np.int16)
+        for e in range(E):
+            k = (rank * E + e) % 64
+            if k not in qbase:
+                # every queued goal is a cell no other agent ever has as a goal (PRIMAL's goals grid holds one id per cell)
+                rs = np.random.RandomState(77000 + k)
+                taken = set(map(tuple, goals[e].tolist()))
+                cand = np.array([c for c in free[rs.permutation(len(free))].tolist() if tuple(c) not in taken], np.int16)
+                qbase[k] = cand[:N * Q].reshape(N, Q, 2)
+            queue[e] = qbase[k]
+        eng.reset(obst, starts, goals)
+        eng.refresh_goal_dist()
+        life = LifelongGoals(eng, queue)
+        n_life = max(min(args.steps, 1000), 1)
+
+        def life_step(t):
+            eng.step_observe(pool[t % 16], want=want, dtype=odt)
+            life.reassign()
+        ms_life = timed(life_step, n_life, 3) / n_life
+        popped = int(life.head.sum().item())
+        lifelong = {"ms_per_step": ms_life, "agent_steps_per_s": world * E * N / (ms_life * 1e-3),
+                    "goal_queue_depth": Q, "reassignments_per_step": popped / (n_life + 3),
+                    "launches_per_step": 3,
+                    "note": "fused step+obs, then mapf_pop_goals and mapf_bfs(dirty) for the agents that arrived; "
+                            "random actions, so arrivals are rare (the dirty-mask BFS launch is mostly early exits)"}
+
     # ---- end to end: pinned host actions in, every output back on the host, through the C-ABI host entry point
     io, bufs, h2d, d2h = eng.make_host_io(obs_dtype=odt)
     host_pool = pool[:4].cpu()
@@ -398,6 +433,7 @@ def main():
                              "observe_only_GBps": (4 * F * F * (4 if args.f32 else 1) + 24 + 8 +
                                                    wl["H"] * wl["W"] / N) * E * N / (ms_obs * 1e-3) / 1e9,
                              "goal_bfs_all_maps": bfs_ms, "goal_maps_per_s": E * N / (bfs_ms * 1e-3)},
+            "lifelong": lifelong,
             "clocks": clocks,
             "stats": dict(zip(sorted(stats), [int(v) for v in svec.tolist()])),
             "device_error_flags": flags,

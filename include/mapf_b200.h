@@ -232,6 +232,15 @@ int mapf_reset(mapf_handle* h, const int8_t* map_dev, const int16_t* starts_dev,
  * rule): overwrite the goals of agents whose dirty flag is set.  goals_dev int16[E,N,2], dirty_dev uint8[E,N]. */
 int mapf_set_goals(mapf_handle* h, const int16_t* goals_dev, const uint8_t* dirty_dev, void* stream);
 
+/* Replaces the lifelong task hand-out itself (MAPF-490-main/Global.cpp:85-94: when an agent has arrived, the front
+ * of its deque becomes its goal and is popped; the deques are filled by generate_tasks, main.cpp:56-85).
+ *   queue_dev int16[E,N,queue_len,2]  per-agent FIFO of (row, col) goals, entry 0 = first re-assignment
+ *   head_dev  int32[E,N]              number of goals already popped (read and advanced here)
+ *   dirty_dev uint8[E,N] or NULL      out: 1 where a goal was re-assigned (the mask mapf_bfs takes), else 0
+ * An agent standing on its goal with head < queue_len receives queue[head]; everything else is untouched. */
+int mapf_pop_goals(mapf_handle* h, const int16_t* queue_dev, int32_t* head_dev, int queue_len, uint8_t* dirty_dev,
+                   void* stream);
+
 /* Replaces MAPF_GRID.step (GRID:85-141) or one full sweep `for id in 1..N: MAPFEnv._step((id, a[id]))`
  * (PRIMAL:549-637).  actions_dev: [E,N] of act_dtype (MAPF_U8 or MAPF_I64). */
 int mapf_step(mapf_handle* h, const void* actions_dev, int act_dtype, const mapf_step_out* out, void* stream);

@@ -502,6 +502,15 @@ int mapf_set_goals(mapf_handle* h, const int16_t* goals_dev, const uint8_t* dirt
   return MAPF_OK;
 }
 
+int mapf_pop_goals(mapf_handle* h, const int16_t* queue_dev, int32_t* head_dev, int queue_len, uint8_t* dirty_dev,
+                   void* stream) {
+  if (!h || !queue_dev || !head_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_pop_goals: NULL argument");
+  if (queue_len < 1) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_pop_goals: queue_len must be >= 1");
+  CK((cudaError_t)mapf_launch_pop_goals(h->d, h->S, queue_dev, head_dev, queue_len, dirty_dev, stream));
+  h->launches++;
+  return MAPF_OK;
+}
+
 // MAPF_BITS output: a specialised field-of-view kernel, and every tile holds whole observation groups (tile strings
 // start on word boundaries).
 static bool bits_supported(const mapf_handle* h) {

@@ -122,6 +122,8 @@ int mapf_launch_reset(const MapfDims& d, const MapfState& S, const int16_t* star
                       const uint8_t* env_mask, void* stream);
 int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, const int16_t* goals, const uint8_t* dirty,
                           void* stream);
+int mapf_launch_pop_goals(const MapfDims& d, const MapfState& S, const int16_t* queue, int32_t* head, int queue_len,
+                          uint8_t* dirty, void* stream);
 int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, const uint8_t* env_mask, int16_t* dist,
                     int primal_costs, void* stream, int* n_launches);   // 8-connected when primal_costs && d.diag
 int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int agent_lo, int agent_hi, const mapf_step_out& out,

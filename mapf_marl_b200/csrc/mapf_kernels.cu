@@ -1426,6 +1426,31 @@ __global__ void mapf_set_goals_kernel(const MapfDims d, const MapfState S, const
   }
 }
 
+// Lifelong task hand-out (MAPF-490-main/Global.cpp:85-94): an agent standing on its goal pops the front of its queue.
+__global__ void mapf_pop_goals_kernel(const MapfDims d, const MapfState S, const int16_t* __restrict__ queue,
+                                      int32_t* __restrict__ head, int Q, uint8_t* __restrict__ dirty) {
+  const long long total = (long long)d.E * d.N;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total;
+       j += (long long)gridDim.x * blockDim.x) {
+    const uchar2 p = ((const uchar2*)S.pos)[j];
+    const uchar2 g = ((const uchar2*)S.goal)[j];
+    const int hd = head[j];
+    const bool pop = p.x == g.x && p.y == g.y && hd < Q;
+    if (dirty) dirty[j] = (uint8_t)pop;
+    if (!pop) continue;
+    const short2 q = ((const short2*)queue)[j * Q + hd];
+    int g0 = q.x, g1 = q.y;
+    if (g0 < 0 || g0 >= d.H || g1 < 0 || g1 >= d.W) {
+      atomicOr(S.err_flags, MAPF_FLAG_BAD_POSITION);
+      g0 = min(max(g0, 0), d.H - 1);
+      g1 = min(max(g1, 0), d.W - 1);
+    }
+    head[j] = hd + 1;
+    ((uchar2*)S.goal)[j] = make_uchar2((unsigned char)g0, (unsigned char)g1);
+    if (d.mode == MAPF_MODE_PRIMAL) S.done[j] = (uint8_t)(p.x == g0 && p.y == g1);
+  }
+}
+
 __global__ void mapf_export16_kernel(long long n, const uint8_t* src, int16_t* dst) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = (int16_t)src[i];
@@ -2053,6 +2078,13 @@ extern "C" int mapf_launch_reset(const MapfDims& d, const MapfState& S, const in
 extern "C" int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, const int16_t* goals,
                                      const uint8_t* dirty, void* stream) {
   mapf_set_goals_kernel<<<grid_for((long long)d.E * d.N, 256), 256, 0, (cudaStream_t)stream>>>(d, S, goals, dirty);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_pop_goals(const MapfDims& d, const MapfState& S, const int16_t* queue, int32_t* head,
+                                     int queue_len, uint8_t* dirty, void* stream) {
+  mapf_pop_goals_kernel<<<grid_for((long long)d.E * d.N, 256), 256, 0, (cudaStream_t)stream>>>(d, S, queue, head,
+                                                                                                queue_len, dirty);
   return (int)cudaGetLastError();
 }
 

@@ -217,6 +217,20 @@ class MapfEngine:
             self._check(self.lib.mapf_set_goals(self._h, self._ptr(g), self._ptr(dmask), self._stream()),
                         "mapf_set_goals")
 
+    def pop_goals(self, queue, head, dirty_out=None):
+        """Lifelong hand-out (MAPF-490-main/Global.cpp:85-94): agents standing on their goal take queue[head] as
+        their new goal.  queue int16 [E,N,Q,2], head int32 [E,N] (advanced in place); returns the uint8 [E,N] mask of
+        re-assigned agents."""
+        assert queue.dtype == torch.int16 and queue.is_cuda and queue.is_contiguous()
+        assert head.dtype == torch.int32 and head.is_cuda and head.is_contiguous()
+        assert tuple(queue.shape[:2]) == (self.E, self.N) and queue.shape[3] == 2 and tuple(head.shape) == (self.E, self.N)
+        if dirty_out is None:
+            dirty_out = self._buf("pop_dirty", (self.E, self.N), torch.uint8)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_pop_goals(self._h, self._ptr(queue), self._ptr(head), int(queue.shape[2]),
+                                                self._ptr(dirty_out), self._stream()), "mapf_pop_goals")
+        return dirty_out
+
     def set_prev_actions(self, prev):
         p = self._to_dev(prev, torch.uint8, (self.E, self.N))
         self._keep = [p]
