@@ -211,6 +211,7 @@ int mapf_destroy(mapf_handle* h) {
   cudaFree((void*)h->S.mag_lut);
   cudaFree((void*)h->S.vec_lut);
   cudaFree(h->S.stats);
+  cudaFree(h->S.bfs_list);
   cudaFree(h->S.err_flags);
   cudaFree(h->S.pos_prev);
   cudaFree(h->S.past);
@@ -403,6 +404,7 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
     h->S.complete_lut = clut;
   }
   ALLOC(h->S.stats, MAPF_N_STATS * 8);
+  ALLOC(h->S.bfs_list, ((size_t)h->d.E * h->d.N + 1) * 4);
   ALLOC(h->S.err_flags, 4);
   double* lut = nullptr;
   const int lut_len = c->mag_lut_host ? c->mag_lut_len : 1;

@@ -1462,15 +1462,33 @@ __global__ void mapf_export16_kernel(long long n, const uint8_t* src, int16_t* d
 // (PARTIAL:931-955 == hop distance; PRIMAL getAstarCosts :407-499 == hop distance from the goal.)
 // smem per warp: 4 bitmaps [H][RWB] (free, visited, frontier A/B) and, when it fits, the int16 map.
 // ------------------------------------------------------------------------------------------------
-__global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty, const uint8_t* env_mask,
-                                int16_t* dist, int RWB, int warps_per_block, int stage_dist, int conn8) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// Masked launches (goal re-assignment, masked reset) first compact the flagged (env, agent) indices into S.bfs_list
+// (count in its last entry) and then run a grid of resident warps over that list: a launch of E*N mostly idle warps
+// costs a block dispatch per 8 maps (150 us at c4 for a few dozen dirty maps), the list costs two small launches.
+__global__ void mapf_bfs_compact_kernel(const MapfDims d, const uint8_t* __restrict__ dirty,
+                                        const uint8_t* __restrict__ env_mask, int32_t* __restrict__ list) {
+  const long long total = (long long)d.E * d.N;
+  int32_t* count = list + total;
+  const int lane = threadIdx.x & 31;
+  for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < total;
+       base += (long long)gridDim.x * blockDim.x) {
+    const long long j = base + lane;
+    bool on = j < total;
+    if (on && dirty) on = dirty[j] != 0;
+    if (on && env_mask) on = env_mask[j / d.N] != 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, on);
+    if (!ballot) continue;
+    int off = 0;
+    if (lane == 0) off = atomicAdd(count, __popc(ballot));
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (on) list[off + __popc(ballot & ((1u << lane) - 1))] = (int32_t)j;
+  }
+}
+
+__device__ __forceinline__ void bfs_smem_one(const MapfDims& d, const MapfState& S, const long long m, int16_t* dist,
+                                             int RWB, int stage_dist, int conn8, unsigned char* smem_raw) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long m = (long long)blockIdx.x * warps_per_block + warp;   // (env, agent) index
-  if (m >= (long long)d.E * d.N) return;
-  if (dirty && !dirty[m]) return;
   const int e = (int)(m / d.N);
-  if (env_mask && !env_mask[e]) return;
   const int H = d.H, W = d.W, items = H * RWB;
   const size_t per_warp = (size_t)4 * items * 4 + (stage_dist ? (((size_t)d.HW * 2 + 15) & ~(size_t)15) : 0);
   unsigned char* base = smem_raw + per_warp * warp;
@@ -1547,6 +1565,20 @@ __global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8
   }
 }
 
+
+__global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const int32_t* __restrict__ list, int16_t* dist,
+                                int RWB, int warps_per_block, int stage_dist, int conn8) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const long long all = (long long)d.E * d.N;
+  const long long total = list ? (long long)list[all] : all;
+  for (long long i = (long long)blockIdx.x * warps_per_block + warp; i < total;
+       i += (long long)gridDim.x * warps_per_block) {
+    bfs_smem_one(d, S, list ? (long long)list[i] : i, dist, RWB, stage_dist, conn8, smem_raw);
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Warp-synchronous BFS for maps up to 64 x 64: the whole map lives in registers, lane l holds rows
 // [l*RPL, (l+1)*RPL) as W-bit masks (Row = uint32_t or uint64_t).  One wavefront step is two shuffles (the rows
@@ -1554,15 +1586,10 @@ __global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const uint8
 // that is staged for the final coalesced store.
 // ------------------------------------------------------------------------------------------------
 template <typename Row, int RPL, bool CONN8>
-__global__ void mapf_bfs_warp_kernel(const MapfDims d, const MapfState S, const uint8_t* dirty,
-                                     const uint8_t* env_mask, int16_t* dist, int warps_per_block) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void bfs_warp_one(const MapfDims& d, const MapfState& S, const long long m, int16_t* dist,
+                                             unsigned char* smem_raw) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long m = (long long)blockIdx.x * warps_per_block + warp;
-  if (m >= (long long)d.E * d.N) return;
-  if (dirty && !dirty[m]) return;
   const int e = (int)(m / d.N);
-  if (env_mask && !env_mask[e]) return;
   const int H = d.H, W = d.W;
   constexpr int RB = sizeof(Row) * 8;
   int16_t* sd = (int16_t*)(smem_raw + (size_t)warp * (((size_t)d.HW * 2 + 15) & ~(size_t)15));
@@ -1630,6 +1657,21 @@ __global__ void mapf_bfs_warp_kernel(const MapfDims d, const MapfState S, const 
     for (int i = lane; i < (d.HW >> 3); i += 32) ((uint4*)gd)[i] = ((const uint4*)sd)[i];
   } else {
     for (int i = lane; i < d.HW; i += 32) gd[i] = sd[i];
+  }
+}
+
+
+template <typename Row, int RPL, bool CONN8>
+__global__ void mapf_bfs_warp_kernel(const MapfDims d, const MapfState S, const int32_t* __restrict__ list,
+                                     int16_t* dist, int warps_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const long long all = (long long)d.E * d.N;
+  const long long total = list ? (long long)list[all] : all;
+  for (long long i = (long long)blockIdx.x * warps_per_block + warp; i < total;
+       i += (long long)gridDim.x * warps_per_block) {
+    bfs_warp_one<Row, RPL, CONN8>(d, S, list ? (long long)list[i] : i, dist, smem_raw);
+    __syncwarp();
   }
 }
 
@@ -2156,11 +2198,23 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
   }
   const long long maps = (long long)d.E * d.N;
   const int conn8 = (primal_costs && d.diag) ? 1 : 0;   // getAstarCosts with DIAGONAL_MOVEMENT, PRIMAL:421-437
+  // masked launch: compact the flagged maps, then a resident grid walks the list
+  const int32_t* list = nullptr;
+  int extra = 0;
+  if (dirty || env_mask) {
+    cudaError_t e = cudaMemsetAsync(S.bfs_list + maps, 0, 4, st);
+    if (e != cudaSuccess) return (int)e;
+    mapf_bfs_compact_kernel<<<grid_for(maps, 256), 256, 0, st>>>(d, dirty, env_mask, S.bfs_list);
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    list = S.bfs_list;
+    extra = 1;
+  }
   if (d.W <= 64 && d.H <= 64) {
     // register-resident warp-synchronous kernel; shared memory only stages the int16 map for the coalesced store
     const int w2 = 8;
     const size_t sm2 = dist_bytes * w2;
-    const long long g2 = (maps + w2 - 1) / w2;
+    long long g2 = (maps + w2 - 1) / w2;
+    if (list) g2 = g2 < 148 * 8 ? g2 : 148 * 8;
     const bool wide = d.W > 32, tall = d.H > 32;
 #define BFS_LAUNCH(ROW, RPL)                                                                                       \
   do {                                                                                                             \
@@ -2173,9 +2227,9 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
       if (e_ != cudaSuccess) return (int)e_;                                                                       \
     }                                                                                                              \
     if (conn8)                                                                                                     \
-      mapf_bfs_warp_kernel<ROW, RPL, true><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, dirty, env_mask, dist, w2);   \
+      mapf_bfs_warp_kernel<ROW, RPL, true><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, list, dist, w2);              \
     else                                                                                                           \
-      mapf_bfs_warp_kernel<ROW, RPL, false><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, dirty, env_mask, dist, w2);  \
+      mapf_bfs_warp_kernel<ROW, RPL, false><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, list, dist, w2);             \
   } while (0)
     if (!wide && !tall) BFS_LAUNCH(uint32_t, 1);
     else if (!wide && tall) BFS_LAUNCH(uint32_t, 2);
@@ -2183,16 +2237,17 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
     else BFS_LAUNCH(unsigned long long, 2);
 #undef BFS_LAUNCH
   } else {
-    const long long grid = (maps + warps - 1) / warps;
-    mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, dirty, env_mask, dist, RWB, warps, stage, conn8);
+    long long grid = (maps + warps - 1) / warps;
+    if (list) grid = grid < 148 * 8 ? grid : 148 * 8;
+    mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, list, dist, RWB, warps, stage, conn8);
   }
   cudaError_t err = cudaGetLastError();
-  *n_launches = 1;
+  *n_launches = 1 + extra;
   if (err == cudaSuccess && primal_costs) {
     mapf_primal_costs_agents_kernel<<<grid_for(maps * d.N, 256), 256, 0, st>>>(d, S, dirty, dist);
     mapf_primal_costs_free_kernel<<<grid_for(maps * d.HW, 256), 256, 0, st>>>(d, dirty, dist);
     err = cudaGetLastError();
-    *n_launches = 3;
+    *n_launches = 3 + extra;
   }
   return (int)err;
 }

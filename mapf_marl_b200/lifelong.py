@@ -10,21 +10,57 @@ import torch
 
 
 class LifelongGoals:
-    def __init__(self, engine, goal_queue):
+    def __init__(self, engine, goal_queue, dist_out=None, overlap=False):
         """goal_queue: int16 [E, N, Q, 2] (row, col) goals; entry 0 is the first REassignment (the initial goals
-        are the ones given to engine.reset)."""
+        are the ones given to engine.reset).
+        dist_out: optional caller-owned int16 [E,N,H,W] tensor kept up to date (otherwise the handle's own maps are
+        refreshed when the engine keeps them).
+        overlap: run the BFS of the re-assigned goals on a high-priority side stream, concurrently with the NEXT
+        step's fused launch (a handful of single-warp BFS runs is pure latency, ~70 us at 64x64; the next pop waits
+        for it, so goals never change under a running BFS).  Call sync() before reading the distance maps."""
         self.engine = engine
         self.queue = torch.as_tensor(goal_queue).to(device=engine.device, dtype=torch.int16).contiguous()
         E, N, Q, _ = self.queue.shape
         assert (E, N) == (engine.E, engine.N)
         self.Q = Q
         self.head = torch.zeros((E, N), dtype=torch.int32, device=engine.device)
+        self.dist_out = dist_out
+        self._side = None
+        if overlap:
+            with torch.cuda.device(engine.device):
+                self._side = torch.cuda.Stream(priority=-1)
+                self._popped = torch.cuda.Event()
+                self._bfs_done = torch.cuda.Event()
+            self._pending = False
+
+    def _bfs(self, d8):
+        if self.dist_out is not None:
+            self.engine.goal_dist(dirty=d8, out=self.dist_out)
+        elif self.engine.has_goal_dist:
+            self.engine.refresh_goal_dist(d8)
 
     def reassign(self, on_goal=None):
         """Pops the next goal of every agent that stands on its goal (the engine's PRIMAL `dones` output is exactly
         that flag; it is accepted for symmetry with the reference loop and not needed).  Returns the dirty mask that
-        was applied, uint8 [E, N]."""
+        was applied, uint8 [E, N] (valid until the next call)."""
+        if self._side is None:
+            d8 = self.engine.pop_goals(self.queue, self.head)
+            self._bfs(d8)
+            return d8
+        main = torch.cuda.current_stream(self.engine.device)
+        if self._pending:
+            main.wait_event(self._bfs_done)          # the previous BFS still reads the goals and the dirty mask
         d8 = self.engine.pop_goals(self.queue, self.head)
-        if self.engine.has_goal_dist:
-            self.engine.refresh_goal_dist(d8)
+        self._popped.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._popped)
+            self._bfs(d8)
+            self._bfs_done.record(self._side)
+        self._pending = True
         return d8
+
+    def sync(self):
+        """Makes the current stream wait for the BFS of the last reassign() (overlap mode)."""
+        if self._side is not None and self._pending:
+            torch.cuda.current_stream(self.engine.device).wait_event(self._bfs_done)
+            self._pending = False

@@ -732,9 +732,11 @@ def test_marl_partial_dropin_class(tmp_path):
     assert env3.reset().shape == (3, env3.get_obs_size())
 
 
-def test_c4_shape_lifelong_goal_reassignment_matches_oracle():
-    """BASELINE config c4: 64x64 warehouse layout, 128 agents, goals popped from a per-agent queue on arrival,
-    distance maps recomputed only for the reassigned goals."""
+@pytest.mark.parametrize("overlap", [False, True])
+def test_c4_shape_lifelong_goal_reassignment_matches_oracle(overlap):
+    """BASELINE config c4: 64x64 warehouse layout, 128 agents, goals popped from a per-agent queue on arrival
+    (mapf_pop_goals), distance maps recomputed only for the reassigned goals (mapf_bfs with the dirty mask: compacted
+    list + resident warps), optionally on a side stream overlapped with the next step."""
     from mapf_marl_b200 import maps
     from mapf_marl_b200.lifelong import LifelongGoals
     from oracle.oracle import MODE_PRIMAL
@@ -759,25 +761,28 @@ def test_c4_shape_lifelong_goal_reassignment_matches_oracle():
     orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F, shared_map=True)
     eng.reset(obst, starts, goals)
     orc.reset(obst, starts, goals)
-    life = LifelongGoals(eng, queue)
     dist = torch.full((E, N, H, W), -9, dtype=torch.int16, device="cuda")
     eng.goal_dist(out=dist)
+    life = LifelongGoals(eng, queue, dist_out=dist, overlap=overlap)
     ref_dist = orc.goal_dist()
     head = np.zeros((E, N), np.int64)
+    cur_goals = goals.copy()
     for t in range(8):
         a = rs.randint(0, 5, (E, N)).astype(np.uint8)
         out = eng.step_observe(torch.as_tensor(a, device="cuda"), want=("dones", "status", "avail", "terminated"))
         ref = orc.primal_sweep(a)
         assert np.array_equal(_np(out["status"]), ref["status"]) and np.array_equal(_np(out["dones"]), ref["dones"])
         dirty = _np(life.reassign(out["dones"]))
+        life.sync()
         ref_dirty = ((ref["dones"] != 0) & (head < Q)).astype(np.uint8)
         assert np.array_equal(dirty, ref_dirty)
         new_goals = np.take_along_axis(queue, np.minimum(head, Q - 1)[..., None, None].repeat(2, -1), 2)[:, :, 0, :]
         head += ref_dirty
         orc.set_goals(new_goals, ref_dirty)
         orc.goal_dist(dirty=ref_dirty, out=ref_dist)
-        eng.goal_dist(dirty=dirty, out=dist)
         assert np.array_equal(_np(dist), ref_dist), t
+        cur_goals[ref_dirty != 0] = new_goals[ref_dirty != 0]
+        assert np.array_equal(_np(eng.goals()), cur_goals), t
         obs, vec = eng.observe()
         robs, rvec = orc.primal_observe()
         assert np.array_equal(_np(obs), robs) and np.array_equal(_bits(_np(vec)), _bits(rvec)), t
