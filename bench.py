@@ -376,6 +376,17 @@ def main():
         ms_e2e_dense = timed(e2e_step, args.e2e_steps, 2) / args.e2e_steps
         eng.host_transport(True)
 
+    # the same call handing the bit stream itself to the host (MAPF_BITS host output, no expansion; informational)
+    ms_e2e_bits = None
+    if eng.bits_supported():
+        io_b, bufs_b, _, d2h_bits = eng.make_host_io(obs_dtype="bits")
+        act_b = bufs_b["actions"].numpy()
+
+        def e2e_bits_step(t):
+            np.copyto(act_b, host_pool_np[t % 4])
+            eng.step_observe_host(io_b)
+        ms_e2e_bits = timed(e2e_bits_step, args.e2e_steps, 2) / args.e2e_steps
+
     # ---- the same host entry point when the policy lives on the GPU (pymarl's controller does): actions come from
     #      the host, reward / terminated go back, the observation stays in device memory for the agent network
     acts_dev = torch.empty((E, N), dtype=torch.uint8, device=dev)
@@ -426,6 +437,11 @@ def main():
                 "value": world * E * N / (ms_e2e_dense * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_dense,
                 "d2h_bytes_per_step": d2h_dense,
                 "note": "informational: the same host call with the observation tensor copied densely over PCIe"},
+            "e2e_bits_to_host": None if ms_e2e_bits is None else {
+                "value": world * E * N / (ms_e2e_bits * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_bits,
+                "d2h_bytes_per_step": d2h_bits,
+                "note": "informational: the same host call with obs_dtype MAPF_BITS (the observation arrives in host "
+                        "memory as a bit stream, one bit per cell; no host expansion)"},
             "e2e_obs_on_device": {"value": world * E * N / (ms_e2e2 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e2,
                                   "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2,
                                   "note": "informational: host actions in, reward/terminated out, observation left "

@@ -266,7 +266,10 @@ int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, co
  * benchmark times.
  * MAPF_U8 / MAPF_F32 field-of-view observations cross PCIe as packed bits (MAPF_BITS, 8x / 32x fewer bytes) in
  * chunks and are expanded to the 0/1 cells of obs_host by the library's host threads while the next chunk is in flight; the
- * result is byte-identical to the dense copy.  mapf_host_transport(h, 0) switches back to the dense copy. */
+ * result is byte-identical to the dense copy.  mapf_host_transport(h, 0) switches back to the dense copy.
+ * io->obs_dtype == MAPF_BITS hands the bit stream itself to the caller (obs_host: ceil(E*N*4*F*F / 32) uint32 words,
+ * bit i of the stream = cell i of the [E,N,4,F,F] tensor, little-endian inside a word) with no host expansion.
+ * The unpack pool uses MAPF_HOST_THREADS threads if that variable is set, else (CPUs of the process) / LOCAL_WORLD_SIZE. */
 int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream);
 
 /* 1 when observations of this handle can be produced as MAPF_BITS. */

@@ -404,7 +404,7 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
     h->S.complete_lut = clut;
   }
   ALLOC(h->S.stats, MAPF_N_STATS * 8);
-  ALLOC(h->S.bfs_list, ((size_t)h->d.E * h->d.N + 1) * 4);
+  ALLOC(h->S.bfs_list, (2 * (size_t)h->d.E * h->d.N + 2) * 4);
   ALLOC(h->S.err_flags, 4);
   double* lut = nullptr;
   const int lut_len = c->mag_lut_host ? c->mag_lut_len : 1;
@@ -727,10 +727,16 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   // uint8 field-of-view observations cross PCIe as bits and are expanded by the host pool (byte-identical result)
   const bool packed = io->obs_host && fov && (io->obs_dtype == MAPF_U8 || io->obs_dtype == MAPF_F32) &&
                       h->packed_transport && bits_supported(h);
+  // MAPF_BITS host output: the bit stream itself goes to the caller's buffer (ceil(cells / 32) words), no expansion
+  const bool bits_out = io->obs_host && fov && io->obs_dtype == MAPF_BITS;
+  if (bits_out && !bits_supported(h))
+    return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_step_observe_host: MAPF_BITS needs a specialised FOV kernel and whole "
+                "observation groups per tile (mapf_obs_bits_supported)");
   const int elem = io->obs_dtype == MAPF_F32 ? 4 : 1;
   size_t obs_bytes = 0;
   if (io->obs_host) {
-    if (fov) obs_bytes = EN * 4 * d.F * d.F * (io->obs_dtype == MAPF_F32 ? 4 : 1);
+    if (bits_out) obs_bytes = (EN * 4 * d.F * d.F + 31) / 32 * 4;
+    else if (fov) obs_bytes = EN * 4 * d.F * d.F * (io->obs_dtype == MAPF_F32 ? 4 : 1);
     else if (d.obs_mode == MAPF_OBS_PARTIAL_WINDOW) obs_bytes = EN * d.posz * 8;
     else obs_bytes = (size_t)d.E * d.HW;
   }
@@ -745,9 +751,12 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   if (io->dones_host) LAZY(h->hs_dones, EN);
   if (io->avail_host) LAZY(h->hs_avail, EN * d.nact);
   if (io->vec_host) LAZY(h->hs_vec, EN * 24);
-  const size_t tile_words = packed ? ((size_t)d.epb * d.N * 4 * d.F * d.F) >> 5 : 0;
+  const size_t tile_words = (packed || bits_out) ? ((size_t)d.epb * d.N * 4 * d.F * d.F) >> 5 : 0;
   const size_t ntiles = ((size_t)d.E + d.epb - 1) / d.epb;
-  if (packed) {
+  if (bits_out) {
+    h->bits_words = ntiles * tile_words;
+    LAZY(h->hs_bits, h->bits_words * 4);
+  } else if (packed) {
     h->bits_words = ntiles * tile_words;
     LAZY(h->hs_bits, h->bits_words * 4);
     if (!h->hp_bits) CK(cudaHostAlloc((void**)&h->hp_bits, h->bits_words * 4, cudaHostAllocDefault));
@@ -766,7 +775,7 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
       LAZY(h->hs_prog, sizeof(prog));
       CK(cudaMemcpyAsync(h->hs_prog, prog, sizeof(prog), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
     }
-  } else if (obs_bytes > h->hs_obs_bytes) {
+  } else if (!bits_out && obs_bytes > h->hs_obs_bytes) {
     cudaFree(h->hs_obs);
     h->hs_obs = nullptr;
     h->hs_obs_bytes = 0;
@@ -781,8 +790,8 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   out.terminated_dev = io->terminated_host ? h->hs_terminated : nullptr;
   out.dones_dev = io->dones_host ? h->hs_dones : nullptr;
   out.avail_dev = io->avail_host ? h->hs_avail : nullptr;
-  void* obs_dev = !io->obs_host ? nullptr : (packed ? (void*)h->hs_bits : h->hs_obs);
-  int rc = run_tile(h, h->hs_actions, MAPF_U8, 0, d.N, &out, obs_dev, packed ? (int)MAPF_BITS : io->obs_dtype,
+  void* obs_dev = !io->obs_host ? nullptr : ((packed || bits_out) ? (void*)h->hs_bits : h->hs_obs);
+  int rc = run_tile(h, h->hs_actions, MAPF_U8, 0, d.N, &out, obs_dev, (packed || bits_out) ? (int)MAPF_BITS : io->obs_dtype,
                     io->vec_host ? h->hs_vec : nullptr, stream);
   if (rc != MAPF_OK) return rc;
   auto copy_small_outputs = [&]() -> int {
@@ -823,7 +832,8 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
     if (!ok) return cuda_fail(h, pc.err, "mapf_step_observe_host: device-to-host transfer");
   } else {
     if ((rc = copy_small_outputs()) != MAPF_OK) return rc;
-    if (io->obs_host) CK(cudaMemcpyAsync(io->obs_host, h->hs_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+    if (io->obs_host)
+      CK(cudaMemcpyAsync(io->obs_host, bits_out ? (void*)h->hs_bits : h->hs_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
   if (trace)

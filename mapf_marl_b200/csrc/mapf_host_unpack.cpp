@@ -8,7 +8,11 @@
 // Bit i of the stream == element i of the output (uint8 0/1 or float32 0.0/1.0; little-endian bit order inside
 // 32-bit words).
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 #include <atomic>
 #include <condition_variable>
@@ -294,10 +298,27 @@ struct MapfUnpackPool {
 
 extern "C" {
 
+// threads <= 0: MAPF_HOST_THREADS if set, else the CPUs this process may run on divided by the number of ranks that
+// share the host (LOCAL_WORLD_SIZE, the torchrun convention): eight ranks with one pool each must not put eight
+// times the core count of spinning workers on the box.  The calling thread works too, hence the "- 1".
 MapfUnpackPool* mapf_unpack_pool_create(int threads) {
   if (threads <= 0) {
-    threads = (int)std::thread::hardware_concurrency();
-    if (threads <= 0) threads = 4;
+    const char* env = getenv("MAPF_HOST_THREADS");
+    if (env && atoi(env) > 0) {
+      threads = atoi(env);
+    } else {
+      int cpus = 0;
+#if defined(__linux__)
+      cpu_set_t set;
+      if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+#endif
+      if (cpus <= 0) cpus = (int)std::thread::hardware_concurrency();
+      if (cpus <= 0) cpus = 4;
+      const char* lws = getenv("LOCAL_WORLD_SIZE");
+      const int ranks = (lws && atoi(lws) > 0) ? atoi(lws) : 1;
+      threads = ranks > 1 ? cpus / ranks - 1 : cpus;
+      if (threads < 1) threads = 1;
+    }
     if (threads > 64) threads = 64;
   }
   try {

@@ -94,7 +94,8 @@ struct MapfState {
   uint8_t* terminated;     // [E]
   const double* complete_lut;
   uint32_t* err_flags;     // [1]
-  int32_t* bfs_list;       // [E*N + 1]: compacted (env, agent) indices of a masked BFS; the last entry is the count
+  int32_t* bfs_list;       // [2 + 2*E*N]: two counters, the compacted (env, agent) indices of a masked BFS, the
+                           // overflow list of the register BFS kernel
 };
 
 // Per-launch arguments of the tile kernel.

@@ -1463,12 +1463,13 @@ __global__ void mapf_export16_kernel(long long n, const uint8_t* src, int16_t* d
 // smem per warp: 4 bitmaps [H][RWB] (free, visited, frontier A/B) and, when it fits, the int16 map.
 // ------------------------------------------------------------------------------------------------
 // Masked launches (goal re-assignment, masked reset) first compact the flagged (env, agent) indices into S.bfs_list
-// (count in its last entry) and then run a grid of resident warps over that list: a launch of E*N mostly idle warps
+// (two counters, then the list, then the overflow list of the register kernel) and then run a grid of resident warps over that list: a launch of E*N mostly idle warps
 // costs a block dispatch per 8 maps (150 us at c4 for a few dozen dirty maps), the list costs two small launches.
 __global__ void mapf_bfs_compact_kernel(const MapfDims d, const uint8_t* __restrict__ dirty,
                                         const uint8_t* __restrict__ env_mask, int32_t* __restrict__ list) {
   const long long total = (long long)d.E * d.N;
-  int32_t* count = list + total;
+  int32_t* count = list;             // [0] flagged maps, [1] overflow (mapf_launch_bfs zeroes both)
+  list += 2;
   const int lane = threadIdx.x & 31;
   for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < total;
        base += (long long)gridDim.x * blockDim.x) {
@@ -1566,12 +1567,13 @@ __device__ __forceinline__ void bfs_smem_one(const MapfDims& d, const MapfState&
 }
 
 
-__global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const int32_t* __restrict__ list, int16_t* dist,
-                                int RWB, int warps_per_block, int stage_dist, int conn8) {
+__global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const int32_t* __restrict__ list,
+                                const int32_t* __restrict__ count, int16_t* dist, int RWB, int warps_per_block,
+                                int stage_dist, int conn8) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const long long all = (long long)d.E * d.N;
-  const long long total = list ? (long long)list[all] : all;
+  const long long total = list ? (long long)*count : all;
   for (long long i = (long long)blockIdx.x * warps_per_block + warp; i < total;
        i += (long long)gridDim.x * warps_per_block) {
     bfs_smem_one(d, S, list ? (long long)list[i] : i, dist, RWB, stage_dist, conn8, smem_raw);
@@ -1582,22 +1584,32 @@ __global__ void mapf_bfs_kernel(const MapfDims d, const MapfState S, const int32
 // ------------------------------------------------------------------------------------------------
 // Warp-synchronous BFS for maps up to 64 x 64: the whole map lives in registers, lane l holds rows
 // [l*RPL, (l+1)*RPL) as W-bit masks (Row = uint32_t or uint64_t).  One wavefront step is two shuffles (the rows
-// above and below) and a handful of logic ops per row; no shared-memory traffic except the int16 distance map
-// that is staged for the final coalesced store.
+// above and below) and a handful of logic ops per row.  The DISTANCES live in registers too, bit-sliced: plane p of a
+// row has bit c set when bit p of cell c's distance is set.  Levels are processed in batches of eight: inside a batch
+// the low three bits of the level are compile-time constants (a cell reached at sub-level i is OR-ed into the planes
+// of i's set bits), the upper five planes take the union of the batch when the batch's base has that bit.  No
+// per-cell work, no divergence and no shared memory until the end, when every lane turns the planes of its own rows
+// into int16 cells (4 cells per multiply-and-mask, walls -1, unreachable -2) and stores them.  Eight planes cover
+// 255 levels; a map whose wavefront is still moving after that is put on the overflow list and redone by the
+// shared-memory kernel (mapf_bfs_kernel), which has no such limit.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) {      // bits 0..3 -> bit 0 of bytes 0..3
+  return (nib * 0x00204081u) & 0x01010101u;
+}
+
 template <typename Row, int RPL, bool CONN8>
-__device__ __forceinline__ void bfs_warp_one(const MapfDims& d, const MapfState& S, const long long m, int16_t* dist,
-                                             unsigned char* smem_raw) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ bool bfs_warp_one(const MapfDims& d, const MapfState& S, const long long m, int16_t* dist) {
+  const int lane = threadIdx.x & 31;
   const int e = (int)(m / d.N);
   const int H = d.H, W = d.W;
   constexpr int RB = sizeof(Row) * 8;
-  int16_t* sd = (int16_t*)(smem_raw + (size_t)warp * (((size_t)d.HW * 2 + 15) & ~(size_t)15));
+  constexpr int NP = 8;
+  const unsigned full = 0xffffffffu;
   int16_t* gd = dist + (size_t)m * d.HW;
   const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
   const uchar2 g = ((const uchar2*)S.goal)[m];
   const Row valid = (W >= RB) ? ~(Row)0 : (((Row)1 << W) - 1);
-  Row freeR[RPL], vis[RPL], f[RPL];
+  Row freeR[RPL], fnv[RPL], f[RPL], D[RPL][NP];      // fnv: free and not yet visited
 #pragma unroll
   for (int k = 0; k < RPL; ++k) {
     const int r = lane * RPL + k;
@@ -1609,69 +1621,118 @@ __device__ __forceinline__ void bfs_warp_one(const MapfDims& d, const MapfState&
       fr = ~wall & valid;
     }
     freeR[k] = fr;
-    const Row start = (r == g.x) ? (((Row)1 << g.y) & fr) : 0;
-    vis[k] = start;
+    const Row start = (r == g.x) ? (((Row)1 << g.y) & fr) : 0;     // level 0: all planes zero
     f[k] = start;
+    fnv[k] = fr & ~start;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) D[k][p] = 0;
   }
-  // distance map staging: walls -1, free -2, goal 0; lanes walk the cells linearly (conflict-free stores), the row's
-  // free mask comes from the lane that owns the row
-  for (int r = 0; r < H; ++r) {
-    const Row fr = __shfl_sync(0xffffffffu, freeR[RPL == 1 ? 0 : (r % RPL)], r / RPL);
-    for (int c = lane; c < W; c += 32) sd[r * W + c] = ((fr >> c) & 1) ? -2 : -1;
-  }
-  __syncwarp();
-  if (lane == 0 && (int)g.x < H && (int)g.y < W && sd[(int)g.x * W + g.y] == -2) sd[(int)g.x * W + g.y] = 0;
-  __syncwarp();
-  for (int level = 1; level < 32767; ++level) {
-    const Row from_above = __shfl_up_sync(0xffffffffu, f[RPL - 1], 1);     // last row of the lane above
-    const Row from_below = __shfl_down_sync(0xffffffffu, f[0], 1);         // first row of the lane below
-    Row nw[RPL];
+  bool open = true;
+  for (int L0 = 0; L0 < (1 << NP); L0 += 8) {
+    Row U[RPL];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) U[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i > 0 || L0 > 0) {
+        // rows beyond the first / last lane come back as the lane's own row, which is adjacent anyway: harmless
+        const Row from_above = __shfl_up_sync(full, f[RPL - 1], 1);     // last row of the lane above
+        const Row from_below = __shfl_down_sync(full, f[0], 1);         // first row of the lane below
+        Row nw[RPL];
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          Row up = (k > 0) ? f[k - 1] : from_above;
+          Row dn = (k < RPL - 1) ? f[k + 1] : from_below;
+          if (CONN8) {                                                    // diagonal neighbours, PRIMAL:421-437
+            up |= (up << 1) | (up >> 1);
+            dn |= (dn << 1) | (dn >> 1);
+          }
+          nw[k] = ((f[k] << 1) | (f[k] >> 1) | up | dn) & fnv[k];
+        }
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          f[k] = nw[k];
+          fnv[k] &= ~nw[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) {
+        if (i & 1) D[k][0] |= f[k];
+        if (i & 2) D[k][1] |= f[k];
+        if (i & 4) D[k][2] |= f[k];
+        U[k] |= f[k];
+      }
+    }
     bool any = false;
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
-      Row up = (k > 0) ? f[k - 1] : (lane > 0 ? from_above : 0);
-      Row dn = (k < RPL - 1) ? f[k + 1] : (lane < 31 ? from_below : 0);
-      if (CONN8) {                                                         // diagonal neighbours, PRIMAL:421-437
-        up |= (up << 1) | (up >> 1);
-        dn |= (dn << 1) | (dn >> 1);
-      }
-      nw[k] = ((f[k] << 1) | (f[k] >> 1) | up | dn) & freeR[k] & ~vis[k];
-      any |= nw[k] != 0;
-    }
 #pragma unroll
-    for (int k = 0; k < RPL; ++k) {
-      vis[k] |= nw[k];
-      f[k] = nw[k];
-      Row x = nw[k];
-      const int r = lane * RPL + k;
-      while (x) {
-        const int b = (RB == 64) ? (__ffsll((long long)x) - 1) : (__ffs((int)x) - 1);
-        x &= x - 1;
-        sd[r * W + b] = (int16_t)level;
+      for (int p = 3; p < NP; ++p)
+        if ((L0 >> p) & 1) D[k][p] |= U[k];
+      any |= f[k] != 0;
+    }
+    if (!__any_sync(full, any)) {
+      open = false;
+      break;
+    }
+  }
+  if (open) return false;                  // deeper than 255 levels: the caller hands the map to the generic kernel
+  // ---- planes -> int16 cells.  Not-visited cells get low byte 0xff (wall) / 0xfe (free) and high byte 0xff.
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) {
+    const int r = lane * RPL + k;
+    const Row wall = ~freeR[k];
+    const Row nv = wall | fnv[k];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) D[k][p] |= (p == 0) ? wall : nv;
+    if (r >= H) continue;
+    int16_t* grow = gd + (size_t)r * W;
+    if ((W & 3) == 0) {
+#pragma unroll
+      for (int q = 0; q < RB / 4; q += 2) {
+        if (4 * q >= W) break;
+        uint32_t o[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t lo = 0;
+#pragma unroll
+          for (int p = 0; p < NP; ++p) lo |= spread4((uint32_t)(D[k][p] >> (4 * (q + h))) & 0xfu) << p;
+          const uint32_t hi = spread4((uint32_t)(nv >> (4 * (q + h))) & 0xfu) * 0xffu;
+          o[2 * h] = __byte_perm(lo, hi, 0x5140);         // cells 0,1 of the group: (lo0, hi0, lo1, hi1)
+          o[2 * h + 1] = __byte_perm(lo, hi, 0x7362);     // cells 2,3
+        }
+        if ((W & 7) == 0) {
+          *(uint4*)(grow + 4 * q) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+          *(uint2*)(grow + 4 * q) = make_uint2(o[0], o[1]);
+          if (4 * (q + 1) < W) *(uint2*)(grow + 4 * (q + 1)) = make_uint2(o[2], o[3]);
+        }
+      }
+    } else {
+      for (int c = 0; c < W; ++c) {
+        uint32_t v = ((uint32_t)(nv >> c) & 1u) * 0xff00u;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) v |= ((uint32_t)(D[k][p] >> c) & 1u) << p;
+        grow[c] = (int16_t)v;
       }
     }
-    if (!__any_sync(0xffffffffu, any)) break;
   }
-  __syncwarp();
-  if ((d.HW & 7) == 0) {
-    for (int i = lane; i < (d.HW >> 3); i += 32) ((uint4*)gd)[i] = ((const uint4*)sd)[i];
-  } else {
-    for (int i = lane; i < d.HW; i += 32) gd[i] = sd[i];
-  }
+  return true;
 }
 
-
+// cnt[0]: length of the list of flagged maps (masked launch), cnt[1]: length of the overflow list
 template <typename Row, int RPL, bool CONN8>
 __global__ void mapf_bfs_warp_kernel(const MapfDims d, const MapfState S, const int32_t* __restrict__ list,
-                                     int16_t* dist, int warps_per_block) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                                     int32_t* __restrict__ cnt, int32_t* __restrict__ overflow, int16_t* dist,
+                                     int warps_per_block) {
   const int warp = threadIdx.x >> 5;
   const long long all = (long long)d.E * d.N;
-  const long long total = list ? (long long)list[all] : all;
+  const long long total = list ? (long long)cnt[0] : all;
   for (long long i = (long long)blockIdx.x * warps_per_block + warp; i < total;
        i += (long long)gridDim.x * warps_per_block) {
-    bfs_warp_one<Row, RPL, CONN8>(d, S, list ? (long long)list[i] : i, dist, smem_raw);
-    __syncwarp();
+    const long long m = list ? (long long)list[i] : i;
+    if (!bfs_warp_one<Row, RPL, CONN8>(d, S, m, dist) && (threadIdx.x & 31) == 0)
+      overflow[atomicAdd(&cnt[1], 1)] = (int32_t)m;
   }
 }
 
@@ -2198,48 +2259,54 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
   }
   const long long maps = (long long)d.E * d.N;
   const int conn8 = (primal_costs && d.diag) ? 1 : 0;   // getAstarCosts with DIAGONAL_MOVEMENT, PRIMAL:421-437
+  // S.bfs_list: [0] number of flagged maps, [1] number of overflowed maps, then the two lists (maps entries each)
+  int32_t* cnt = S.bfs_list;
+  int32_t* flagged = S.bfs_list + 2;
+  int32_t* overflow = flagged + maps;
+  {
+    cudaError_t e = cudaMemsetAsync(cnt, 0, 8, st);
+    if (e != cudaSuccess) return (int)e;
+  }
   // masked launch: compact the flagged maps, then a resident grid walks the list
   const int32_t* list = nullptr;
   int extra = 0;
   if (dirty || env_mask) {
-    cudaError_t e = cudaMemsetAsync(S.bfs_list + maps, 0, 4, st);
-    if (e != cudaSuccess) return (int)e;
     mapf_bfs_compact_kernel<<<grid_for(maps, 256), 256, 0, st>>>(d, dirty, env_mask, S.bfs_list);
-    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-    list = S.bfs_list;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    list = flagged;
     extra = 1;
   }
+  const long long resident = 148 * 8;
   if (d.W <= 64 && d.H <= 64) {
-    // register-resident warp-synchronous kernel; shared memory only stages the int16 map for the coalesced store
+    // register-resident warp-synchronous kernel (no shared memory); maps deeper than 255 levels go to the generic
+    // kernel through the overflow list (normally empty: that launch ends at once)
     const int w2 = 8;
-    const size_t sm2 = dist_bytes * w2;
     long long g2 = (maps + w2 - 1) / w2;
-    if (list) g2 = g2 < 148 * 8 ? g2 : 148 * 8;
+    if (list) g2 = g2 < resident ? g2 : resident;
     const bool wide = d.W > 32, tall = d.H > 32;
-#define BFS_LAUNCH(ROW, RPL)                                                                                       \
-  do {                                                                                                             \
-    if (sm2 > 48 * 1024) {                                                                                         \
-      cudaError_t e_ = cudaFuncSetAttribute(mapf_bfs_warp_kernel<ROW, RPL, false>,                                 \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);                \
-      if (e_ == cudaSuccess)                                                                                       \
-        e_ = cudaFuncSetAttribute(mapf_bfs_warp_kernel<ROW, RPL, true>,                                            \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);                          \
-      if (e_ != cudaSuccess) return (int)e_;                                                                       \
-    }                                                                                                              \
-    if (conn8)                                                                                                     \
-      mapf_bfs_warp_kernel<ROW, RPL, true><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, list, dist, w2);              \
-    else                                                                                                           \
-      mapf_bfs_warp_kernel<ROW, RPL, false><<<(unsigned)g2, w2 * 32, sm2, st>>>(d, S, list, dist, w2);             \
+#define BFS_LAUNCH(ROW, RPL)                                                                                          \
+  do {                                                                                                                \
+    if (conn8)                                                                                                        \
+      mapf_bfs_warp_kernel<ROW, RPL, true><<<(unsigned)g2, w2 * 32, 0, st>>>(d, S, list, cnt, overflow, dist, w2);    \
+    else                                                                                                              \
+      mapf_bfs_warp_kernel<ROW, RPL, false><<<(unsigned)g2, w2 * 32, 0, st>>>(d, S, list, cnt, overflow, dist, w2);   \
   } while (0)
     if (!wide && !tall) BFS_LAUNCH(uint32_t, 1);
     else if (!wide && tall) BFS_LAUNCH(uint32_t, 2);
     else if (wide && !tall) BFS_LAUNCH(unsigned long long, 1);
     else BFS_LAUNCH(unsigned long long, 2);
 #undef BFS_LAUNCH
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    long long go = (maps + warps - 1) / warps;
+    go = go < 148 * 2 ? go : 148 * 2;
+    mapf_bfs_kernel<<<(unsigned)go, warps * 32, smem, st>>>(d, S, overflow, cnt + 1, dist, RWB, warps, stage, conn8);
+    extra += 1;
   } else {
     long long grid = (maps + warps - 1) / warps;
-    if (list) grid = grid < 148 * 8 ? grid : 148 * 8;
-    mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, list, dist, RWB, warps, stage, conn8);
+    if (list) grid = grid < resident ? grid : resident;
+    mapf_bfs_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(d, S, list, cnt, dist, RWB, warps, stage, conn8);
   }
   cudaError_t err = cudaGetLastError();
   *n_launches = 1 + extra;

@@ -374,7 +374,11 @@ class MapfEngine:
             bufs["avail"] = torch.empty((E, N, self.n_actions), dtype=torch.uint8).pin_memory()
         odt = I8
         if "obs" in want:
-            if self.obs_mode == OBS_PRIMAL_FOV:
+            if self.obs_mode == OBS_PRIMAL_FOV and obs_dtype == "bits":
+                # the bit stream itself (bit i = cell i of [E,N,4,F,F]); int32 words, no host expansion
+                bufs["obs"] = torch.empty((self.packed_obs_bytes() // 4,), dtype=torch.int32).pin_memory()
+                odt = BITS
+            elif self.obs_mode == OBS_PRIMAL_FOV:
                 bufs["obs"] = torch.empty((E, N, 4, self.F, self.F), dtype=obs_dtype).pin_memory()
                 odt = U8 if obs_dtype == torch.uint8 else F32
             else:

@@ -2,7 +2,7 @@
 # Profiling recipe for the c3 bench command (run on the GPU box through gpurun, ONE GPU):
 #   1. the plain run must exit 0 first; 2. launch list; 3. one `--set full` capture per kernel of interest.
 # Tile-kernel launch order inside `bench.py --steps 5 --warmup 3`: 0-25 fused step+obs (eager warm-up, graph replays,
-# eager leg), 26-33 observe only, 34-41 step only.
+# eager leg), 26-33 fused with bit-packed observation output, 34-41 observe only, 42-49 step only.
 set -e
 TAG=${1:-r1}
 OUT=gpurun_out
@@ -11,7 +11,8 @@ $BENCH > $OUT/${TAG}_plain.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_c3.csv $BENCH > $OUT/${TAG}_ncu_launches.log 2>&1
 NCU="ncu --set full --clock-control none --import-source on -f"
 $NCU -k regex:mapf_tile_kernel -s 5 -c 1 -o $OUT/${TAG}_fused_c3 $BENCH > $OUT/${TAG}_ncu_fused.log 2>&1
-$NCU -k regex:mapf_tile_kernel -s 28 -c 1 -o $OUT/${TAG}_obs_c3 $BENCH > $OUT/${TAG}_ncu_obs.log 2>&1
-$NCU -k regex:mapf_tile_kernel -s 36 -c 1 -o $OUT/${TAG}_step_c3 $BENCH > $OUT/${TAG}_ncu_step.log 2>&1
-$NCU -k regex:mapf_bfs -s 1 -c 1 -o $OUT/${TAG}_bfs_c3 $BENCH > $OUT/${TAG}_ncu_bfs.log 2>&1
+$NCU -k regex:mapf_tile_kernel -s 36 -c 1 -o $OUT/${TAG}_obs_c3 $BENCH > $OUT/${TAG}_ncu_obs.log 2>&1
+$NCU -k regex:mapf_tile_kernel -s 44 -c 1 -o $OUT/${TAG}_step_c3 $BENCH > $OUT/${TAG}_ncu_step.log 2>&1
+$NCU -k regex:mapf_tile_kernel -s 28 -c 1 -o $OUT/${TAG}_bits_c3 $BENCH > $OUT/${TAG}_ncu_bits.log 2>&1
+$NCU -k regex:mapf_bfs_warp -s 1 -c 1 -o $OUT/${TAG}_bfs_c3 $BENCH > $OUT/${TAG}_ncu_bfs.log 2>&1
 ls -la $OUT | grep ${TAG}_

@@ -2,7 +2,7 @@
 """Per-phase critical path of one tile (cycles), from a debug build of the library:
 
     cd mapf_marl_b200/csrc && nvcc -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo \
-        -std=c++17 -Xcompiler -fPIC -shared -DMAPF_PHASE_TIMING -o ../libmapf_b200_dbg.so mapf_kernels.cu mapf_capi.cu
+        -std=c++17 -Xcompiler -fPIC -shared -DMAPF_PHASE_TIMING -o ../libmapf_b200_dbg.so mapf_kernels.cu mapf_capi.cu mapf_host_unpack.cpp
     python profiles/phase_probe.py          (on the GPU box)
 
 The middle block of the grid records clock64() at every phase boundary (PHASE_MARK in mapf_kernels.cu)."""
@@ -25,11 +25,11 @@ NAMES = ["stage", "phase A", "phase B", "phase C", "avail + agent bitmap", "phas
 
 def main():
     lib = _lib.load()
-    for name in ("c2", "c3"):
+    for name in ("c2", "c3", "c4"):
         wl = bench.WORKLOADS[name]
         E, N = wl["E"], wl["N"]
         obst, starts, goals = bench.make_world(wl, E, 0)
-        eng = MapfEngine(E, N, wl["H"], wl["W"], mode="primal", fov=wl["F"])
+        eng = MapfEngine(E, N, wl["H"], wl["W"], mode="primal", fov=wl["F"], shared_map=wl["warehouse"])
         eng.reset(obst, starts, goals)
         acts = torch.randint(0, 5, (E, N), device="cuda", dtype=torch.uint8)
         for _ in range(5):

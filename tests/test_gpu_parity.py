@@ -440,6 +440,24 @@ def test_host_buffer_entry_point_matches_device_path(case):
     bufs["actions"].copy_(torch.as_tensor(act))
     b.step_observe_host(io)
     assert np.array_equal(raw[3:].reshape(E, N, 4, F, F), _np(out["obs"]))
+    # the bit stream itself as the host output (no expansion): bit i == cell i
+    if b.bits_supported():
+        iob, bufsb, _, d2hb = b.make_host_io(obs_dtype="bits")
+        assert d2hb == d2h - obs_bytes + b.packed_obs_bytes()
+        bufsb["obs"].fill_(-1)
+        act = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        out = a.step_observe(torch.as_tensor(act, device="cuda"))
+        bufsb["actions"].copy_(torch.as_tensor(act))
+        b.step_observe_host(iob)
+        got = np.unpackbits(bufsb["obs"].numpy().view(np.uint8), bitorder="little")[:E * N * 4 * F * F]
+        assert np.array_equal(got, _np(out["obs"]).reshape(-1))
+        for k in ("reward", "terminated", "dones", "avail", "vec"):
+            assert torch.equal(out[k].cpu(), bufsb[k]), k
+    else:
+        from mapf_marl_b200.engine import MapfError
+        iob, bufsb, _, _ = b.make_host_io(obs_dtype="bits")
+        with pytest.raises(MapfError):
+            b.step_observe_host(iob)
 
 
 @pytest.mark.parametrize("case", [(64, 8, 20, 20, 11), (37, 32, 32, 32, 11), (9, 128, 64, 64, 11), (40, 6, 12, 12, 10),
@@ -470,6 +488,54 @@ def test_bit_packed_observation_equals_the_uint8_tensor(case):
     from mapf_marl_b200.engine import MapfError
     with pytest.raises(MapfError):
         gen.observe(dtype="bits")
+
+
+@pytest.mark.parametrize("shape", [(32, 32), (64, 64), (40, 28), (20, 20), (30, 30), (64, 31), (31, 64)],
+                         ids=lambda c: "%dx%d" % c)
+def test_goal_dist_serpentine_maps_deeper_than_255_levels(shape):
+    """The register BFS keeps distances in eight bit planes (255 levels); deeper maps (a serpentine corridor through
+    the whole grid) overflow to the shared-memory kernel.  Mixed batch: serpentine, open and random maps, goals on
+    both ends, with and without a dirty mask; every row width class of the store path (W % 8 == 0, W % 4 == 0, odd)."""
+    from mapf_marl_b200 import maps
+    from oracle.oracle import MODE_PRIMAL
+    H, W = shape
+    E, N = 6, 3
+    obst = np.zeros((E, H, W), np.int8)
+    for e in (0, 1, 2):                                   # wall rows with a gap at alternating ends
+        for r in range(1, H, 2):
+            obst[e, r, :] = 1
+            obst[e, r, (W - 1) if (r // 2) % 2 == 0 else 0] = 0
+    rs = np.random.RandomState(H * 100 + W)
+    obst[4] = (rs.rand(H, W) < 0.25)
+    obst[5] = (rs.rand(H, W) < 0.35)
+    starts = np.zeros((E, N, 2), np.int16)
+    goals = np.zeros((E, N, 2), np.int16)
+    for e in range(E):
+        free = np.argwhere(obst[e] == 0)
+        idx = rs.permutation(len(free))
+        starts[e] = free[idx[:N]]
+        goals[e] = free[idx[N:2 * N]]
+    last = H - 1 if (H - 1) % 2 == 0 else H - 2          # last corridor row
+    goals[0, 0] = (0, 0)                                   # far end of the corridor: depth ~ H*W/2
+    goals[1, 1] = (last, 0)
+    goals[2, 2] = (last, W - 1)
+    eng = _engine(E, N, H, W, mode="primal", fov=5)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=5)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    ref = orc.goal_dist()
+    if H * W >= 1024:
+        assert ref.max() > 255
+    got = _np(eng.goal_dist())
+    assert np.array_equal(got, ref)
+    assert np.array_equal(_np(eng.goal_dist(primal_costs=True)), orc.goal_dist(primal_costs=True))
+    dirty = np.zeros((E, N), np.uint8)
+    dirty[0, 0] = dirty[2, 2] = dirty[3, 1] = dirty[5, 0] = 1
+    out = torch.full((E, N, H, W), 77, dtype=torch.int16, device="cuda")
+    eng.goal_dist(dirty=dirty, out=out)
+    got = _np(out)
+    assert np.array_equal(got[dirty != 0], ref[dirty != 0])
+    assert (got[dirty == 0] == 77).all()
 
 
 def test_set_goals_and_dirty_bfs():
