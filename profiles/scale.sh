@@ -7,5 +7,5 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 $TR bench.py --gpus $N --no-cpu > $OUT/r1_bench_c3_${N}gpu.json 2> $OUT/r1_bench_c3_${N}gpu.err
 $TR bench.py --gpus $N --workload c5 --no-cpu --steps 200 --warmup 5 --e2e-steps 4 > $OUT/r1_bench_c5_${N}gpu.json 2> $OUT/r1_bench_c5_${N}gpu.err
 $TR bench.py --gpus $N --impl reference --steps 3 --warmup 1 > $OUT/r1_bench_reference_arm_${N}gpu.json 2>> $OUT/r1_bench_c3_${N}gpu.err
-tail -2 $OUT/r1_bench_c3_${N}gpu.err $OUT/r1_bench_c5_${N}gpu.err
+tail -n 2 $OUT/r1_bench_c3_${N}gpu.err $OUT/r1_bench_c5_${N}gpu.err
 cat $OUT/r1_bench_c3_${N}gpu.json $OUT/r1_bench_c5_${N}gpu.json $OUT/r1_bench_reference_arm_${N}gpu.json | cut -c1-900
