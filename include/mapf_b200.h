@@ -254,7 +254,10 @@ int mapf_step_agents(mapf_handle* h, const void* actions_dev, int act_dtype, int
  *   MAPF_OBS_FULLMAP:    obs_dev int8[E, H*W] (MAPF_I8); vec_dev ignored.
  *   MAPF_OBS_PRIMAL_FOV: obs_dev [E,N,4,F,F] of obs_dtype (MAPF_U8 or MAPF_F32; MAPF_BITS: the same cells as a
  *                        bit stream), channel order [poss_map, goal_map, goals_map, obs_map] (PRIMAL:386);
- *                        vec_dev double[E,N,3] = [dx/mag, dy/mag, mag] or NULL. */
+ *                        vec_dev double[E,N,3] = [dx/mag, dy/mag, mag] or NULL.
+ *   MAPF_OBS_PARTIAL_WINDOW (MARL_PARTIAL_ENV.get_obs, PARTIAL:312-382): obs_dev [E,N,2*W*W + 13*K] of MAPF_F64 (the
+ *                        reference's dtype) or MAPF_F32 (the same values rounded once at the store: what pymarl's
+ *                        episode batch keeps, src/run.py:133-140); vec_dev ignored. */
 int mapf_observe(mapf_handle* h, void* obs_dev, int obs_dtype, double* vec_dev, void* stream);
 
 /* mapf_step followed by mapf_observe in ONE kernel launch (state is staged in shared memory once). */

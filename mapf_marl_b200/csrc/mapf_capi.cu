@@ -310,6 +310,8 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   d.HW = d.H * d.W;
   d.F = c->obs_mode == MAPF_OBS_PRIMAL_FOV ? c->fov : 0;
   d.P = d.F / 2 > 1 ? d.F / 2 : 1;
+  // the PARTIAL observation reads its window straight from the padded bit rows: pad by half a window
+  if (c->obs_mode == MAPF_OBS_PARTIAL_WINDOW && c->obs_window / 2 > d.P) d.P = c->obs_window / 2;
   d.PR = d.H + 2 * d.P;
   d.RW = ((d.W + 2 * d.P - 1) >> 5) + 2;
   d.RW |= 1;   // odd row stride: the bit rows of 32 agents spread over all shared-memory banks (an even stride
@@ -545,7 +547,8 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
                                            "(mapf_obs_bits_supported)");
     if (fov && obs_dtype != MAPF_U8 && obs_dtype != MAPF_F32 && obs_dtype != MAPF_BITS)
       return fail(h, MAPF_ERR_INVALID_ARG, "FOV observations are MAPF_U8, MAPF_F32 or MAPF_BITS");
-    if (pwin && obs_dtype != MAPF_F64) return fail(h, MAPF_ERR_INVALID_ARG, "PARTIAL window observations are MAPF_F64");
+    if (pwin && obs_dtype != MAPF_F64 && obs_dtype != MAPF_F32)
+      return fail(h, MAPF_ERR_INVALID_ARG, "PARTIAL window observations are MAPF_F64 or MAPF_F32");
     if (!fov && !pwin && obs_dtype != MAPF_I8)
       return fail(h, MAPF_ERR_INVALID_ARG, "full-map observations are MAPF_I8");
   }
@@ -585,7 +588,7 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
                          (cudaStream_t)stream));
   }
   if (pwin && obs) {
-    CK((cudaError_t)mapf_launch_partial_obs(h->d, h->S, (double*)obs, stream));
+    CK((cudaError_t)mapf_launch_partial_obs(h->d, h->S, obs, obs_dtype == MAPF_F32, stream));
     h->launches++;
   }
   if (generic_obs) {
@@ -739,7 +742,7 @@ int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream)
   if (io->obs_host) {
     if (bits_out) obs_bytes = (EN * 4 * d.F * d.F + 31) / 32 * 4;
     else if (fov) obs_bytes = EN * 4 * d.F * d.F * (io->obs_dtype == MAPF_F32 ? 4 : 1);
-    else if (d.obs_mode == MAPF_OBS_PARTIAL_WINDOW) obs_bytes = EN * d.posz * 8;
+    else if (d.obs_mode == MAPF_OBS_PARTIAL_WINDOW) obs_bytes = EN * d.posz * (io->obs_dtype == MAPF_F32 ? 4 : 8);
     else obs_bytes = (size_t)d.E * d.HW;
   }
 #define LAZY(ptr, bytes)                                                \

@@ -130,7 +130,7 @@ int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty,
                     int primal_costs, void* stream, int* n_launches);   // 8-connected when primal_costs && d.diag
 int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int agent_lo, int agent_hi, const mapf_step_out& out,
                          void* stream, int* n_launches);
-int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, double* obs, void* stream);
+int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, void* obs, int f32, void* stream);
 int mapf_launch_partial_state(const MapfDims& d, const MapfState& S, long long* state, void* stream);
 int mapf_launch_export16(const MapfDims& d, const uint8_t* src_u8x2, int16_t* dst, void* stream);
 int mapf_tile_has_fov(int F);

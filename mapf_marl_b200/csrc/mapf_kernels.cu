@@ -1911,133 +1911,161 @@ __global__ void mapf_primal_costs_free_kernel(const MapfDims d, const uint8_t* d
 }
 
 // ------------------------------------------------------------------------------------------------
-// PARTIAL observation (get_obs_agent, PARTIAL:319-382): double[E][N][2*W*W + 13*K].
-// One block per environment: the agent-count grid is built in shared memory, each agent's K-1 nearest agents are
-// selected (stable order by L2 distance == order by squared integer distance, ties by index; the agent itself has
-// distance H*W, :560-567), then thread q writes element q of the environment's observation block (coalesced).
+// PARTIAL observation (get_obs_agent, PARTIAL:319-382): T[E][N][2*W*W + 13*K], T = double (the reference's dtype) or
+// float (what pymarl's episode batch stores, src/run.py:133-140: the double is rounded once, at the store).
+// One block of 128 threads per environment.
+//   * walls come straight from the obstacle bit rows (copied to shared memory; they are padded by half a window of
+//     wall cells, so a window cell is one unchecked bit test at `agent base + thread offset`), agent counts from a
+//     zero-filled byte map padded the same way;
+//   * the K-1 nearest agents of every agent (stable order by L2 distance == order by squared integer distance, ties
+//     by index; the agent itself has distance H*W, :560-567): one warp per agent, one lane per candidate, every key
+//     (distance^2 << 8 | index) computed once, K-1 warp-wide minima (REDUX); the square roots of the selected
+//     distances and the goal-vector features are computed afterwards with all lanes busy;
+//   * thread q decodes element q of an agent's observation ONCE (window cell or feature slot) and walks the N
+//     agents: for one agent consecutive lanes write consecutive elements (coalesced streaming stores).
 // ------------------------------------------------------------------------------------------------
-__global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, double* obs) {
+template <typename T>
+__global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* obs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int e = blockIdx.x, N = d.N, W = d.W, H = d.H, Wn = d.pW, K = d.pK;
-  // shared memory: per-cell code (bit 15 = wall, low bits = agents on the cell), positions, the K selected agents of
-  // every agent with their distances, the observer-independent features
+  const int e = blockIdx.x, N = d.N, Wn = d.pW, K = d.pK;
+  const int half = Wn / 2, Wp = d.W + Wn, Hp = d.H + Wn;     // count map: `half` empty cells on every side (+1 spare)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   size_t off = 0;
-  uint16_t* code = (uint16_t*)(smem_raw + off);              // [H*W]
-  off += ((size_t)d.HW * 2 + 15) & ~(size_t)15;
-  double* kdist = (double*)(smem_raw + off);                 // [N][K]
+  uint32_t* obw = (uint32_t*)(smem_raw + off);               // [bm_words] obstacle bit rows (padding = wall)
+  off += (size_t)d.bm_words * 4;
+  uint8_t* cnt = smem_raw + off;                             // [Hp*Wp] agents per cell (0 on walls)
+  off += ((size_t)Hp * Wp + 15) & ~(size_t)15;
+  double* kdist = (double*)(smem_raw + off);                 // [N][K] squared distances as keys first, then distances
   off += (size_t)N * K * 8;
   double* feat = (double*)(smem_raw + off);                  // [N][13]
   off += (size_t)N * 13 * 8;
+  int* cbase = (int*)(smem_raw + off);                       // [N] count-map index of the window's top-left cell
+  off += ((size_t)N * 4 + 15) & ~(size_t)15;
+  int* bbase = (int*)(smem_raw + off);                       // [N] bit index of the same cell in the obstacle rows
+  off += ((size_t)N * 4 + 15) & ~(size_t)15;
   uchar2* spos = (uchar2*)(smem_raw + off);                  // [N]
   off += ((size_t)N * 2 + 15) & ~(size_t)15;
   uint8_t* knn = smem_raw + off;                             // [N][K] ids, 255 = empty row
   const uchar2* goal = (const uchar2*)S.goal + (size_t)e * N;
   const uchar2* start = (const uchar2*)S.start + (size_t)e * N;
   const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
-  for (int a = threadIdx.x; a < N; a += blockDim.x) spos[a] = ((const uchar2*)S.pos)[(size_t)e * N + a];
-  for (int c = threadIdx.x; c < d.HW; c += blockDim.x) {
-    const int r = fast_div(c, d.invW), cc = c - r * W;
-    code[c] = bm_test(ob, d.RW, d.P, r, cc) ? (uint16_t)0x8000u : (uint16_t)0;
+  const int rowbits = d.RW * 32;
+  for (int i = threadIdx.x; i < (d.bm_words >> 2); i += blockDim.x) ((uint4*)obw)[i] = ((const uint4*)ob)[i];
+  for (int i = threadIdx.x; i < ((Hp * Wp + 15) >> 4); i += blockDim.x) ((uint4*)cnt)[i] = make_uint4(0, 0, 0, 0);
+  for (int a = threadIdx.x; a < N; a += blockDim.x) {
+    const uchar2 p = ((const uchar2*)S.pos)[(size_t)e * N + a];
+    spos[a] = p;
+    cbase[a] = (int)p.x * Wp + p.y;                          // map cell (i, j) sits at count-map (i + half, j + half)
+    bbase[a] = ((int)p.x + d.P - half) * rowbits + (int)p.y + d.P - half;   // d.P >= half (mapf_create)
   }
   __syncthreads();
   for (int a = threadIdx.x; a < N; a += blockDim.x) {
-    const int cell = (int)spos[a].x * W + spos[a].y;
-    atomicAdd((unsigned int*)(code + (cell & ~1)), 1u << (16 * (cell & 1)));
+    const uchar2 p = spos[a];
+    if (!bm_test(obw, d.RW, d.P, p.x, p.y)) byte_inc(cnt, cbase[a] + half * Wp + half);   // walls show 0 agents
   }
-  // K - 1 nearest agents of every agent: stable order by L2 distance == order by (squared integer distance, index),
-  // i.e. by the packed key (distance^2 << 8 | index); the agent itself sorts last (its distance is H*W, larger than
-  // any real one, :560-567).  `tpa` lanes share one agent: each scans a slice of the candidates, a shuffle-min
-  // combines them -- every warp of the block takes part.
+  // K - 1 nearest agents
   const int k_m1 = min(N, K) - 1;
-  int tpa = 1;
-  while (tpa < 32 && tpa * 2 * N <= (int)blockDim.x) tpa *= 2;
-  const int per_pass = blockDim.x / tpa, part = threadIdx.x & (tpa - 1);
-  constexpr int kSelf = 1 << 22, kNone = 0x7fffffff;         // kSelf > 2 * 254^2
-  for (int a0 = 0; a0 < N; a0 += per_pass) {
-    const int a = a0 + (int)(threadIdx.x / tpa);
-    const bool live = a < N;
-    const uchar2 p = live ? spos[a] : make_uchar2(0, 0);
-    int last_pk = -1;
-    if (live && part == 0) {
+  constexpr unsigned kSelf = 1u << 22, kNone = 0x7fffffffu;  // kSelf > 2 * 254^2
+  constexpr int kMaxPerLane = 8;                             // N <= 255
+  for (int a = warp; a < N; a += nwarps) {
+    const uchar2 p = spos[a];
+    unsigned key[kMaxPerLane];
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int b = lane + 32 * i;
+      key[i] = kNone;
+      if (b < N) {
+        const uchar2 q = spos[b];
+        const int dx = (int)p.x - (int)q.x, dy = (int)p.y - (int)q.y;
+        key[i] = (((b == a) ? kSelf : (unsigned)(dx * dx + dy * dy)) << 8) | (unsigned)b;
+      }
+      if (32 * (i + 1) >= N) break;
+    }
+    if (lane == 0) {
       knn[a * K] = (uint8_t)a;                               // knn_agents.insert(0, agent_id), :352
       kdist[a * K] = (double)d.HW;
     }
     for (int r = 0; r < K - 1; ++r) {
-      int best = kNone;
-      if (live && r < k_m1) {
-        for (int b = part; b < N; b += tpa) {
-          const uchar2 q = spos[b];
-          const int dx = (int)p.x - (int)q.x, dy = (int)p.y - (int)q.y;
-          const int pk = (((b == a) ? kSelf : dx * dx + dy * dy) << 8) | b;
-          if (pk > last_pk && pk < best) best = pk;
+      unsigned best = kNone;
+      if (r < k_m1) {
+        unsigned mine = kNone;
+#pragma unroll
+        for (int i = 0; i < kMaxPerLane; ++i) {
+          mine = min(mine, key[i]);
+          if (32 * (i + 1) >= N) break;
+        }
+        best = __reduce_min_sync(0xffffffffu, mine);
+#pragma unroll
+        for (int i = 0; i < kMaxPerLane; ++i) {
+          if (key[i] == best) key[i] = kNone;                // keys are unique (the index is part of them)
+          if (32 * (i + 1) >= N) break;
         }
       }
-      for (int o = tpa >> 1; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-      if (best != kNone) last_pk = best;
-      if (live && part == 0) {
-        const int b = best & 255, key = best >> 8;
+      if (lane == 0) {
+        const int b = (int)(best & 255u);
         knn[a * K + 1 + r] = best == kNone ? (uint8_t)255 : (uint8_t)b;
-        kdist[a * K + 1 + r] = best == kNone ? -1.0 : (b == a ? (double)d.HW : __dsqrt_rn((double)key));
+        // the squared distance for now (exact in a double); -1 marks an empty row, H*W^2 the agent itself
+        kdist[a * K + 1 + r] = best == kNone ? -1.0 : (b == a ? (double)d.HW * (double)d.HW : (double)(best >> 8));
       }
     }
   }
-  // the 13 features of every agent that do not depend on the observer (:353-371; column 11 = kdist)
-  for (int q = threadIdx.x; q < N * 13; q += blockDim.x) {
-    const int na = q / 13, f = q - 13 * na;
+  // positions, goal vectors and counters of every agent: one thread per agent (:353-371; column 11 = kdist)
+  for (int na = threadIdx.x; na < N; na += blockDim.x) {
     const uchar2 q0 = spos[na], g = goal[na], st = start[na];
     const int dx = (int)g.x - (int)q0.x, dy = (int)g.y - (int)q0.y;
-    double v;
-    switch (f) {
-      case 0: v = q0.x; break;
-      case 1: v = q0.y; break;
-      case 2: v = st.x; break;
-      case 3: v = st.y; break;
-      case 4: v = g.x; break;
-      case 5: v = g.y; break;
-      case 6:
-      case 7: {                                            // __update_goal_vectors, :957-972
-        const double norm = __dsqrt_rn((double)(dx * dx + dy * dy));
-        v = norm != 0.0 ? __ddiv_rn((double)(f == 6 ? dx : dy), norm) : 0.0;
-        break;
-      }
-      case 8: v = __dsqrt_rn((double)(dx * dx + dy * dy)); break;
-      case 9: v = S.pnode[(size_t)e * N + na]; break;
-      case 10: v = S.pedge[(size_t)e * N + na]; break;
-      case 11: v = 0.0; break;
-      default: v = S.agent_steps[(size_t)e * N + na]; break;
-    }
-    feat[q] = v;
+    const double norm = __dsqrt_rn((double)(dx * dx + dy * dy));   // __update_goal_vectors, :957-972
+    double* f = feat + na * 13;
+    f[0] = q0.x;
+    f[1] = q0.y;
+    f[2] = st.x;
+    f[3] = st.y;
+    f[4] = g.x;
+    f[5] = g.y;
+    f[6] = norm != 0.0 ? __ddiv_rn((double)dx, norm) : 0.0;
+    f[7] = norm != 0.0 ? __ddiv_rn((double)dy, norm) : 0.0;
+    f[8] = norm;
+    f[9] = S.pnode[(size_t)e * N + na];
+    f[10] = S.pedge[(size_t)e * N + na];
+    f[11] = 0.0;
+    f[12] = S.agent_steps[(size_t)e * N + na];
   }
   __syncthreads();
-  // output: thread t owns the element indices t, t + blockDim, ... of EVERY agent's block -- the index is decoded once
-  // (window cell or feature slot), then the agents are walked; for one agent consecutive lanes write consecutive
-  // doubles (coalesced streaming stores).
-  const int osz = d.posz, ww = Wn * Wn, half = Wn / 2;
-  double* out = obs + (size_t)e * N * osz;
+  for (int q = threadIdx.x; q < N * K; q += blockDim.x) {    // squared distances -> distances, all lanes busy
+    const double v = kdist[q];
+    if (v > 0.0 && q % K != 0) kdist[q] = __dsqrt_rn(v);
+  }
+  __syncthreads();
+  const int osz = d.posz, ww = Wn * Wn;
+  T* out = obs + (size_t)e * N * osz;
   for (int idx = threadIdx.x; idx < osz; idx += blockDim.x) {
-    double* o = out + idx;
+    T* o = out + idx;
     if (idx < 2 * ww) {                                      // the two W x W maps, :326-342
       const bool agents_map = idx >= ww;
       const int c = agents_map ? idx - ww : idx;
       const int wi = c / Wn, wj = c - wi * Wn;
-      const int di = wi - half, dj = wj - half;
-      for (int a = 0; a < N; ++a, o += osz) {
-        const uchar2 p = spos[a];
-        const int i = (int)p.x + di, jx = (int)p.y + dj;
-        unsigned int cd = 0x8000u;                           // outside the map counts as a wall
-        if ((unsigned)i < (unsigned)H && (unsigned)jx < (unsigned)W) cd = code[i * W + jx];
-        const bool wall = (cd & 0x8000u) != 0;
-        const double v = agents_map ? (wall ? 0.0 : (double)(cd & 0x7fffu)) : (wall ? 1.0 : 0.0);
-        __stcs(o, v);
+      if (!agents_map) {                                     // 1 on walls and outside the map
+        const int boff = wi * rowbits + wj;
+#pragma unroll 4
+        for (int a = 0; a < N; ++a, o += osz) {
+          const int bit = bbase[a] + boff;
+          __stcs(o, (T)((obw[bit >> 5] >> (bit & 31)) & 1u));
+        }
+      } else {                                               // agents standing on the cell
+        const uint8_t* cp = cnt + wi * Wp + wj;
+#pragma unroll 4
+        for (int a = 0; a < N; ++a, o += osz) __stcs(o, (T)(int)cp[cbase[a]]);
       }
     } else {                                                 // K x 13 features, :344-371
       const int f0 = idx - 2 * ww;
       const int row = f0 / 13, f = f0 - 13 * row;
+      const double* src = (f == 11) ? kdist + row : feat + f;
+      const int stride = (f == 11) ? K : 0;
+#pragma unroll 4
       for (int a = 0; a < N; ++a, o += osz) {
         const int na = knn[a * K + row];
-        double v = -1.0;
-        if (na != 255) v = (f == 11) ? kdist[a * K + row] : feat[na * 13 + f];
-        __stcs(o, v);
+        // column 11 is the observer's distance to the row's agent, the others are that agent's own features
+        const double v = (na == 255) ? -1.0 : ((f == 11) ? src[a * stride] : src[na * 13]);
+        __stcs(o, (T)v);
       }
     }
   }
@@ -2217,14 +2245,20 @@ extern "C" int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int a
   return (int)err;
 }
 
-extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, double* obs, void* stream) {
-  const size_t smem = (((size_t)d.HW * 2 + 15) & ~(size_t)15) + (size_t)d.N * d.pK * 8 + (size_t)d.N * 13 * 8 +
+extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, void* obs, int f32, void* stream) {
+  const size_t smem = (size_t)d.bm_words * 4 + (((size_t)(d.H + d.pW) * (d.W + d.pW) + 15) & ~(size_t)15) +
+                      (size_t)d.N * d.pK * 8 + (size_t)d.N * 13 * 8 + 2 * (((size_t)d.N * 4 + 15) & ~(size_t)15) +
                       (((size_t)d.N * 2 + 15) & ~(size_t)15) + (size_t)d.N * d.pK + 16;
+  const int threads = 128;   // more threads per block were measured slower (fewer blocks overlap their serial phases)
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(mapf_partial_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = f32 ? cudaFuncSetAttribute(mapf_partial_obs_kernel<float>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(mapf_partial_obs_kernel<double>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  mapf_partial_obs_kernel<<<d.E, 128, smem, (cudaStream_t)stream>>>(d, S, obs);
+  if (f32) mapf_partial_obs_kernel<float><<<d.E, threads, smem, (cudaStream_t)stream>>>(d, S, (float*)obs);
+  else mapf_partial_obs_kernel<double><<<d.E, threads, smem, (cudaStream_t)stream>>>(d, S, (double*)obs);
   return (int)cudaGetLastError();
 }
 

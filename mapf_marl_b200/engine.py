@@ -291,6 +291,10 @@ class MapfEngine:
             vec = self._buf("vec", (self.E, self.N, 3), torch.float64) if want_vec else None
             return obs, vec, (U8 if dtype == torch.uint8 else F32)
         if self.obs_mode == OBS_PARTIAL_WINDOW:
+            # float64 like the reference's get_obs; float32 = the same values rounded once at the store (what
+            # pymarl's episode batch keeps, src/run.py:133-140)
+            if dtype == torch.float32:
+                return self._buf("obs_partial32", (self.E, self.N, self.obs_size), torch.float32), None, F32
             return self._buf("obs_partial", (self.E, self.N, self.obs_size), torch.float64), None, F64
         obs = self._buf("state", (self.E, self.H * self.W), torch.int8)
         return obs, None, I8

@@ -46,6 +46,10 @@ def main():
                      "agent_steps_per_s": E * N / (ms_fused * 1e-3), "obs_bytes_per_step": obs.numel() * obs.element_size(),
                      "obs_GBps": obs.numel() * obs.element_size() / (ms_obs * 1e-3) / 1e9}
         if mode == "partial":
+            ms_obs32 = timed(lambda t: eng.observe(dtype=torch.float32), 300)
+            o32, _ = eng.observe(dtype=torch.float32)
+            out[mode]["observe_f32_ms"] = ms_obs32
+            out[mode]["obs_f32_GBps"] = o32.numel() * 4 / (ms_obs32 * 1e-3) / 1e9
             ms_reset = timed(lambda t: eng.reset(obst, starts, goals), 5, 1)
             out[mode]["reset_with_goal_maps_ms"] = ms_reset
         eng.close()
