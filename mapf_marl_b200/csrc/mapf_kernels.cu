@@ -1935,7 +1935,7 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
   off += (size_t)d.bm_words * 4;
   uint8_t* cnt = smem_raw + off;                             // [Hp*Wp] agents per cell (0 on walls)
   off += ((size_t)Hp * Wp + 15) & ~(size_t)15;
-  double* kdist = (double*)(smem_raw + off);                 // [N][K] squared distances as keys first, then distances
+  double* kdist = (double*)(smem_raw + off);                 // [N][K] distances to the selected agents
   off += (size_t)N * K * 8;
   double* feat = (double*)(smem_raw + off);                  // [N][13]
   off += (size_t)N * 13 * 8;
@@ -1945,6 +1945,8 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
   off += ((size_t)N * 4 + 15) & ~(size_t)15;
   uchar2* spos = (uchar2*)(smem_raw + off);                  // [N]
   off += ((size_t)N * 2 + 15) & ~(size_t)15;
+  unsigned* kkey = (unsigned*)(smem_raw + off);              // [N][K] selected keys (distance^2 << 8 | index)
+  off += ((size_t)N * K * 4 + 15) & ~(size_t)15;
   uint8_t* knn = smem_raw + off;                             // [N][K] ids, 255 = empty row
   const uchar2* goal = (const uchar2*)S.goal + (size_t)e * N;
   const uchar2* start = (const uchar2*)S.start + (size_t)e * N;
@@ -1981,32 +1983,32 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
       }
       if (32 * (i + 1) >= N) break;
     }
-    if (lane == 0) {
-      knn[a * K] = (uint8_t)a;                               // knn_agents.insert(0, agent_id), :352
-      kdist[a * K] = (double)d.HW;
+    // round r's winner stays in lane r + 1; one parallel store after the rounds
+    unsigned sel = lane == 0 ? (unsigned)a : kNone;          // row 0: knn_agents.insert(0, agent_id), :352
+    for (int r = 0; r < k_m1; ++r) {
+      unsigned mine = kNone;
+#pragma unroll
+      for (int i = 0; i < kMaxPerLane; ++i) {
+        mine = min(mine, key[i]);
+        if (32 * (i + 1) >= N) break;
+      }
+      const unsigned best = __reduce_min_sync(0xffffffffu, mine);
+#pragma unroll
+      for (int i = 0; i < kMaxPerLane; ++i) {
+        if (key[i] == best) key[i] = kNone;                  // keys are unique (the index is part of them)
+        if (32 * (i + 1) >= N) break;
+      }
+      if (lane == r + 1) sel = best;
+      if (r + 1 >= 32 && lane == 0) {                        // more than 32 rows (K > 32): stored as they come
+        knn[a * K + r + 1] = best == kNone ? (uint8_t)255 : (uint8_t)(best & 255u);
+        kkey[a * K + r + 1] = best;
+      }
     }
-    for (int r = 0; r < K - 1; ++r) {
-      unsigned best = kNone;
-      if (r < k_m1) {
-        unsigned mine = kNone;
-#pragma unroll
-        for (int i = 0; i < kMaxPerLane; ++i) {
-          mine = min(mine, key[i]);
-          if (32 * (i + 1) >= N) break;
-        }
-        best = __reduce_min_sync(0xffffffffu, mine);
-#pragma unroll
-        for (int i = 0; i < kMaxPerLane; ++i) {
-          if (key[i] == best) key[i] = kNone;                // keys are unique (the index is part of them)
-          if (32 * (i + 1) >= N) break;
-        }
-      }
-      if (lane == 0) {
-        const int b = (int)(best & 255u);
-        knn[a * K + 1 + r] = best == kNone ? (uint8_t)255 : (uint8_t)b;
-        // the squared distance for now (exact in a double); -1 marks an empty row, H*W^2 the agent itself
-        kdist[a * K + 1 + r] = best == kNone ? -1.0 : (b == a ? (double)d.HW * (double)d.HW : (double)(best >> 8));
-      }
+    for (int r = lane; r < K; r += 32) {
+      if (r >= 32 && r <= k_m1) continue;                    // written by its round
+      const unsigned v = r < 32 ? sel : kNone;               // rows past the last round are empty
+      knn[a * K + r] = v == kNone ? (uint8_t)255 : (uint8_t)(v & 255u);
+      kkey[a * K + r] = v;
     }
   }
   // positions, goal vectors and counters of every agent: one thread per agent (:353-371; column 11 = kdist)
@@ -2030,9 +2032,10 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
     f[12] = S.agent_steps[(size_t)e * N + na];
   }
   __syncthreads();
-  for (int q = threadIdx.x; q < N * K; q += blockDim.x) {    // squared distances -> distances, all lanes busy
-    const double v = kdist[q];
-    if (v > 0.0 && q % K != 0) kdist[q] = __dsqrt_rn(v);
+  for (int q = threadIdx.x; q < N * K; q += blockDim.x) {    // keys -> distances, all lanes busy
+    const unsigned v = kkey[q];
+    // row 0 is the agent itself: distance H*W (:560-567); empty rows: -1
+    kdist[q] = (q % K == 0) ? (double)d.HW : (v == kNone ? -1.0 : __dsqrt_rn((double)(v >> 8)));
   }
   __syncthreads();
   const int osz = d.posz, ww = Wn * Wn;
@@ -2248,7 +2251,8 @@ extern "C" int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int a
 extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, void* obs, int f32, void* stream) {
   const size_t smem = (size_t)d.bm_words * 4 + (((size_t)(d.H + d.pW) * (d.W + d.pW) + 15) & ~(size_t)15) +
                       (size_t)d.N * d.pK * 8 + (size_t)d.N * 13 * 8 + 2 * (((size_t)d.N * 4 + 15) & ~(size_t)15) +
-                      (((size_t)d.N * 2 + 15) & ~(size_t)15) + (size_t)d.N * d.pK + 16;
+                      (((size_t)d.N * 2 + 15) & ~(size_t)15) + (((size_t)d.N * d.pK * 4 + 15) & ~(size_t)15) +
+                      (size_t)d.N * d.pK + 16;
   const int threads = 128;   // more threads per block were measured slower (fewer blocks overlap their serial phases)
   if (smem > 48 * 1024) {
     cudaError_t e = f32 ? cudaFuncSetAttribute(mapf_partial_obs_kernel<float>,

@@ -712,7 +712,8 @@ def test_partial_engine_matches_reference_trace(name):
 
 
 @pytest.mark.parametrize("case", [(96, 15, 8, 8, 0.0, 5, 5, 30), (40, 32, 32, 32, 0.2, 11, 8, 60),
-                                  (25, 7, 12, 12, 0.1, 4, 9, 20), (8, 100, 24, 24, 0.05, 3, 4, 15)],
+                                  (25, 7, 12, 12, 0.1, 4, 9, 20), (8, 100, 24, 24, 0.05, 3, 4, 15),
+                                  (6, 70, 20, 20, 0.05, 6, 40, 8)],
                          ids=lambda c: "E%d_N%d_%dx%d" % c[:4])
 def test_partial_batch_matches_oracle(case):
     from oracle.oracle import MODE_PARTIAL
