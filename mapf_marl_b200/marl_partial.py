@@ -31,7 +31,7 @@ class MARL_PARTIAL_ENV(MultiAgentEnv):
                  seed=None, render='human', move_reward=-0.01, stay_reward=-0.02, stay_goal_reward=0,
                  node_collide_reward=-1, edge_collide_reward=-1, env_collide_reward=-1, complete_reward=1000,
                  complete_fac=1.5, debug=False, visual=False, gamma=0.99, output=False, n_envs=1, device=None,
-                 strict=True):
+                 strict=True, obs_float32=False):
         assert os.path.exists(grid_file_path)
         if output:
             raise NotImplementedError("output=True (randomised collision repair, marl_partial.py:645-820) is "
@@ -44,6 +44,9 @@ class MARL_PARTIAL_ENV(MultiAgentEnv):
         self._debug_mode = debug
         self._output_mode = output
         self._strict = strict
+        # vector envs only: observations as float32 device tensors (the dtype pymarl's episode batch stores,
+        # src/run.py:133-140), written by the kernel itself instead of float64 followed by a cast
+        self._obs_dtype = torch.float32 if (obs_float32 and int(n_envs) > 1) else torch.float64
         self._n_agents = self.n_agents = n_agents
         self.n_envs = int(n_envs)
         self._seed = random.randint(0, 9999)         # same draws, in the same order, as marl_partial.py:59-62
@@ -153,7 +156,7 @@ class MARL_PARTIAL_ENV(MultiAgentEnv):
                                                   'node': out["node"], 'edge': out["edge"]}
 
     def get_obs(self):
-        obs, _ = self.engine.observe()
+        obs, _ = self.engine.observe(dtype=self._obs_dtype)
         return obs[0].cpu().numpy() if self.n_envs == 1 else obs
 
     def get_obs_agent(self, agent_id):

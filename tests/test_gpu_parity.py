@@ -860,9 +860,11 @@ def test_c4_shape_lifelong_goal_reassignment_matches_oracle(overlap):
     assert int(head.sum()) > E * N // 4          # several hundred reassignments happened
 
 
-def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path):
+@pytest.mark.parametrize("obs_float32", [False, True])
+def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path, obs_float32):
     """The pymarl rollout loop over a device-resident vector env: what lands in the batch equals a rollout of the
-    CPU oracle driven by the same actions (PARTIAL env, the one the reference registers)."""
+    CPU oracle driven by the same actions (PARTIAL env, the one the reference registers); with obs_float32 the kernel
+    writes the batch's float32 observations itself."""
     from mapf_marl_b200.batched_runner import BatchedRunner
     from mapf_marl_b200.marl_partial import MARL_PARTIAL_ENV
     from oracle.oracle import MODE_PARTIAL
@@ -872,7 +874,8 @@ def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path
     kw = dict(obs_window=5, obs_knn_agents=4, move_reward=-0.01, stay_reward=-0.02, stay_goal_reward=0,
               node_collide_reward=-1, edge_collide_reward=-1, env_collide_reward=-1, complete_reward=1000,
               complete_fac=1.5, gamma=0.99)
-    env = MARL_PARTIAL_ENV(mp, sp, n_agents=N, episode_limit=limit, render="none", n_envs=B, **kw)
+    env = MARL_PARTIAL_ENV(mp, sp, n_agents=N, episode_limit=limit, render="none", n_envs=B,
+                           obs_float32=obs_float32, **kw)
 
     class RandomMAC:
         def __init__(self):
@@ -892,6 +895,7 @@ def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path
     mac = RandomMAC()
     runner = BatchedRunner(env, mac)
     batch = runner.run(test_mode=False)
+    assert env.get_obs().dtype == (torch.float32 if obs_float32 else torch.float64)
     H, W = g["obst"].shape
     orc = _oracle(B, N, H, W, MODE_PARTIAL, episode_limit=limit)
     orc.partial_config(**kw)
