@@ -1948,6 +1948,8 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
   unsigned* kkey = (unsigned*)(smem_raw + off);              // [N][K] selected keys (distance^2 << 8 | index)
   off += ((size_t)N * K * 4 + 15) & ~(size_t)15;
   uint8_t* knn = smem_raw + off;                             // [N][K] ids, 255 = empty row
+  off += ((size_t)N * K + 15) & ~(size_t)15;
+  unsigned char* dec_raw = smem_raw + off;                  // [posz] u32 decode table of the sector-aligned path
   const uchar2* goal = (const uchar2*)S.goal + (size_t)e * N;
   const uchar2* start = (const uchar2*)S.start + (size_t)e * N;
   const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
@@ -1998,8 +2000,9 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
         if (key[i] == best) key[i] = kNone;                  // keys are unique (the index is part of them)
         if (32 * (i + 1) >= N) break;
       }
-      if (lane == r + 1) sel = best;
-      if (r + 1 >= 32 && lane == 0) {                        // more than 32 rows (K > 32): stored as they come
+      if (r < 31) {
+        if (lane == r + 1) sel = best;
+      } else if (lane == 0) {                                // more than 32 rows (K > 32): stored as they come
         knn[a * K + r + 1] = best == kNone ? (uint8_t)255 : (uint8_t)(best & 255u);
         kkey[a * K + r + 1] = best;
       }
@@ -2040,6 +2043,62 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
   __syncthreads();
   const int osz = d.posz, ww = Wn * Wn;
   T* out = obs + (size_t)e * N * osz;
+  if (sizeof(T) == 8 && (osz & 3) != 0) {
+    // float64 with agent blocks that do not start on 32-byte sectors (c3-shaped: 307 elements): a warp's 256-byte
+    // store would straddle sectors at both ends, and those partial-sector writes hold the kernel at 4.3 TB/s (blocks
+    // of 4k elements reach 5.6-6.3 TB/s, profiles/partial_align_probe.py).  Here the element -> source decode goes
+    // through a table in shared memory, and for every agent the threads are shifted so that each warp's store starts
+    // on a sector of the output.
+    uint32_t* dec = (uint32_t*)dec_raw;                     // [osz]: kind << 28 | payload
+    for (int idx = threadIdx.x; idx < osz; idx += blockDim.x) {
+      uint32_t v;
+      if (idx < 2 * ww) {
+        const bool agents_map = idx >= ww;
+        const int c = agents_map ? idx - ww : idx;
+        const int wi = c / Wn, wj = c - wi * Wn;
+        v = agents_map ? ((1u << 28) | (uint32_t)(wi * Wp + wj)) : (uint32_t)(wi * rowbits + wj);
+      } else {
+        const int f0 = idx - 2 * ww;
+        const int row = f0 / 13, f = f0 - 13 * row;
+        v = ((f == 11 ? 3u : 2u) << 28) | (uint32_t)(f == 11 ? row : row * 16 + f);
+      }
+      dec[idx] = v;
+    }
+    __syncthreads();
+    // agents a = 4j + k share their shift (4j * osz elements are a whole number of sectors): for each k the thread
+    // decodes its element once and walks the agents k, k + 4, ... exactly like the unshifted loops below
+    const size_t step4 = (size_t)4 * osz;
+    for (int base = 0; base < osz + 3; base += blockDim.x) {
+#pragma unroll 1
+      for (int k = 0; k < 4 && k < N; ++k) {
+        double* o = (double*)out + (size_t)k * osz;
+        const int idx = base + (int)threadIdx.x - (int)(((uintptr_t)o >> 3) & 3);   // elements past the last sector start
+        if (idx < 0 || idx >= osz) continue;
+        o += idx;
+        const uint32_t dv = dec[idx];
+        const int kind = (int)(dv >> 28), pay = (int)(dv & 0x0fffffffu);
+        if (kind == 0) {                                     // 1 on walls and outside the map
+          for (int a = k; a < N; a += 4, o += step4) {
+            const int bit = bbase[a] + pay;
+            __stcs(o, (double)((obw[bit >> 5] >> (bit & 31)) & 1u));
+          }
+        } else if (kind == 1) {                              // agents standing on the cell
+          const uint8_t* cp = cnt + pay;
+          for (int a = k; a < N; a += 4, o += step4) __stcs(o, (double)(int)cp[cbase[a]]);
+        } else if (kind == 3) {                              // distance to the row's agent
+          for (int a = k; a < N; a += 4, o += step4)
+            __stcs(o, (knn[a * K + pay] == 255) ? -1.0 : kdist[a * K + pay]);
+        } else {                                             // the row's agent's own features
+          const int row = pay >> 4, f = pay & 15;
+          for (int a = k; a < N; a += 4, o += step4) {
+            const int na = knn[a * K + row];
+            __stcs(o, (na == 255) ? -1.0 : feat[na * 13 + f]);
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int idx = threadIdx.x; idx < osz; idx += blockDim.x) {
     T* o = out + idx;
     if (idx < 2 * ww) {                                      // the two W x W maps, :326-342
@@ -2252,7 +2311,7 @@ extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, vo
   const size_t smem = (size_t)d.bm_words * 4 + (((size_t)(d.H + d.pW) * (d.W + d.pW) + 15) & ~(size_t)15) +
                       (size_t)d.N * d.pK * 8 + (size_t)d.N * 13 * 8 + 2 * (((size_t)d.N * 4 + 15) & ~(size_t)15) +
                       (((size_t)d.N * 2 + 15) & ~(size_t)15) + (((size_t)d.N * d.pK * 4 + 15) & ~(size_t)15) +
-                      (size_t)d.N * d.pK + 16;
+                      (((size_t)d.N * d.pK + 15) & ~(size_t)15) + (size_t)d.posz * 4 + 16;
   const int threads = 128;   // more threads per block were measured slower (fewer blocks overlap their serial phases)
   if (smem > 48 * 1024) {
     cudaError_t e = f32 ? cudaFuncSetAttribute(mapf_partial_obs_kernel<float>,
