@@ -385,6 +385,10 @@ class MapfEngine:
             elif self.obs_mode == OBS_PRIMAL_FOV:
                 bufs["obs"] = torch.empty((E, N, 4, self.F, self.F), dtype=obs_dtype).pin_memory()
                 odt = U8 if obs_dtype == torch.uint8 else F32
+            elif self.obs_mode == OBS_PARTIAL_WINDOW:
+                pdt = torch.float32 if obs_dtype == torch.float32 else torch.float64
+                bufs["obs"] = torch.empty((E, N, self.obs_size), dtype=pdt).pin_memory()
+                odt = F32 if pdt == torch.float32 else F64
             else:
                 bufs["obs"] = torch.empty((E, self.H * self.W), dtype=torch.int8).pin_memory()
         if "vec" in want and self.obs_mode == OBS_PRIMAL_FOV:

@@ -460,6 +460,31 @@ def test_host_buffer_entry_point_matches_device_path(case):
             b.step_observe_host(iob)
 
 
+@pytest.mark.parametrize("mode", ["grid", "partial"])
+def test_host_buffer_entry_point_other_modes(mode):
+    """mapf_step_observe_host for the GRID (int8 full map) and PARTIAL (float64 / float32 window + K-nearest block)
+    observations: dense copies, equal to the device path."""
+    from mapf_marl_b200 import maps
+    E, N, H, W = 40, 6, 14, 14
+    obst, starts, goals = maps.synthetic_batch(21, E, H, W, 0.15, N, distinct=0)
+    kw = dict(episode_limit=50) if mode == "grid" else dict(episode_limit=50, obs_window=5, obs_knn_agents=4)
+    a = _engine(E, N, H, W, mode=mode, **kw)
+    b = _engine(E, N, H, W, mode=mode, **kw)
+    a.reset(obst, starts, goals)
+    b.reset(obst, starts, goals)
+    rs = np.random.RandomState(3)
+    for dt in ((torch.float64, torch.float32) if mode == "partial" else (torch.int8,)):
+        io, bufs, h2d, d2h = b.make_host_io(obs_dtype=dt, want=("reward", "terminated", "dones", "avail", "obs"))
+        assert bufs["obs"].dtype == dt
+        for t in range(3):
+            act = rs.randint(0, 5, (E, N)).astype(np.uint8)
+            out = a.step_observe(torch.as_tensor(act, device="cuda"), dtype=dt)
+            bufs["actions"].copy_(torch.as_tensor(act))
+            b.step_observe_host(io)
+            for k in ("reward", "terminated", "dones", "avail", "obs"):
+                assert torch.equal(out[k].cpu(), bufs[k]), (k, t, dt)
+
+
 @pytest.mark.parametrize("case", [(64, 8, 20, 20, 11), (37, 32, 32, 32, 11), (9, 128, 64, 64, 11), (40, 6, 12, 12, 10),
                                   (24, 16, 16, 16, 5)], ids=lambda c: "E%d_N%d_%dx%d_F%d" % c)
 def test_bit_packed_observation_equals_the_uint8_tensor(case):
