@@ -1688,24 +1688,51 @@ __device__ __forceinline__ bool bfs_warp_one(const MapfDims& d, const MapfState&
     if (r >= H) continue;
     int16_t* grow = gd + (size_t)r * W;
     if ((W & 3) == 0) {
+      // 32 cells at a time: an 8 x 8 bit-matrix transpose per byte lane (three rounds of masked delta swaps between
+      // the plane words) leaves, in byte g of word r, the low byte of cell 8g + r; PRMTs gather them into cell order
+      // and interleave the high bytes (0xff on not-visited cells)
 #pragma unroll
-      for (int q = 0; q < RB / 4; q += 2) {
-        if (4 * q >= W) break;
-        uint32_t o[4];
+      for (int hh = 0; hh < RB / 32; ++hh) {
+        if (32 * hh >= W) break;
+        uint32_t a[NP];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t lo = 0;
+        for (int p = 0; p < NP; ++p) a[p] = (uint32_t)(D[k][p] >> (32 * hh));
+#define BFS_SWAP(x, y, sft, m)                         \
+  do {                                                 \
+    const uint32_t t_ = (((x) >> (sft)) ^ (y)) & (m);  \
+    (y) ^= t_;                                         \
+    (x) ^= t_ << (sft);                                \
+  } while (0)
+        BFS_SWAP(a[0], a[1], 1, 0x55555555u); BFS_SWAP(a[2], a[3], 1, 0x55555555u);
+        BFS_SWAP(a[4], a[5], 1, 0x55555555u); BFS_SWAP(a[6], a[7], 1, 0x55555555u);
+        BFS_SWAP(a[0], a[2], 2, 0x33333333u); BFS_SWAP(a[1], a[3], 2, 0x33333333u);
+        BFS_SWAP(a[4], a[6], 2, 0x33333333u); BFS_SWAP(a[5], a[7], 2, 0x33333333u);
+        BFS_SWAP(a[0], a[4], 4, 0x0f0f0f0fu); BFS_SWAP(a[1], a[5], 4, 0x0f0f0f0fu);
+        BFS_SWAP(a[2], a[6], 4, 0x0f0f0f0fu); BFS_SWAP(a[3], a[7], 4, 0x0f0f0f0fu);
+#undef BFS_SWAP
+        const uint32_t nvh = (uint32_t)(nv >> (32 * hh));
 #pragma unroll
-          for (int p = 0; p < NP; ++p) lo |= spread4((uint32_t)(D[k][p] >> (4 * (q + h))) & 0xfu) << p;
-          const uint32_t hi = spread4((uint32_t)(nv >> (4 * (q + h))) & 0xfu) * 0xffu;
-          o[2 * h] = __byte_perm(lo, hi, 0x5140);         // cells 0,1 of the group: (lo0, hi0, lo1, hi1)
-          o[2 * h + 1] = __byte_perm(lo, hi, 0x7362);     // cells 2,3
-        }
-        if ((W & 7) == 0) {
-          *(uint4*)(grow + 4 * q) = make_uint4(o[0], o[1], o[2], o[3]);
-        } else {
-          *(uint2*)(grow + 4 * q) = make_uint2(o[0], o[1]);
-          if (4 * (q + 1) < W) *(uint2*)(grow + 4 * (q + 1)) = make_uint2(o[2], o[3]);
+        for (int q = 0; q < 8; q += 2) {                       // groups of four cells, two groups per 16-byte store
+          if (32 * hh + 4 * q >= W) break;
+          uint32_t o[4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            constexpr uint32_t kPick[4] = {0x0040u, 0x0051u, 0x0062u, 0x0073u};   // byte g of x, byte g of y
+            const int g = (q + h) >> 1, r0 = 4 * ((q + h) & 1);
+            const uint32_t t01 = __byte_perm(a[r0], a[r0 + 1], kPick[g]);
+            const uint32_t t23 = __byte_perm(a[r0 + 2], a[r0 + 3], kPick[g]);
+            const uint32_t lo = __byte_perm(t01, t23, 0x5410);
+            const uint32_t hi = spread4((nvh >> (4 * (q + h))) & 0xfu) * 0xffu;
+            o[2 * h] = __byte_perm(lo, hi, 0x5140);         // cells 0,1 of the group: (lo0, hi0, lo1, hi1)
+            o[2 * h + 1] = __byte_perm(lo, hi, 0x7362);     // cells 2,3
+          }
+          int16_t* dst = grow + 32 * hh + 4 * q;
+          if ((W & 7) == 0) {
+            *(uint4*)dst = make_uint4(o[0], o[1], o[2], o[3]);
+          } else {
+            *(uint2*)dst = make_uint2(o[0], o[1]);
+            if (32 * hh + 4 * (q + 1) < W) *(uint2*)(dst + 4) = make_uint2(o[2], o[3]);
+          }
         }
       }
     } else {
