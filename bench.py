@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--f32", action="store_true", help="emit float32 observations instead of uint8")
+    ap.add_argument("--lean", action="store_true",
+                    help="no repeat passes and no extra clock-sampling load: a fixed launch order for the ncu recipes")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: library banners (NCCL prints its version to stdout) are sent to stderr
     global _REAL_STDOUT
@@ -298,7 +300,7 @@ def main():
     ms_step = ms_total / args.steps
     # four more passes over the same K steps (informational: spread of the measurement; `value` is the first pass)
     repeats = [ms_step]
-    for _ in range(4):
+    for _ in range(0 if args.lean else 4):
         if graph is not None:
             repeats.append(timed(lambda t: graph.replay(), args.steps // chunk, 0) / args.steps)
         else:
@@ -308,7 +310,7 @@ def main():
     ms_eager = timed(lambda t: eng.step_observe(pool[t % 16], want=want, dtype=odt), n_eager, 3) / n_eager
     # the clock sampler (2 ms period) keeps running through the eager leg of the same kernel; a very short run
     # (small --steps) is followed by more of the same load, untimed, until the sampler has seen about 0.3 s of it
-    if sampler:
+    if sampler and not args.lean:
         t_load = time.perf_counter()
         while len(sampler.sm) < 100 and time.perf_counter() - t_load < 0.5:
             for t in range(50):

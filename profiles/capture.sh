@@ -1,7 +1,7 @@
 #!/bin/bash
 # Profiling recipe for the c3 bench command (run on the GPU box through gpurun, ONE GPU):
 #   1. the plain run must exit 0 first; 2. launch list; 3. one `--set full` capture per kernel of interest.
-# Tile-kernel launch order inside `bench.py --steps 5 --warmup 3`: 0-25 fused step+obs (eager warm-up, graph replays,
+# Tile-kernel launch order inside `bench.py --steps 5 --warmup 3 --lean`: 0-25 fused step+obs (eager warm-up, graph replays,
 # eager leg), 26-33 fused with bit-packed observation output, 34-41 observe only, 42-49 step only.
 # gpurun brings back at most 64 MiB of gpurun_out/ (local contents included) and a report with sources is ~11 MB:
 # the reports are written to /tmp on the box, summarised there, and only the fused one travels (KEEP_REPORTS=1: all).
@@ -10,7 +10,7 @@ TAG=${1:-r1}
 OUT=gpurun_out
 REP=/tmp/ncu_${TAG}
 mkdir -p $REP
-BENCH="python bench.py --steps 5 --warmup 3 --no-cpu --e2e-steps 2"
+BENCH="python bench.py --steps 5 --warmup 3 --no-cpu --e2e-steps 2 --lean"
 $BENCH > $OUT/${TAG}_plain.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_c3.csv $BENCH > $OUT/${TAG}_ncu_launches.log 2>&1
 NCU="ncu --set full --clock-control none --import-source on -f"
