@@ -236,3 +236,25 @@ def test_host_unpack_pool_progressive_publish():
         assert np.array_equal(out[:cells], want)
         assert (out[cells:] == 7).all()
     lib.mapf_unpack_pool_destroy(pool)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU: exactly one JSON line
+    on stdout with the contract's keys, the C oracle port as `cpu_baseline`, zero bytes in `e2e`."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--workload", "c2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "agent-steps/sec (step+obs)" and d["unit"] == "agent-steps/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
