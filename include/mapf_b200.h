@@ -280,6 +280,8 @@ int mapf_obs_bits_supported(const mapf_handle* h);
 /* packed != 0 (default): bit-packed PCIe transport in mapf_step_observe_host when supported; 0: dense copies.
  * Returns the mode now in effect (1 packed, 0 dense). */
 int mapf_host_transport(mapf_handle* h, int packed);
+/* The transport mode in effect (1 packed, 0 dense) without changing it. */
+int mapf_host_transport_get(const mapf_handle* h);
 
 /* Replaces get_avail_actions (GRID:198-224) / _listNextValidActions(id, prev_action) (PRIMAL:639-667)
  * for the current state.  avail_dev uint8[E,N,5]. */
@@ -292,6 +294,11 @@ int mapf_avail(mapf_handle* h, uint8_t* avail_dev, void* stream);
  *   primal_costs != 0 reproduces getAstarCosts' quirk: unreachable cells keep `state` (0 or the id
  *   of the agent standing there, PRIMAL:496-498). */
 int mapf_bfs(mapf_handle* h, const uint8_t* dirty_dev, int16_t* dist_dev, int primal_costs, void* stream);
+
+/* mapf_avail with an explicit prev_action per agent (uint8[E,N], PRIMAL action ids) instead of the stored one: the
+ * read-only query `_listNextValidActions(id, prev_action)` (PRIMAL:639-667) -- the handle's state, including the
+ * stored previous actions, is left untouched. */
+int mapf_avail_prev(mapf_handle* h, const uint8_t* prev_dev, uint8_t* avail_dev, void* stream);
 
 /* Overrides the stored previous action of every agent (uint8[E,N], PRIMAL action ids).  mapf_avail removes
  * the opposite of this action, which is how `_listNextValidActions(id, prev_action)` (PRIMAL:639, 664) takes an

@@ -83,7 +83,9 @@ PROTOTYPES = {
     "mapf_step_observe_host": (_i, [_vp, ctypes.POINTER(MapfHostIO), _vp]),
     "mapf_obs_bits_supported": (_i, [_vp]),
     "mapf_host_transport": (_i, [_vp, _i]),
+    "mapf_host_transport_get": (_i, [_vp]),
     "mapf_avail": (_i, [_vp, _vp, _vp]),
+    "mapf_avail_prev": (_i, [_vp, _vp, _vp, _vp]),
     "mapf_bfs": (_i, [_vp, _vp, _vp, _i, _vp]),
     "mapf_set_prev_actions": (_i, [_vp, _vp, _vp]),
     "mapf_get_positions": (_i, [_vp, _vp, _vp]),

@@ -633,6 +633,19 @@ int mapf_avail(mapf_handle* h, uint8_t* avail_dev, void* stream) {
   return run_tile(h, nullptr, 0, 0, h->d.N, &out, nullptr, 0, nullptr, stream);
 }
 
+int mapf_avail_prev(mapf_handle* h, const uint8_t* prev_dev, uint8_t* avail_dev, void* stream) {
+  if (!h || !avail_dev || !prev_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_avail_prev: NULL argument");
+  mapf_step_out out;
+  memset(&out, 0, sizeof(out));
+  out.avail_dev = avail_dev;
+  // a launch without a step never writes the state: pointing it at the caller's prev_action array is a pure query
+  uint8_t* stored = h->S.prev_action;
+  h->S.prev_action = const_cast<uint8_t*>(prev_dev);
+  const int rc = run_tile(h, nullptr, 0, 0, h->d.N, &out, nullptr, 0, nullptr, stream);
+  h->S.prev_action = stored;
+  return rc;
+}
+
 int mapf_bfs(mapf_handle* h, const uint8_t* dirty_dev, int16_t* dist_dev, int primal_costs, void* stream) {
   if (!h) return MAPF_ERR_INVALID_ARG;
   int16_t* dist = dist_dev ? dist_dev : h->S.goal_dist;
@@ -717,6 +730,8 @@ int mapf_host_transport(mapf_handle* h, int packed) {
   h->packed_transport = packed ? 1 : 0;
   return (h->packed_transport && bits_supported(h)) ? 1 : 0;
 }
+
+int mapf_host_transport_get(const mapf_handle* h) { return (h && h->packed_transport && bits_supported(h)) ? 1 : 0; }
 
 int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream) {
   if (!h || !io || !io->actions_host) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_step_observe_host: NULL argument");

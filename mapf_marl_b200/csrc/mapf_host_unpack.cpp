@@ -15,6 +15,7 @@
 #endif
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -291,7 +292,16 @@ struct MapfUnpackPool {
   bool finish(int (*poll)(void*) = nullptr, void* poll_arg = nullptr) {
     work(poll, poll_arg);
     std::unique_lock<std::mutex> lk(mu);
-    cv_done.wait(lk, [&]() { return active == 0; });
+    // Timed wait: once the caller has no block left to claim it is the only thread that can notice a failed stream
+    // (the workers would spin on words that never arrive), so it keeps polling until every worker has left the job.
+    while (!cv_done.wait_for(lk, std::chrono::milliseconds(2), [&]() { return active == 0; })) {
+      if (poll && !aborted.load(std::memory_order_relaxed)) {
+        lk.unlock();
+        const bool failed = poll(poll_arg) != 0;
+        lk.lock();
+        if (failed) aborted.store(true, std::memory_order_relaxed);
+      }
+    }
     return !aborted.load(std::memory_order_relaxed);
   }
 };

@@ -465,6 +465,14 @@ __device__ void primal_mid_outputs_diag(const MapfDims& d, const Smem& s, const 
   }
 }
 
+// __is_cell_obstacle of GRID (GRID:278) and PARTIAL (PARTIAL:521): `_full_obs[cell] == -1`.  _full_obs is -1 on walls
+// PLUS the number of agents on the cell (GRID:299), so a wall cell that holds an agent -- the reference's .scen x/y
+// transposition produces such starts -- is NOT an obstacle: neighbours may enter it and the action masks open up.
+// `cnt` is the count grid the reference would be looking at (pre-step inside step(), rebuilt for the masks).
+__device__ __forceinline__ bool count_obstacle(const MapfDims& d, const uint32_t* ob, const uint8_t* cnt, int r, int c) {
+  return bm_test(ob, d.RW, d.P, r, c) && cnt[gcell(d, r, c)] == 0;
+}
+
 // GRID phase A for agent j (GRID:99-118): move unless wall / border, done latch, new-position counts.
 __device__ __forceinline__ void grid_phase_a(const MapfDims& d, const Smem& s, int j, int el, int step_now,
                                              unsigned int& c_env, unsigned int& c_arr) {
@@ -479,7 +487,7 @@ __device__ __forceinline__ void grid_phase_a(const MapfDims& d, const Smem& s, i
     if (act < 4) {                                                   // __agent_step, GRID:319-342
       const int t0 = (int)p.x + (act == 0 ? -1 : (act == 1 ? 1 : 0));
       const int t1 = (int)p.y + (act == 2 ? -1 : (act == 3 ? 1 : 0));
-      if (bm_test(ob, d.RW, d.P, t0, t1)) flag = 1;
+      if (count_obstacle(d, ob, s.grida + el * d.grid_bytes, t0, t1)) flag = 1;
       else np = make_uchar2((unsigned char)t0, (unsigned char)t1);
     }
     if (flag) r = __dadd_rn(r, d.collide_reward);                    // GRID:105-106
@@ -516,7 +524,7 @@ __device__ __forceinline__ void partial_phase_a(const MapfDims& d, const Smem& s
     if (act < 4) {                                                   // __agent_step, :618-643
       const int t0 = (int)p.x + (act == 0 ? -1 : (act == 1 ? 1 : 0));
       const int t1 = (int)p.y + (act == 2 ? -1 : (act == 3 ? 1 : 0));
-      if (bm_test(ob, d.RW, d.P, t0, t1)) flag = 1;
+      if (count_obstacle(d, ob, s.grida + el * d.grid_bytes, t0, t1)) flag = 1;
       else np = make_uchar2((unsigned char)t0, (unsigned char)t1);
     }
     if (flag) r = __dadd_rn(r, d.p_envc);                            // :203-205
@@ -717,9 +725,15 @@ __device__ __forceinline__ void fov_goal_bits_half(uint32_t* str, int j, int jen
 // ------------------------------------------------------------------------------------------------
 // SINGLE: the tile holds at most kThreads agents (the host guarantees it), so every per-agent / per-environment loop is
 // one guarded pass -- no loop counters, compares and back edges around each phase (worth 7 % of the c3 step).
-template <int F, int MODE, bool SINGLE>
-__global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims d, const MapfTileLayout L,
+// ROLL (mapf_rollout; needs SINGLE): A.T consecutive steps in ONE launch.  The tile stays resident in shared memory and
+// in the registers of the threads that own its agents: the obstacle rows are staged once, positions / done flags / step
+// counters never make the round trip through global memory between steps, and step t+1's actions are fetched while
+// step t is still being computed.  Step t's outputs go to element offset t * (size of one step's output) of every
+// output pointer (time-major [T, E, ...] storage); the state in the handle is kept current after every step.
+template <int F, int MODE, bool SINGLE, bool ROLL>
+__global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(const MapfDims d, const MapfTileLayout L,
                                                              const MapfState S, const MapfTileArgs A) {
+  static_assert(!ROLL || SINGLE, "rollouts keep the agents in the registers of their threads");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned int stat[MAPF_N_STATS];
   __shared__ unsigned int bad_flag;
@@ -751,6 +765,13 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     uint8_t dn, pv, atg;
     long long av;
   };
+  size_t a0t = a0;   // first agent of the tile in the outputs of the current step (a0 + t * E * N in a rollout)
+  size_t e0t = (size_t)e0;
+  int t_roll = 0;
+  auto load_action = [&](int j, size_t at) -> long long {
+    return (A.act_dtype == MAPF_I64) ? ((const long long*)A.actions)[at + j]
+                                     : (long long)((const uint8_t*)A.actions)[at + j];
+  };
   auto load_rec = [&](int j, AgentRec& r) {
     r.p = ((const uchar2*)S.pos)[a0 + j];
     r.g = ((const uchar2*)S.goal)[a0 + j];
@@ -763,9 +784,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     r.av = -1;
     if (do_step) {
       const int el = fast_div(j, d.invN), a = j - el * N;
-      if (a >= A.agent_lo && a < A.agent_hi)
-        r.av = (A.act_dtype == MAPF_I64) ? ((const long long*)A.actions)[a0 + j]
-                                         : (long long)((const uint8_t*)A.actions)[a0 + j];
+      if (a >= A.agent_lo && a < A.agent_hi) r.av = load_action(j, a0);
     }
   };
   bool bad = false;
@@ -802,6 +821,12 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
   if (tid < na) load_rec(tid, r0);
   int sc0 = 0;
   if (tid < ne) sc0 = S.step_count[e0 + tid];
+  for (;;) {   // one iteration per step of a rollout; a single pass otherwise
+  if (ROLL && t_roll > 0) {
+    bad = false;
+    if (tid < MAPF_N_STATS) stat[tid] = 0;
+    if (tid == 0) bad_flag = 0;
+  }
   {
     // zero the agent bit rows and the occupancy grid(s): they are adjacent in the tile layout, one loop clears them
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -810,9 +835,11 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
 #pragma unroll 1
     for (int i = tid; i < nz; i += kThreads) zp[i] = z;
   }
-  if (tid < nvec) odst[tid] = ob0;
+  if (!ROLL || t_roll == 0) {
+    if (tid < nvec) odst[tid] = ob0;
 #pragma unroll 1
-  for (int i = tid + kThreads; i < nvec; i += kThreads) odst[i] = __ldg(osrc + i);
+    for (int i = tid + kThreads; i < nvec; i += kThreads) odst[i] = __ldg(osrc + i);
+  }
   if (tid < ne) {
     envcnt[tid] = 0;
     envcnt2[tid] = 0;
@@ -833,6 +860,8 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
   }
   __syncthreads();
   if (bad) bad_flag = 1;
+  long long next_av = -1;   // rollout: the action of the NEXT step, in flight while this step is computed
+  if (ROLL && t_roll + 1 < A.T && tid < na) next_av = load_action(tid, a0t + (size_t)d.E * N);
 
   PHASE_MARK(1);
   // ---- phase A: occupancy of the current positions (PRIMAL State.state ids, PRIMAL:32-47; GRID agent counts,
@@ -848,14 +877,19 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
       if (do_step) primal_phase_a<diag>(d, s, A, j, el, a);
     } else {
       byte_inc(grid, cell);
-      if (do_step) {
-        const int step_now = envstep[el] + 1;                        // GRID:93, PARTIAL:178
-        if (partial) partial_phase_a(d, s, S, a0 + j, j, el, step_now, c0, c3);
-        else grid_phase_a(d, s, j, el, step_now, c0, c3);
-      }
     }
   }
   __syncthreads();
+  if (!primal && do_step) {
+    // GRID / PARTIAL moves test `_full_obs == -1` (count_obstacle), i.e. they read the finished pre-step count grid
+    for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
+      const int el = fast_div(j, d.invN);
+      const int step_now = envstep[el] + 1;                          // GRID:93, PARTIAL:178
+      if (partial) partial_phase_a(d, s, S, a0 + j, j, el, step_now, c0, c3);
+      else grid_phase_a(d, s, j, el, step_now, c0, c3);
+    }
+    __syncthreads();
+  }
 
   if (do_step) {
   PHASE_MARK(2);
@@ -980,14 +1014,15 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
         const int opp = (act == 0) ? -1 : (((act + 1) & 3) + 1);
         if (opp > 0) m &= (uint8_t)~(1u << opp);
       } else {                                                       // get_avail_agent_actions, GRID:203-224
+        const uint8_t* grid = gridcur + el * d.grid_bytes;           // the rebuilt _full_obs counts, GRID:132-140
         m = 16;
-        m |= bm_test(ob, d.RW, d.P, (int)p.x - 1, (int)p.y) ? 0 : 1;
-        m |= bm_test(ob, d.RW, d.P, (int)p.x + 1, (int)p.y) ? 0 : 2;
-        m |= bm_test(ob, d.RW, d.P, (int)p.x, (int)p.y - 1) ? 0 : 4;
-        m |= bm_test(ob, d.RW, d.P, (int)p.x, (int)p.y + 1) ? 0 : 8;
+        m |= count_obstacle(d, ob, grid, (int)p.x - 1, (int)p.y) ? 0 : 1;
+        m |= count_obstacle(d, ob, grid, (int)p.x + 1, (int)p.y) ? 0 : 2;
+        m |= count_obstacle(d, ob, grid, (int)p.x, (int)p.y - 1) ? 0 : 4;
+        m |= count_obstacle(d, ob, grid, (int)p.x, (int)p.y + 1) ? 0 : 8;
       }
       // [E,N,5] mask straight from the register: 5 byte stores per agent (the L2 merges the partial sectors)
-      uint8_t* o = A.out.avail_dev + 5 * (a0 + j);
+      uint8_t* o = A.out.avail_dev + 5 * (a0t + j);
       o[0] = m & 1;
       o[1] = (m >> 1) & 1;
       o[2] = (m >> 2) & 1;
@@ -1002,13 +1037,13 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
   if (do_step) {
     for (int el = tid, it_ = 0; el < ne && (!SINGLE || it_ == 0); el += kThreads, ++it_) {
       const bool all = envcnt[el] == N;        // PRIMAL State.done (:159-165) / GRID episode_done (:267)
-      if (A.out.terminated_dev) A.out.terminated_dev[e0 + el] = all ? 1 : 0;
+      if (A.out.terminated_dev) A.out.terminated_dev[e0t + el] = all ? 1 : 0;
       if (primal) {
         if (A.out.reward_dev) {
           double tot = 0.0;
 #pragma unroll 8   // the adds are one dependent chain (the reference's order); unrolling lets the loads run ahead
           for (int i = A.agent_lo; i < A.agent_hi; ++i) tot = __dadd_rn(tot, s.rew[el * N + i]);
-          A.out.reward_dev[e0 + el] = tot;
+          A.out.reward_dev[e0t + el] = tot;
         }
         if (A.agent_lo == 0) S.step_count[e0 + el] = envstep[el] + 1;
       } else if (partial) {
@@ -1023,14 +1058,14 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
           }
         }
         if (A.out.reward_dev)
-          A.out.reward_dev[e0 + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // PARTIAL:310
-        if (A.out.terminated_dev) A.out.terminated_dev[e0 + el] = term ? 1 : 0;
+          A.out.reward_dev[e0t + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // PARTIAL:310
+        if (A.out.terminated_dev) A.out.terminated_dev[e0t + el] = term ? 1 : 0;
         S.terminated[e0 + el] = term ? 1 : 0;
         S.total_coll[e0 + el] += envcnt2[el] / 2;                                      // PARTIAL:250
         S.step_count[e0 + el] = step_now;
       } else {
         if (A.out.reward_dev)
-          A.out.reward_dev[e0 + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // GRID:141
+          A.out.reward_dev[e0t + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // GRID:141
         S.step_count[e0 + el] = envstep[el] + 1;
       }
       if (d.collect_stats && all) atomicAdd(&S.stats[MAPF_STAT_EPISODES_DONE], 1ull);
@@ -1047,9 +1082,10 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     // state write-back and the per-agent outputs: thread j stores agent j's records (byte stores of a warp cover
     // whole 32-byte sectors; a shared-memory staging pass costs more instructions than it saves transactions)
     for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
-      const size_t gj = a0 + j;
+      const size_t gj = a0 + j, gt = a0t + j;   // the handle's state / this step's outputs
       const uint8_t dn = s.done[j];
-      ((uchar2*)S.pos)[gj] = s.posnew[j];
+      const uchar2 pn = s.posnew[j];
+      ((uchar2*)S.pos)[gj] = pn;
       S.done[gj] = dn;
       S.prev_action[gj] = s.act[j];
       if (partial) {
@@ -1057,34 +1093,40 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
         S.pnode[gj] = s.node[j];
         S.pedge[gj] = s.edge[j];
       }
+      if (ROLL) {   // the agent's record for the next step stays in this thread's registers
+        r0.p = pn;
+        r0.dn = dn;
+        if (partial) r0.atg = s.atgoal[j];
+      }
       if (diag) ((uchar2*)S.past)[gj] = s.pastnew[j];
-      if (A.out.dones_dev) A.out.dones_dev[gj] = dn;
-      if (A.out.status_dev) A.out.status_dev[gj] = s.status[j];
-      if (A.out.agent_reward_dev) A.out.agent_reward_dev[gj] = s.rew[j];
-      if (A.out.node_dev) A.out.node_dev[gj] = primal ? 0 : (int16_t)s.node[j];
-      if (A.out.edge_dev) A.out.edge_dev[gj] = primal ? 0 : (int16_t)s.edge[j];
-      if (A.out.valid_dev) A.out.valid_dev[gj] = primal ? ((s.flag[j] >> 1) & 1) : 1;
-      if (primal && A.out.done_mid_dev) A.out.done_mid_dev[gj] = (s.flag[j] >> 2) & 1;
+      if (A.out.dones_dev) A.out.dones_dev[gt] = dn;
+      if (A.out.status_dev) A.out.status_dev[gt] = s.status[j];
+      if (A.out.agent_reward_dev) A.out.agent_reward_dev[gt] = s.rew[j];
+      if (A.out.node_dev) A.out.node_dev[gt] = primal ? 0 : (int16_t)s.node[j];
+      if (A.out.edge_dev) A.out.edge_dev[gt] = primal ? 0 : (int16_t)s.edge[j];
+      if (A.out.valid_dev) A.out.valid_dev[gt] = primal ? ((s.flag[j] >> 1) & 1) : 1;
+      if (primal && A.out.done_mid_dev) A.out.done_mid_dev[gt] = (s.flag[j] >> 2) & 1;
     }
     if constexpr (diag) {
-      if (A.out.next_mid_dev) write_mask_n(A.out.next_mid_dev + 9 * a0, s.nextmid16, na, 9, tid);
+      if (A.out.next_mid_dev) write_mask_n(A.out.next_mid_dev + 9 * a0t, s.nextmid16, na, 9, tid);
     } else {
-      if (primal && A.out.next_mid_dev) write_mask5(A.out.next_mid_dev + 5 * a0, s.nextmid, na, tid);
+      if (primal && A.out.next_mid_dev) write_mask5(A.out.next_mid_dev + 5 * a0t, s.nextmid, na, tid);
     }
   }
   if constexpr (diag) {
-    if (want_avail) write_mask_n(A.out.avail_dev + 9 * a0, s.mask16, na, 9, tid);
+    if (want_avail) write_mask_n(A.out.avail_dev + 9 * a0t, s.mask16, na, 9, tid);
   }
   if (tid == 0 && bad_flag) atomicOr(S.err_flags, MAPF_FLAG_BAD_ACTION);
 
   PHASE_MARK(6);
-  // ---- observation
-  if (A.obs == nullptr && A.vec == nullptr) return;
+  // ---- observation (a `break` leaves the observation of this step)
+  do {
+  if (A.obs == nullptr && A.vec == nullptr) break;
 
   if (d.obs_mode == MAPF_OBS_FULLMAP) {
     // get_obs / get_state, GRID:143-196: -1 on walls, else the number of agents on the cell.
-    if (A.obs == nullptr) return;
-    int8_t* out = (int8_t*)A.obs + (size_t)e0 * d.HW;
+    if (A.obs == nullptr) break;
+    int8_t* out = (int8_t*)A.obs + e0t * d.HW;
     if ((d.W & 3) == 0) {
       // four cells of a row per thread: one funnel shift for the wall bits, four count bytes, one packed 32-bit store
       const int q4 = d.HW >> 2;
@@ -1101,7 +1143,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
           o32[q] = __vsub4(cnt, wall);                               // `+= 1` on a -1 cell per agent, GRID:299
         }
       }
-      return;
+      break;
     }
     for (int i = tid; i < ne * d.HW; i += kThreads) {
       const int el = i / d.HW, cell = i - el * d.HW;
@@ -1110,7 +1152,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
       const int cnt = gridcur[el * d.grid_bytes + gcell(d, r, c)];
       out[i] = bm_test(ob, d.RW, d.P, r, c) ? (int8_t)(cnt - 1) : (int8_t)cnt;   // `+= 1` on a -1 cell, GRID:299
     }
-    return;
+    break;
   }
 
   if constexpr (F > 0) {
@@ -1165,7 +1207,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
         const int dx = (int)g.x - (int)p.x, dy = (int)g.y - (int)p.y;
         const double2 u = __ldg(vt);                                 // |dx| / mag, |dy| / mag (IEEE division is
         const double2 m = __ldg(vt + 1);                             // sign-symmetric; 0 / mag = +0.0 either way)
-        double* v = A.vec + 3 * (a0 + j);
+        double* v = A.vec + 3 * (a0t + j);
         v[0] = dx < 0 ? -u.x : u.x;
         v[1] = dy < 0 ? -u.y : u.y;
         v[2] = m.x;
@@ -1184,7 +1226,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
       }
     }
     __syncthreads();
-    if (A.obs == nullptr) return;
+    if (A.obs == nullptr) break;
 
   PHASE_MARK(8);
     // phase 2: expand the tile's bit string; thread q writes output bytes [16q, 16q+16)
@@ -1192,11 +1234,11 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
     if (A.obs_dtype == MAPF_BITS) {
       // the strings as they are: tile t starts at word a0 * NB / 32 (the host only selects this output when every
       // tile holds whole groups, so the tile's first bit sits on a word boundary)
-      uint32_t* out = (uint32_t*)A.obs + ((a0 * T::NB) >> 5);
+      uint32_t* out = (uint32_t*)A.obs + ((a0t * T::NB) >> 5);
       const int nw = (int)((nbits + 31) >> 5);
       for (int q = tid; q < nw; q += kThreads) out[q] = s.str[q];
     } else if (A.obs_dtype == MAPF_U8) {
-      uint8_t* out = (uint8_t*)A.obs + a0 * T::NB;
+      uint8_t* out = (uint8_t*)A.obs + a0t * T::NB;
       const int lead = (int)((16 - ((uintptr_t)out & 15)) & 15);   // 0 unless the tile holds an odd number of groups
       if (lead == 0) {
         const int nchunk = (int)(nbits >> 4);
@@ -1232,7 +1274,7 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
           out[b] = (s.str[b >> 5] >> (b & 31)) & 1u;
       }
     } else {
-      float* out = (float*)A.obs + a0 * T::NB;
+      float* out = (float*)A.obs + a0t * T::NB;
       const int nchunk = (int)(nbits >> 2);
       for (int q = tid; q < nchunk; q += kThreads) {
         const uint32_t nib = (s.str[q >> 3] >> ((q & 7) << 2)) & 15u;
@@ -1245,7 +1287,16 @@ __global__ void __launch_bounds__(kThreads, 12) mapf_tile_kernel(const MapfDims 
       }
     }
   }
+  } while (0);
   PHASE_MARK(9);
+  if (!ROLL || ++t_roll >= A.T) break;
+  // ---- next step of the rollout: outputs move on by one step, the agents' records are already in registers
+  a0t += (size_t)d.E * N;
+  e0t += (size_t)d.E;
+  r0.av = next_av;
+  sc0 += 1;
+  __syncthreads();   // the bit strings alias the step scratch the next staging pass is about to write
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1992,7 +2043,12 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
   __syncthreads();
   for (int a = threadIdx.x; a < N; a += blockDim.x) {
     const uchar2 p = spos[a];
-    if (!bm_test(obw, d.RW, d.P, p.x, p.y)) byte_inc(cnt, cbase[a] + half * Wp + half);   // walls show 0 agents
+    // `_full_obs` is -1 + k on a wall cell holding k agents (PARTIAL:592): the first agent only lifts the cell to 0
+    // (no longer an obstacle, :339; nobody counted, :341), the others count
+    const int pr = (int)p.x + d.P, pc = (int)p.y + d.P;
+    const uint32_t bit = 1u << (pc & 31);
+    uint32_t* wp = &obw[pr * d.RW + (pc >> 5)];
+    if ((*wp & bit) == 0 || (atomicAnd(wp, ~bit) & bit) == 0) byte_inc(cnt, cbase[a] + half * Wp + half);
   }
   // K - 1 nearest agents
   const int k_m1 = min(N, K) - 1;

@@ -3,6 +3,10 @@
 Thin host-side wrapper over the C ABI (include/mapf_b200.h): torch is used only for device
 memory, streams and dtype plumbing.  All arithmetic happens in csrc/mapf_kernels.cu.
 
+Ownership of outputs: step / step_observe / observe / avail / positions / ... return ENGINE-OWNED tensors that the
+next call of the same method overwrites in place (no allocation on the hot path).  Keep a value across calls with
+`.clone()`, or hand the call your own storage (`out=` of step_observe / observe, `rollout()`).
+
 Vector API (device tensors, no host round trips):
     eng = MapfEngine(n_envs=E, n_agents=N, height=H, width=W, mode="primal", fov=11)
     eng.reset(obst, starts, goals)                       # obst [E,H,W] (or [H,W] shared), starts/goals [E,N,2]
@@ -321,10 +325,18 @@ class MapfEngine:
             outs["vec"] = vec
         return outs
 
-    def avail(self):
+    def avail(self, prev=None):
+        """Action masks of the current state.  prev (uint8 [E,N]): evaluate `_listNextValidActions(id, prev_action)`
+        with these previous actions instead of the stored ones -- a pure query, nothing in the handle changes."""
         out = self._buf("out_avail", (self.E, self.N, self.n_actions), torch.uint8)
         with torch.cuda.device(self.device):
-            self._check(self.lib.mapf_avail(self._h, self._ptr(out), self._stream()), "mapf_avail")
+            if prev is None:
+                self._check(self.lib.mapf_avail(self._h, self._ptr(out), self._stream()), "mapf_avail")
+            else:
+                p = self._to_dev(prev, torch.uint8, (self.E, self.N))
+                self._keep = [p]
+                self._check(self.lib.mapf_avail_prev(self._h, self._ptr(p), self._ptr(out), self._stream()),
+                            "mapf_avail_prev")
         return out
 
     def goal_dist(self, dirty=None, primal_costs=False, out=None):
@@ -412,8 +424,7 @@ class MapfEngine:
         """Query (packed=None) or set the PCIe transport of step_observe_host: 1 = bit-packed + host expansion,
         0 = dense copies.  Returns the mode in effect."""
         if packed is None:
-            packed = getattr(self, "_packed_transport", True)
-        self._packed_transport = bool(packed)
+            return int(self.lib.mapf_host_transport_get(self._h))       # side-effect free
         return int(self.lib.mapf_host_transport(self._h, int(bool(packed))))
 
     def packed_obs_bytes(self):

@@ -222,10 +222,11 @@ class MAPFEnv(object):
         return self._listNextValidActions(agent_id), on_goal, False
 
     def _listNextValidActions(self, agent_id, prev_action=0, episode=0):
+        # a read-only query like the reference's (prev_action is an argument, mapf_primal.py:639): the engine's stored
+        # last actions -- which later avail() calls and sweeps rely on -- stay as they are
         prev = torch.zeros((self.n_envs, self.num_agents), dtype=torch.uint8)
         prev[:, agent_id - 1] = int(prev_action)
-        self.engine.set_prev_actions(prev)
-        mask = self.engine.avail()[0, agent_id - 1].cpu().tolist()
+        mask = self.engine.avail(prev=prev)[0, agent_id - 1].cpu().tolist()
         return [a for a in range(self.n_actions) if mask[a]]
 
     def _step(self, action_input, episode=0):

@@ -36,6 +36,12 @@ def random_obstacles(rs, height, width, density):
 
 def label_components(obst):
     """4-connected component label of every free cell (-1 on obstacles)."""
+    try:
+        from scipy import ndimage
+        lab, _ = ndimage.label(np.asarray(obst) == 0)      # default structure: 4-connectivity
+        return lab.astype(np.int32) - 1
+    except ImportError:
+        pass
     H, W = obst.shape
     lab = np.full((H, W), -1, np.int32)
     cur = 0
@@ -60,20 +66,25 @@ def place_agents_and_goals(rs, obst, n_agents):
     """Distinct start cells and distinct goal cells, every goal inside its agent's connected region
     (the constraint PRIMAL's _setWorld enforces, mapf_primal.py:317-337)."""
     lab = label_components(obst)
-    free = np.argwhere(lab >= 0)
-    if len(free) < 2 * n_agents:
+    W = obst.shape[1]
+    flat = np.flatnonzero(lab.ravel() >= 0)                  # free cells in row-major order
+    if len(flat) < 2 * n_agents:
         raise ValueError("map too dense for %d agents" % n_agents)
-    order = rs.permutation(len(free))
-    starts = free[order[:n_agents]]
-    taken = np.zeros(obst.shape, bool)
+    order = rs.permutation(len(flat))
+    sflat = flat[order[:n_agents]]
+    labf = lab.ravel()
+    region = {}                                              # label -> its not-yet-taken cells, row-major
     goals = np.zeros((n_agents, 2), np.int64)
     for k in range(n_agents):
-        region = np.argwhere((lab == lab[starts[k, 0], starts[k, 1]]) & ~taken)
-        if len(region) == 0:
+        lk = int(labf[sflat[k]])
+        cells = region.get(lk)
+        if cells is None:
+            cells = region[lk] = np.flatnonzero(labf == lk).tolist()
+        if len(cells) == 0:
             raise ValueError("no free goal cell left in agent %d's region" % k)
-        g = region[rs.randint(len(region))]
-        goals[k] = g
-        taken[g[0], g[1]] = True
+        g = cells.pop(int(rs.randint(len(cells))))
+        goals[k] = (g // W, g % W)
+    starts = np.stack([sflat // W, sflat % W], axis=1)
     return starts.astype(np.int16), goals.astype(np.int16)
 
 

@@ -148,14 +148,18 @@ void oracle_grid_reset(oracle_env* o, const int8_t* map, const int16_t* starts, 
   for (int e = 0; e < o->E; ++e) grid_rebuild_full_obs(o, e);
 }
 
-/* __is_valid GRID:270 and __is_cell_obstacle GRID:278 (obstacle == grid value -1). */
-static int grid_free(const oracle_env* o, const int8_t* m, int p0, int p1) {
+/* __is_valid GRID:270 and __is_cell_obstacle GRID:278 / PARTIAL:521: a cell is an obstacle iff `_full_obs` reads -1
+ * there.  `_full_obs` is -1 on walls PLUS the number of agents on the cell (GRID:299), so a wall cell that holds an
+ * agent (the .scen x/y transposition of GRID:432-443 produces such starts) reads >= 0 and is NOT an obstacle.
+ * `st` is the environment's _full_obs as it stands when the reference evaluates the test: the pre-step grid inside
+ * step() (it is only rebuilt at GRID:132-135), the rebuilt grid for the avail masks (GRID:140). */
+static int grid_free(const oracle_env* o, const int16_t* st, int p0, int p1) {
   if (!(0 <= p0 && p0 < o->H && 0 <= p1 && p1 < o->W)) return 0;
-  return m[p0 * o->W + p1] == 0;
+  return st[p0 * o->W + p1] != -1;
 }
 
 /* get_avail_agent_actions, GRID:203-224. */
-static void grid_avail_agent(const oracle_env* o, const int8_t* m, int p0, int p1, uint8_t* out5) {
+static void grid_avail_agent(const oracle_env* o, const int16_t* m, int p0, int p1, uint8_t* out5) {
   out5[0] = (uint8_t)grid_free(o, m, p0 - 1, p1);
   out5[1] = (uint8_t)grid_free(o, m, p0 + 1, p1);
   out5[2] = (uint8_t)grid_free(o, m, p0, p1 - 1);
@@ -166,7 +170,7 @@ static void grid_avail_agent(const oracle_env* o, const int8_t* m, int p0, int p
 void oracle_grid_avail(const oracle_env* o, uint8_t* avail) {
 #pragma omp parallel for schedule(static) num_threads(o->threads)
   for (int e = 0; e < o->E; ++e) {
-    const int8_t* m = env_map(o, e);
+    const int16_t* m = o->state + (size_t)e * o->H * o->W;
     for (int i = 0; i < o->N; ++i) {
       const int16_t* p = o->pos + ((size_t)e * o->N + i) * 2;
       grid_avail_agent(o, m, p[0], p[1], avail + ((size_t)e * o->N + i) * 5);
@@ -216,7 +220,7 @@ static int grid_step_env(oracle_env* o, int e, const uint8_t* act, double* rewar
                          double* agent_reward, int8_t* envflag, int16_t* node_out, int16_t* edge_out,
                          uint8_t* avail, int16_t* scratch /* [2N + H*W] */) {
   const int N = o->N, W = o->W;
-  const int8_t* m = env_map(o, e);
+  const int16_t* m = o->state + (size_t)e * o->H * W;   /* _full_obs: pre-step until GRID:132 rebuilds it */
   int16_t* pos = o->pos + (size_t)e * N * 2;
   const int16_t* goal = o->goal + (size_t)e * N * 2;
   uint8_t* done = o->done + (size_t)e * N;
@@ -697,7 +701,7 @@ void oracle_partial_reset(oracle_env* o, const int8_t* map, const int16_t* start
 static int partial_step_env(oracle_env* o, int e, const uint8_t* act, double* reward, uint8_t* terminated_out,
                             double* agent_reward, uint8_t* avail, int16_t* scratch) {
   const int N = o->N, W = o->W, H = o->H;
-  const int8_t* m = env_map(o, e);
+  const int16_t* m = o->state + (size_t)e * H * W;      /* _full_obs: pre-step until :279 rebuilds it */
   int16_t* pos = o->pos + (size_t)e * N * 2;
   const int16_t* goal = o->goal + (size_t)e * N * 2;
   uint8_t* done = o->done + (size_t)e * N;

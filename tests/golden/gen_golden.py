@@ -152,6 +152,19 @@ def gen_grid():
     run_grid("grid_intint", obst, starts, goals, acts, step_reward=-1, collide_reward=-10)
     run_grid("grid_fcis", obst, starts, goals, acts, step_reward=-1, collide_reward=-0.3)
     run_grid("grid_ff", obst, starts, goals, acts, step_reward=-0.1, collide_reward=-0.3, episode_limit=30)
+    # agents standing ON wall cells (the reference allows it: the .scen x/y transposition produces such starts).  A wall
+    # cell holding k agents reads -1 + k in _full_obs, so __is_cell_obstacle (GRID:278) no longer sees an obstacle:
+    # neighbours may walk onto it and the avail mask opens up.  4x4 known-answer case first, then a dense random one.
+    obst = np.zeros((4, 4), bool)
+    obst[1, 1] = True
+    run_grid("grid_onwall4", obst, [(1, 1), (0, 1), (2, 1), (3, 3)], [(3, 0), (1, 1), (0, 0), (1, 1)],
+             np.array([[4, 1, 0, 0], [4, 4, 4, 0], [3, 4, 4, 0], [4, 0, 1, 2], [0, 1, 4, 1], [1, 4, 3, 0]]))
+    rs = np.random.RandomState(8)
+    obst = rs.rand(7, 7) < 0.35
+    allc = [(i, j) for i in range(7) for j in range(7)]
+    starts = [allc[i] for i in rs.randint(0, len(allc), 12)]      # anywhere, walls included
+    goals = [allc[i] for i in rs.randint(0, len(allc), 12)]
+    run_grid("grid_onwall7", obst, starts, goals, rs.randint(0, 5, [80, 12]), step_reward=-0.5, collide_reward=-3)
     # real MovingAI map + scen through the reference's own parser (x/y quirk included)
     random.seed(11)
     mp = os.path.join(REF_SRC, "mapf_baseline", "mapf-map", "random-32-32-20.map")

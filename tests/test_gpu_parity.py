@@ -62,7 +62,10 @@ def test_grid_engine_matches_reference_trace(name):
     # grid_real32 goes through the reference's own .scen parser, whose x/y transposition (GRID:443-445) puts
     # some agents on obstacle cells; the trace is reproduced all the same and the engine reports the fact.
     from mapf_marl_b200 import _lib
-    assert eng.error_flags() == (_lib.FLAG_START_ON_WALL if name == "grid_real32" else 0)
+    # (grid_onwall*: agents deliberately start on walls, where `_full_obs` reads -1 + count, GRID:278, 299)
+    on_wall = bool(g["obst"][g["starts"][:, 0], g["starts"][:, 1]].any())
+    assert on_wall == (name in ("grid_real32", "grid_onwall4", "grid_onwall7"))
+    assert eng.error_flags() == (_lib.FLAG_START_ON_WALL if on_wall else 0)
 
 
 @pytest.mark.parametrize("name", golden_names("PRIMAL"))
@@ -287,6 +290,10 @@ GRID_CASES = [
     (33, 10, 6, 6, 0.05, -0.01, -10, 40, 25),       # crowded, episode limit reached
     (16, 32, 32, 32, 0.2, -1, -10, 12, 10000),       # all-int rewards
     (8, 130, 40, 40, 0.1, -0.01, -0.5, 6, 10000),    # more than 128 agents
+    # starts anywhere, walls included (negative density = |density| with on-wall starts): a wall cell holding an agent
+    # reads -1 + count in `_full_obs`, is no obstacle (GRID:278) and may be entered (pinned by grid_onwall4/7)
+    (96, 12, 7, 7, -0.35, -0.5, -3, 40, 10000),
+    (20, 140, 24, 24, -0.3, -0.01, -10, 10, 10000),
 ]
 
 
@@ -296,11 +303,12 @@ def test_grid_batch_matches_oracle(case, sum_mode):
     from oracle.oracle import MODE_GRID
     E, N, H, W, dens, sr, cr, T, limit = case
     rs = np.random.RandomState(E * 7 + N)
-    obst = (rs.rand(E, H, W) < dens).astype(np.uint8)
+    on_wall = dens < 0
+    obst = (rs.rand(E, H, W) < abs(dens)).astype(np.uint8)
     starts = np.zeros((E, N, 2), np.int16)
     goals = np.zeros((E, N, 2), np.int16)
     for e in range(E):
-        free = np.argwhere(obst[e] == 0)
+        free = np.argwhere(obst[e] >= 0) if on_wall else np.argwhere(obst[e] == 0)
         starts[e] = free[rs.randint(0, len(free), N)]      # overlapping starts are legal in GRID
         goals[e] = free[rs.randint(0, len(free), N)]
     eng = _engine(E, N, H, W, mode="grid", episode_limit=limit, step_reward=sr, collide_reward=cr,
@@ -326,7 +334,8 @@ def test_grid_batch_matches_oracle(case, sum_mode):
         assert np.array_equal(_np(eng.positions()), orc.positions()), t
         assert np.array_equal(_np(state), orc.grid_state()), t
         assert np.array_equal(_np(eng.step_count()), orc.step_count()), t
-    assert eng.error_flags() == 0
+    from mapf_marl_b200 import _lib
+    assert eng.error_flags() == (_lib.FLAG_START_ON_WALL if on_wall else 0)
 
 
 # ------------------------------------------------------------------------------------------ API behaviour
@@ -793,6 +802,38 @@ def test_partial_batch_matches_oracle(case):
             o32 = _np(eng.observe(dtype=torch.float32)[0])
             assert o32.dtype == np.float32 and np.array_equal(o32.view(np.uint32), robs.astype(np.float32).view(np.uint32)), t
     assert eng.error_flags() == 0
+
+
+def test_partial_agents_on_wall_cells_follow_the_full_obs_count_rule():
+    """marl_partial.py tests `_full_obs == -1` like mapf_gridworld.py does (:521, :339-342): a wall cell that holds an
+    agent is no obstacle for moves, masks and the window maps, and shows count - 1 agents.  (The reference's own reset
+    cannot produce such a state from a valid .scen; the oracle carries the rule, the engine must agree with it.)"""
+    from oracle.oracle import MODE_PARTIAL
+    E, N, H, W, Wn, K, limit = 48, 10, 9, 9, 5, 4, 30
+    rs = np.random.RandomState(5)
+    obst = (rs.rand(E, H, W) < 0.3).astype(np.uint8)
+    cells = np.argwhere(np.ones((H, W), bool))
+    starts = np.stack([cells[rs.randint(0, len(cells), N)] for _ in range(E)]).astype(np.int16)
+    goals = np.stack([cells[rs.randint(0, len(cells), N)] for _ in range(E)]).astype(np.int16)
+    kw = dict(obs_window=Wn, obs_knn_agents=K, move_reward=-0.01, stay_reward=-0.02, stay_goal_reward=0.3,
+              node_collide_reward=-1, edge_collide_reward=-1.5, env_collide_reward=-1, complete_reward=100,
+              complete_fac=1.5, gamma=0.97)
+    eng = _engine(E, N, H, W, mode="partial", episode_limit=limit, **kw)
+    orc = _oracle(E, N, H, W, MODE_PARTIAL, episode_limit=limit)
+    orc.partial_config(**kw)
+    eng.reset(obst, starts, goals)
+    orc.reset(obst, starts, goals)
+    assert np.array_equal(_bits(_np(eng.observe()[0])), _bits(orc.partial_observe()))
+    assert np.array_equal(_np(eng.avail()), orc.grid_avail())
+    for t in range(20):
+        a = rs.randint(0, 5, (E, N)).astype(np.uint8)
+        out = eng.step_observe(torch.as_tensor(a, device="cuda"), want=PARTIAL_WANT)
+        ref = orc.partial_step(a)
+        for k in ("terminated", "dones", "node", "edge", "avail"):
+            assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        assert np.array_equal(_bits(_np(out["agent_reward"])), _bits(ref["agent_reward"])), t
+        assert np.array_equal(_np(eng.positions()), orc.positions()), t
+        assert np.array_equal(_bits(_np(out["obs"])), _bits(orc.partial_observe())), t
 
 
 def test_marl_partial_dropin_class(tmp_path):
