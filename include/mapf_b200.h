@@ -162,8 +162,11 @@ typedef struct mapf_cfg {
 
 /* Outputs of one step.  Every pointer is a device pointer and may be NULL (not written). */
 typedef struct mapf_step_out {
-  /* [E] team reward.  GRID: `sum(rewards)` folded left to right (GRID:141).
-   * PRIMAL: the same fold over the per-agent rewards (convenience, no reference counterpart). */
+  /* [E] team reward.  GRID / PARTIAL: `sum(rewards)` exactly as the interpreter folds it (GRID:141, PARTIAL:310).
+   * PRIMAL: the PAIRWISE sum of the per-agent rewards of the swept agents (a convenience with no reference
+   * counterpart -- MAPFEnv._step returns per-agent rewards only): leaves r[0..N) (+0.0 outside the swept range), padded
+   * with +0.0 to the next power of two, y[i] += y[i + s] for s = 1, 2, 4, ...; a fixed order, so the bits do not
+   * depend on tile shapes or GPU counts. */
   double* reward_dev;
   /* [E].  GRID: episode_done(), GRID:267.  PRIMAL: world.done() after the sweep, PRIMAL:159-165. */
   uint8_t* terminated_dev;
@@ -264,6 +267,20 @@ int mapf_observe(mapf_handle* h, void* obs_dev, int obs_dtype, double* vec_dev, 
 int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, const mapf_step_out* out,
                       void* obs_dev, int obs_dtype, double* vec_dev, void* stream);
 
+/* n_steps consecutive mapf_step_observe calls with pre-supplied actions in ONE call -- and, for PRIMAL (without
+ * diagonal movement / blocking reward) and GRID batches whose tiles hold one thread per agent, in ONE kernel launch:
+ * the tile's state stays in shared memory and registers between the steps, only the per-step outputs stream out
+ * (the reference's equivalent is the env loop of its runner,
+ * MARL-curve-main/src/runners/parallel_runner.py:127-171, driven by a fixed action sequence).
+ *   actions_dev [n_steps, E, N] of act_dtype.
+ *   Every non-NULL pointer of *out, obs_dev and vec_dev is TIME-MAJOR: [n_steps, <the shape mapf_step_observe
+ *   documents>]; step t's outputs are exactly what the t-th of n_steps consecutive mapf_step_observe calls writes.
+ * One step's actions and one step's observation must be multiples of 16 bytes. */
+int mapf_rollout(mapf_handle* h, const void* actions_dev, int act_dtype, int n_steps, const mapf_step_out* out,
+                 void* obs_dev, int obs_dtype, double* vec_dev, void* stream);
+/* 1 when mapf_rollout runs as a single launch for this handle and observation dtype (otherwise n_steps launches). */
+int mapf_rollout_in_one_launch(const mapf_handle* h, int obs_dtype);
+
 /* Host-buffer form of mapf_step_observe: copies io->actions_host to the device, runs the fused
  * kernel, copies the requested outputs back and waits for them.  This is the call the e2e
  * benchmark times.
@@ -274,6 +291,13 @@ int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, co
  * bit i of the stream = cell i of the [E,N,4,F,F] tensor, little-endian inside a word) with no host expansion.
  * The unpack pool uses MAPF_HOST_THREADS threads if that variable is set, else (CPUs of the process) / LOCAL_WORLD_SIZE. */
 int mapf_step_observe_host(mapf_handle* h, const mapf_host_io* io, void* stream);
+
+/* Host-side helper for consumers of the MAPF_BITS host output (io->obs_dtype == MAPF_BITS): expands cells
+ * [first_cell, first_cell + n_cells) of the bit stream bits_host into out_host as MAPF_U8 (0/1) or MAPF_F32 (0.0/1.0)
+ * on the calling thread -- a lazy view: a CPU consumer pays the 8x / 32x larger bytes only for the environments it
+ * actually reads (environment e of an [E,N,4,F,F] observation is cells [e*N*4*F*F, (e+1)*N*4*F*F)).  Pure host code:
+ * a transport decode of values the GPU computed, no handle and no CUDA call involved. */
+int mapf_host_unpack(const void* bits_host, uint64_t first_cell, uint64_t n_cells, void* out_host, int out_dtype);
 
 /* 1 when observations of this handle can be produced as MAPF_BITS. */
 int mapf_obs_bits_supported(const mapf_handle* h);
@@ -317,6 +341,21 @@ int mapf_get_step_count(mapf_handle* h, int32_t* step_count_dev, void* stream);
  * (`_each_goal_cost`), agent_steps_dev int32[E,N] (`_agent_step_count`); any pointer may be NULL. */
 int mapf_partial_state(mapf_handle* h, int64_t* state_dev, uint8_t* at_goal_dev, int32_t* goal_cost_dev,
                        int32_t* agent_steps_dev, void* stream);
+
+/* A random policy for rollouts and benchmarks, drawn on the device (the reference's runners sample random actions
+ * from the action mask on the host, e.g. MARL-curve-main/src/envs/marl_partial.py's __main__ loop): the action of
+ * (env, agent) is a counter hash of (seed, env_offset + env, step, agent), uniform over the n_actions actions, or --
+ * with avail_dev uint8[E,N,A] -- uniform over the agent's available actions.  A pure function of the GLOBAL env index
+ * env_offset + env, so the shards of a batch draw exactly what the unsharded batch would.  actions_dev [E,N] of
+ * act_dtype (MAPF_U8 or MAPF_I64). */
+int mapf_random_actions(mapf_handle* h, const uint8_t* avail_dev, uint32_t seed, uint32_t step, int64_t env_offset,
+                        void* actions_dev, int act_dtype, void* stream);
+
+/* MAPF_MODE_PARTIAL: from now on every observation launch of this handle (mapf_observe, mapf_step_observe,
+ * mapf_rollout) also writes get_state() (PARTIAL:384-393) to state_dev int64[E,3] -- the state rides along with the
+ * observation kernel instead of costing a launch of its own per environment step.  NULL unbinds.  The pointer is
+ * re-read at every launch; rebinding between launches (e.g. to the next time slice of an episode batch) is free. */
+int mapf_partial_bind_state_out(mapf_handle* h, int64_t* state_dev);
 
 /* Copies the int64[MAPF_N_STATS] counters to stats_host (waits for the stream). */
 int mapf_stats(mapf_handle* h, int64_t* stats_host, void* stream);

@@ -80,7 +80,10 @@ PROTOTYPES = {
     "mapf_step_agents": (_i, [_vp, _vp, _i, _i, _i, ctypes.POINTER(MapfStepOut), _vp]),
     "mapf_observe": (_i, [_vp, _vp, _i, _vp, _vp]),
     "mapf_step_observe": (_i, [_vp, _vp, _i, ctypes.POINTER(MapfStepOut), _vp, _i, _vp, _vp]),
+    "mapf_rollout": (_i, [_vp, _vp, _i, _i, ctypes.POINTER(MapfStepOut), _vp, _i, _vp, _vp]),
+    "mapf_rollout_in_one_launch": (_i, [_vp, _i]),
     "mapf_step_observe_host": (_i, [_vp, ctypes.POINTER(MapfHostIO), _vp]),
+    "mapf_host_unpack": (_i, [_vp, ctypes.c_uint64, ctypes.c_uint64, _vp, _i]),
     "mapf_obs_bits_supported": (_i, [_vp]),
     "mapf_host_transport": (_i, [_vp, _i]),
     "mapf_host_transport_get": (_i, [_vp]),
@@ -93,6 +96,8 @@ PROTOTYPES = {
     "mapf_get_dones": (_i, [_vp, _vp, _vp]),
     "mapf_get_step_count": (_i, [_vp, _vp, _vp]),
     "mapf_partial_state": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mapf_random_actions": (_i, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _i64, _vp, _i, _vp]),
+    "mapf_partial_bind_state_out": (_i, [_vp, _vp]),
     "mapf_stats": (_i, [_vp, _vp, _vp]),
     "mapf_error_flags": (_i, [_vp, _vp, _vp]),
     "mapf_launch_count": (_i64, [_vp]),

@@ -2,121 +2,218 @@
 device-resident vector environment instead of `batch_size_run` worker processes and pipes.
 
 The reference's rollout pays, per env step, a pickle over a Pipe in both directions, an actions GPU->CPU copy and
-obs/state/avail numpy->torch copies.  Here the environments live on the GPU: actions are
-consumed from the controller without `.cpu()`, and obs / state / avail_actions / reward / terminated are written
-into the episode batch as device tensors.
+obs/state/avail numpy->torch copies.  Here the environments live on the GPU and the loop never
+touches the host:
 
-Protocols (the same calls ParallelRunner makes):
-    env     : a vector env of this package with n_envs == batch size (MARL_PARTIAL_ENV, MAPF_GRID):
-              reset(), step(actions[B, N]) -> (reward[B], terminated[B], info), get_obs(), get_state(),
-              get_avail_actions(), get_env_info(), get_stats()
-    mac     : init_hidden(batch_size); select_actions(batch, t_ep, t_env, bs, test_mode) -> LongTensor [len(bs), N]
-    batch   : new_batch() returns an object with update(data, bs=..., ts=..., mark_filled=...) -- pymarl's
-              EpisodeBatch, or DeviceEpisodeBatch below.
+  * the episode batch is TIME-MAJOR device storage ([T+1, B, ...] per key, DeviceEpisodeBatch) and the fused kernel
+    writes obs / avail_actions / state / reward / terminated of a step straight into its time slices (the `out=`
+    argument of MapfEngine.step_observe): no staging tensors, no copies;
+  * one engine launch per environment step for the PRIMAL and GRID envs (two for PARTIAL, whose observation is its own
+    kernel; its get_state() triple rides along with it);
+  * no `.item()`, `.tolist()`, `.nonzero()` in the loop: finished environments keep stepping with the STAY action and
+    their entries are masked by `filled`, exactly the mask pymarl's learners apply; whether every environment has
+    finished is checked every `check_every` steps (ONE host sync per check);
+  * `cuda_graph=True`: the loop body of every block of `check_every` steps -- controller, masking, the engine launch,
+    bookkeeping -- is captured once into a CUDA graph and replayed, so an environment step costs no Python or launch
+    latency at all (controllers must then keep their per-episode state in device tensors they update in place;
+    RandomMAC's draws are a function of (seed, step) and therefore repeat from replay to replay).
+
+Protocols:
+    env : a vector env of this package (MARL_PARTIAL_ENV / MAPF_GRID with n_envs > 1, PrimalVecEnv) providing
+          rollout_spec(), reset_into(batch), step_into(actions, t, batch), stay_action, get_env_info(), get_stats()
+    mac : init_hidden(batch_size); select_actions(batch, t_ep, t_env, bs, test_mode) -> integer tensor [B, N] on the
+          device (bs is always slice(None): the whole batch, like pymarl's controllers accept)
 """
 import torch
 
 
 class DeviceEpisodeBatch:
-    """Minimal device-resident stand-in for pymarl's EpisodeBatch (components/episode_buffer.py:7-134): one tensor
-    [B, T+1, ...] per scheme key with the dtypes of run.py:133-140 (obs/state/reward float32, avail_actions int32,
-    actions int64, terminated uint8) plus `filled`."""
+    """Device-resident stand-in for pymarl's EpisodeBatch (components/episode_buffer.py:7-134).
 
-    def __init__(self, env_info, batch_size, device):
-        B, T, N = batch_size, env_info["episode_limit"] + 1, env_info["n_agents"]
-        self.batch_size, self.max_seq_length, self.device = B, T, device
-        z = lambda shape, dt: torch.zeros((B, T) + shape, dtype=dt, device=device)  # noqa: E731
-        self.data = {
-            "state": z((env_info["state_shape"],), torch.float32),
-            "obs": z((N, env_info["obs_shape"]), torch.float32),
-            "avail_actions": z((N, env_info["n_actions"]), torch.int32),
-            "actions": z((N, 1), torch.int64),
-            "reward": z((1,), torch.float32),
-            "terminated": z((1,), torch.uint8),
-            "filled": z((1,), torch.int64),
-        }
+    Storage is time-major, `tm[key]` = [T+1, B, ...], so that one time step of one key is a contiguous block a kernel
+    can write; `batch[key]` is the [B, T+1, ...] view pymarl code indexes (`batch["avail_actions"][:, t]`).  Keys and
+    per-step shapes come from the env's rollout_spec(); dtypes are the kernel's own (uint8 masks / flags, float64
+    rewards, the env's observation dtype) -- the values pymarl's scheme (run.py:133-148) would hold, before its casts.
+    Entries of (env, t) pairs with filled == 0 are undefined (pymarl leaves zeros there); consumers mask with `filled`.
+    """
 
-    def update(self, data, bs=slice(None), ts=slice(None), mark_filled=True):
-        if isinstance(bs, list):
-            bs = torch.as_tensor(bs, dtype=torch.int64, device=self.device)
-        for k, v in data.items():
-            dst = self.data[k]
-            v = torch.as_tensor(v, device=self.device).to(dst.dtype)
-            dst[bs, ts] = v.reshape((-1,) + dst.shape[2:]) if not isinstance(ts, slice) else v
-        if mark_filled:
-            self.data["filled"][bs, ts] = 1
+    def __init__(self, spec, batch_size, max_seq_length, n_agents, device):
+        self.batch_size, self.max_seq_length, self.device = batch_size, max_seq_length, device
+        self.views = dict(spec.get("_views", {}))
+        self.tm = {}
+        for k, v in spec.items():
+            if k != "_views":
+                shape, dt = v
+                self.tm[k] = torch.zeros((max_seq_length, batch_size) + tuple(shape), dtype=dt, device=device)
+        self.tm["actions"] = torch.zeros((max_seq_length, batch_size, n_agents, 1), dtype=torch.int64, device=device)
+        self.tm["filled"] = torch.zeros((max_seq_length, batch_size, 1), dtype=torch.uint8, device=device)
 
     def __getitem__(self, k):
-        return self.data[k]
+        if k in self.views:
+            return self.views[k](self.tm).transpose(0, 1)
+        return self.tm[k].transpose(0, 1)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.tm.values())
 
 
 class BatchedRunner:
-    def __init__(self, env, mac, new_batch=None, test_nepisode=0):
+    def __init__(self, env, mac, check_every=8, max_steps=None, cuda_graph=False):
         self.env, self.mac = env, mac
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = None
         self.batch_size = env.n_envs
         self.env_info = env.get_env_info()
         self.episode_limit = self.env_info["episode_limit"]
+        self.max_steps = min(self.episode_limit, max_steps) if max_steps else self.episode_limit
+        self.check_every = max(int(check_every), 1)
         self.device = env.engine.device
-        self.new_batch = new_batch or (lambda: DeviceEpisodeBatch(self.env_info, self.batch_size, self.device))
         self.t = 0
         self.t_env = 0
         self.train_returns, self.test_returns = [], []
         self.train_stats, self.test_stats = {}, {}
+        self.batch = None
 
     def get_env_info(self):
         return self.env_info
 
-    def reset(self):
-        self.batch = self.new_batch()
-        self.env.reset()
-        self.batch.update({"state": self.env.get_state(), "avail_actions": self.env.get_avail_actions(),
-                           "obs": self.env.get_obs()}, ts=0)
-        self.t = 0
-        self.env_steps_this_run = 0
+    def new_batch(self):
+        return DeviceEpisodeBatch(self.env.rollout_spec(), self.batch_size, self.max_steps + 1,
+                                  self.env_info["n_agents"], self.device)
 
-    def run(self, test_mode=False):
+    def reset(self, reuse_batch=False):
+        if not (reuse_batch and self.batch is not None):
+            self.batch = self.new_batch()
+        else:
+            self.batch.tm["filled"].zero_()
+        self.env.reset_into(self.batch)                      # obs / avail_actions / state of t = 0
+        self.batch.tm["filled"][0] = 1
+        self.t = 0
+
+    def _step_body(self, t, st, test_mode):
+        """Environment step t of the episode; every tensor it touches is persistent (graph-capturable)."""
+        B, batch = self.batch_size, self.batch
+        alive = st["alive"]
+        actions = self.mac.select_actions(batch, t_ep=t, t_env=self.t_env, bs=slice(None), test_mode=test_mode)
+        actions = actions.reshape(B, -1)
+        # finished environments idle; their entries stay masked (filled == 0)
+        actions = torch.where(alive.unsqueeze(1), actions, torch.full_like(actions, self.env.stay_action))
+        batch.tm["actions"][t] = actions.unsqueeze(-1)
+        self.env.step_into(actions, t, batch)                # reward / terminated -> t ; obs / avail / state -> t + 1
+        # parallel_runner.py:150-153: a termination is recorded unless the env flags it as `episode_limit` in its
+        # info; the MAPF envs of the reference never set that key, so limit terminations are recorded too
+        term = batch.tm["terminated"][t].reshape(B) != 0
+        st["returns"] += torch.where(alive, batch.tm["reward"][t].reshape(B).double(), st["zero"])
+        st["lengths"] += alive
+        batch.tm["filled"][t + 1] = alive.unsqueeze(-1)      # the step's data exists for envs that were still running
+        alive.logical_and_(~term)
+
+    def run(self, test_mode=False, reuse_batch=False):
         """One episode in every environment; returns the filled batch (parallel_runner.py:91-206)."""
-        self.reset()
+        reuse_batch = reuse_batch or self.cuda_graph         # captured graphs hold the batch's addresses
+        self.reset(reuse_batch)
         B, dev = self.batch_size, self.device
-        episode_returns = torch.zeros(B, dtype=torch.float64, device=dev)
-        episode_lengths = torch.zeros(B, dtype=torch.int64, device=dev)
-        terminated = torch.zeros(B, dtype=torch.bool, device=dev)
+        if getattr(self, "_st", None) is None:
+            self._st = {"returns": torch.zeros(B, dtype=torch.float64, device=dev),
+                        "lengths": torch.zeros(B, dtype=torch.int64, device=dev),
+                        "alive": torch.ones(B, dtype=torch.bool, device=dev),
+                        "zero": torch.zeros(B, dtype=torch.float64, device=dev)}
+        st = self._st
+        st["returns"].zero_()
+        st["lengths"].zero_()
+        st["alive"].fill_(True)
         self.mac.init_hidden(batch_size=B)
-        N = self.env_info["n_agents"]
-        stay = torch.full((B, N), 4, dtype=torch.int64, device=dev)
-        while True:
-            alive = (~terminated).nonzero(as_tuple=False).flatten()
-            if alive.numel() == 0 or self.t >= self.episode_limit:
-                break
-            actions = self.mac.select_actions(self.batch, t_ep=self.t, t_env=self.t_env, bs=alive.tolist(),
-                                              test_mode=test_mode)
-            actions = actions.to(dev).reshape(alive.numel(), N)
-            self.batch.update({"actions": actions.unsqueeze(-1)}, bs=alive, ts=self.t, mark_filled=False)
-            full = stay.clone()
-            full[alive] = actions                                  # finished environments idle; their data is masked
-            reward, term, info = self.env.step(full)
-            term = term.bool()
-            episode_returns[alive] += reward[alive].double()
-            episode_lengths[alive] += 1
-            if not test_mode:
-                self.env_steps_this_run += int(alive.numel())
-            # parallel_runner.py:150-153: a termination is recorded unless the env flags it as `episode_limit` in its
-            # info; the MAPF envs of the reference never set that key, so limit terminations are recorded too
-            limit_flag = info.get("episode_limit") if isinstance(info, dict) else None
-            rec = term if limit_flag is None else (term & ~torch.as_tensor(limit_flag, device=dev).bool())
-            self.batch.update({"reward": reward[alive].float().unsqueeze(-1),
-                               "terminated": rec[alive].to(torch.uint8).unsqueeze(-1)},
-                              bs=alive, ts=self.t, mark_filled=False)
-            terminated = terminated | term
-            self.t += 1
-            self.batch.update({"state": self.env.get_state()[alive], "avail_actions": self.env.get_avail_actions()[alive],
-                               "obs": self.env.get_obs()[alive]}, bs=alive, ts=self.t, mark_filled=True)
+        C, T = self.check_every, self.max_steps
+        blocks = [range(t0, min(t0 + C, T)) for t0 in range(0, T, C)]
+        if self.cuda_graph and self._graphs is None and getattr(self, "_warm", False):
+            # capture after one eager episode (library handles, controller buffers and the batch all exist by now)
+            self._graphs = []
+            pool = None
+            torch.cuda.synchronize()
+            for blk in blocks:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    for t in blk:
+                        self._step_body(t, st, test_mode)
+                pool = g.pool()
+                self._graphs.append(g)
+            # the capture pass does not execute anything: restore the start-of-episode state and replay below
+            st["returns"].zero_()
+            st["lengths"].zero_()
+            st["alive"].fill_(True)
+            self.mac.init_hidden(batch_size=B)
+        for k, blk in enumerate(blocks):
+            if self._graphs is not None:
+                self._graphs[k].replay()
+            else:
+                for t in blk:
+                    self._step_body(t, st, test_mode)
+            self.t = blk[-1] + 1
+            if self.t < T and not bool(st["alive"].any()):
+                break                                        # the only host synchronisation of the loop
+        self._warm = True
+        n_steps = int(st["lengths"].sum().item())
         if not test_mode:
-            self.t_env += self.env_steps_this_run
+            self.t_env += n_steps
         stats = self.test_stats if test_mode else self.train_stats
         stats["n_episodes"] = B + stats.get("n_episodes", 0)
-        stats["ep_length"] = int(episode_lengths.sum().item()) + stats.get("ep_length", 0)
+        stats["ep_length"] = n_steps + stats.get("ep_length", 0)
         for k, v in self.env.get_stats().items():
             stats["env_" + k] = v
-        (self.test_returns if test_mode else self.train_returns).extend(episode_returns.tolist())
+        (self.test_returns if test_mode else self.train_returns).extend(st["returns"].tolist())
         return self.batch
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Controllers for benchmarks and tests (the learner side of pymarl is out of scope; these only produce actions)
+# ----------------------------------------------------------------------------------------------------------------
+class RandomMAC:
+    """Uniform over the available actions, drawn on the device by the engine's counter-hash kernel
+    (mapf_random_actions): one launch, no host round trip, a function of (seed, episode, step, env, agent)."""
+
+    def __init__(self, engine, seed=0, env_offset=0):
+        self.engine, self.seed, self.env_offset, self.episode = engine, int(seed), int(env_offset), -1
+
+    def init_hidden(self, batch_size):
+        self.episode += 1
+
+    def select_actions(self, batch, t_ep, t_env, bs=slice(None), test_mode=False):
+        return self.engine.random_actions(self.seed + 7919 * self.episode, t_ep, avail=batch.tm["avail_actions"][t_ep],
+                                          env_offset=self.env_offset)
+
+
+class RNNAgentMAC:
+    """pymarl's recurrent agent (MARL-curve-main/src/modules/agents/rnn_agent.py:12-21: Linear -> GRUCell -> Linear,
+    shared by all agents) with greedy masked action selection, in plain torch: random-init weights, bf16 first layer.
+    The network is a caller of the environment path, not part of it."""
+
+    def __init__(self, obs_dim, n_actions, device, hidden=64, extra_dim=0, seed=0):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        mk = lambda *s: (torch.randn(*s, generator=g) * 0.05).to(device)   # noqa: E731
+        self.w1 = mk(obs_dim, hidden).to(torch.bfloat16)
+        self.w1x = mk(extra_dim, hidden) if extra_dim else None
+        self.b1 = mk(hidden)
+        self.gru = torch.nn.GRUCell(hidden, hidden).to(device)
+        self.w2, self.b2 = mk(hidden, n_actions), mk(n_actions)
+        self.hidden = hidden
+        self.h = None
+
+    def init_hidden(self, batch_size):
+        if self.h is not None:
+            self.h.zero_()                  # in place: a captured rollout graph keeps reading this tensor
+
+    @torch.no_grad()
+    def select_actions(self, batch, t_ep, t_env, bs=slice(None), test_mode=False):
+        obs = batch.tm["obs"][t_ep]                                       # [B, N, D]
+        B, N = obs.shape[0], obs.shape[1]
+        x = obs.reshape(B * N, -1).to(torch.bfloat16) @ self.w1
+        x = x.float() + self.b1
+        if self.w1x is not None:
+            x = x + batch.tm["obs_vec"][t_ep].reshape(B * N, -1).float() @ self.w1x
+        x = torch.relu(x)
+        if self.h is None:
+            self.h = torch.zeros(B * N, self.hidden, device=x.device)
+        self.h.copy_(self.gru(x, self.h))
+        q = self.h @ self.w2 + self.b2
+        q = q.masked_fill(batch.tm["avail_actions"][t_ep].reshape(B * N, -1) == 0, float("-inf"))
+        return q.argmax(-1).reshape(B, N)

@@ -21,6 +21,7 @@ struct mapf_handle {
   MapfState S;
   int device;
   int fov_fast;        // a specialised tile kernel exists for cfg.fov
+  int64_t* partial_state_out;   // mapf_partial_bind_state_out: get_state() written by every observation launch
   int64_t launches;
   int mag_lut_len;
   // device staging for the *_host entry points (allocated on first use)
@@ -46,6 +47,7 @@ struct mapf_handle {
 extern "C" {
 struct MapfUnpackPool* mapf_unpack_pool_create(int threads);
 void mapf_unpack_pool_destroy(struct MapfUnpackPool* p);
+int mapf_host_unpack_range(const uint32_t* bits, uint64_t first_cell, uint64_t n_cells, void* out, int elem_bytes);
 int mapf_unpack_pool_expand_streamed(struct MapfUnpackPool* p, const uint32_t* bits, void* out, size_t cells,
                                      int elem_bytes, const volatile uint32_t* ready_words, int (*poll)(void*),
                                      void* poll_arg);
@@ -110,7 +112,7 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L, bool s
   L->isint_off = take(na);
   L->atgoal_off = take(na);
   L->rew_off = take(8 * na);
-  L->envrew_off = take(8 * epb);
+  L->envrew_off = take(8 * epb * ((d.N + 31) / 32));
   L->envterm_off = take(epb);
   L->envcnt_off = take(4 * epb);
   L->envcnt2_off = take(4 * epb);
@@ -327,6 +329,7 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   d.step_is_int = c->step_reward_is_int;
   d.collide_is_int = c->collide_reward_is_int;
   d.collect_stats = c->collect_stats;
+  d.rsum_mode = (32 % c->n_agents == 0) ? 1 : ((c->n_agents % 32 == 0) ? 2 : 0);
   d.blocking = c->blocking_reward ? 1 : 0;
   d.blocking_cost = c->blocking_cost;
   d.diag = c->diagonal_movement ? 1 : 0;
@@ -524,9 +527,10 @@ static bool bits_supported(const mapf_handle* h) {
 }
 
 static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, int hi, const mapf_step_out* out,
-                    void* obs, int obs_dtype, double* vec, void* stream) {
+                    void* obs, int obs_dtype, double* vec, void* stream, int n_steps = 1) {
   MapfTileArgs A;
   memset(&A, 0, sizeof(A));
+  A.T = n_steps;
   A.actions = actions;
   A.act_dtype = act_dtype;
   A.do_step = actions != nullptr;
@@ -588,7 +592,8 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
                          (cudaStream_t)stream));
   }
   if (pwin && obs) {
-    CK((cudaError_t)mapf_launch_partial_obs(h->d, h->S, obs, obs_dtype == MAPF_F32, stream));
+    CK((cudaError_t)mapf_launch_partial_obs(h->d, h->S, obs, obs_dtype == MAPF_F32, (long long*)h->partial_state_out,
+                                            stream));
     h->launches++;
   }
   if (generic_obs) {
@@ -623,6 +628,76 @@ int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, co
                       void* obs_dev, int obs_dtype, double* vec_dev, void* stream) {
   if (!h || !actions_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_step_observe: NULL argument");
   return run_tile(h, actions_dev, act_dtype, 0, h->d.N, out, obs_dev, obs_dtype, vec_dev, stream);
+}
+
+// Can `n_steps` consecutive steps with these outputs run as ONE launch (the ROLL instantiation of the tile kernel)?
+static bool rollout_in_kernel(const mapf_handle* h, const void* obs, int obs_dtype, const double* vec) {
+  const MapfDims& d = h->d;
+  if (!mapf_tile_has_rollout(d.mode) || d.diag || d.blocking) return false;
+  if (d.epb * d.N > MAPF_TILE_THREADS) return false;                       // one thread per agent of the tile
+  const bool fov = d.obs_mode == MAPF_OBS_PRIMAL_FOV;
+  if (fov && !h->fov_fast && (obs || vec)) return false;                    // generic-F observation kernel
+  if (d.obs_mode == MAPF_OBS_PARTIAL_WINDOW) return false;
+  if (obs && obs_dtype == MAPF_BITS && (((size_t)d.E * d.N * 4 * d.F * d.F) & 31) != 0) return false;
+  if (obs && obs_dtype != MAPF_BITS && fov &&
+      (((size_t)d.E * d.N * 4 * d.F * d.F * (obs_dtype == MAPF_F32 ? 4 : 1)) & 15) != 0)
+    return false;                                                          // every step's block starts 16-byte aligned
+  return true;
+}
+
+int mapf_rollout_in_one_launch(const mapf_handle* h, int obs_dtype) {
+  if (!h) return 0;
+  int dummy = 0;
+  return rollout_in_kernel(h, &dummy, obs_dtype, nullptr) ? 1 : 0;
+}
+
+int mapf_rollout(mapf_handle* h, const void* actions_dev, int act_dtype, int n_steps, const mapf_step_out* out,
+                 void* obs_dev, int obs_dtype, double* vec_dev, void* stream) {
+  if (!h || !actions_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_rollout: NULL argument");
+  if (n_steps < 1) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_rollout: n_steps must be >= 1");
+  const MapfDims& d = h->d;
+  if (n_steps == 1 || rollout_in_kernel(h, obs_dev, obs_dtype, vec_dev))
+    return run_tile(h, actions_dev, act_dtype, 0, d.N, out, obs_dev, obs_dtype, vec_dev, stream, n_steps);
+  // configurations without the in-kernel loop: the same result from n_steps consecutive launches
+  const size_t EN = (size_t)d.E * d.N, E = (size_t)d.E;
+  size_t obs_step = 0;   // bytes of one step's observation
+  if (obs_dev) {
+    if (d.obs_mode == MAPF_OBS_PRIMAL_FOV) {
+      const size_t cells = EN * 4 * d.F * d.F;
+      if (obs_dtype == MAPF_BITS) {
+        if (cells & 31) return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_rollout: MAPF_BITS needs E*N*4*F*F to be a multiple of 32");
+        obs_step = cells / 8;
+      } else {
+        obs_step = cells * (obs_dtype == MAPF_F32 ? 4 : 1);
+      }
+    } else if (d.obs_mode == MAPF_OBS_PARTIAL_WINDOW) {
+      obs_step = EN * d.posz * (obs_dtype == MAPF_F32 ? 4 : 8);
+    } else {
+      obs_step = E * d.HW;
+    }
+    if (obs_step & 15) return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_rollout: one step's observation must be a multiple of 16 bytes");
+  }
+  if (act_dtype != MAPF_U8 && act_dtype != MAPF_I64) return fail(h, MAPF_ERR_INVALID_ARG, "actions must be MAPF_U8 or MAPF_I64");
+  if ((EN * (act_dtype == MAPF_I64 ? 8 : 1)) & 15)
+    return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_rollout: one step's actions must be a multiple of 16 bytes");
+  for (int t = 0; t < n_steps; ++t) {
+    mapf_step_out o;
+    memset(&o, 0, sizeof(o));
+    if (out) {
+      o = *out;
+#define ADV(field, count) if (o.field) o.field += (size_t)t * (count)
+      ADV(reward_dev, E); ADV(terminated_dev, E); ADV(agent_reward_dev, EN); ADV(dones_dev, EN); ADV(status_dev, EN);
+      ADV(node_dev, EN); ADV(edge_dev, EN); ADV(valid_dev, EN); ADV(done_mid_dev, EN); ADV(next_mid_dev, EN * d.nact);
+      ADV(avail_dev, EN * d.nact); ADV(blocking_dev, EN);
+#undef ADV
+    }
+    const char* a = (const char*)actions_dev + (size_t)t * EN * (act_dtype == MAPF_I64 ? 8 : 1);
+    void* ob = obs_dev ? (void*)((char*)obs_dev + (size_t)t * obs_step) : nullptr;
+    double* vc = vec_dev ? vec_dev + (size_t)t * EN * 3 : nullptr;
+    const int rc = run_tile(h, a, act_dtype, 0, d.N, &o, ob, obs_dtype, vc, stream);
+    if (rc != MAPF_OK) return rc;
+  }
+  return MAPF_OK;
 }
 
 int mapf_avail(mapf_handle* h, uint8_t* avail_dev, void* stream) {
@@ -708,6 +783,23 @@ int mapf_partial_state(mapf_handle* h, int64_t* state_dev, uint8_t* at_goal_dev,
   return MAPF_OK;
 }
 
+int mapf_random_actions(mapf_handle* h, const uint8_t* avail_dev, uint32_t seed, uint32_t step, int64_t env_offset,
+                        void* actions_dev, int act_dtype, void* stream) {
+  if (!h || !actions_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_random_actions: NULL argument");
+  if (act_dtype != MAPF_U8 && act_dtype != MAPF_I64) return fail(h, MAPF_ERR_INVALID_ARG, "actions must be MAPF_U8 or MAPF_I64");
+  CK((cudaError_t)mapf_launch_random_actions(h->d, avail_dev, seed, step, (long long)env_offset, actions_dev,
+                                             act_dtype == MAPF_I64, stream));
+  h->launches++;
+  return MAPF_OK;
+}
+
+int mapf_partial_bind_state_out(mapf_handle* h, int64_t* state_dev) {
+  if (!h) return MAPF_ERR_INVALID_ARG;
+  if (h->d.mode != MAPF_MODE_PARTIAL) return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_partial_bind_state_out: mode is not PARTIAL");
+  h->partial_state_out = state_dev;
+  return MAPF_OK;
+}
+
 int mapf_stats(mapf_handle* h, int64_t* stats_host, void* stream) {
   if (!h || !stats_host) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_stats: NULL argument");
   CK(cudaMemcpyAsync(stats_host, h->S.stats, MAPF_N_STATS * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -729,6 +821,13 @@ int mapf_host_transport(mapf_handle* h, int packed) {
   if (!h) return 0;
   h->packed_transport = packed ? 1 : 0;
   return (h->packed_transport && bits_supported(h)) ? 1 : 0;
+}
+
+int mapf_host_unpack(const void* bits_host, uint64_t first_cell, uint64_t n_cells, void* out_host, int out_dtype) {
+  if (out_dtype != MAPF_U8 && out_dtype != MAPF_F32) return MAPF_ERR_INVALID_ARG;
+  return mapf_host_unpack_range((const uint32_t*)bits_host, first_cell, n_cells, out_host, out_dtype == MAPF_F32 ? 4 : 1) == 0
+             ? MAPF_OK
+             : MAPF_ERR_INVALID_ARG;
 }
 
 int mapf_host_transport_get(const mapf_handle* h) { return (h && h->packed_transport && bits_supported(h)) ? 1 : 0; }

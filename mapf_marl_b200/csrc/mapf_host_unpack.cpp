@@ -14,6 +14,7 @@
 #include <sched.h>
 #endif
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -363,5 +364,30 @@ void mapf_unpack_pool_run(MapfUnpackPool* p, const uint32_t* bits, void* out, si
 }
 
 int mapf_unpack_pool_threads(const MapfUnpackPool* p) { return p ? (int)p->workers.size() : 0; }
+
+// include/mapf_b200.h: mapf_host_unpack -- expands cells [first_cell, first_cell + n_cells) of a host bit stream on the
+// CALLING thread (a CPU consumer of the MAPF_BITS host output expands only the environments it reads).
+// elem_bytes: 1 (uint8 0/1) or 4 (float32 0.0/1.0).
+int mapf_host_unpack_range(const uint32_t* bits, uint64_t first_cell, uint64_t n_cells, void* out, int elem_bytes) {
+  if (!bits || !out || (elem_bytes != 1 && elem_bytes != 4)) return -1;
+  uint8_t* dst = (uint8_t*)out;
+  uint64_t c = first_cell, done = 0;
+  auto scalar_cells = [&](uint64_t cnt) {          // cell by cell: the unaligned head / tail of the range
+    for (uint64_t k = 0; k < cnt; ++k, ++c, ++done) {
+      const uint32_t b = (bits[c >> 5] >> (c & 31)) & 1u;
+      if (elem_bytes == 1) dst[done] = (uint8_t)b;
+      else ((float*)dst)[done] = (float)b;
+    }
+  };
+  if (c & 31) scalar_cells(std::min<uint64_t>(n_cells, 32 - (c & 31)));
+  const uint64_t words = (n_cells - done) >> 5;
+  if (words) {
+    pick_unpack(elem_bytes)(bits + (c >> 5), dst + done * elem_bytes, (size_t)words);
+    c += words << 5;
+    done += words << 5;
+  }
+  scalar_cells(n_cells - done);
+  return 0;
+}
 
 }  // extern "C"

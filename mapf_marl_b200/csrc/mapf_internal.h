@@ -30,6 +30,8 @@ struct MapfDims {
   int GW;        // words per group string = G * 4*F*F / 32
   int sum_mode, step_is_int, collide_is_int;
   int collect_stats;
+  int rsum_mode;         // PRIMAL team reward tree: 1 = N divides 32 (whole tree inside a warp), 2 = 32 divides N
+                         // (32-agent blocks inside warps, the rest by one thread), 0 = one thread per environment
   int blocking;          // PRIMAL blocking reward enabled
   int diag;              // PRIMAL DIAGONAL_MOVEMENT
   int nact;              // 5, or 9 with diagonal movement
@@ -54,7 +56,7 @@ struct MapfTileLayout {
   int res_off, dep_off;  // u8 [epb*N]
   int act_off, status_off, done_off, flag_off, avail_off, nextmid_off, node_off, edge_off, isint_off;  // u8 [epb*N]
   int rew_off;      // double [epb*N]
-  int envrew_off;   // double [epb]
+  int envrew_off;   // double [epb * max(1, N / 32)]: partial sums of the pairwise team reward
   int envterm_off;  // u8 [epb] (padded)
   int envcnt_off;   // int [epb]: per-environment counters (agents on goal / done)
   int envcnt2_off;  // int [epb]: PARTIAL: sum of node flags + edge counts
@@ -108,6 +110,7 @@ struct MapfTileArgs {
   void* obs;               // FOV: [E][N][4][F][F] u8/f32 ; FULLMAP: [E][H*W] i8 ; NULL: no observation
   int obs_dtype;
   double* vec;             // [E][N][3] or NULL
+  int T;                   // steps in this launch (mapf_rollout): actions / outputs / obs / vec are [T][...], T >= 1
 };
 
 #ifdef __cplusplus
@@ -130,10 +133,14 @@ int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty,
                     int primal_costs, void* stream, int* n_launches);   // 8-connected when primal_costs && d.diag
 int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int agent_lo, int agent_hi, const mapf_step_out& out,
                          void* stream, int* n_launches);
-int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, void* obs, int f32, void* stream);
+int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, void* obs, int f32, long long* state_out,
+                            void* stream);
 int mapf_launch_partial_state(const MapfDims& d, const MapfState& S, long long* state, void* stream);
 int mapf_launch_export16(const MapfDims& d, const uint8_t* src_u8x2, int16_t* dst, void* stream);
+int mapf_launch_random_actions(const MapfDims& d, const uint8_t* avail, uint32_t seed, uint32_t step,
+                               long long env_offset, void* out, int i64, void* stream);
 int mapf_tile_has_fov(int F);
+int mapf_tile_has_rollout(int mode);
 int mapf_configure_tile(int F, int mode, int smem_bytes);
 #ifdef __cplusplus
 }

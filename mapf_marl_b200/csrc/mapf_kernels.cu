@@ -52,7 +52,7 @@ struct Smem {
   uint8_t *act, *done, *flag, *avail, *nextmid, *node, *edge, *isint;
   int8_t* status;
   double* rew;
-  double* envrew;
+  double* envrew;    // PRIMAL: per-environment partial sums of the pairwise team reward (one per 32 agents)
   uint8_t* envterm;
   uint8_t* atgoal;
   uchar2 *pastold, *pastnew;     // diagonal mode: agents_past before / after the sweep
@@ -198,6 +198,63 @@ __device__ double py_sum(const double* x, const uint8_t* is_int, int n, int sum_
   }
   if (in_float && c != 0.0 && isfinite(c)) acc = __dadd_rn(acc, c);
   return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PRIMAL team reward (mapf_step_out.reward_dev; MAPFEnv._step only returns per-agent rewards, so the team value has no
+// reference counterpart and its summation order is this library's to define): the PAIRWISE sum of the per-agent
+// rewards -- leaves x[0..N) (agents outside the swept range count as +0.0), padded with +0.0 to the next power of two,
+// y[i] += y[i + s] for s = 1, 2, 4, ...  A fixed binary tree: log2(N) dependent double adds instead of the N of a left
+// fold (one thread folding the 128 rewards of a c4 environment was 20 % of that tile's critical path), and the same
+// bits on any tile shape.  TreeSum evaluates that tree from left to right with a binary-counter stack.
+// ------------------------------------------------------------------------------------------------
+struct TreeSum {
+  double st[9];      // st[k]: sum of a finished subtree of 2^k leaves waiting for its right sibling
+  unsigned n = 0;
+  __device__ __forceinline__ void push(double v) {
+    unsigned idx = n++;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (idx & 1u) {
+        v = __dadd_rn(st[k], v);
+        idx >>= 1;
+      } else {
+        st[k] = v;
+        break;
+      }
+    }
+  }
+  __device__ __forceinline__ double finish() {
+    if (n == 0) return 0.0;
+    while (n & (n - 1)) push(0.0);
+    double r = st[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k)   // compile-time indices only: the stack stays in registers
+      if (n == (1u << k)) r = st[k];
+    return r;
+  }
+};
+
+// The same tree over the cnt <= 8 block sums p[0..cnt) of one environment (cnt = N / 32), a few live registers.
+__device__ __forceinline__ double tree_sum8(const double* p, int cnt) {
+  auto ld = [&](int k) { return k < cnt ? p[k] : 0.0; };
+  double tot = p[0];
+  if (cnt > 1) {
+    tot = __dadd_rn(tot, p[1]);
+    if (cnt > 2) {
+      tot = __dadd_rn(tot, __dadd_rn(p[2], ld(3)));
+      if (cnt > 4) tot = __dadd_rn(tot, __dadd_rn(__dadd_rn(p[4], ld(5)), __dadd_rn(ld(6), ld(7))));
+    }
+  }
+  return tot;
+}
+
+// Any N: one thread walks the agents of its environment (kept out of line: its stack of partial sums must not cost the
+// hot instantiations registers or a stack frame).
+__device__ __noinline__ double tree_sum_agents(const double* rew, int N, int lo, int hi) {
+  TreeSum ts;
+  for (int i = 0; i < N; ++i) ts.push((i >= lo && i < hi) ? rew[i] : 0.0);
+  return ts.finish();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -822,6 +879,7 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
   int sc0 = 0;
   if (tid < ne) sc0 = S.step_count[e0 + tid];
   for (;;) {   // one iteration per step of a rollout; a single pass otherwise
+  PHASE_MARK(10);
   if (ROLL && t_roll > 0) {
     bad = false;
     if (tid < MAPF_N_STATS) stat[tid] = 0;
@@ -948,6 +1006,15 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
         flag = primal ? primal_phase_c<diag>(d, s, j, el, a, c0, c1, c3)
                       : grid_phase_c(d, s, j, el, a, partial, envcnt2, c1, c2);
       }
+      if (primal && d.rsum_mode != 0 && A.out.reward_dev != nullptr) {
+        // pairwise team reward, the part of the tree that lives inside a warp: segments of N | 32 agents, or the
+        // N / 32 aligned blocks of a larger environment (see TreeSum)
+        const int a = active ? j - el * N : 0;
+        double v = (active && a >= A.agent_lo && a < A.agent_hi) ? s.rew[j] : 0.0;
+        const int span = N < 32 ? N : 32;
+        for (int sft = 1; sft < span; sft <<= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, sft));
+        if (active && (a & (span - 1)) == 0) s.envrew[d.rsum_mode == 1 ? el : el * (N >> 5) + (a >> 5)] = v;
+      }
       // per-environment count of agents on goal (PRIMAL) / done (GRID), one shared-memory atomic per (warp, env)
       const unsigned peers = __match_any_sync(0xffffffffu, el);
       const unsigned bf = __ballot_sync(0xffffffffu, flag);
@@ -1040,9 +1107,14 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
       if (A.out.terminated_dev) A.out.terminated_dev[e0t + el] = all ? 1 : 0;
       if (primal) {
         if (A.out.reward_dev) {
-          double tot = 0.0;
-#pragma unroll 8   // the adds are one dependent chain (the reference's order); unrolling lets the loads run ahead
-          for (int i = A.agent_lo; i < A.agent_hi; ++i) tot = __dadd_rn(tot, s.rew[el * N + i]);
+          double tot;
+          if (d.rsum_mode == 1) {
+            tot = s.envrew[el];                                      // the whole tree was inside one warp
+          } else if (d.rsum_mode == 2) {
+            tot = tree_sum8(s.envrew + el * (N >> 5), N >> 5);
+          } else {
+            tot = tree_sum_agents(s.rew + el * N, N, A.agent_lo, A.agent_hi);
+          }
           A.out.reward_dev[e0t + el] = tot;
         }
         if (A.agent_lo == 0) S.step_count[e0 + el] = envstep[el] + 1;
@@ -1070,6 +1142,7 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
       }
       if (d.collect_stats && all) atomicAdd(&S.stats[MAPF_STAT_EPISODES_DONE], 1ull);
     }
+    PHASE_MARK(11);
     if (d.collect_stats) {   // one global atomic per counter per tile; the per-agent counters were complete at the barrier
       if (tid == 0) {
         if (!primal || A.agent_lo == 0) atomicAdd(&S.stats[MAPF_STAT_ENV_STEPS], (unsigned long long)ne);
@@ -1078,6 +1151,7 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
         atomicAdd(&S.stats[tid], (unsigned long long)stat[tid]);
       }
     }
+    PHASE_MARK(12);
     if (partial) __syncthreads();   // phase D changed done / rewards of whole environments
     // state write-back and the per-agent outputs: thread j stores agent j's records (byte stores of a warp cover
     // whole 32-byte sectors; a shared-memory staging pass costs more instructions than it saves transactions)
@@ -1499,6 +1573,51 @@ __global__ void mapf_pop_goals_kernel(const MapfDims d, const MapfState S, const
     head[j] = hd + 1;
     ((uchar2*)S.goal)[j] = make_uchar2((unsigned char)g0, (unsigned char)g1);
     if (d.mode == MAPF_MODE_PRIMAL) S.done[j] = (uint8_t)(p.x == g0 && p.y == g1);
+  }
+}
+
+// Counter-based random policy (mapf_random_actions): action of (env, agent) at `step` = a 32-bit mix of
+// (seed, GLOBAL env index, step, agent) -- the same function as mapf_marl_b200/workloads.py hash_actions_np -- taken
+// uniformly over {0..nact-1}, or over the set bits of the agent's action mask (the r-th available action,
+// r = hash mod popcount).  A pure function of the global env index: shards of a batch draw what the whole batch would.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 15;
+  x *= 0x2C1B3C6Du;
+  x ^= x >> 12;
+  x *= 0x297A2D39u;
+  x ^= x >> 15;
+  return x;
+}
+
+__global__ void mapf_random_actions_kernel(const MapfDims d, const uint8_t* __restrict__ avail, uint32_t seed,
+                                           uint32_t step, long long env_offset, uint8_t* out8, long long* out64) {
+  const long long total = (long long)d.E * d.N;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total;
+       j += (long long)gridDim.x * blockDim.x) {
+    const long long e = j / d.N;
+    const uint32_t a = (uint32_t)(j - e * d.N);
+    const uint32_t x = (uint32_t)(e + env_offset) * 0x9E3779B1u + step * 0x85EBCA77u + a * 0xC2B2AE3Du +
+                       seed * 0x27D4EB2Fu;
+    const uint32_t h = mix32(mix32(x) + 0x165667B1u) >> 8;
+    int act;
+    if (avail == nullptr) {
+      act = (int)((h * (uint32_t)d.nact) >> 24);
+    } else {
+      const uint8_t* m = avail + j * d.nact;
+      int cnt = 0;
+      for (int k = 0; k < d.nact; ++k) cnt += m[k] != 0;
+      act = 0;
+      if (cnt > 0) {
+        int r = (int)(h % (uint32_t)cnt);
+        for (int k = 0; k < d.nact; ++k)
+          if (m[k] != 0 && r-- == 0) {
+            act = k;
+            break;
+          }
+      }
+    }
+    if (out8) out8[j] = (uint8_t)act;
+    if (out64) out64[j] = act;
   }
 }
 
@@ -1956,9 +2075,9 @@ __global__ void mapf_blocking_finish_kernel(const MapfDims d, const MapfState S,
        j += (long long)gridDim.x * blockDim.x) {
     if (agent_reward) agent_reward[j] = S.last_reward[j];
     if (reward && (j % d.N) == 0) {
-      double tot = 0.0;
-      for (int a = agent_lo; a < agent_hi; ++a) tot = __dadd_rn(tot, S.last_reward[j + a]);
-      reward[j / d.N] = tot;
+      TreeSum ts;                                                    // the same pairwise order as the tile kernel
+      for (int a = 0; a < d.N; ++a) ts.push((a >= agent_lo && a < agent_hi) ? S.last_reward[j + a] : 0.0);
+      reward[j / d.N] = ts.finish();
     }
   }
 }
@@ -2003,7 +2122,7 @@ __global__ void mapf_primal_costs_free_kernel(const MapfDims d, const uint8_t* d
 //     agents: for one agent consecutive lanes write consecutive elements (coalesced streaming stores).
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* obs) {
+__global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* obs, long long* state_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int e = blockIdx.x, N = d.N, Wn = d.pW, K = d.pK;
   const int half = Wn / 2, Wp = d.W + Wn, Hp = d.H + Wn;     // count map: `half` empty cells on every side (+1 spare)
@@ -2032,6 +2151,15 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
   const uchar2* start = (const uchar2*)S.start + (size_t)e * N;
   const uint32_t* ob = S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e * d.bm_words);
   const int rowbits = d.RW * 32;
+  if (state_out != nullptr && threadIdx.x == blockDim.x - 1) {
+    // get_state (PARTIAL:384-393) rides along with the observation when the caller bound an output for it
+    // (mapf_partial_bind_state_out): the last thread has the least to do in the phases below
+    long long sum = 0;
+    for (int i = 0; i < N; ++i) sum += S.goal_cost[(size_t)e * N + i];
+    state_out[3 * e] = S.total_coll[e];
+    state_out[3 * e + 1] = S.step_count[e];
+    state_out[3 * e + 2] = sum;
+  }
   for (int i = threadIdx.x; i < (d.bm_words >> 2); i += blockDim.x) ((uint4*)obw)[i] = ((const uint4*)ob)[i];
   for (int i = threadIdx.x; i < ((Hp * Wp + 15) >> 4); i += blockDim.x) ((uint4*)cnt)[i] = make_uint4(0, 0, 0, 0);
   for (int a = threadIdx.x; a < N; a += blockDim.x) {
@@ -2227,24 +2355,41 @@ __global__ void mapf_partial_state_kernel(const MapfDims d, const MapfState S, l
   }
 }
 
+// In-kernel rollouts (ROLL) exist for the modes whose whole step, observation included, is this one kernel: PRIMAL
+// (without diagonal movement) and GRID.  PARTIAL observes in its own kernel, the diagonal mode is off the hot path.
+template <int MODE>
+constexpr bool kHasRoll = (MODE == MAPF_MODE_PRIMAL || MODE == MAPF_MODE_GRID);
+
 template <int F, int MODE>
 cudaError_t launch_tile_f(const MapfDims& d, const MapfTileLayout& L, const MapfState& S, const MapfTileArgs& A,
                           cudaStream_t st) {
   const int grid = (d.E + d.epb - 1) / d.epb;
-  // the diagonal mode is off the hot path: it only has the looped instantiation
-  if (MODE != MAPF_MODE_PRIMAL_DIAG && d.epb * d.N <= kThreads)
-    mapf_tile_kernel<F, MODE, (MODE != MAPF_MODE_PRIMAL_DIAG)><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
+  constexpr bool kSingle = MODE != MAPF_MODE_PRIMAL_DIAG;   // the diagonal mode only has the looped instantiation
+  if (A.T > 1) {
+    if constexpr (kHasRoll<MODE>) {
+      if (d.epb * d.N > kThreads) return cudaErrorInvalidValue;
+      mapf_tile_kernel<F, MODE, true, true><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
+      return cudaGetLastError();
+    } else {
+      return cudaErrorInvalidValue;
+    }
+  }
+  if (kSingle && d.epb * d.N <= kThreads)
+    mapf_tile_kernel<F, MODE, kSingle, false><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
   else
-    mapf_tile_kernel<F, MODE, false><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
+    mapf_tile_kernel<F, MODE, false, false><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A);
   return cudaGetLastError();
 }
 
 template <int F, int MODE>
 cudaError_t configure_tile_f(int smem_bytes) {
   const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-  cudaError_t e = cudaFuncSetAttribute(mapf_tile_kernel<F, MODE, false>, attr, smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(mapf_tile_kernel<F, MODE, false, false>, attr, smem_bytes);
   if (e == cudaSuccess && MODE != MAPF_MODE_PRIMAL_DIAG)
-    e = cudaFuncSetAttribute(mapf_tile_kernel<F, MODE, (MODE != MAPF_MODE_PRIMAL_DIAG)>, attr, smem_bytes);
+    e = cudaFuncSetAttribute(mapf_tile_kernel<F, MODE, (MODE != MAPF_MODE_PRIMAL_DIAG), false>, attr, smem_bytes);
+  if constexpr (kHasRoll<MODE>) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mapf_tile_kernel<F, MODE, true, true>, attr, smem_bytes);
+  }
   return e;
 }
 
@@ -2268,6 +2413,11 @@ extern "C" int mapf_debug_phase_clocks(long long* out32) {
 // Specialised tile kernels: PRIMAL with a field of view F (and F = 0: step only, the observation of an unlisted F
 // comes from the generic kernel), GRID and PARTIAL without a window.
 #define MAPF_FOR_EACH_FOV(X) X(3) X(5) X(7) X(9) X(10) X(11)
+
+// 1 when mapf_launch_tile accepts A.T > 1 for this mode (the caller also needs epb * N <= MAPF_TILE_THREADS).
+extern "C" int mapf_tile_has_rollout(int mode) {
+  return (mode == MAPF_MODE_PRIMAL || mode == MAPF_MODE_GRID) ? 1 : 0;
+}
 
 extern "C" int mapf_tile_has_fov(int F) {
   switch (F) {
@@ -2390,7 +2540,8 @@ extern "C" int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int a
   return (int)err;
 }
 
-extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, void* obs, int f32, void* stream) {
+extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, void* obs, int f32, long long* state_out,
+                                       void* stream) {
   const size_t smem = (size_t)d.bm_words * 4 + (((size_t)(d.H + d.pW) * (d.W + d.pW) + 15) & ~(size_t)15) +
                       (size_t)d.N * d.pK * 8 + (size_t)d.N * 13 * 8 + 2 * (((size_t)d.N * 4 + 15) & ~(size_t)15) +
                       (((size_t)d.N * 2 + 15) & ~(size_t)15) + (((size_t)d.N * d.pK * 4 + 15) & ~(size_t)15) +
@@ -2403,13 +2554,20 @@ extern "C" int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, vo
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  if (f32) mapf_partial_obs_kernel<float><<<d.E, threads, smem, (cudaStream_t)stream>>>(d, S, (float*)obs);
-  else mapf_partial_obs_kernel<double><<<d.E, threads, smem, (cudaStream_t)stream>>>(d, S, (double*)obs);
+  if (f32) mapf_partial_obs_kernel<float><<<d.E, threads, smem, (cudaStream_t)stream>>>(d, S, (float*)obs, state_out);
+  else mapf_partial_obs_kernel<double><<<d.E, threads, smem, (cudaStream_t)stream>>>(d, S, (double*)obs, state_out);
   return (int)cudaGetLastError();
 }
 
 extern "C" int mapf_launch_partial_state(const MapfDims& d, const MapfState& S, long long* state, void* stream) {
   mapf_partial_state_kernel<<<grid_for(d.E, 256), 256, 0, (cudaStream_t)stream>>>(d, S, state);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_random_actions(const MapfDims& d, const uint8_t* avail, uint32_t seed, uint32_t step,
+                                          long long env_offset, void* out, int i64, void* stream) {
+  mapf_random_actions_kernel<<<grid_for((long long)d.E * d.N, 256), 256, 0, (cudaStream_t)stream>>>(
+      d, avail, seed, step, env_offset, i64 ? nullptr : (uint8_t*)out, i64 ? (long long*)out : nullptr);
   return (int)cudaGetLastError();
 }
 

@@ -186,18 +186,31 @@ class MapfEngine:
             raise ValueError("actions must have shape (%d, %d), got %s" % (self.E, self.N, tuple(a.shape)))
         return a, (U8 if a.dtype == torch.uint8 else I64)
 
-    def _step_out(self, want):
+    def _step_out(self, want, out=None, T=None):
+        """The mapf_step_out descriptor for the outputs in `want`.  out: optional dict of CALLER-OWNED tensors (e.g.
+        slices of an episode batch) the kernel writes into directly; T: leading time dimension of a rollout."""
         so = MapfStepOut()
         outs = {}
+        lead = (self.E,) if T is None else (int(T), self.E)
         for name in want:
             if name not in _OUT_SPECS:
                 raise KeyError("unknown step output %r (choose from %s)" % (name, ", ".join(STEP_OUT_FIELDS)))
             dtype, suffix = _OUT_SPECS[name]
-            shape = tuple(self.n_actions if k == -1 else k for k in suffix(self.N))
-            t = self._buf("out_" + name, (self.E,) + shape, dtype)
+            shape = lead + tuple(self.n_actions if k == -1 else k for k in suffix(self.N))
+            t = out.get(name) if out else None
+            if t is None:
+                t = self._buf(("out_" if T is None else "roll_") + name, shape, dtype)
+            else:
+                self._check_out(name, t, shape, dtype)
             setattr(so, name + "_dev", t.data_ptr())
             outs[name] = t
         return so, outs
+
+    def _check_out(self, name, t, shape, dtype):
+        if (not isinstance(t, torch.Tensor) or t.device != self.device or t.dtype != dtype or not t.is_contiguous()
+                or t.numel() != int(np.prod(shape))):
+            raise ValueError("out[%r] must be a contiguous %s tensor with %d elements on %s" %
+                             (name, dtype, int(np.prod(shape)), self.device))
 
     # ------------------------------------------------------------------ state
     def reset(self, obst=None, starts=None, goals=None, env_mask=None):
@@ -280,27 +293,62 @@ class MapfEngine:
         self._check(rc, "mapf_step")
         return outs
 
-    def _obs_buffers(self, dtype, want_vec):
+    def _obs_buffers(self, dtype, want_vec, out=None, T=None):
+        have_all = bool(out) and out.get("obs") is not None and (not want_vec or out.get("vec") is not None
+                                                                  or self.obs_mode != OBS_PRIMAL_FOV)
+        # caller-owned storage for everything: only the shapes are needed (no engine buffer is allocated)
+        mk = (lambda name, shape, dt: torch.empty(shape, dtype=dt, device="meta")) if have_all else self._buf
+        obs, vec, odt = self._obs_buffers_own(dtype, want_vec, T, mk)
+        if out:
+            if out.get("obs") is not None:
+                self._check_out("obs", out["obs"], tuple(obs.shape), obs.dtype)
+                obs = out["obs"]
+            if vec is not None and out.get("vec") is not None:
+                self._check_out("vec", out["vec"], tuple(vec.shape), vec.dtype)
+                vec = out["vec"]
+        return obs, vec, odt
+
+    def _obs_buffers_own(self, dtype, want_vec, T=None, mk=None):
+        mk = mk or self._buf
+        if T is not None:
+            # time-major rollout storage: one engine-owned tensor per (dtype, T)
+            lead = (int(T),)
+            if self.obs_mode == OBS_PRIMAL_FOV:
+                vec = mk("roll_vec", lead + (self.E, self.N, 3), torch.float64) if want_vec else None
+                if dtype == "bits":
+                    cells = self.E * self.N * 4 * self.F * self.F
+                    if cells % 32:
+                        raise ValueError("bit-packed rollouts need E*N*4*F*F to be a multiple of 32")
+                    return mk("roll_obs_bits", lead + (cells // 8,), torch.uint8), vec, BITS
+                if dtype not in (torch.uint8, torch.float32):
+                    raise ValueError("FOV observations are uint8, float32 or 'bits'")
+                return (mk("roll_obs_%s" % dtype, lead + (self.E, self.N, 4, self.F, self.F), dtype), vec,
+                        U8 if dtype == torch.uint8 else F32)
+            if self.obs_mode == OBS_PARTIAL_WINDOW:
+                pdt = torch.float32 if dtype == torch.float32 else torch.float64
+                return (mk("roll_obs_partial_%s" % pdt, lead + (self.E, self.N, self.obs_size), pdt), None,
+                        F32 if pdt == torch.float32 else F64)
+            return mk("roll_state", lead + (self.E, self.H * self.W), torch.int8), None, I8
         if self.obs_mode == OBS_PRIMAL_FOV:
             if dtype == "bits":
                 # one bit per cell, bit i of the stream == element i of the uint8 tensor (little-endian bit order):
                 # np.unpackbits(obs.cpu().numpy(), bitorder="little")[:E*N*4*F*F] gives the cells back
                 nwords = (self.E * self.N * 4 * self.F * self.F + 31) // 32
-                obs = self._buf("obs_bits", (nwords * 4,), torch.uint8)
-                vec = self._buf("vec", (self.E, self.N, 3), torch.float64) if want_vec else None
+                obs = mk("obs_bits", (nwords * 4,), torch.uint8)
+                vec = mk("vec", (self.E, self.N, 3), torch.float64) if want_vec else None
                 return obs, vec, BITS
             if dtype not in (torch.uint8, torch.float32):
                 raise ValueError("FOV observations are uint8, float32 or 'bits'")
-            obs = self._buf("obs_%s" % dtype, (self.E, self.N, 4, self.F, self.F), dtype)
-            vec = self._buf("vec", (self.E, self.N, 3), torch.float64) if want_vec else None
+            obs = mk("obs_%s" % dtype, (self.E, self.N, 4, self.F, self.F), dtype)
+            vec = mk("vec", (self.E, self.N, 3), torch.float64) if want_vec else None
             return obs, vec, (U8 if dtype == torch.uint8 else F32)
         if self.obs_mode == OBS_PARTIAL_WINDOW:
             # float64 like the reference's get_obs; float32 = the same values rounded once at the store (what
             # pymarl's episode batch keeps, src/run.py:133-140)
             if dtype == torch.float32:
-                return self._buf("obs_partial32", (self.E, self.N, self.obs_size), torch.float32), None, F32
-            return self._buf("obs_partial", (self.E, self.N, self.obs_size), torch.float64), None, F64
-        obs = self._buf("state", (self.E, self.H * self.W), torch.int8)
+                return mk("obs_partial32", (self.E, self.N, self.obs_size), torch.float32), None, F32
+            return mk("obs_partial", (self.E, self.N, self.obs_size), torch.float64), None, F64
+        obs = mk("state", (self.E, self.H * self.W), torch.int8)
         return obs, None, I8
 
     def observe(self, dtype=torch.uint8, want_vec=True):
@@ -311,11 +359,13 @@ class MapfEngine:
                         "mapf_observe")
         return obs, vec
 
-    def step_observe(self, actions, want=DEFAULT_WANT, dtype=torch.uint8, want_vec=True):
-        """Fused step + observation: one kernel launch."""
+    def step_observe(self, actions, want=DEFAULT_WANT, dtype=torch.uint8, want_vec=True, out=None):
+        """Fused step + observation: one kernel launch.  out: optional dict name -> caller-owned contiguous tensor
+        ("obs", "vec" and any step output) that the kernel writes into directly, e.g. the time slice t of a
+        time-major episode batch; everything else lands in engine-owned tensors (valid until the next call)."""
         a, adt = self._actions(actions)
-        so, outs = self._step_out(want)
-        obs, vec, odt = self._obs_buffers(dtype, want_vec)
+        so, outs = self._step_out(want, out)
+        obs, vec, odt = self._obs_buffers(dtype, want_vec, out)
         self._keep = [a]
         with torch.cuda.device(self.device):
             self._check(self.lib.mapf_step_observe(self._h, self._ptr(a), adt, ctypes.byref(so), self._ptr(obs), odt,
@@ -324,6 +374,56 @@ class MapfEngine:
         if vec is not None:
             outs["vec"] = vec
         return outs
+
+    def rollout(self, actions, want=DEFAULT_WANT, dtype=torch.uint8, want_vec=True, out=None, observe=True):
+        """T consecutive fused steps with pre-supplied actions [T,E,N] in one call (mapf_rollout) -- one kernel launch
+        for PRIMAL / GRID batches whose tiles hold one thread per agent (rollout_in_one_launch()).  Returns
+        time-major tensors: out["obs"] [T,E,N,4,F,F], out["reward"] [T,E], ...; step t's entries equal what the t-th
+        of T consecutive step_observe() calls returns."""
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions))
+        if actions.dtype not in (torch.uint8, torch.int64):
+            actions = actions.to(torch.int64)
+        a = actions.to(self.device).contiguous()
+        if a.dim() != 3 or tuple(a.shape[1:]) != (self.E, self.N):
+            raise ValueError("actions must have shape (T, %d, %d), got %s" % (self.E, self.N, tuple(a.shape)))
+        T = int(a.shape[0])
+        so, outs = self._step_out(want, out, T)
+        obs = vec = None
+        odt = U8
+        if observe:
+            obs, vec, odt = self._obs_buffers(dtype, want_vec, out, T)
+        self._keep = [a]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_rollout(self._h, self._ptr(a), U8 if a.dtype == torch.uint8 else I64, T,
+                                              ctypes.byref(so), self._ptr(obs), odt, self._ptr(vec), self._stream()),
+                        "mapf_rollout")
+        if obs is not None:
+            outs["obs"] = obs
+        if vec is not None:
+            outs["vec"] = vec
+        return outs
+
+    def random_actions(self, seed, step, avail=None, env_offset=0, out=None, dtype=torch.int64):
+        """Counter-hash random policy on the device (mapf_random_actions): uniform over the actions, or over the set
+        bits of `avail` (uint8 [E,N,A]).  Same values as workloads.hash_actions_np(seed, env_offset + arange(E), step,
+        N, avail=...)."""
+        if out is None:
+            out = self._buf("rand_actions_%s" % dtype, (self.E, self.N), dtype)
+        else:
+            self._check_out("actions", out, (self.E, self.N), dtype)
+        if avail is not None:
+            self._check_out("avail", avail, (self.E, self.N, self.n_actions), torch.uint8)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_random_actions(self._h, self._ptr(avail), int(seed) & 0xFFFFFFFF,
+                                                     int(step) & 0xFFFFFFFF, int(env_offset), self._ptr(out),
+                                                     U8 if dtype == torch.uint8 else I64, self._stream()),
+                        "mapf_random_actions")
+        return out
+
+    def rollout_in_one_launch(self, dtype=torch.uint8):
+        odt = BITS if dtype == "bits" else (F32 if dtype == torch.float32 else U8)
+        return bool(self.lib.mapf_rollout_in_one_launch(self._h, odt))
 
     def avail(self, prev=None):
         """Action masks of the current state.  prev (uint8 [E,N]): evaluate `_listNextValidActions(id, prev_action)`
@@ -357,6 +457,14 @@ class MapfEngine:
         self._keep = [dmask]
         with torch.cuda.device(self.device):
             self._check(self.lib.mapf_bfs(self._h, self._ptr(dmask), None, 0, self._stream()), "mapf_bfs")
+
+    def bind_partial_state_out(self, state):
+        """PARTIAL: every later observation launch also writes get_state() into `state` (int64 [E,3], caller-owned);
+        None unbinds.  One launch less per environment step than partial_state()."""
+        if state is not None:
+            self._check_out("state", state, (self.E, 3), torch.int64)
+        self._bound_state = state          # keeps the storage alive while it is bound
+        self._check(self.lib.mapf_partial_bind_state_out(self._h, self._ptr(state)), "mapf_partial_bind_state_out")
 
     def partial_state(self, want=("state", "at_goal", "goal_cost", "agent_steps")):
         """MARL_PARTIAL_ENV bookkeeping: state int64 [E,3] = get_state(); at_goal u8, goal_cost / agent_steps i32 [E,N]."""
@@ -416,6 +524,21 @@ class MapfEngine:
             # FOV observations cross PCIe as packed bits and are expanded by the library's host threads
             d2h += self.packed_obs_bytes() - bufs["obs"].numel() * bufs["obs"].element_size()
         return io, bufs, h2d, d2h
+
+    def unpack_host_obs(self, bits, env_lo=0, env_hi=None, out=None, dtype=torch.uint8):
+        """Lazy view of a MAPF_BITS host observation (the "obs" buffer of make_host_io(obs_dtype="bits")): expands
+        only environments [env_lo, env_hi) into a [n, N, 4, F, F] host tensor (mapf_host_unpack, calling thread)."""
+        env_hi = self.E if env_hi is None else int(env_hi)
+        per_env = self.N * 4 * self.F * self.F
+        n = env_hi - int(env_lo)
+        if out is None:
+            out = torch.empty((n, self.N, 4, self.F, self.F), dtype=dtype)
+        assert out.is_contiguous() and out.numel() == n * per_env and out.dtype == dtype and not out.is_cuda
+        rc = self.lib.mapf_host_unpack(ctypes.c_void_p(bits.data_ptr()), int(env_lo) * per_env, n * per_env,
+                                       ctypes.c_void_p(out.data_ptr()), U8 if dtype == torch.uint8 else F32)
+        if rc != 0:
+            raise MapfError("mapf_host_unpack failed (%d)" % rc)
+        return out
 
     def bits_supported(self):
         return bool(self.lib.mapf_obs_bits_supported(self._h))

@@ -116,6 +116,7 @@ class MAPF_GRID(MultiAgentEnv):
         self._node_collision_agents = [0 for _ in self.agents]
         self._edge_collision_agents = [0 for _ in self.agents]
         self._avail_actions = None
+        self._last = None
         self._refresh_positions()
         return self.get_obs()
 
@@ -147,22 +148,50 @@ class MAPF_GRID(MultiAgentEnv):
             self._avail_actions = out["avail"][0].cpu().tolist()
             self._refresh_positions()
             return reward, self._agent_dones, {'_step_count': self._step_count}
-        out = self.engine.step(agents_action, want=_STEP_WANT)
+        # vector envs: ONE launch steps and produces what get_obs / get_state / get_avail_actions return
+        out = self.engine.step_observe(agents_action, want=_STEP_WANT)
         self._step_count += 1
         self._last = out
         return out["reward"], out["terminated"], {'_step_count': self._step_count, 'dones': out["dones"],
                                                   'node': out["node"], 'edge': out["edge"]}
 
+    # ------------------------------------------------------------------ BatchedRunner protocol (vector envs)
+    stay_action = 4
+
+    def rollout_spec(self):
+        N, HW = self._n_agents, self.get_state_size()
+        # every agent observes the same flattened map (:165-182): stored once as `state`, `obs` is a stride-0 view
+        return {"state": ((HW,), torch.int8), "avail_actions": ((N, 5), torch.uint8), "reward": ((1,), torch.float64),
+                "terminated": ((1,), torch.uint8),
+                "_views": {"obs": lambda tm: tm["state"].unsqueeze(2).expand(-1, -1, N, -1)}}
+
+    def reset_into(self, batch):
+        self.reset()
+        batch.tm["state"][0].copy_(self.get_state())
+        batch.tm["avail_actions"][0].copy_(self.get_avail_actions())
+
+    def step_into(self, actions, t, batch):
+        tm = batch.tm
+        self._last = self.engine.step_observe(actions, want=("reward", "terminated", "avail"),
+                                              out={"obs": tm["state"][t + 1], "avail": tm["avail_actions"][t + 1],
+                                                   "reward": tm["reward"][t], "terminated": tm["terminated"][t]})
+        self._step_count += 1
+
+    def _state_tensor(self):
+        if self.n_envs > 1 and self._last is not None and "obs" in self._last:
+            return self._last["obs"]
+        return self.engine.observe()[0]
+
     def get_obs(self):
         """[N, H*W] int64 (n_envs == 1) -- every agent sees the same flattened map (:143-183)."""
-        state, _ = self.engine.observe()
+        state = self._state_tensor()
         if self.n_envs == 1:
             row = state[0].cpu().numpy().astype(np.int64)
             return np.repeat(row[None, :], self._n_agents, axis=0)
         return state[:, None, :].expand(self.n_envs, self._n_agents, state.shape[1])
 
     def get_obs_agent(self, agent_id):
-        state, _ = self.engine.observe()
+        state = self._state_tensor()
         if self.n_envs == 1:
             return state[0].cpu().numpy().astype(np.int64)
         return state
@@ -171,7 +200,7 @@ class MAPF_GRID(MultiAgentEnv):
         return self._grid_shape[0] * self._grid_shape[1]
 
     def get_state(self):
-        state, _ = self.engine.observe()
+        state = self._state_tensor()
         if self.n_envs == 1:
             return state[0].cpu().numpy().astype(np.int64)
         return state
@@ -180,6 +209,8 @@ class MAPF_GRID(MultiAgentEnv):
         return self._grid_shape[0] * self._grid_shape[1]
 
     def get_avail_actions(self):
+        if self.n_envs > 1 and self._last is not None and "avail" in self._last:
+            return self._last["avail"]
         av = self.engine.avail()
         if self.n_envs == 1:
             self._avail_actions = av[0].cpu().tolist()

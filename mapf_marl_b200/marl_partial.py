@@ -80,6 +80,8 @@ class MARL_PARTIAL_ENV(MultiAgentEnv):
         self._node_collision_agents = None
         self._edge_collision_agents = None
         self._avail_actions = None
+        self._vlast = None       # vector envs: outputs of the last fused step (what the getters return)
+        self._vstate = None
 
     # __setup_agent, marl_partial.py:907-929
     def _setup_agent(self):
@@ -122,6 +124,7 @@ class MARL_PARTIAL_ENV(MultiAgentEnv):
         self._agent_dones = [False for _ in self.agents]
         self._node_collision_agents = [0 for _ in self.agents]
         self._edge_collision_agents = [0 for _ in self.agents]
+        self._vlast = None
         self._refresh()
         return self.get_obs()
 
@@ -150,12 +153,44 @@ class MARL_PARTIAL_ENV(MultiAgentEnv):
             self._edge_collision_agents = [int(v) for v in out["edge"][0].cpu().tolist()]
             self._refresh()
             return reward, self._terminated, {'_step_count': self._step_count}
-        out = self.engine.step(agents_action, want=_WANT)
+        # vector envs: ONE call produces everything the getters return (the tile kernel steps, the observation kernel
+        # writes obs and the get_state() triple): two launches per environment step instead of four
+        if self._vstate is None:
+            self._vstate = torch.zeros((self.n_envs, 3), dtype=torch.int64, device=self.engine.device)
+        self.engine.bind_partial_state_out(self._vstate)
+        out = self.engine.step_observe(agents_action, want=_WANT, dtype=self._obs_dtype)
         self._step_count += 1
+        self._vlast = out
         return out["reward"], out["terminated"], {'_step_count': self._step_count, 'dones': out["dones"],
                                                   'node': out["node"], 'edge': out["edge"]}
 
+    # ------------------------------------------------------------------ BatchedRunner protocol (vector envs)
+    stay_action = 4
+
+    def rollout_spec(self):
+        N = self._n_agents
+        return {"obs": ((N, self.get_obs_size()), self._obs_dtype), "state": ((3,), torch.int64),
+                "avail_actions": ((N, 5), torch.uint8), "reward": ((1,), torch.float64),
+                "terminated": ((1,), torch.uint8)}
+
+    def reset_into(self, batch):
+        self.engine.bind_partial_state_out(batch.tm["state"][0])
+        obs = self.reset()                                   # engine-owned tensors of the t = 0 observation
+        batch.tm["obs"][0].copy_(obs)
+        batch.tm["avail_actions"][0].copy_(self.get_avail_actions())
+
+    def step_into(self, actions, t, batch):
+        tm = batch.tm
+        self.engine.bind_partial_state_out(tm["state"][t + 1])
+        self._vlast = self.engine.step_observe(actions, want=("reward", "terminated", "avail"), dtype=self._obs_dtype,
+                                               out={"obs": tm["obs"][t + 1], "avail": tm["avail_actions"][t + 1],
+                                                    "reward": tm["reward"][t], "terminated": tm["terminated"][t]})
+        self._vstate = tm["state"][t + 1]
+        self._step_count += 1
+
     def get_obs(self):
+        if self.n_envs > 1 and self._vlast is not None and "obs" in self._vlast:
+            return self._vlast["obs"]
         obs, _ = self.engine.observe(dtype=self._obs_dtype)
         return obs[0].cpu().numpy() if self.n_envs == 1 else obs
 
@@ -168,6 +203,8 @@ class MARL_PARTIAL_ENV(MultiAgentEnv):
         return 2 * (self._obs_window ** 2) + self._obs_knn_agents * self._n_features
 
     def get_state(self):
+        if self.n_envs > 1 and self._vlast is not None and self._vstate is not None:
+            return self._vstate
         st = self.engine.partial_state(want=("state",))["state"]
         return st[0].cpu().numpy() if self.n_envs == 1 else st
 
@@ -177,6 +214,8 @@ class MARL_PARTIAL_ENV(MultiAgentEnv):
     def get_avail_actions(self):
         if self.n_envs == 1:
             return self._avail_actions
+        if self._vlast is not None and "avail" in self._vlast:
+            return self._vlast["avail"]
         return self.engine.avail()
 
     def get_avail_agent_actions(self, agent_id):

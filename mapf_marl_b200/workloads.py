@@ -122,14 +122,29 @@ def hash_actions_torch(seed, env_lo, n_envs, t, n_agents, device, n_actions=5, a
     return torch.where(cnt > 0, pick.to(torch.uint8).argmax(-1), torch.zeros_like(cnt)).to(torch.uint8)
 
 
+_CK_A, _CK_B, _CK_MUL = 0x9E3779B97F4A7C15 - (1 << 64), 0x7F4A7C15, 1000003     # int64 two's-complement constants
+
+
 def state_checksum_np(*arrays):
-    """Order-sensitive 64-bit checksum of integer arrays (positions, packed observation words, ...): the value
-    bench.py prints as rank0_state_checksum -- it must not depend on how many GPUs shared the batch."""
-    acc = np.uint64(0xCBF29CE484222325)
+    """Index-weighted 64-bit checksum of integer arrays (positions, packed observation words, ...), wrap-around int64
+    arithmetic: the value bench.py prints as rank0_state_checksum.  It must not depend on how many GPUs shared the
+    batch.  state_checksum_torch computes the same number on the device."""
+    acc = np.int64(0)
     with np.errstate(over="ignore"):
         for arr in arrays:
-            v = np.ascontiguousarray(arr).view(np.uint8).astype(np.uint64).ravel()
-            idx = np.arange(1, v.size + 1, dtype=np.uint64)
-            part = np.bitwise_xor.reduce((v + np.uint64(1)) * (idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x7F4A7C15)))
-            acc = (acc ^ part) * np.uint64(0x100000001B3)
-    return int(acc)
+            v = np.ascontiguousarray(arr).view(np.uint8).astype(np.int64).ravel()
+            idx = np.arange(v.size, dtype=np.int64)
+            part = ((v + np.int64(1)) * (idx * np.int64(_CK_A) + np.int64(_CK_B))).sum(dtype=np.int64)
+            acc = acc * np.int64(_CK_MUL) + part
+    return int(acc) & 0xFFFFFFFFFFFFFFFF
+
+
+def state_checksum_torch(*tensors):
+    import torch
+    acc = None
+    for t in tensors:
+        v = t.contiguous().view(torch.uint8).reshape(-1).to(torch.int64)
+        idx = torch.arange(v.numel(), dtype=torch.int64, device=v.device)
+        part = ((v + 1) * (idx * _CK_A + _CK_B)).sum()
+        acc = part if acc is None else acc * _CK_MUL + part
+    return int(acc.item()) & 0xFFFFFFFFFFFFFFFF

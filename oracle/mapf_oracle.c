@@ -502,6 +502,18 @@ static void primal_valid_actions(const oracle_env* o, int e, int id, int prev_ac
   if (opp >= 0) out[opp] = 0;                                       /* PRIMAL:664-665 */
 }
 
+/* The engine's PRIMAL team reward (include/mapf_b200.h, mapf_step_out.reward_dev; no reference counterpart): the
+ * pairwise sum of x[0..n) -- leaves padded with +0.0 to the next power of two, y[i] += y[i + s] for s = 1, 2, 4, ... */
+static double pairwise_sum(const double* x, int n) {
+  double y[256];
+  int m = 1;
+  while (m < n) m <<= 1;
+  for (int i = 0; i < m; ++i) y[i] = i < n ? x[i] : 0.0;
+  for (int s = 1; s < m; s <<= 1)
+    for (int i = 0; i + s < m; i += 2 * s) y[i] = y[i] + y[i + s];
+  return n > 0 ? y[0] : 0.0;
+}
+
 /* One sweep `for id in lo+1..hi: _step((id, a))`, PRIMAL:549-637 without the observation
  * (observe_all is separate) and with the blocking reward fenced off (returns 0, see refload.py). */
 int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, int8_t* status_out,
@@ -512,7 +524,8 @@ int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, i
   const int N = o->N;
 #pragma omp parallel for schedule(static) num_threads(o->threads) reduction(+ : bad)
   for (int e = 0; e < o->E; ++e) {
-    double total = 0.0;
+    double rloc[256];
+    for (int i = 0; i < N; ++i) rloc[i] = 0.0;
     if (lo == 0) o->step_count[e] += 1;
     for (int i = lo; i < hi; ++i) {
       size_t k = (size_t)e * N + i;
@@ -533,7 +546,7 @@ int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, i
         else if (status < 0) r = o->collision_reward;
         else r = o->action_cost;
       }
-      total += r;
+      rloc[i] = r;
       const int16_t* p = o->pos + k * 2;
       const int16_t* g = o->goal + k * 2;
       int on_goal = (p[0] == g[0] && p[1] == g[1]);                 /* PRIMAL:633 */
@@ -553,7 +566,7 @@ int oracle_primal_sweep(oracle_env* o, const uint8_t* actions, int lo, int hi, i
         primal_valid_actions(o, e, i + 1, prev, avail + (size_t)(o->diagonal ? 9 : 5) * k);
       }
     if (terminated) terminated[e] = (uint8_t)primal_done(o, e);
-    if (reward) reward[e] = total;
+    if (reward) reward[e] = pairwise_sum(rloc, N);
   }
   return bad;
 }

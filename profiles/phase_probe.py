@@ -15,7 +15,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["MAPF_B200_LIB"] = os.path.join(ROOT, "mapf_marl_b200", "libmapf_b200_dbg.so")
-import bench  # noqa: E402
 from mapf_marl_b200 import _lib  # noqa: E402
 from mapf_marl_b200.engine import MapfEngine  # noqa: E402
 
@@ -25,23 +24,33 @@ NAMES = ["stage", "phase A", "phase B", "phase C", "avail + agent bitmap", "phas
 
 def main():
     lib = _lib.load()
+    from mapf_marl_b200.workloads import WORKLOADS, make_world
+    T = 16
     for name in ("c2", "c3", "c4"):
-        wl = bench.WORKLOADS[name]
+        wl = WORKLOADS[name]
         E, N = wl["E"], wl["N"]
-        obst, starts, goals = bench.make_world(wl, E, 0)
+        obst, starts, goals = make_world(wl, E, 0)
         eng = MapfEngine(E, N, wl["H"], wl["W"], mode="primal", fov=wl["F"], shared_map=wl["warehouse"])
         eng.reset(obst, starts, goals)
-        acts = torch.randint(0, 5, (E, N), device="cuda", dtype=torch.uint8)
-        for _ in range(5):
-            eng.step_observe(acts)
-        torch.cuda.synchronize()
-        buf = (ctypes.c_longlong * 32)()
-        lib.mapf_debug_phase_clocks(buf)
-        c = [buf[i] for i in range(10)]
-        print(name, "tile critical path of the middle block (SM cycles):")
-        for i in range(9):
-            print("   %-24s %8d" % (NAMES[i], c[i + 1] - c[i]))
-        print("   %-24s %8d" % ("total", c[9] - c[0]))
+        acts = torch.randint(0, 5, (T, E, N), device="cuda", dtype=torch.uint8)
+        for roll in (False, True):
+            for _ in range(5):
+                if roll:
+                    eng.rollout(acts)
+                else:
+                    eng.step_observe(acts[0])
+            torch.cuda.synchronize()
+            buf = (ctypes.c_longlong * 32)()
+            lib.mapf_debug_phase_clocks(buf)
+            c = [buf[i] for i in range(11)]
+            c[0] = c[10]                      # start of the (last) step's staging pass
+            print(name, "rollout (last of %d steps)" % T if roll else "single step",
+                  "-- tile critical path of the middle block (SM cycles):")
+            for i in range(9):
+                print("   %-24s %8d" % (NAMES[i], c[i + 1] - c[i]))
+            print("   %-24s %8d" % ("total", c[9] - c[0]))
+            print("   inside phase D: per-env part %d, statistics atomics %d, write-back %d" % (
+                buf[11] - c[5], buf[12] - buf[11], c[6] - buf[12]))
 
 
 if __name__ == "__main__":

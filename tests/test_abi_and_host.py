@@ -240,21 +240,56 @@ def test_host_unpack_pool_progressive_publish():
 
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU: exactly one JSON line
-    on stdout with the contract's keys, the C oracle port as `cpu_baseline`, zero bytes in `e2e`."""
+    on stdout with the contract's keys, the UNMODIFIED Python reference as `cpu_baseline` (kind "reference", one worker
+    process per host core), the C oracle port beside it as `cpu_port`, zero bytes in `e2e`."""
     import json
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1", "--workload", "c2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                         text=True, timeout=600)
+                          "--warmup", "1", "--workload", "c2", "--envs", "256"], stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "agent-steps/sec (step+obs)" and d["unit"] == "agent-steps/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    cores = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == cores
+    assert d["cpu_baseline"]["value"] == d["value"] and "UNMODIFIED" in d["cpu_baseline"]["sample"]
+    assert d["cpu_port"]["kind"] == "port" and d["cpu_port"]["value"] > d["value"]      # C beats Python
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_reference_worker_steps_exactly_what_the_oracle_steps():
+    """The CPU baseline's worker (oracle/ref_worker.py, the UNMODIFIED mapf_primal.MAPFEnv) and the C oracle -- hence
+    the GPU arm, which is tested against the oracle -- advance the same worlds with the same counter-hash actions: the
+    digest of the worker's outputs is recomputed from the oracle's outputs."""
+    import numpy as np
+    import pytest
+    from mapf_marl_b200 import workloads
+    from oracle import Oracle, refload
+    from oracle.oracle import MODE_PRIMAL
+    from oracle import ref_worker
+    if not refload.available():
+        pytest.skip("reference files not available (neither /root/reference nor oracle/_ref)")
+    primal = refload.load_primal()
+    wl = dict(workloads.WORKLOADS["c2"])
+    n_envs, lo, T, N, F = 6, 37, 5, wl["N"], wl["F"]
+    envs = ref_worker.build_envs(primal, wl, lo, n_envs, 1000)
+    obst, starts, goals = workloads.make_world(wl, n_envs, lo)
+    orc = Oracle(n_envs, N, wl["H"], wl["W"], MODE_PRIMAL, fov=F, threads=1)
+    orc.reset(obst, starts, goals)
+    for t in range(T):
+        acts = workloads.hash_actions_np(1234, range(lo, lo + n_envs), t, N)
+        got = sum(ref_worker.joint_step(env, acts[e], N) for e, env in enumerate(envs))
+        out = orc.primal_sweep(acts)
+        obs, _ = orc.primal_observe()
+        want = int(out["dones"].sum()) + int(out["valid"].sum()) + int(out["next_mid"].sum()) + int(obs[:, :, 0].sum())
+        # joint_step counts on_goal as _step returns it (mid-sweep == the agent's own final flag), valid, len(nextActions)
+        assert got == want, (t, got, want)
+        for e, env in enumerate(envs):
+            assert [tuple(p) for p in env.getPositions()] == [tuple(int(v) for v in p) for p in orc.positions()[e]]

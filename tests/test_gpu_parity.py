@@ -24,7 +24,8 @@ def _oracle(*a, **k):
 
 
 def _bits(x):
-    return np.ascontiguousarray(x).view(np.uint64)
+    x = np.ascontiguousarray(x)
+    return x.view(np.uint32 if x.dtype == np.float32 else np.uint64)
 
 
 def _np(t):
@@ -927,11 +928,12 @@ def test_c4_shape_lifelong_goal_reassignment_matches_oracle(overlap):
 
 
 @pytest.mark.parametrize("obs_float32", [False, True])
-def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path, obs_float32):
-    """The pymarl rollout loop over a device-resident vector env: what lands in the batch equals a rollout of the
-    CPU oracle driven by the same actions (PARTIAL env, the one the reference registers); with obs_float32 the kernel
-    writes the batch's float32 observations itself."""
-    from mapf_marl_b200.batched_runner import BatchedRunner
+@pytest.mark.parametrize("check_every", [1, 5])
+def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path, obs_float32, check_every):
+    """The pymarl rollout loop over a device-resident vector env: what lands in the (time-major, kernel-written)
+    batch equals a rollout of the CPU oracle driven by the same actions (PARTIAL env, the one the reference
+    registers); entries are compared wherever `filled` says pymarl would have data."""
+    from mapf_marl_b200.batched_runner import BatchedRunner, RandomMAC
     from mapf_marl_b200.marl_partial import MARL_PARTIAL_ENV
     from oracle.oracle import MODE_PARTIAL
     g = load_golden("partial_empty8_crowd")
@@ -942,49 +944,127 @@ def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path
               complete_fac=1.5, gamma=0.99)
     env = MARL_PARTIAL_ENV(mp, sp, n_agents=N, episode_limit=limit, render="none", n_envs=B,
                            obs_float32=obs_float32, **kw)
-
-    class RandomMAC:
-        def __init__(self):
-            self.gen = torch.Generator(device="cuda").manual_seed(5)
-            self.log = []
-
-        def init_hidden(self, batch_size):
-            self.batch_size = batch_size
-
-        def select_actions(self, batch, t_ep, t_env, bs, test_mode=False):
-            avail = batch["avail_actions"][bs, t_ep]                      # [len(bs), N, 5]
-            probs = avail.float() + 1e-9
-            a = torch.multinomial(probs.reshape(-1, 5), 1, generator=self.gen).reshape(len(bs), -1)
-            self.log.append((list(bs), a.cpu().numpy()))
-            return a
-
-    mac = RandomMAC()
-    runner = BatchedRunner(env, mac)
+    runner = BatchedRunner(env, RandomMAC(env.engine, seed=5), check_every=check_every)
+    l0 = env.engine.launch_count()
     batch = runner.run(test_mode=False)
-    assert env.get_obs().dtype == (torch.float32 if obs_float32 else torch.float64)
+    T = runner.t                                             # env steps the loop executed
+    _cache = {}
+    bn = lambda k: _cache.setdefault(k, _np(batch[k]))       # noqa: E731
+    # two launches per environment step (tile kernel + PARTIAL observation kernel carrying get_state)
+    n_reset = 3 + 2                                          # reset: reset + BFS (+overflow) ; observe + avail
+    assert env.engine.launch_count() - l0 <= 2 * T + T + n_reset + 2      # + the random policy: one kernel per step
+    odt = np.float32 if obs_float32 else np.float64
+    assert bn("obs").dtype == odt
     H, W = g["obst"].shape
     orc = _oracle(B, N, H, W, MODE_PARTIAL, episode_limit=limit)
     orc.partial_config(**kw)
     orc.reset(np.repeat(g["obst"][None], B, 0), env._starts, env._goals)
-    obs0 = orc.partial_observe()
-    assert np.array_equal(_np(batch["obs"][:, 0]), obs0.astype(np.float32))
-    assert (_np(batch["filled"][:, 0]) == 1).all()
+    assert np.array_equal(bn("obs")[:, 0], orc.partial_observe().astype(odt))
+    assert np.array_equal(bn("state")[:, 0], orc.partial_state())
+    assert (bn("filled")[:, 0] == 1).all()
     alive = np.ones(B, bool)
-    for t, (bs, a) in enumerate(mac.log):
-        assert bs == np.nonzero(alive)[0].tolist()
-        full = np.full((B, N), 4, np.uint8)
-        full[bs] = a
-        ref = orc.partial_step(full)
+    returns = np.zeros(B)
+    for t in range(T):
+        a = bn("actions")[:, t, :, 0]
+        assert (a[~alive] == 4).all()                        # finished environments idle
+        ref = orc.partial_step(a.astype(np.uint8))
         robs = orc.partial_observe()
-        assert np.array_equal(_np(batch["actions"][bs, t, :, 0]), a)
-        assert np.array_equal(_np(batch["reward"][bs, t, 0]), ref["reward"][bs].astype(np.float32))
-        assert np.array_equal(_np(batch["obs"][bs, t + 1]), robs[bs].astype(np.float32))
-        assert np.array_equal(_np(batch["avail_actions"][bs, t + 1]), ref["avail"][bs].astype(np.int32))
-        assert np.array_equal(_np(batch["state"][bs, t + 1]), orc.partial_state()[bs].astype(np.float32))
-        assert np.array_equal(_np(batch["terminated"][bs, t, 0]), ref["terminated"][bs])
+        bs = np.nonzero(alive)[0]
+        assert np.array_equal(bn("filled")[:, t + 1, 0].astype(bool), alive), t
+        assert np.array_equal(_bits(bn("reward")[bs, t, 0]), _bits(ref["reward"][bs])), t
+        assert np.array_equal(bn("obs")[bs, t + 1], robs[bs].astype(odt)), t
+        assert np.array_equal(bn("avail_actions")[bs, t + 1], ref["avail"][bs]), t
+        assert np.array_equal(bn("state")[bs, t + 1], orc.partial_state()[bs]), t
+        assert np.array_equal(bn("terminated")[bs, t, 0], ref["terminated"][bs]), t
+        # the actions the MAC chose were available
+        assert (np.take_along_axis(bn("avail_actions")[bs, t], a[bs][..., None], -1) == 1).all(), t
+        returns[bs] += ref["reward"][bs]
         alive &= ~ref["terminated"].astype(bool)
-    assert runner.t_env == sum(len(bs) for bs, _ in mac.log)
-    assert runner.train_stats["n_episodes"] == B and len(runner.train_returns) == B
+    assert not alive.any() or T == limit
+    assert runner.t_env == int(bn("filled")[:, 1:, 0].sum())
+    assert runner.train_stats["n_episodes"] == B and np.allclose(runner.train_returns, returns)
+    # the vector env's own step(): one fused call, getters served from it
+    env.reset()
+    l1 = env.engine.launch_count()
+    r, term, info = env.step(torch.full((B, N), 4, dtype=torch.int64, device="cuda"))
+    obs, st, av = env.get_obs(), env.get_state(), env.get_avail_actions()
+    assert env.engine.launch_count() - l1 == 2
+    orc.reset(np.repeat(g["obst"][None], B, 0), env._starts, env._goals)
+    ref = orc.partial_step(np.full((B, N), 4, np.uint8))
+    assert np.array_equal(_np(obs), orc.partial_observe().astype(odt)) and np.array_equal(_np(st), orc.partial_state())
+    assert np.array_equal(_np(av), ref["avail"]) and np.array_equal(_bits(_np(r)), _bits(ref["reward"]))
+
+
+def test_batched_runner_primal_vec_env_one_launch_per_step_and_grid_env(tmp_path):
+    """PrimalVecEnv (BASELINE config 5's env) through the runner: one engine launch per environment step, the batch
+    equals an oracle rollout under the same actions; MAPF_GRID's vector step is one launch too."""
+    from mapf_marl_b200 import maps
+    from mapf_marl_b200.batched_runner import BatchedRunner, RandomMAC, RNNAgentMAC
+    from mapf_marl_b200.vec_env import PrimalVecEnv
+    from oracle.oracle import MODE_PRIMAL
+    E, N, H, W, F, T = 48, 8, 20, 20, 11, 10
+    obst, starts, goals = maps.synthetic_batch(21, E, H, W, 0.2, N, distinct=0)
+    env = PrimalVecEnv(obst, starts, goals, fov=F, episode_limit=T)
+    for mac, graph in ((RandomMAC(env.engine, seed=3), False), (RNNAgentMAC(4 * F * F, 5, "cuda", extra_dim=3), False),
+                       (RandomMAC(env.engine, seed=4), True)):
+        runner = BatchedRunner(env, mac, check_every=4, cuda_graph=graph)
+        n_mac = T if isinstance(mac, RandomMAC) else 0          # the random policy is one engine kernel per step
+        if graph:
+            runner.run()                                         # eager warm-up episode; the next run captures + replays
+            mac.episode = -1                                     # same draws as the warm-up: (seed, episode 0, step)
+        l0 = env.engine.launch_count()
+        batch = runner.run()
+        assert runner.t == T
+        if graph:
+            assert runner._graphs is not None and len(runner._graphs) == 3
+        _cache = {}
+        bn = lambda k, _c=_cache, _b=batch: _c.setdefault(k, _np(_b[k]))   # noqa: E731
+        # reset (2 kernels) + observe + avail at t = 0, then ONE launch per environment step (+ the random policy's)
+        if not graph:
+            assert env.engine.launch_count() - l0 == 4 + T + n_mac
+        orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F)
+        orc.reset(obst, starts, goals)
+        robs, rvec = orc.primal_observe()
+        assert np.array_equal(bn("obs")[:, 0].reshape(robs.shape), robs)
+        alive = np.ones(E, bool)
+        for t in range(T):
+            a = bn("actions")[:, t, :, 0].astype(np.uint8)
+            assert (np.take_along_axis(bn("avail_actions")[:, t], a[..., None].astype(np.int64), -1) == 1)[alive].all()
+            ref = orc.primal_sweep(a)
+            robs, rvec = orc.primal_observe()
+            bs = np.nonzero(alive)[0]
+            assert np.array_equal(bn("obs")[bs, t + 1].reshape((len(bs),) + robs.shape[1:]), robs[bs]), t
+            assert np.array_equal(_bits(bn("obs_vec")[bs, t + 1]), _bits(rvec[bs])), t
+            assert np.array_equal(_bits(bn("state")[bs, t + 1]), _bits(rvec[bs].reshape(len(bs), -1))), t
+            assert np.array_equal(bn("avail_actions")[bs, t + 1], ref["avail"][bs]), t
+            assert np.array_equal(_bits(bn("reward")[bs, t, 0]), _bits(ref["reward"][bs])), t
+            term = ref["terminated"].astype(bool) | (t + 1 >= T)
+            assert np.array_equal(bn("terminated")[bs, t, 0].astype(bool), term[bs]), t
+            alive &= ~term
+    env.close()
+    # MAPF_GRID as a vector env: step() is one launch and serves get_obs / get_state / get_avail_actions; the runner
+    # stores the shared full-map observation once (obs is a stride-0 view over the agents)
+    from mapf_marl_b200.mapf_gridworld import MAPF_GRID
+    from oracle.oracle import MODE_GRID
+    gobst = (np.random.RandomState(1).rand(10, 10) < 0.1).astype(np.uint8)
+    mp, sp = _write_movingai(tmp_path, gobst)
+    genv = MAPF_GRID(mp, sp, n_agents=4, episode_limit=9, render="none", n_envs=16)
+    genv.reset()
+    l1 = genv.engine.launch_count()
+    acts = torch.as_tensor(np.random.RandomState(2).randint(0, 5, (16, 4)), device="cuda")
+    r, term, info = genv.step(acts)
+    st, av, ob = genv.get_state(), genv.get_avail_actions(), genv.get_obs()
+    assert genv.engine.launch_count() - l1 == 1
+    orc = _oracle(16, 4, 10, 10, MODE_GRID, episode_limit=9)
+    orc.reset(np.repeat(gobst[None], 16, 0), genv._starts, genv._goals)
+    ref = orc.grid_step(_np(acts).astype(np.uint8))
+    assert np.array_equal(_np(st), orc.grid_state()) and np.array_equal(_np(av), ref["avail"])
+    assert tuple(ob.shape) == (16, 4, 100) and np.array_equal(_np(ob[:, 2]), orc.grid_state())
+    assert np.array_equal(_bits(_np(r)), _bits(ref["reward"]))
+    runner = BatchedRunner(genv, RandomMAC(genv.engine, seed=1), check_every=3)
+    batch = runner.run()
+    assert tuple(batch["obs"].shape) == (16, 10, 4, 100) and tuple(batch["state"].shape) == (16, 10, 100)
+    assert runner.t == 9 and bool((batch["terminated"][:, 8] == 1).all())     # the episode limit ends every env
 
 
 @pytest.mark.parametrize("case", [(3, 255, 40, 40, 11, 0.05), (3, 7, 200, 200, 11, 0.2), (2, 5, 255, 255, 9, 0.1),
@@ -1265,3 +1345,91 @@ def test_fused_step_is_cuda_graph_capturable_and_replays_bit_exactly():
         assert np.array_equal(_np(out["obs"]), robs), t
         assert np.array_equal(_bits(_np(out["vec"])), _bits(rvec)), t
     assert eng.error_flags() == 0
+
+
+# ------------------------------------------------------------------------------------------ mapf_rollout
+ROLLOUT_CASES = [
+    # (mode, E, N, H, W, F, density, T, obs dtype, engine kwargs)
+    ("primal", 300, 8, 20, 20, 11, 0.2, 9, torch.uint8, {}),            # c2 shape, ragged last tile
+    ("primal", 64, 32, 32, 32, 11, 0.3, 7, torch.uint8, {}),            # c3 shape
+    ("primal", 64, 32, 32, 32, 11, 0.3, 5, "bits", {}),
+    ("primal", 16, 32, 32, 32, 11, 0.3, 4, torch.float32, {}),
+    ("primal", 48, 6, 12, 12, 5, 0.1, 12, torch.uint8, {}),             # small even-odd FOV, N does not divide 128
+    ("primal", 8, 128, 64, 64, 11, 0.05, 5, torch.uint8, {}),           # c4 shape: one environment per tile
+    ("primal", 4, 140, 40, 40, 11, 0.05, 3, torch.uint8, {}),           # > 128 agents: falls back to T launches
+    ("primal", 32, 10, 16, 16, 7, 0.1, 6, torch.uint8, {"diagonal_movement": True}),   # fallback (diagonal mode)
+    ("grid", 200, 4, 10, 10, 0, 0.1, 11, None, {"episode_limit": 8}),   # the episode limit is hit inside the rollout
+    ("grid", 40, 32, 32, 32, 0, 0.2, 6, None, {}),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ROLLOUT_CASES, ids=lambda c: "%s_E%d_N%d_%dx%d_T%d_%s" % (c[0], c[1], c[2], c[3], c[4], c[7], str(c[8]).split(".")[-1]))
+def test_rollout_equals_consecutive_fused_steps(case):
+    """mapf_rollout(T steps, one launch where supported) == T consecutive mapf_step_observe calls, bit for bit, for
+    every per-step output and for the state left in the handle."""
+    from mapf_marl_b200 import maps
+    mode, E, N, H, W, F, dens, T, odt, kw = case
+    obst, starts, goals = maps.synthetic_batch(11, E, H, W, dens, N, distinct=0)
+    nact = 9 if kw.get("diagonal_movement") else 5
+    rs = np.random.RandomState(T * 31 + N)
+    acts = torch.as_tensor(rs.randint(0, nact, (T, E, N)).astype(np.uint8), device="cuda")
+    want = (("reward", "terminated", "agent_reward", "dones", "status", "valid", "avail", "done_mid", "next_mid")
+            if mode == "primal" else GRID_WANT)
+    mk = lambda: _engine(E, N, H, W, mode=mode, fov=F or 11, **kw)   # noqa: E731
+    a, b = mk(), mk()
+    a.reset(obst, starts, goals)
+    b.reset(obst, starts, goals)
+    okw = dict(dtype=odt) if odt is not None else {}
+    expect_one = mode in ("primal", "grid") and N <= 128 and not kw.get("diagonal_movement")
+    assert a.rollout_in_one_launch(odt if odt is not None else torch.uint8) == expect_one
+    for rnd in range(2):                      # the second rollout starts from the state the first one left
+        l0 = a.launch_count()
+        ro = a.rollout(acts, want=want, **okw)
+        assert a.launch_count() - l0 == (1 if expect_one else T)
+        ro = {k: v.clone() for k, v in ro.items()}
+        for t in range(T):
+            so = b.step_observe(acts[t], want=want, **okw)
+            for k in so:
+                x, y = _np(ro[k][t]), _np(so[k])
+                if x.dtype.kind == "f":
+                    x, y = _bits(x), _bits(y)
+                assert np.array_equal(x.reshape(-1), y.reshape(-1)), (k, t, rnd)
+        assert np.array_equal(_np(a.positions()), _np(b.positions()))
+        assert np.array_equal(_np(a.dones()), _np(b.dones()))
+        assert np.array_equal(_np(a.step_count()), _np(b.step_count()))
+        assert np.array_equal(_np(a.avail()), _np(b.avail()))          # prev_action state
+    assert a.stats() == b.stats()
+    assert a.error_flags() == 0 and b.error_flags() == 0
+
+
+@pytest.mark.gpu
+def test_rollout_partial_mode_and_caller_owned_storage():
+    """PARTIAL rollouts run as T launches per kernel but give the same time-major outputs; `out=` writes straight
+    into caller-owned (episode-batch style) storage."""
+    from mapf_marl_b200 import maps
+    E, N, H, W, T = 24, 6, 10, 10, 8
+    obst, starts, goals = maps.synthetic_batch(5, E, H, W, 0.0, N, distinct=0)
+    kw = dict(mode="partial", episode_limit=30, obs_window=5, obs_knn_agents=3)
+    a, b = _engine(E, N, H, W, **kw), _engine(E, N, H, W, **kw)
+    a.reset(obst, starts, goals)
+    b.reset(obst, starts, goals)
+    acts = torch.as_tensor(np.random.RandomState(2).randint(0, 5, (T, E, N)).astype(np.uint8), device="cuda")
+    store = {"obs": torch.zeros((T, E, N, a.obs_size), dtype=torch.float32, device="cuda"),
+             "reward": torch.zeros((T, E), dtype=torch.float64, device="cuda")}
+    ro = a.rollout(acts, want=("reward", "terminated", "avail"), dtype=torch.float32, out=store)
+    assert ro["obs"].data_ptr() == store["obs"].data_ptr() and ro["reward"].data_ptr() == store["reward"].data_ptr()
+    for t in range(T):
+        so = b.step_observe(acts[t], want=("reward", "terminated", "avail"), dtype=torch.float32)
+        assert np.array_equal(_np(store["obs"][t]).view(np.uint32), _np(so["obs"]).view(np.uint32)), t
+        assert np.array_equal(_bits(_np(store["reward"][t])), _bits(_np(so["reward"]))), t
+        assert np.array_equal(_np(ro["terminated"][t]), _np(so["terminated"])), t
+        assert np.array_equal(_np(ro["avail"][t]), _np(so["avail"])), t
+    # step_observe(out=...) into a time slice of the same storage
+    c = _engine(E, N, H, W, **kw)
+    c.reset(obst, starts, goals)
+    store2 = torch.zeros_like(store["obs"])
+    for t in range(T):
+        so = c.step_observe(acts[t], want=("reward",), dtype=torch.float32, out={"obs": store2[t]})
+        assert so["obs"].data_ptr() == store2[t].data_ptr()
+    assert torch.equal(store2, store["obs"])
