@@ -604,53 +604,133 @@ def test_set_goals_and_dirty_bfs():
 
 
 # ------------------------------------------------------------------------------------------ full-size invariants
-@pytest.mark.parametrize("cfg", [(4096, 8, 20, 20, 0.2), (16384, 32, 32, 32, 0.3)], ids=["c2", "c3"])
-def test_full_size_invariants(cfg):
-    """BASELINE sizes, where the scalar oracle would take minutes: properties that hold for any input."""
-    from mapf_marl_b200 import maps
+FULL_SIZE = [
+    # (workload, envs, global env offset): the BASELINE.json configurations at their full per-GPU sizes
+    ("c2", 4096, 0),
+    ("c3", 16384, 0),
+    ("c4", 8192, 0),                      # shared warehouse map, lifelong goal reassignment every step
+    ("c5", 131072, 7 * 131072),           # the last GPU's shard of the 1M-env sweep on 8 GPUs
+]
+
+
+@pytest.mark.parametrize("cfg", FULL_SIZE, ids=lambda c: "%s_E%d_off%d" % c)
+def test_full_size_every_env_every_step_matches_oracle(cfg):
+    """Every environment of every BASELINE configuration, at full size, against the CPU oracle (all host threads)
+    after EVERY one of 16 steps: status, per-agent and team rewards, dones, valid, terminated, action masks, positions,
+    the 4-channel observation and the goal vectors, bit for bit.  Worlds and actions are functions of the GLOBAL
+    environment index (>= 4096 distinct worlds; the c5 case is the shard a rank with env_offset 7 * 131072 owns);
+    even steps draw uniform actions, odd steps draw from the action mask (agents keep moving and arrive).  c4 pops
+    new goals from per-agent queues whenever agents arrive (LifelongGoals) and re-runs the BFS of those goals."""
+    from mapf_marl_b200 import workloads
+    from mapf_marl_b200.lifelong import LifelongGoals
     from oracle.oracle import MODE_PRIMAL
-    E, N, H, W, dens = cfg
-    F = 11
-    obst, starts, goals = maps.synthetic_batch(1000, E, H, W, dens, N, distinct=64)
-    eng = _engine(E, N, H, W, mode="primal", fov=F)
+    name, E, lo = cfg
+    wl = workloads.WORKLOADS[name]
+    N, H, W, F = wl["N"], wl["H"], wl["W"], wl["F"]
+    shared = wl["warehouse"]
+    distinct = 0 if E <= 4096 else 4096
+    obst, starts, goals = workloads.make_world(wl, E, lo, distinct=distinct)
+    assert len({starts[e].tobytes() for e in range(min(E, 4096))}) >= min(E, 2048)       # genuinely different worlds
+    eng = _engine(E, N, H, W, mode="primal", fov=F, shared_map=shared)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F, shared_map=shared)
     eng.reset(obst, starts, goals)
-    gen = torch.Generator(device="cuda").manual_seed(0)
-    obst_d = torch.as_tensor(obst, device="cuda").bool()
-    for t in range(6):
-        act = torch.randint(0, 5, (E, N), generator=gen, device="cuda", dtype=torch.uint8)
-        out = eng.step_observe(act, want=("status", "dones", "valid", "avail", "terminated"))
-        pos = eng.positions().long()
-        # agents stand on free cells and never share a cell (sequential claim)
-        e_idx = torch.arange(E, device="cuda")[:, None].expand(E, N)
-        assert not obst_d[e_idx, pos[..., 0], pos[..., 1]].any()
-        cell = pos[..., 0] * W + pos[..., 1]
-        assert (torch.sort(cell, dim=1).values.diff(dim=1) != 0).all()
-        obs = out["obs"].clone()
-        assert obs.max().item() <= 1
-        c = F // 2
-        assert (obs[:, :, 0, c, c] == 1).all()                       # the agent sees itself
-        assert (obs[:, :, 3, c, c] == 0).all()                       # ... on a free cell
-        # number of visible agents == agents within the window (computed independently with torch)
-        d = (pos[:, :, None, :] - pos[:, None, :, :])
-        vis = ((d[..., 0] >= -c) & (d[..., 0] <= F - 1 - c) & (d[..., 1] >= -c) & (d[..., 1] <= F - 1 - c)).sum(-1)
-        assert torch.equal(obs[:, :, 0].flatten(2).sum(-1).long(), vis)
-        assert (obs[:, :, 1].flatten(2).sum(-1) <= 1).all()
-        # the fused kernel, the separate observe launch and the byte-wise generic kernel agree
-        sep, vec = eng.observe()
-        assert torch.equal(sep, obs)
-        assert torch.equal((out["status"] >= 0), out["valid"].bool())
-    # the first environments against the oracle (the batch repeats 64 distinct worlds)
-    n = 64
-    orc = _oracle(n, N, H, W, MODE_PRIMAL, fov=F)
-    orc.reset(obst[:n], starts[:n], goals[:n])
-    gen = torch.Generator(device="cuda").manual_seed(0)
-    for t in range(6):
-        act = torch.randint(0, 5, (E, N), generator=gen, device="cuda", dtype=torch.uint8)
-        orc.primal_sweep(_np(act[:n]))
-    robs, rvec = orc.primal_observe()
-    assert np.array_equal(_np(obs[:n]), robs)
-    assert np.array_equal(_bits(_np(vec[:n])), _bits(rvec))
-    assert np.array_equal(_np(eng.positions()[:n]), orc.positions())
+    orc.reset(obst, starts, goals)
+    want = ("status", "agent_reward", "reward", "dones", "valid", "terminated", "avail")
+    life = None
+    if shared:
+        Q = 4
+        queue = workloads.make_goal_queue(wl, obst, goals, E, lo, depth=Q, distinct=distinct)
+        dist = torch.full((E, N, H, W), -9, dtype=torch.int16, device="cuda")
+        eng.goal_dist(out=dist)
+        life = LifelongGoals(eng, queue, dist_out=dist, overlap=True)
+        head = np.zeros((E, N), np.int64)
+        cur_goals = goals.copy()
+        ref_dist = orc.goal_dist()
+        assert np.array_equal(_np(dist), ref_dist)
+    avail = eng.avail()
+    assert np.array_equal(_np(avail), orc.primal_avail())
+    arrivals = 0
+    for t in range(16):
+        act = workloads.hash_actions_torch(99, lo, E, t, N, "cuda", avail=avail if t % 2 else None)
+        a_np = _np(act)
+        assert np.array_equal(a_np, workloads.hash_actions_np(99, range(lo, lo + E), t, N,
+                                                              avail=_np(avail) if t % 2 else None))
+        out = eng.step_observe(act, want=want)
+        ref = orc.primal_sweep(a_np)
+        for k in ("status", "dones", "valid", "terminated", "avail"):
+            assert np.array_equal(_np(out[k]), ref[k]), (k, t)
+        assert np.array_equal(_bits(_np(out["agent_reward"])), _bits(ref["agent_reward"])), t
+        assert np.array_equal(_bits(_np(out["reward"])), _bits(ref["reward"])), t
+        assert np.array_equal(_np(eng.positions()), orc.positions()), t
+        robs, rvec = orc.primal_observe()
+        assert np.array_equal(_bits(_np(out["vec"])), _bits(rvec)), t
+        # the observation is compared on the device, in slabs that bound the host-side staging
+        slab = max(1, (1 << 28) // (N * 4 * F * F))
+        for e0 in range(0, E, slab):
+            assert torch.equal(out["obs"][e0:e0 + slab], torch.as_tensor(robs[e0:e0 + slab], device="cuda")), (t, e0)
+        avail = out["avail"]
+        arrivals += int(ref["dones"].sum())
+        if life is not None:                                  # lifelong: arrived agents take the next queued goal
+            dirty = _np(life.reassign(out["dones"]))
+            life.sync()
+            ref_dirty = ((ref["dones"] != 0) & (head < Q)).astype(np.uint8)
+            assert np.array_equal(dirty, ref_dirty), t
+            new_goals = np.take_along_axis(queue, np.minimum(head, Q - 1)[..., None, None].repeat(2, -1), 2)[:, :, 0, :]
+            head += ref_dirty
+            orc.set_goals(new_goals, ref_dirty)
+            orc.goal_dist(dirty=ref_dirty, out=ref_dist)
+            if t % 8 == 7:
+                assert np.array_equal(_np(dist), ref_dist), t
+            cur_goals[ref_dirty != 0] = new_goals[ref_dirty != 0]
+            assert np.array_equal(_np(eng.goals()), cur_goals), t
+    assert arrivals > 0 and eng.error_flags() == 0
+    if life is not None:
+        assert int(head.sum()) > 0
+
+
+def test_sharded_engines_equal_the_unsharded_engine_bitwise():
+    """SURVEY section 8e on the device: two engines of E/2 environments built from the global indices [0, E/2) and
+    [E/2, E) produce, environment by environment, exactly what one engine of E environments produces."""
+    from mapf_marl_b200 import workloads
+    wl = workloads.WORKLOADS["c3"]
+    E, N, F = 2048, wl["N"], wl["F"]
+    mk = lambda n: _engine(n, N, wl["H"], wl["W"], mode="primal", fov=F)   # noqa: E731
+    whole, parts = mk(E), [mk(E // 2), mk(E // 2)]
+    whole.reset(*workloads.make_world(wl, E, 0, distinct=0))
+    for r, p in enumerate(parts):
+        p.reset(*workloads.make_world(wl, E // 2, r * E // 2, distinct=0))
+    want = ("reward", "terminated", "agent_reward", "dones", "status", "avail")
+    av = [None, None, None]
+    for t in range(12):
+        outs = []
+        for k, (eng, lo, n) in enumerate([(whole, 0, E), (parts[0], 0, E // 2), (parts[1], E // 2, E // 2)]):
+            act = eng.random_actions(5, t, avail=av[k] if t % 2 else None, env_offset=lo, dtype=torch.uint8)
+            o = eng.step_observe(act, want=want, dtype="bits")
+            av[k] = o["avail"]
+            outs.append({kk: v.clone() for kk, v in o.items()})
+            outs[-1]["pos"] = eng.positions().clone()
+            outs[-1]["act"] = act.clone()
+        for kk in outs[0]:
+            joined = torch.cat([outs[1][kk], outs[2][kk]])
+            assert torch.equal(outs[0][kk].view(torch.uint8), joined.view(torch.uint8)), (kk, t)
+    cs = workloads.state_checksum_torch
+    assert cs(outs[0]["pos"][:E // 2], outs[0]["avail"][:E // 2]) == cs(outs[1]["pos"], outs[1]["avail"])
+    assert cs(outs[0]["pos"][:E // 2]) == workloads.state_checksum_np(_np(outs[1]["pos"]))
+
+
+def test_random_actions_kernel_equals_the_numpy_counter_hash():
+    from mapf_marl_b200 import workloads
+    E, N = 300, 7
+    eng = _engine(E, N, 12, 12, mode="primal", fov=5)
+    rs = np.random.RandomState(0)
+    avail = (rs.rand(E, N, 5) < 0.5).astype(np.uint8)
+    avail[..., 0] |= (avail.sum(-1) == 0)
+    for seed, step, off in ((0, 0, 0), (1234, 17, 5000), (2 ** 31 + 5, 70000, 7 * 131072)):
+        a = eng.random_actions(seed, step, env_offset=off, dtype=torch.uint8)
+        assert np.array_equal(_np(a), workloads.hash_actions_np(seed, range(off, off + E), step, N))
+        b = eng.random_actions(seed, step, avail=torch.as_tensor(avail, device="cuda"), env_offset=off)
+        assert b.dtype == torch.int64
+        assert np.array_equal(_np(b), workloads.hash_actions_np(seed, range(off, off + E), step, N, avail=avail))
 
 
 def test_primal_convoys_cycles_and_long_dependency_chains_match_oracle():
