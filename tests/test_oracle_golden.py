@@ -46,8 +46,8 @@ def test_primal_oracle_matches_reference_trace(name):
     N = g["starts"].shape[0]
     F = int(g["fov"])
     o = Oracle(1, N, H, W, MODE_PRIMAL, fov=F)
-    o.set_blocking(bool(g.get("blocking_enabled", 0)))
-    o.set_diagonal(bool(g.get("diagonal", 0)))
+    o.set_blocking(bool(g["blocking_enabled"]))
+    o.set_diagonal(bool(g["diagonal"]))
     o.reset(g["obst"][None], g["starts"][None], g["goals"][None])
     obs, vec = o.primal_observe()
     assert np.array_equal(obs[0], g["obs0"])
