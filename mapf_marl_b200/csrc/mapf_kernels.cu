@@ -1798,10 +1798,15 @@ __device__ __forceinline__ bool bfs_warp_one(const MapfDims& d, const MapfState&
     for (int p = 0; p < NP; ++p) D[k][p] = 0;
   }
   bool open = true;
+#pragma unroll 4   // bits 3 and 4 of the level become compile-time constants inside the unrolled body (two upper planes less to mask)
   for (int L0 = 0; L0 < (1 << NP); L0 += 8) {
-    Row U[RPL];
+    // The kernel is bound by the integer ALU pipe (LOP3 / SHF: one warp instruction per two cycles per scheduler), the
+    // FMA pipe (IMAD) idles.  Every update below whose operands are DISJOINT bit sets is therefore written as an
+    // add / subtract instead of an or / and-not -- a cell is reached exactly once, so the frontier never overlaps the
+    // distance planes or leaves the free-and-not-visited set -- which lets ptxas place it on the FMA pipe (IMAD.IADD).
+    Row fnv0[RPL];
 #pragma unroll
-    for (int k = 0; k < RPL; ++k) U[k] = 0;
+    for (int k = 0; k < RPL; ++k) fnv0[k] = fnv[k];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i > 0 || L0 > 0) {
@@ -1817,28 +1822,29 @@ __device__ __forceinline__ bool bfs_warp_one(const MapfDims& d, const MapfState&
             up |= (up << 1) | (up >> 1);
             dn |= (dn << 1) | (dn >> 1);
           }
-          nw[k] = ((f[k] << 1) | (f[k] >> 1) | up | dn) & fnv[k];
+          // (the right shift stays a SHF: as IMAD.HI -- __umulhi(f, 1u << 31) -- it measured 5 % slower)
+          nw[k] = ((f[k] + f[k]) | (f[k] >> 1) | up | dn) & fnv[k];
         }
 #pragma unroll
         for (int k = 0; k < RPL; ++k) {
           f[k] = nw[k];
-          fnv[k] &= ~nw[k];
+          fnv[k] -= nw[k];                 // nw is a subset of fnv
         }
       }
 #pragma unroll
       for (int k = 0; k < RPL; ++k) {
-        if (i & 1) D[k][0] |= f[k];
-        if (i & 2) D[k][1] |= f[k];
-        if (i & 4) D[k][2] |= f[k];
-        U[k] |= f[k];
+        if (i & 1) D[k][0] += f[k];        // disjoint: this cell's distance bits are written once
+        if (i & 2) D[k][1] += f[k];
+        if (i & 4) D[k][2] += f[k];
       }
     }
     bool any = false;
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
+      const Row U = fnv0[k] - fnv[k];      // everything reached in this batch (level 0 has all planes zero anyway)
 #pragma unroll
       for (int p = 3; p < NP; ++p)
-        if ((L0 >> p) & 1) D[k][p] |= U[k];
+        if ((L0 >> p) & 1) D[k][p] += U;
       any |= f[k] != 0;
     }
     if (!__any_sync(full, any)) {
