@@ -333,8 +333,13 @@ def main():
         ms = timed_passes(one_pass, n_pass, sync_ranks)
         return ms, chunk, graph is not None
 
-    def action_pool(n_envs, lo, n=16):
-        return torch.stack([workloads.hash_actions_torch(ACTION_SEED, lo, n_envs, t, N, dev) for t in range(n)])
+    def gen_actions(engine, lo, t, avail=None, seed=ACTION_SEED):
+        """uint8 [E, N] actions of step t: the engine's counter-hash kernel (mapf_random_actions; tested equal to
+        workloads.hash_actions_np, which the CPU arms use) keyed by the GLOBAL env index."""
+        return engine.random_actions(seed, t, avail=avail, env_offset=lo, dtype=torch.uint8)
+
+    def action_pool(engine, lo, n=16):
+        return torch.stack([gen_actions(engine, lo, t).clone() for t in range(n)])
 
     # ---- the engine of the headline configuration
     obst, starts, goals = make_world(wl, E, env_lo)
@@ -350,13 +355,13 @@ def main():
     #      (a function of the GLOBAL env indices this rank owns: identical for rank 0 at any GPU count)
     eng.reset(obst, starts, goals)
     for t in range(args.warmup + args.steps):
-        last = eng.step_observe(workloads.hash_actions_torch(ACTION_SEED, env_lo, E, t, N, dev), want=WANT,
+        last = eng.step_observe(gen_actions(eng, env_lo, t), want=WANT,
                                 dtype="bits" if eng.bits_supported() else torch.uint8)
     checksum = workloads.state_checksum_torch(eng.positions(), last["obs"], last["avail"], last["terminated"])
     stats_canonical = eng.stats()
 
     # ---- device-resident throughput (the fused step+observation kernel), clocks sampled meanwhile
-    pool = action_pool(E, env_lo)
+    pool = action_pool(eng, env_lo)
     for t in range(args.warmup):
         eng.step_observe(pool[t % 16], want=WANT, dtype=odt)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -416,7 +421,7 @@ def main():
         rec = torch.empty((T_rec, E, N), dtype=torch.uint8, device=dev)
         s0 = eng.stats()
         for t in range(T_rec):
-            rec[t] = workloads.hash_actions_torch(ACTION_SEED + 1, env_lo, E, t, N, dev, avail=avail)
+            rec[t] = gen_actions(eng, env_lo, t, avail=avail, seed=ACTION_SEED + 1)
             avail = eng.step_observe(rec[t], want=WANT, dtype=odt)["avail"]
         s1 = eng.stats()
         g_m = torch.cuda.CUDAGraph()
@@ -621,7 +626,7 @@ def main():
                 ex = MapfEngine(Ex, wlx["N"], wlx["H"], wlx["W"], mode="primal", fov=wlx["F"],
                                 shared_map=wlx["warehouse"], goal_dist=wlx["warehouse"], device=dev)
                 ex.reset(o, s, g)
-                px = torch.stack([workloads.hash_actions_torch(ACTION_SEED, lo, Ex, t, wlx["N"], dev) for t in range(8)])
+                px = action_pool(ex, lo, 8)
                 for t in range(3):
                     ex.step_observe(px[t], want=WANT, dtype=odt)
                 ms, ck, gr = measure_fused(ex, px, 20, min_total_ms=100.0, min_passes=5, max_passes=200,

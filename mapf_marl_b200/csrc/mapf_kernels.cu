@@ -809,6 +809,13 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
   int* envcnt2 = (int*)(smem_raw + L.envcnt2_off);
   const bool do_step = A.do_step != 0;
   const bool need_mid = primal && do_step && ((A.out.done_mid_dev != nullptr) || (A.out.next_mid_dev != nullptr));
+  // The fused step+observation launch of the 5-action PRIMAL mode does not need a pass of its own for the agent bit map
+  // and the action masks: phase C sets the agent bit of the cell it just decided, and the masks fall out of the window
+  // rows the observation reads anyway (a neighbour cell is free iff neither its wall nor its agent bit is set).  One
+  // pass over the agents and one block-wide barrier less per step.
+  const bool fused_avail = MODE == MAPF_MODE_PRIMAL && SINGLE && F >= 3 && do_step && A.obs != nullptr &&
+                           A.out.avail_dev != nullptr;
+  int my_act = 0;   // fused_avail: the agent's action, kept across the barrier behind which the scratch bytes are reused
 
   PHASE_MARK(0);
   // ---- stage the tile (one exposed global-memory latency): obstacle bitmaps, per-agent records, zeroed grids
@@ -1005,6 +1012,11 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
         const int a = j - el * N;
         flag = primal ? primal_phase_c<diag>(d, s, j, el, a, c0, c1, c3)
                       : grid_phase_c(d, s, j, el, a, partial, envcnt2, c1, c2);
+        if (F > 0 && fused_avail) {
+          const uchar2 pn = s.posnew[j];
+          const int pc = (int)pn.y + d.P;
+          atomicOr(&s.agt[el * d.bm_words + ((int)pn.x + d.P) * d.RW + (pc >> 5)], 1u << (pc & 31));
+        }
       }
       if (primal && d.rsum_mode != 0 && A.out.reward_dev != nullptr) {
         // pairwise team reward, the part of the tree that lives inside a warp: segments of N | 32 agents, or the
@@ -1043,7 +1055,7 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
   // ---- agent bitmap of the post-step positions + available-action masks
   const uint8_t* gridcur = (!primal && do_step) ? s.gridb : s.grida;
   const bool want_avail = A.out.avail_dev != nullptr;
-  for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
+  for (int j = tid, it_ = 0; !fused_avail && j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
     const int el = fast_div(j, d.invN);
     const uchar2 p = s.posnew[j];
     if (F > 0) {
@@ -1097,7 +1109,7 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
       o[4] = (m >> 4) & 1;
     }
   }
-  __syncthreads();
+  if (!fused_avail || need_mid) __syncthreads();   // (fused_avail: the barrier behind phase C already covers phase D)
 
   PHASE_MARK(5);
   // ---- phase D + state write-back + the small per-agent / per-env outputs (coalesced over the tile)
@@ -1162,6 +1174,7 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
       ((uchar2*)S.pos)[gj] = pn;
       S.done[gj] = dn;
       S.prev_action[gj] = s.act[j];
+      my_act = s.act[j];
       if (partial) {
         S.at_goal[gj] = s.atgoal[j];
         S.pnode[gj] = s.node[j];
@@ -1256,6 +1269,27 @@ __global__ void __launch_bounds__(kThreads, ROLL ? 10 : 12) mapf_tile_kernel(con
       if (valid) {
         uint32_t w[T::NW];
         fov_window_planes<F>(w, d, s.obst + (d.shared_map ? 0 : el * d.bm_words), s.agt + el * d.bm_words, p);
+        if constexpr (F >= 3 && MODE == MAPF_MODE_PRIMAL) {
+          if (fused_avail) {
+            // _listNextValidActions (PRIMAL:639-667) from the window planes: the agent sits at window cell (P, P); a
+            // direction is open iff the neighbour cell shows neither a wall / border (channel 3) nor an agent (channel 0)
+            constexpr int Pw = F / 2;
+            auto open_cell = [&](int wi, int wj) -> uint32_t {
+              const int i0 = wi * F + wj, i3 = 3 * T::FF + wi * F + wj;          // compile-time bit positions
+              return (((w[i0 >> 5] >> (i0 & 31)) | (w[i3 >> 5] >> (i3 & 31))) & 1u) ^ 1u;
+            };
+            uint32_t m = 1u | (open_cell(Pw, Pw + 1) << 1) | (open_cell(Pw + 1, Pw) << 2) |
+                         (open_cell(Pw, Pw - 1) << 3) | (open_cell(Pw - 1, Pw) << 4);      // dirDict, PRIMAL:28
+            const int opp = (my_act == 0) ? -1 : (((my_act + 1) & 3) + 1);                // opposite_actions, :26
+            if (opp > 0) m &= ~(1u << opp);
+            uint8_t* o = A.out.avail_dev + 5 * (a0t + j);
+            o[0] = m & 1;
+            o[1] = (m >> 1) & 1;
+            o[2] = (m >> 2) & 1;
+            o[3] = (m >> 3) & 1;
+            o[4] = (m >> 4) & 1;
+          }
+        }
 #pragma unroll
         for (int q = 0; q < T::CW; ++q) vis[q] = w[q];
         if ((T::FF & 31) != 0) vis[T::CW - 1] &= (1u << (T::FF & 31)) - 1u;
