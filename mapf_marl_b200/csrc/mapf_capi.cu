@@ -136,14 +136,14 @@ static const int kMaxSmem = 227 * 1024;
 
 // Environments per tile: up to 128 agents per 128-thread block, a multiple of the alignment the
 // 16-byte observation chunks need, and -- for small batches, which are one latency-bound wave -- enough tiles to
-// put four on every one of the 148 SMs (c2: 4096 envs x 8 agents run 8.8 us per step with 4 envs per tile,
+// put six on every one of the 148 SMs (c2: 4096 envs x 8 agents run 8.7 us per step with 4 envs per tile, 9.3 with 6,
 // 10.2 us with 16).
 static int choose_epb(MapfDims& d, MapfTileLayout* L) {
   const int lcm = d.G % 4 == 0 ? d.G : (4 % d.G == 0 ? 4 : d.G * 4 / gcd_i(d.G, 4));
   const int mult = lcm / gcd_i(d.N, lcm);
   int epb = (MAPF_TILE_THREADS / d.N) / mult * mult;
   if (epb < mult) epb = mult;
-  while (epb > mult && (d.E + epb - 1) / epb < 4 * 148 && epb * d.N > 32) epb -= mult;
+  while (epb > mult && (d.E + epb - 1) / epb < 6 * 148 && epb * d.N > 32) epb -= mult;
   if (const char* env = getenv("MAPF_B200_EPB")) {   // tuning knob for experiments: environments per tile
     const int want = atoi(env);
     if (want >= mult) epb = want / mult * mult;
