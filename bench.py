@@ -398,7 +398,8 @@ def main():
                                                    max(5, int(200.0 / max(ms_step * T_roll, 1e-3)) // 4)))) / T_roll
             roll = {"ms_per_step": ms_roll, "steps_per_launch": T_roll, "one_launch": eng.rollout_in_one_launch(odt),
                     "agent_steps_per_s": world * E * N / (ms_roll * 1e-3),
-                    "frac_of_hbm_peak": wl["bytes_per_agent_step"] * E * N / (ms_roll * 1e-3) / 1e9 / measured_peak()[0]}
+                    "frac_of_hbm_peak": (wl["bytes_per_agent_step"] + (3 * 4 * F * F if args.f32 else 0)) * E * N /
+                    (ms_roll * 1e-3) / 1e9 / measured_peak()[0]}
         except Exception as exc:
             roll = {"error": repr(exc)}
         line_extra["rollout_kernel"] = roll
