@@ -786,7 +786,7 @@ __device__ __forceinline__ void fov_goal_bits_half(uint32_t* str, int j, int jen
 // in the registers of the threads that own its agents: the obstacle rows are staged once, positions / done flags / step
 // counters never make the round trip through global memory between steps, and step t+1's actions are fetched while
 // step t is still being computed.  Step t's outputs go to element offset t * (size of one step's output) of every
-// output pointer (time-major [T, E, ...] storage); the state in the handle is kept current after every step.
+// output pointer (time-major [T, E, ...] storage); the handle's state and statistics are written after the last step.
 // WIDE (rollouts only): 64 registers per thread instead of 48.  A batch small enough to be resident all at once (c2) is
 // bound by the dependent instruction chain of a step, not by occupancy: without the register cap the chain has no
 // spills and a better schedule (7.1 -> 6.7 us per c2 step); large batches keep the 10-blocks-per-SM variant.
@@ -889,14 +889,20 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
   if (tid < na) load_rec(tid, r0);
   int sc0 = 0;
   if (tid < ne) sc0 = S.step_count[e0 + tid];
+  const bool incr = ROLL && MODE == MAPF_MODE_PRIMAL && fused_avail;
+  unsigned int c0 = 0, c1 = 0, c2 = 0, c3 = 0;   // statistics of this thread's agents (a rollout flushes them once)
+  unsigned int ep_done = 0;                      // thread per environment: steps that ended with everybody on goal
   for (;;) {   // one iteration per step of a rollout; a single pass otherwise
   PHASE_MARK(10);
-  if (ROLL && t_roll > 0) {
-    bad = false;
-    if (tid < MAPF_N_STATS) stat[tid] = 0;
-    if (tid == 0) bad_flag = 0;
-  }
-  {
+  // Rollouts: `last` = the step after which state and statistics go back to global memory (every step otherwise).
+  // `fresh` = the occupancy grid and the agent bit rows are rebuilt from the positions; false in the later steps of a
+  // PRIMAL rollout, where both are simply what the previous step left behind: the sweep vacates and enters cells in
+  // the id grid anyway, and the agent bits are cleared where an agent left (before the barrier of phase B) and set
+  // where it arrived (phase C).  That saves the zero fill, the rebuild and one block-wide barrier per step.
+  const bool last = !ROLL || t_roll + 1 >= A.T;
+  const bool fresh = !(incr && t_roll > 0);
+  bad = false;
+  if (fresh) {
     // zero the agent bit rows and the occupancy grid(s): they are adjacent in the tile layout, one loop clears them
     const uint4 z = make_uint4(0, 0, 0, 0);
     const int nz = (L.grida_off - L.agt_off + d.epb * d.grid_bytes * ((!primal && do_step) ? 2 : 1)) >> 4;
@@ -927,22 +933,21 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
       store_rec(j, r);
     }
   }
-  __syncthreads();
-  if (bad) bad_flag = 1;
+  if (fresh) __syncthreads();   // (not fresh: phase A below only touches the agent's own records)
+  if (bad) bad_flag = 1;        // sticky for the whole launch
   long long next_av = -1;   // rollout: the action of the NEXT step, in flight while this step is computed
   if (ROLL && t_roll + 1 < A.T && tid < na) next_av = load_action(tid, a0t + (size_t)d.E * N);
 
   PHASE_MARK(1);
   // ---- phase A: occupancy of the current positions (PRIMAL State.state ids, PRIMAL:32-47; GRID agent counts,
   //      GRID:299) and the agent-independent part of the step
-  unsigned int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
     const int el = fast_div(j, d.invN), a = j - el * N;
     const uchar2 p = s.posold[j];
     uint8_t* grid = s.grida + el * d.grid_bytes;
     const int cell = gcell(d, p.x, p.y);
     if (primal) {
-      grid[cell] = (uint8_t)(a + 1);
+      if (fresh) grid[cell] = (uint8_t)(a + 1);
       if (do_step) primal_phase_a<diag>(d, s, A, j, el, a);
     } else {
       byte_inc(grid, cell);
@@ -999,7 +1004,12 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
       for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_)   // vacate the old cells; phase C enters the new ones
         if (s.res[j] == RES_MOVED) {
           const uchar2 p = s.posold[j];
-          s.grida[fast_div(j, d.invN) * d.grid_bytes + gcell(d, p.x, p.y)] = 0;
+          const int el = fast_div(j, d.invN);
+          s.grida[el * d.grid_bytes + gcell(d, p.x, p.y)] = 0;
+          if (F > 0 && incr) {   // the agent bit rows live across the steps of the rollout: the cell is left
+            const int pc = (int)p.y + d.P;
+            atomicAnd(&s.agt[el * d.bm_words + ((int)p.x + d.P) * d.RW + (pc >> 5)], ~(1u << (pc & 31)));
+          }
         }
       __syncthreads();
       }
@@ -1036,7 +1046,7 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
       const unsigned bf = __ballot_sync(0xffffffffu, flag);
       if (active && lane == __ffs(peers) - 1) atomicAdd(&envcnt[el], __popc(bf & peers));
     }
-    if (d.collect_stats) {
+    if (d.collect_stats && last) {
       c0 = __reduce_add_sync(0xffffffffu, c0);
       c1 = __reduce_add_sync(0xffffffffu, c1);
       c2 = __reduce_add_sync(0xffffffffu, c2);
@@ -1133,7 +1143,7 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
           }
           A.out.reward_dev[e0t + el] = tot;
         }
-        if (A.agent_lo == 0) S.step_count[e0 + el] = envstep[el] + 1;
+        if (A.agent_lo == 0 && last) S.step_count[e0 + el] = envstep[el] + 1;
       } else if (partial) {
         const int step_now = envstep[el] + 1;
         bool term = (S.terminated[e0 + el] != 0) || (step_now >= d.episode_limit);     // PARTIAL:224-226
@@ -1154,15 +1164,17 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
       } else {
         if (A.out.reward_dev)
           A.out.reward_dev[e0t + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // GRID:141
-        S.step_count[e0 + el] = envstep[el] + 1;
+        if (last) S.step_count[e0 + el] = envstep[el] + 1;
       }
-      if (d.collect_stats && all) atomicAdd(&S.stats[MAPF_STAT_EPISODES_DONE], 1ull);
+      ep_done += all ? 1u : 0u;
+      if (d.collect_stats && last && ep_done) atomicAdd(&S.stats[MAPF_STAT_EPISODES_DONE], (unsigned long long)ep_done);
     }
     PHASE_MARK(11);
-    if (d.collect_stats) {   // one global atomic per counter per tile; the per-agent counters were complete at the barrier
+    if (d.collect_stats && last) {   // one global atomic per counter per tile (a rollout: once for all its steps)
+      const unsigned long long nsteps = ROLL ? (unsigned long long)A.T : 1ull;
       if (tid == 0) {
-        if (!primal || A.agent_lo == 0) atomicAdd(&S.stats[MAPF_STAT_ENV_STEPS], (unsigned long long)ne);
-        atomicAdd(&S.stats[MAPF_STAT_AGENT_STEPS], (unsigned long long)(ne * (primal ? A.agent_hi - A.agent_lo : N)));
+        if (!primal || A.agent_lo == 0) atomicAdd(&S.stats[MAPF_STAT_ENV_STEPS], nsteps * ne);
+        atomicAdd(&S.stats[MAPF_STAT_AGENT_STEPS], nsteps * (unsigned long long)(ne * (primal ? A.agent_hi - A.agent_lo : N)));
       } else if (tid < MAPF_N_STATS && stat[tid] != 0) {
         atomicAdd(&S.stats[tid], (unsigned long long)stat[tid]);
       }
@@ -1175,10 +1187,12 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
       const size_t gj = a0 + j, gt = a0t + j;   // the handle's state / this step's outputs
       const uint8_t dn = s.done[j];
       const uchar2 pn = s.posnew[j];
-      ((uchar2*)S.pos)[gj] = pn;
-      S.done[gj] = dn;
-      S.prev_action[gj] = s.act[j];
       my_act = s.act[j];
+      if (last) {   // the handle's state (a rollout keeps it in registers until its last step)
+        ((uchar2*)S.pos)[gj] = pn;
+        S.done[gj] = dn;
+        S.prev_action[gj] = (uint8_t)my_act;
+      }
       if (partial) {
         S.at_goal[gj] = s.atgoal[j];
         S.pnode[gj] = s.node[j];
