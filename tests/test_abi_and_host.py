@@ -293,3 +293,72 @@ def test_reference_worker_steps_exactly_what_the_oracle_steps():
         assert got == want, (t, got, want)
         for e, env in enumerate(envs):
             assert [tuple(p) for p in env.getPositions()] == [tuple(int(v) for v in p) for p in orc.positions()[e]]
+
+
+def test_host_unpack_expands_any_cell_range_of_a_bit_stream():
+    """mapf_host_unpack (the lazy view over a MAPF_BITS host observation): any [first_cell, first_cell + n) range, word
+    aligned or not, as uint8 or float32, touches exactly n output elements.  Pure host code: runs without a GPU."""
+    import numpy as np
+    from mapf_marl_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(0)
+    bits = rs.randint(0, 2 ** 32, 2000, dtype=np.uint64).astype(np.uint32)
+    cells = np.unpackbits(bits.view(np.uint8), bitorder="little")
+    for first, n in [(0, 64000), (0, 0), (5, 100), (37, 3000), (64, 31), (31, 1), (96, 640), (1, 63999), (15488 * 3, 15488)]:
+        for dt, npdt in ((_lib.U8, np.uint8), (_lib.F32, np.float32)):
+            out = np.full(n + 8, 7, npdt)
+            rc = lib.mapf_host_unpack(bits.ctypes.data, first, n, out.ctypes.data, dt)
+            assert rc == 0
+            assert np.array_equal(out[:n], cells[first:first + n].astype(npdt)) and (out[n:] == 7).all(), (first, n, dt)
+    assert lib.mapf_host_unpack(bits.ctypes.data, 0, 32, bits.ctypes.data, _lib.I64) != 0      # unsupported dtype
+
+
+def test_counter_hash_actions_and_checksum_agree_between_numpy_and_torch():
+    """The inputs of every arm: workloads.hash_actions_np (CPU reference workers, oracle) == hash_actions_torch (the
+    GPU test of mapf_random_actions closes the triangle); state_checksum_np == state_checksum_torch."""
+    import numpy as np
+    import torch
+    from mapf_marl_b200 import workloads as w
+    for seed, lo, t, n in ((1234, 0, 0, 32), (7, 917504, 19, 8), (2 ** 31 + 3, 5, 70001, 5)):
+        a = w.hash_actions_np(seed, range(lo, lo + 97), t, n)
+        assert a.dtype == np.uint8 and a.max() <= 4
+        assert np.array_equal(a, w.hash_actions_torch(seed, lo, 97, t, n, "cpu").numpy())
+        av = (np.random.RandomState(t % 1000).rand(97, n, 5) < 0.5).astype(np.uint8)
+        av[..., 0] |= av.sum(-1) == 0
+        m = w.hash_actions_np(seed, range(lo, lo + 97), t, n, avail=av)
+        assert np.array_equal(m, w.hash_actions_torch(seed, lo, 97, t, n, "cpu", avail=torch.as_tensor(av)).numpy())
+        assert (np.take_along_axis(av, m[..., None].astype(np.int64), -1) == 1).all()
+    # a shard draws what the whole batch draws for its environments
+    whole = w.hash_actions_np(5, range(0, 64), 3, 6)
+    assert np.array_equal(whole[40:], w.hash_actions_np(5, range(40, 64), 3, 6))
+    # roughly uniform
+    big = w.hash_actions_np(1, range(20000), 0, 16)
+    assert np.abs(np.bincount(big.ravel(), minlength=5) / big.size - 0.2).max() < 0.01
+    x = np.random.RandomState(0).randint(-300, 300, (50, 7, 2)).astype(np.int16)
+    y = np.random.RandomState(1).randint(0, 2 ** 31, 12345).astype(np.int32)
+    assert w.state_checksum_np(x, y) == w.state_checksum_torch(torch.as_tensor(x), torch.as_tensor(y))
+    assert w.state_checksum_np(x, y) != w.state_checksum_np(y, x)
+
+
+def test_reference_staging_archive_roundtrip(tmp_path):
+    """oracle/stage_ref.py: the archive that carries the reference's own files to the GPU box unpacks to files whose
+    sha256 equal the manifest (and the originals, where /root/reference is present)."""
+    import hashlib
+    import json
+    import os
+    import pytest
+    from oracle import stage_ref
+    if stage_ref.stage() is None and not os.path.exists(stage_ref.ARCHIVE):
+        pytest.skip("no reference tree and no staged archive")
+    root = stage_ref.unpack(str(tmp_path))
+    man = json.load(open(os.path.join(stage_ref.DST, "MANIFEST.json")))["files"]
+    assert sorted(man) == sorted(stage_ref.FILES)
+    for rel, sha in man.items():
+        data = open(os.path.join(root, rel), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == sha
+        src = os.path.join(stage_ref.SRC, rel)
+        if os.path.exists(src):
+            assert open(src, "rb").read() == data
+    # no reference source is tracked by git: the staging directory is ignored
+    ign = open(os.path.join(os.path.dirname(stage_ref.HERE), ".gitignore")).read()
+    assert "oracle/_ref/" in ign
