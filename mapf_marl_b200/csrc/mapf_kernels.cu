@@ -27,7 +27,8 @@
 
 #ifdef MAPF_PHASE_TIMING
 __device__ long long g_phase_clk[32];
-#define PHASE_MARK(i) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) g_phase_clk[i] = clock64(); } while (0)
+// (a rollout records its second-to-last step: the last one also flushes state and statistics)
+#define PHASE_MARK(i) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && (A.T < 2 || t_roll + 2 == A.T)) g_phase_clk[i] = clock64(); } while (0)
 #else
 #define PHASE_MARK(i) do { } while (0)
 #endif
@@ -821,7 +822,6 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
                            A.out.avail_dev != nullptr;
   int my_act = 0;   // fused_avail: the agent's action, kept across the barrier behind which the scratch bytes are reused
 
-  PHASE_MARK(0);
   // ---- stage the tile (one exposed global-memory latency): obstacle bitmaps, per-agent records, zeroed grids
   if (tid < MAPF_N_STATS) stat[tid] = 0;
   if (tid == 0) bad_flag = 0;

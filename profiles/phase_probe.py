@@ -18,6 +18,7 @@ os.environ["MAPF_B200_LIB"] = os.path.join(ROOT, "mapf_marl_b200", "libmapf_b200
 from mapf_marl_b200 import _lib  # noqa: E402
 from mapf_marl_b200.engine import MapfEngine  # noqa: E402
 
+WANT = tuple(os.environ.get("PROBE_WANT", "reward,terminated,dones,avail").split(","))
 NAMES = ["stage", "phase A", "phase B", "phase C", "avail + agent bitmap", "phase D + write-back", "obs start",
          "phase 1", "phase 2"]
 
@@ -36,9 +37,9 @@ def main():
         for roll in (False, True):
             for _ in range(5):
                 if roll:
-                    eng.rollout(acts)
+                    eng.rollout(acts, want=WANT)
                 else:
-                    eng.step_observe(acts[0])
+                    eng.step_observe(acts[0], want=WANT)
             torch.cuda.synchronize()
             buf = (ctypes.c_longlong * 32)()
             lib.mapf_debug_phase_clocks(buf)
