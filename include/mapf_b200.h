@@ -269,7 +269,8 @@ int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, co
 
 /* n_steps consecutive mapf_step_observe calls with pre-supplied actions in ONE call -- and, for PRIMAL (without
  * diagonal movement / blocking reward) and GRID batches whose tiles hold one thread per agent, in ONE kernel launch:
- * the tile's state stays in shared memory and registers between the steps, only the per-step outputs stream out
+ * the tile's state stays in shared memory and registers between the steps, only the per-step outputs stream out;
+ * small PRIMAL batches go through a pipelined kernel (mapf_rollout_plan)
  * (the reference's equivalent is the env loop of its runner,
  * MARL-curve-main/src/runners/parallel_runner.py:127-171, driven by a fixed action sequence).
  *   actions_dev [n_steps, E, N] of act_dtype.
@@ -280,6 +281,11 @@ int mapf_rollout(mapf_handle* h, const void* actions_dev, int act_dtype, int n_s
                  void* obs_dev, int obs_dtype, double* vec_dev, void* stream);
 /* 1 when mapf_rollout runs as a single launch for this handle and observation dtype (otherwise n_steps launches). */
 int mapf_rollout_in_one_launch(const mapf_handle* h, int obs_dtype);
+/* Which kernel a rollout with an observation of obs_dtype would use: 0 = n_steps launches of the step kernel, 1 = the
+ * step kernel's in-kernel loop, 2 = the pipelined kernel for small PRIMAL batches (at most 32 agents per environment,
+ * every 32-agent tile resident at once: one warp sweeps step t+1 while three build the observation of step t).
+ * mid_outputs != 0: the caller also wants done_mid / next_mid / blocking, which only the step kernel produces. */
+int mapf_rollout_plan(const mapf_handle* h, int n_steps, int obs_dtype, int mid_outputs);
 
 /* Host-buffer form of mapf_step_observe: copies io->actions_host to the device, runs the fused
  * kernel, copies the requested outputs back and waits for them.  This is the call the e2e

@@ -82,6 +82,7 @@ PROTOTYPES = {
     "mapf_step_observe": (_i, [_vp, _vp, _i, ctypes.POINTER(MapfStepOut), _vp, _i, _vp, _vp]),
     "mapf_rollout": (_i, [_vp, _vp, _i, _i, ctypes.POINTER(MapfStepOut), _vp, _i, _vp, _vp]),
     "mapf_rollout_in_one_launch": (_i, [_vp, _i]),
+    "mapf_rollout_plan": (_i, [_vp, _i, _i, _i]),
     "mapf_step_observe_host": (_i, [_vp, ctypes.POINTER(MapfHostIO), _vp]),
     "mapf_host_unpack": (_i, [_vp, ctypes.c_uint64, ctypes.c_uint64, _vp, _i]),
     "mapf_obs_bits_supported": (_i, [_vp]),

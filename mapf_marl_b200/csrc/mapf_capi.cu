@@ -651,12 +651,56 @@ int mapf_rollout_in_one_launch(const mapf_handle* h, int obs_dtype) {
   return rollout_in_kernel(h, &dummy, obs_dtype, nullptr) ? 1 : 0;
 }
 
+// How mapf_rollout runs: 2 = the pipelined kernel (small PRIMAL batches: every tile resident at once, step t+1 under
+// the observation of step t), 1 = the tile kernel's in-kernel loop, 0 = n_steps consecutive launches.
+static int rollout_plan(const mapf_handle* h, int n_steps, bool has_obs, int obs_dtype, bool mid_outputs) {
+  static const int pipe_env = getenv("MAPF_B200_PIPE") ? atoi(getenv("MAPF_B200_PIPE")) : -1;   // experiments: 0 off, 1 force
+  const MapfDims& d = h->d;
+  int dummy = 0;
+  const bool in_kernel = rollout_in_kernel(h, has_obs ? &dummy : nullptr, obs_dtype, nullptr);
+  if (n_steps >= 2 && has_obs && in_kernel && !mid_outputs && pipe_env != 0 && mapf_pipe_supported(d) &&
+      (pipe_env == 1 || mapf_pipe_tiles(d) <= 148 * 8))   // all tiles resident at 8 blocks per SM
+    return 2;
+  return (n_steps == 1 || in_kernel) ? 1 : 0;
+}
+
+int mapf_rollout_plan(const mapf_handle* h, int n_steps, int obs_dtype, int mid_outputs) {
+  return h ? rollout_plan(h, n_steps, true, obs_dtype, mid_outputs != 0) : 0;
+}
+
 int mapf_rollout(mapf_handle* h, const void* actions_dev, int act_dtype, int n_steps, const mapf_step_out* out,
                  void* obs_dev, int obs_dtype, double* vec_dev, void* stream) {
   if (!h || !actions_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_rollout: NULL argument");
   if (n_steps < 1) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_rollout: n_steps must be >= 1");
   const MapfDims& d = h->d;
-  if (n_steps == 1 || rollout_in_kernel(h, obs_dev, obs_dtype, vec_dev))
+  const int plan = rollout_plan(h, n_steps, obs_dev != nullptr, obs_dtype,
+                                out && (out->done_mid_dev || out->next_mid_dev || out->blocking_dev));
+  if (plan == 2) {
+    int rc;
+    if ((rc = check_aligned(h, actions_dev, "actions_dev")) != MAPF_OK) return rc;
+    if ((rc = check_aligned(h, obs_dev, "obs_dev")) != MAPF_OK) return rc;
+    if ((rc = check_aligned(h, vec_dev, "vec_dev")) != MAPF_OK) return rc;
+    if (act_dtype != MAPF_U8 && act_dtype != MAPF_I64)
+      return fail(h, MAPF_ERR_INVALID_ARG, "actions must be MAPF_U8 or MAPF_I64");
+    if (obs_dtype != MAPF_U8 && obs_dtype != MAPF_F32 && obs_dtype != MAPF_BITS)
+      return fail(h, MAPF_ERR_INVALID_ARG, "FOV observations are MAPF_U8, MAPF_F32 or MAPF_BITS");
+    MapfTileArgs A;
+    memset(&A, 0, sizeof(A));
+    A.T = n_steps;
+    A.actions = actions_dev;
+    A.act_dtype = act_dtype;
+    A.do_step = 1;
+    A.agent_lo = 0;
+    A.agent_hi = d.N;
+    if (out) A.out = *out;
+    A.obs = obs_dev;
+    A.obs_dtype = obs_dtype;
+    A.vec = vec_dev;
+    CK((cudaError_t)mapf_launch_pipe(d, h->S, A, stream));
+    h->launches++;
+    return MAPF_OK;
+  }
+  if (plan == 1)
     return run_tile(h, actions_dev, act_dtype, 0, d.N, out, obs_dev, obs_dtype, vec_dev, stream, n_steps);
   // configurations without the in-kernel loop: the same result from n_steps consecutive launches
   const size_t EN = (size_t)d.E * d.N, E = (size_t)d.E;

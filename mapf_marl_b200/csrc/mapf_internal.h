@@ -141,6 +141,9 @@ int mapf_launch_random_actions(const MapfDims& d, const uint8_t* avail, uint32_t
                                long long env_offset, void* out, int i64, void* stream);
 int mapf_tile_has_fov(int F);
 int mapf_tile_has_rollout(int mode);
+int mapf_pipe_supported(const MapfDims& d);
+int mapf_pipe_tiles(const MapfDims& d);
+int mapf_launch_pipe(const MapfDims& d, const MapfState& S, const MapfTileArgs& A, void* stream);
 int mapf_configure_tile(int F, int mode, int smem_bytes);
 #ifdef __cplusplus
 }

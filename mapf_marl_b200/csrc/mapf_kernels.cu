@@ -1426,6 +1426,395 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// mapf_pipe_kernel<F>: mapf_rollout for SMALL PRIMAL batches -- a two-stage pipeline inside the block.
+//
+// A batch like c2 (4096 envs x 8 agents) is resident on the GPU all at once, and in mapf_tile_kernel<.., ROLL> every
+// tile then walks ONE dependent chain of ~11 000 cycles per step (step phases ~5 900, observation phases ~4 700): there
+// is no second tile to hide it behind, issue slots are half empty, HBM a third used.  Here a tile is at most 32 agents
+// (one thread per agent) and its block of four warps splits into two ROLES that run concurrently:
+//   warp 0      STEP role: the sweep of step t+1 (phases A-D of the tile kernel, barriers are __syncwarp), the small
+//               per-step outputs, then a SNAPSHOT of the post-step tile state (positions, actions, id grid, agent bit
+//               rows: < 4 KB) into buffer t & 1;
+//   warps 1-3   OBSERVATION role: window planes, action masks, goal bits and goal vectors of step t from snapshot
+//               t & 1 (one thread per agent), then the bit -> byte expansion with all 96 threads.
+// Named barriers (bar.sync / bar.arrive, ids 1-4) hand the two snapshot buffers back and forth: "ready[b]" (step role
+// arrives, observation role waits) and "free[b]" (the other way round); barrier 5 is the observation role's own.  The
+// chain of a step becomes max(step role, observation role) instead of their sum.  Same helper functions, same
+// results: the parity tests compare mapf_rollout with consecutive mapf_step_observe calls bit for bit.
+// Restrictions (the launcher falls back to the ROLL kernel otherwise): 5-action PRIMAL, odd specialised F, at most 32
+// agents per environment, full sweeps, no mid-sweep outputs, observation requested.
+// ------------------------------------------------------------------------------------------------
+struct MapfPipeLayout {
+  int obst_off;                 // [shared ? 1 : epb][bm_words] u32
+  int grid_off, agt_off;        // live id grid [epb][grid_bytes] and agent bit rows [epb][bm_words] (adjacent)
+  int snap_off[2];              // snapshots of the two, same shape, adjacent
+  int snappos_off[2];           // uchar2 [32]
+  int snapact_off[2];           // u8 [32]
+  int goal_off, posold_off, posnew_off;   // uchar2 [32]
+  int mv_off;                   // u32 [32]
+  int res_off, dep_off, act_off, status_off, done_off, flag_off;   // u8 [32]
+  int rew_off;                  // double [32]
+  int envrew_off;               // double [32]
+  int envcnt_off;               // int [32]
+  int str_off;                  // observation bit strings
+  int live_bytes;               // bytes of (id grid + agent bit rows) of the tile: what a snapshot copies
+  int total_bytes;
+};
+
+// Barrier ids are IMMEDIATES: with a register id ptxas reserves all 16 barriers of the CTA, and the SM then holds 4 such
+// CTAs instead of 8 (measured: the pipelined kernel ran in two waves).
+template <int ID>
+__device__ __forceinline__ void named_sync(int count) {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void named_arrive(int count) {
+  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+
+#ifdef MAPF_PHASE_TIMING
+#define PIPE_MARK(i, leader) do { if (blockIdx.x == gridDim.x / 2 && (leader) && t + 2 == nsteps) g_phase_clk[i] = clock64(); } while (0)
+#else
+#define PIPE_MARK(i, leader) do { } while (0)
+#endif
+
+template <int F>
+__global__ void __launch_bounds__(kThreads, 8) mapf_pipe_kernel(const MapfDims d, const MapfPipeLayout L, const MapfState S,
+                                                                const MapfTileArgs A, const int epb) {
+  static_assert(kThreads == 128 && (F & 1) == 1 && F >= 3, "one step warp + three observation warps; symmetric windows");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using T = Fov<F>;
+  constexpr unsigned full = 0xffffffffu;
+  constexpr int kObsThreads = kThreads - 32;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int N = d.N;
+  const int e0 = blockIdx.x * epb;
+  const int ne = min(epb, d.E - e0);
+  const int na = ne * N;                                   // <= 32: one lane of the step warp per agent
+  const size_t a0 = (size_t)e0 * N, EN = (size_t)d.E * N;
+  uint32_t* obst = (uint32_t*)(smem_raw + L.obst_off);
+  uchar2* goal = (uchar2*)(smem_raw + L.goal_off);
+  const int nsteps = A.T;
+
+  // ---- both roles: the obstacle rows of the tile, once
+  {
+    const int nvec = ((d.shared_map ? 1 : ne) * d.bm_words) >> 2;
+    const uint4* osrc = (const uint4*)(S.obst_bits + (d.shared_map ? (size_t)0 : (size_t)e0 * d.bm_words));
+    for (int i = tid; i < nvec; i += kThreads) ((uint4*)obst)[i] = __ldg(osrc + i);
+  }
+  if (tid < na) goal[tid] = ((const uchar2*)S.goal)[a0 + tid];
+  __syncthreads();
+
+  if (tid < 32) {
+    // =========================================================== STEP role (warp 0) ================================
+    Smem s;
+    s.obst = obst;
+    s.agt = (uint32_t*)(smem_raw + L.agt_off);
+    s.grida = smem_raw + L.grid_off;
+    s.gridb = s.grida;
+    s.posold = (uchar2*)(smem_raw + L.posold_off);
+    s.posnew = (uchar2*)(smem_raw + L.posnew_off);
+    s.goal = goal;
+    s.mv = (uint32_t*)(smem_raw + L.mv_off);
+    s.res = smem_raw + L.res_off;
+    s.dep = smem_raw + L.dep_off;
+    s.act = smem_raw + L.act_off;
+    s.status = (int8_t*)(smem_raw + L.status_off);
+    s.done = smem_raw + L.done_off;
+    s.flag = smem_raw + L.flag_off;
+    s.rew = (double*)(smem_raw + L.rew_off);
+    s.envrew = (double*)(smem_raw + L.envrew_off);
+    int* envcnt = (int*)(smem_raw + L.envcnt_off);
+    const int j = lane;
+    const bool active = j < na;
+    const int el = active ? fast_div(j, d.invN) : 0, a = active ? j - el * N : 0;
+    uchar2 p = make_uchar2(0, 0);
+    int sc = 0;
+    if (active) p = ((const uchar2*)S.pos)[a0 + j];
+    if (lane < ne) sc = S.step_count[e0 + lane];
+    auto load_action = [&](size_t at) -> long long {
+      return (A.act_dtype == MAPF_I64) ? ((const long long*)A.actions)[at + j]
+                                       : (long long)((const uint8_t*)A.actions)[at + j];
+    };
+    long long av = active ? load_action(a0) : 0;
+    // the live id grid (PRIMAL State.state, PRIMAL:32-47) and agent bit rows: built once, then kept up to date
+    for (int i = lane; i < (L.live_bytes >> 4); i += 32) ((uint4*)(smem_raw + L.grid_off))[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    if (active) {
+      s.grida[el * d.grid_bytes + gcell(d, p.x, p.y)] = (uint8_t)(a + 1);
+      const int pc = (int)p.y + d.P;
+      atomicOr(&s.agt[el * d.bm_words + ((int)p.x + d.P) * d.RW + (pc >> 5)], 1u << (pc & 31));
+    }
+    __syncwarp();
+    unsigned int c0 = 0, c1 = 0, c3 = 0, ep_done = 0;
+    bool bad = false;
+    int act = 0;
+    uint8_t dn = 0;
+    size_t a0t = a0, e0t = (size_t)e0;
+    for (int t = 0; t < nsteps; ++t, a0t += EN, e0t += (size_t)d.E) {
+      const int b = t & 1;
+      PIPE_MARK(16, lane == 0);
+      long long next_av = 0;
+      if (t + 1 < nsteps && active) next_av = load_action(a0t + EN);
+      if (active) {
+        long long v = av;
+        if (v < 0 || v > 4) {                                          // PRIMAL:556 assert
+          bad = true;
+          v = 0;
+        }
+        act = (int)v;
+        s.posold[j] = p;
+        s.posnew[j] = p;
+        s.act[j] = (uint8_t)act;
+        primal_phase_a<false>(d, s, A, j, el, a);                      // reads only this agent's records + the walls
+      }
+      if (lane < ne) envcnt[lane] = 0;
+      __syncwarp();
+      // ---- phase B: the ordered sweep, resolved in parallel (primal_classify)
+      bool pending = false;
+      if (active) {
+        const uint8_t r = primal_classify(d, s, j, el, a);
+        s.res[j] = r;
+        pending = (r == RES_UNRESOLVED);
+      }
+      __syncwarp();
+      while (__any_sync(full, pending)) {
+        pending = false;
+        if (active && s.res[j] == RES_UNRESOLVED) {
+          const int k = el * N + s.dep[j];
+          const uint8_t rk = s.res[k];
+          if (rk == RES_UNRESOLVED) {
+            s.dep[j] = s.dep[k];                                       // pointer jumping
+            pending = true;
+          } else {
+            s.res[j] = rk;
+          }
+        }
+        __syncwarp();
+      }
+      if (active && s.res[j] == RES_MOVED) {                           // vacate: id grid and agent bit
+        s.grida[el * d.grid_bytes + gcell(d, p.x, p.y)] = 0;
+        const int pc = (int)p.y + d.P;
+        atomicAnd(&s.agt[el * d.bm_words + ((int)p.x + d.P) * d.RW + (pc >> 5)], ~(1u << (pc & 31)));
+      }
+      __syncwarp();
+      // ---- phase C: outcome, reward, arrival; the new cell enters the id grid and the agent bit rows
+      bool on_goal = false;
+      uchar2 pn = p;
+      if (active) {
+        on_goal = primal_phase_c<false>(d, s, j, el, a, c0, c1, c3);
+        pn = s.posnew[j];
+        dn = s.done[j];
+        const int pc = (int)pn.y + d.P;
+        atomicOr(&s.agt[el * d.bm_words + ((int)pn.x + d.P) * d.RW + (pc >> 5)], 1u << (pc & 31));
+      }
+      if (d.rsum_mode == 1 && A.out.reward_dev != nullptr) {           // pairwise team reward inside the warp (N | 32)
+        double v = active ? s.rew[j] : 0.0;
+        for (int sft = 1; sft < N; sft <<= 1) v = __dadd_rn(v, __shfl_down_sync(full, v, sft));
+        if (active && a == 0) s.envrew[el] = v;
+      }
+      {
+        const unsigned peers = __match_any_sync(full, active ? el : -1);
+        const unsigned bf = __ballot_sync(full, on_goal);
+        if (active && lane == __ffs(peers) - 1) envcnt[el] = __popc(bf & peers);
+      }
+      __syncwarp();
+      // ---- phase D (lane per environment) + the small per-agent outputs of this step
+      if (lane < ne) {
+        const bool all = envcnt[lane] == N;                            // State.done, PRIMAL:159-165
+        if (A.out.terminated_dev) A.out.terminated_dev[e0t + lane] = all ? 1 : 0;
+        if (A.out.reward_dev)
+          A.out.reward_dev[e0t + lane] = d.rsum_mode == 1 ? s.envrew[lane]
+                                                           : tree_sum_agents(s.rew + lane * N, N, 0, N);
+        ep_done += all ? 1u : 0u;
+      }
+      if (active) {
+        const size_t gt = a0t + j;
+        if (A.out.dones_dev) A.out.dones_dev[gt] = dn;
+        if (A.out.status_dev) A.out.status_dev[gt] = s.status[j];
+        if (A.out.agent_reward_dev) A.out.agent_reward_dev[gt] = s.rew[j];
+        if (A.out.node_dev) A.out.node_dev[gt] = 0;
+        if (A.out.edge_dev) A.out.edge_dev[gt] = 0;
+        if (A.out.valid_dev) A.out.valid_dev[gt] = (s.flag[j] >> 1) & 1;
+      }
+      // ---- hand the post-step state to the observation role: wait until it has let go of buffer b (step t - 2)
+      PIPE_MARK(17, lane == 0);
+      if (t >= 2) {
+        if (b) named_sync<4>(kThreads);
+        else named_sync<3>(kThreads);
+      }
+      PIPE_MARK(18, lane == 0);
+      if (active) {
+        ((uchar2*)(smem_raw + (b ? L.snappos_off[1] : L.snappos_off[0])))[j] = pn;
+        (smem_raw + (b ? L.snapact_off[1] : L.snapact_off[0]))[j] = (uint8_t)act;
+      }
+      {
+        const uint4* src = (const uint4*)(smem_raw + L.grid_off);
+        uint4* dst = (uint4*)(smem_raw + (b ? L.snap_off[1] : L.snap_off[0]));
+        for (int i = lane; i < (L.live_bytes >> 4); i += 32) dst[i] = src[i];
+      }
+      __threadfence_block();
+      if (b) named_arrive<2>(kThreads);
+      else named_arrive<1>(kThreads);
+      PIPE_MARK(19, lane == 0);
+      p = pn;
+      av = next_av;
+    }
+    // ---- the handle's state and statistics, once
+    if (active) {
+      ((uchar2*)S.pos)[a0 + j] = p;
+      S.done[a0 + j] = dn;
+      S.prev_action[a0 + j] = (uint8_t)act;
+    }
+    if (lane < ne) S.step_count[e0 + lane] = sc + nsteps;
+    if (__any_sync(full, bad) && lane == 0) atomicOr(S.err_flags, MAPF_FLAG_BAD_ACTION);
+    if (d.collect_stats) {
+      c0 = __reduce_add_sync(full, c0);
+      c1 = __reduce_add_sync(full, c1);
+      c3 = __reduce_add_sync(full, c3);
+      ep_done = __reduce_add_sync(full, ep_done);
+      if (lane == 0) {
+        atomicAdd(&S.stats[MAPF_STAT_ENV_STEPS], (unsigned long long)ne * nsteps);
+        atomicAdd(&S.stats[MAPF_STAT_AGENT_STEPS], (unsigned long long)na * nsteps);
+        if (c0) atomicAdd(&S.stats[MAPF_STAT_ENV_COLLISIONS], (unsigned long long)c0);
+        if (c1) atomicAdd(&S.stats[MAPF_STAT_NODE_COLLISIONS], (unsigned long long)c1);
+        if (c3) atomicAdd(&S.stats[MAPF_STAT_GOAL_ARRIVALS], (unsigned long long)c3);
+        if (ep_done) atomicAdd(&S.stats[MAPF_STAT_EPISODES_DONE], (unsigned long long)ep_done);
+      }
+    }
+  } else {
+    // =========================================================== OBSERVATION role (warps 1-3) =======================
+    const int ot = tid - 32;                               // 0 .. 95; agent ot of the tile when ot < na
+    const int j = ot;
+    const bool valid = j < na;
+    const int el = valid ? fast_div(j, d.invN) : 0;
+    uint32_t* str = (uint32_t*)(smem_raw + L.str_off);
+    const uchar2 g = valid ? goal[j] : make_uchar2(0, 0);
+    size_t a0t = a0;
+    for (int t = 0; t < nsteps; ++t, a0t += EN) {
+      const int b = t & 1;
+      PIPE_MARK(20, ot == 0);
+      if (b) named_sync<2>(kThreads);                      // snapshot b holds the state after step t
+      else named_sync<1>(kThreads);
+      PIPE_MARK(21, ot == 0);
+      const uchar2* pos = (const uchar2*)(smem_raw + (b ? L.snappos_off[1] : L.snappos_off[0]));
+      const uint8_t* idgrid = smem_raw + (b ? L.snap_off[1] : L.snap_off[0]);
+      const uint32_t* agt = (const uint32_t*)(smem_raw + (b ? L.snap_off[1] : L.snap_off[0]) + (L.agt_off - L.grid_off));
+      // ---- phase 1: one thread per agent
+      uint32_t first = 0;
+      uint32_t vis[T::CW];
+      int w0 = 0, sh = 0;
+      uchar2 p = make_uchar2(0, 0);
+      const double2* vt = nullptr;
+      if (valid) {
+        p = pos[j];
+        if (A.vec != nullptr) {
+          vt = (const double2*)S.vec_lut + 2 * (abs((int)g.x - (int)p.x) * d.W + abs((int)g.y - (int)p.y));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(vt));
+        }
+        uint32_t w[T::NW];
+        fov_window_planes<F>(w, d, obst + (d.shared_map ? 0 : el * d.bm_words), agt + el * d.bm_words, p);
+        if (A.out.avail_dev != nullptr) {                  // _listNextValidActions from the window planes (see the tile kernel)
+          constexpr int Pw = F / 2;
+          auto open_cell = [&](int wi, int wj) -> uint32_t {
+            const int i0 = wi * F + wj, i3 = 3 * T::FF + wi * F + wj;
+            return (((w[i0 >> 5] >> (i0 & 31)) | (w[i3 >> 5] >> (i3 & 31))) & 1u) ^ 1u;
+          };
+          uint32_t m = 1u | (open_cell(Pw, Pw + 1) << 1) | (open_cell(Pw + 1, Pw) << 2) | (open_cell(Pw, Pw - 1) << 3) |
+                       (open_cell(Pw - 1, Pw) << 4);
+          const int my_act = (smem_raw + (b ? L.snapact_off[1] : L.snapact_off[0]))[j];
+          const int opp = (my_act == 0) ? -1 : (((my_act + 1) & 3) + 1);
+          if (opp > 0) m &= ~(1u << opp);
+          uint8_t* o = A.out.avail_dev + 5 * (a0t + j);
+          o[0] = m & 1;
+          o[1] = (m >> 1) & 1;
+          o[2] = (m >> 2) & 1;
+          o[3] = (m >> 3) & 1;
+          o[4] = (m >> 4) & 1;
+        }
+#pragma unroll
+        for (int q = 0; q < T::CW; ++q) vis[q] = w[q];
+        if ((T::FF & 31) != 0) vis[T::CW - 1] &= (1u << (T::FF & 31)) - 1u;
+        vis[((F / 2) * F + F / 2) >> 5] &= ~(1u << (((F / 2) * F + F / 2) & 31));   // not the agent itself
+        const int grp = j / d.G, k = j - grp * d.G;
+        const int boff = k * T::NB;
+        w0 = grp * d.GW + (boff >> 5);
+        sh = boff & 31;
+        const int nwords = (sh + T::NB + 31) >> 5;
+        uint32_t prev = 0;
+#pragma unroll
+        for (int q = 0; q <= T::NW; ++q) {
+          const uint32_t cur = (q < T::NW) ? w[q] : 0u;
+          const uint32_t o = __funnelshift_l(prev, cur, sh);
+          prev = cur;
+          if (q == 0) first = o;
+          if (q < nwords && !(q == 0 && sh > 0)) str[w0 + q] = o;
+        }
+        if (A.vec != nullptr) {                            // PRIMAL:380-385
+          const int dx = (int)g.x - (int)p.x, dy = (int)g.y - (int)p.y;
+          const double2 u = __ldg(vt);
+          const double2 m = __ldg(vt + 1);
+          double* v = A.vec + 3 * (a0t + j);
+          v[0] = dx < 0 ? -u.x : u.x;
+          v[1] = dy < 0 ? -u.y : u.y;
+          v[2] = m.x;
+        }
+      }
+      PIPE_MARK(22, ot == 0);
+      named_sync<5>(kObsThreads);
+      if (valid) {
+        if (sh > 0) atomicOr(&str[w0], first);
+        fov_goal_bits_half<F>(str, j, el * N, vis, d.GS, idgrid + el * d.grid_bytes, goal, p, g);
+      }
+      // this thread is done with snapshot b; the step role may refill it once all 96 have said so
+      if (t + 2 < nsteps) {
+        if (b) named_arrive<4>(kThreads);
+        else named_arrive<3>(kThreads);
+      }
+      named_sync<5>(kObsThreads);
+      PIPE_MARK(23, ot == 0);
+      // ---- phase 2: expand the tile's bit string with all observation threads
+      const size_t nbits = (size_t)na * T::NB;
+      if (A.obs_dtype == MAPF_BITS) {
+        uint32_t* out = (uint32_t*)A.obs + ((a0t * T::NB) >> 5);
+        const int nw = (int)((nbits + 31) >> 5);
+        for (int q = ot; q < nw; q += kObsThreads) out[q] = str[q];
+      } else if (A.obs_dtype == MAPF_U8) {
+        uint8_t* out = (uint8_t*)A.obs + a0t * T::NB;
+        const int nchunk = (int)(nbits >> 4);
+        const uint16_t* s16 = (const uint16_t*)str;
+#pragma unroll 2
+        for (int q = ot; q < nchunk; q += kObsThreads) {
+          const uint32_t h = s16[q];
+          uint4 v;
+          v.x = expand4(h & 15u);
+          v.y = expand4((h >> 4) & 15u);
+          v.z = expand4((h >> 8) & 15u);
+          v.w = expand4(h >> 12);
+          st_stream16(out + ((size_t)q << 4), v);
+        }
+        for (int bb = (nchunk << 4) + ot; bb < (int)nbits; bb += kObsThreads) out[bb] = (str[bb >> 5] >> (bb & 31)) & 1u;
+      } else {
+        float* out = (float*)A.obs + a0t * T::NB;
+        const int nchunk = (int)(nbits >> 2);
+        for (int q = ot; q < nchunk; q += kObsThreads) {
+          const uint32_t nib = (str[q >> 3] >> ((q & 7) << 2)) & 15u;
+          uint4 v;
+          v.x = (nib & 1u) ? 0x3f800000u : 0u;
+          v.y = (nib & 2u) ? 0x3f800000u : 0u;
+          v.z = (nib & 4u) ? 0x3f800000u : 0u;
+          v.w = (nib & 8u) ? 0x3f800000u : 0u;
+          st_stream16(out + ((size_t)q << 2), v);
+        }
+      }
+      PIPE_MARK(24, ot == 0);
+      // (the next step's phase 1 overwrites the strings only after its "ready" barrier, which every observation
+      // thread reaches after finishing this expansion)
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic-F observation (any F in [1, 255]); byte-wise gather, used when no specialised tile kernel
 // exists for F and as an independent cross-check of the bit-string path in the tests.
 // One thread per (agent, window cell).
@@ -2535,6 +2924,75 @@ extern "C" int mapf_launch_tile(const MapfDims& d, const MapfTileLayout& L, cons
   switch (F) {
     case 0: return (int)launch_tile_f<0, MAPF_MODE_PRIMAL>(d, L, S, A, st);
 #define X(f) case f: return (int)launch_tile_f<f, MAPF_MODE_PRIMAL>(d, L, S, A, st);
+    MAPF_FOR_EACH_FOV(X)
+#undef X
+    default:
+      return (int)cudaErrorInvalidValue;
+  }
+}
+
+// ---- the pipelined rollout kernel (mapf_pipe_kernel): which handles qualify, and its launch
+static int pipe_epb(const MapfDims& d) { return d.N <= 32 ? 32 / d.N : 0; }
+
+static bool pipe_layout(const MapfDims& d, int epb, MapfPipeLayout* L) {
+  int off = 0;
+  auto take = [&](int bytes) {
+    const int o = off;
+    off = (off + bytes + 15) / 16 * 16;
+    return o;
+  };
+  L->obst_off = take((d.shared_map ? 1 : epb) * d.bm_words * 4);
+  L->grid_off = take(epb * d.grid_bytes);
+  L->agt_off = take(epb * d.bm_words * 4);
+  L->live_bytes = off - L->grid_off;
+  for (int b = 0; b < 2; ++b) L->snap_off[b] = take(L->live_bytes);
+  for (int b = 0; b < 2; ++b) L->snappos_off[b] = take(64);
+  for (int b = 0; b < 2; ++b) L->snapact_off[b] = take(32);
+  L->goal_off = take(64);
+  L->posold_off = take(64);
+  L->posnew_off = take(64);
+  L->mv_off = take(128);
+  L->res_off = take(32);
+  L->dep_off = take(32);
+  L->act_off = take(32);
+  L->status_off = take(32);
+  L->done_off = take(32);
+  L->flag_off = take(32);
+  L->rew_off = take(256);
+  L->envrew_off = take(256);
+  L->envcnt_off = take(128);
+  L->str_off = take(((32 + d.G - 1) / d.G) * d.GW * 4 + 16);
+  L->total_bytes = off;
+  return off <= 48 * 1024;
+}
+
+// 1 when mapf_rollout can run this handle's steps through the pipelined kernel (5-action PRIMAL with an odd specialised
+// field of view, at most 32 agents per environment, tiles of whole 8-agent string groups, tile state within 48 KB).
+extern "C" int mapf_pipe_supported(const MapfDims& d) {
+  if (d.mode != MAPF_MODE_PRIMAL || d.diag || d.blocking || d.obs_mode != MAPF_OBS_PRIMAL_FOV) return 0;
+  if (!mapf_tile_has_fov(d.F) || (d.F & 1) == 0 || d.F < 3) return 0;
+  const int epb = pipe_epb(d);
+  if (epb < 1 || (epb * d.N) % 8 != 0 || d.G != 8) return 0;
+  MapfPipeLayout L;
+  return pipe_layout(d, epb, &L) ? 1 : 0;
+}
+
+extern "C" int mapf_pipe_tiles(const MapfDims& d) { return (d.E + pipe_epb(d) - 1) / pipe_epb(d); }
+
+extern "C" int mapf_launch_pipe(const MapfDims& d, const MapfState& S, const MapfTileArgs& A, void* stream) {
+  const int epb = pipe_epb(d);
+  MapfPipeLayout L;
+  if (epb < 1 || !pipe_layout(d, epb, &L)) return (int)cudaErrorInvalidValue;
+  const int grid = (d.E + epb - 1) / epb;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d.F) {
+#define X(f)                                                                              \
+  case f:                                                                                 \
+    if constexpr ((f & 1) == 1) {                                                         \
+      mapf_pipe_kernel<f><<<grid, kThreads, L.total_bytes, st>>>(d, L, S, A, epb);        \
+      return (int)cudaGetLastError();                                                     \
+    }                                                                                     \
+    return (int)cudaErrorInvalidValue;
     MAPF_FOR_EACH_FOV(X)
 #undef X
     default:

@@ -425,6 +425,12 @@ class MapfEngine:
         odt = BITS if dtype == "bits" else (F32 if dtype == torch.float32 else U8)
         return bool(self.lib.mapf_rollout_in_one_launch(self._h, odt))
 
+    def rollout_plan(self, n_steps, dtype=torch.uint8, mid_outputs=False):
+        """'pipelined' / 'in_kernel' / 'per_step': how rollout() would run (mapf_rollout_plan)."""
+        odt = BITS if dtype == "bits" else (F32 if dtype == torch.float32 else U8)
+        return ("per_step", "in_kernel", "pipelined")[int(self.lib.mapf_rollout_plan(self._h, int(n_steps), odt,
+                                                                                  int(bool(mid_outputs))))]
+
     def avail(self, prev=None):
         """Action masks of the current state.  prev (uint8 [E,N]): evaluate `_listNextValidActions(id, prev_action)`
         with these previous actions instead of the stored ones -- a pure query, nothing in the handle changes."""

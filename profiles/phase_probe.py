@@ -52,6 +52,11 @@ def main():
             print("   %-24s %8d" % ("total", c[9] - c[0]))
             print("   inside phase D: per-env part %d, statistics atomics %d, write-back %d" % (
                 buf[11] - c[5], buf[12] - buf[11], c[6] - buf[12]))
+            if roll and buf[16]:
+                print("   pipelined kernel, step role: sweep %d, wait for a free snapshot %d, snapshot + signal %d" % (
+                    buf[17] - buf[16], buf[18] - buf[17], buf[19] - buf[18]))
+                print("   pipelined kernel, observation role: wait for the snapshot %d, window phase %d, goal bits %d, "
+                      "expansion %d" % (buf[21] - buf[20], buf[22] - buf[21], buf[23] - buf[22], buf[24] - buf[23]))
 
 
 if __name__ == "__main__":

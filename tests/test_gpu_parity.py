@@ -1435,6 +1435,13 @@ ROLLOUT_CASES = [
     ("primal", 64, 32, 32, 32, 11, 0.3, 5, "bits", {}),
     ("primal", 16, 32, 32, 32, 11, 0.3, 4, torch.float32, {}),
     ("primal", 48, 6, 12, 12, 5, 0.1, 12, torch.uint8, {}),             # small even-odd FOV, N does not divide 128
+    # small batches run through the pipelined kernel (32-agent tiles, step role + observation role):
+    ("primal", 37, 4, 12, 12, 7, 0.1, 9, torch.uint8, {}),              # 8 envs per tile, ragged last tile (5 envs)
+    ("primal", 5, 16, 24, 24, 9, 0.1, 6, torch.uint8, {}),              # 2 envs per tile, last tile holds one
+    ("primal", 16, 2, 8, 8, 3, 0.0, 13, torch.uint8, {}),               # 16 envs per tile, F = 3 (strings share words)
+    ("primal", 40, 1, 6, 6, 5, 0.1, 5, "bits", {}),                     # single-agent environments, 32 per tile
+    ("primal", 33, 8, 6, 6, 5, 0.05, 20, torch.uint8, {}),              # crowded 6x6 maps: convoys and robot collisions
+    ("primal", 12, 32, 40, 40, 11, 0.2, 6, torch.float32, {}),          # one 32-agent environment per tile, W > 32
     ("primal", 8, 128, 64, 64, 11, 0.05, 5, torch.uint8, {}),           # c4 shape: one environment per tile
     ("primal", 4, 140, 40, 40, 11, 0.05, 3, torch.uint8, {}),           # > 128 agents: falls back to T launches
     ("primal", 32, 10, 16, 16, 7, 0.1, 6, torch.uint8, {"diagonal_movement": True}),   # fallback (diagonal mode)
@@ -1444,8 +1451,9 @@ ROLLOUT_CASES = [
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mid", [True, False], ids=["mid_outputs", "plain"])
 @pytest.mark.parametrize("case", ROLLOUT_CASES, ids=lambda c: "%s_E%d_N%d_%dx%d_T%d_%s" % (c[0], c[1], c[2], c[3], c[4], c[7], str(c[8]).split(".")[-1]))
-def test_rollout_equals_consecutive_fused_steps(case):
+def test_rollout_equals_consecutive_fused_steps(case, mid):
     """mapf_rollout(T steps, one launch where supported) == T consecutive mapf_step_observe calls, bit for bit, for
     every per-step output and for the state left in the handle."""
     from mapf_marl_b200 import maps
@@ -1454,8 +1462,12 @@ def test_rollout_equals_consecutive_fused_steps(case):
     nact = 9 if kw.get("diagonal_movement") else 5
     rs = np.random.RandomState(T * 31 + N)
     acts = torch.as_tensor(rs.randint(0, nact, (T, E, N)).astype(np.uint8), device="cuda")
-    want = (("reward", "terminated", "agent_reward", "dones", "status", "valid", "avail", "done_mid", "next_mid")
-            if mode == "primal" else GRID_WANT)
+    # with the mid-sweep outputs the rollout stays in the tile kernel; without them small PRIMAL batches run through
+    # the pipelined kernel (mapf_pipe_kernel)
+    want = (("reward", "terminated", "agent_reward", "dones", "status", "valid", "avail") +
+            (("done_mid", "next_mid") if mid else ())) if mode == "primal" else GRID_WANT
+    if mode != "primal" and not mid:
+        pytest.skip("GRID has no mid-sweep outputs")
     mk = lambda: _engine(E, N, H, W, mode=mode, fov=F or 11, **kw)   # noqa: E731
     a, b = mk(), mk()
     a.reset(obst, starts, goals)
@@ -1463,13 +1475,16 @@ def test_rollout_equals_consecutive_fused_steps(case):
     okw = dict(dtype=odt) if odt is not None else {}
     expect_one = mode in ("primal", "grid") and N <= 128 and not kw.get("diagonal_movement")
     assert a.rollout_in_one_launch(odt if odt is not None else torch.uint8) == expect_one
+    plan = a.rollout_plan(T, odt if odt is not None else torch.uint8, mid_outputs=mid)
+    small_primal = (mode == "primal" and not kw and N <= 32 and F % 2 == 1 and ((32 // N) * N) % 8 == 0)
+    assert plan == ("pipelined" if (small_primal and not mid) else ("in_kernel" if expect_one else "per_step"))
     for rnd in range(2):                      # the second rollout starts from the state the first one left
         l0 = a.launch_count()
         ro = a.rollout(acts, want=want, **okw)
         assert a.launch_count() - l0 == (1 if expect_one else T)
         ro = {k: v.clone() for k, v in ro.items()}
         for t in range(T):
-            so = b.step_observe(acts[t], want=want, **okw)
+            so = b.step_observe(acts[t].clone(), want=want, **okw)   # (a time slice need not be 16-byte aligned)
             for k in so:
                 x, y = _np(ro[k][t]), _np(so[k])
                 if x.dtype.kind == "f":
