@@ -397,6 +397,7 @@ def main():
             ms_roll = float(np.median(timed_passes(lambda: eng.rollout(racts, want=WANT, dtype=odt),
                                                    max(5, int(200.0 / max(ms_step * T_roll, 1e-3)) // 4)))) / T_roll
             roll = {"ms_per_step": ms_roll, "steps_per_launch": T_roll, "one_launch": eng.rollout_in_one_launch(odt),
+                    "kernel": eng.rollout_plan(T_roll, odt),
                     "agent_steps_per_s": world * E * N / (ms_roll * 1e-3),
                     "frac_of_hbm_peak": (wl["bytes_per_agent_step"] + (3 * 4 * F * F if args.f32 else 0)) * E * N /
                     (ms_roll * 1e-3) / 1e9 / measured_peak()[0]}
@@ -627,7 +628,7 @@ def main():
                 ex = MapfEngine(Ex, wlx["N"], wlx["H"], wlx["W"], mode="primal", fov=wlx["F"],
                                 shared_map=wlx["warehouse"], goal_dist=wlx["warehouse"], device=dev)
                 ex.reset(o, s, g)
-                px = action_pool(ex, lo, 8)
+                px = action_pool(ex, lo, 16)
                 for t in range(3):
                     ex.step_observe(px[t], want=WANT, dtype=odt)
                 ms, ck, gr = measure_fused(ex, px, 20, min_total_ms=100.0, min_passes=5, max_passes=200,
@@ -642,10 +643,11 @@ def main():
                     ra = px.contiguous()
                     for _ in range(2):
                         ex.rollout(ra, want=WANT, dtype=odt)
-                    n_r = max(5, int(100.0 / max(us * 8e-3, 1e-3)))
+                    n_r = max(5, int(100.0 / max(us * 16e-3, 1e-3)))
                     usr = float(np.median(timed_passes(lambda: ex.rollout(ra, want=WANT, dtype=odt), min(n_r, 200),
-                                                       sync_ranks=False))) / 8 * 1e3
+                                                       sync_ranks=False))) / 16 * 1e3
                     ent["rollout_kernel_us_per_step"] = usr
+                    ent["rollout_kernel"] = ex.rollout_plan(16, odt)
                     ent["rollout_kernel_frac_of_hbm_peak"] = bytes_step / (usr * 1e-6) / 1e9 / peak
                 except Exception as exc:
                     ent["rollout_kernel_error"] = repr(exc)

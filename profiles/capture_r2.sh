@@ -22,12 +22,14 @@ for WL in c4 c2; do
   $B2 > $OUT/${TAG}_plain_$WL.json 2> $OUT/${TAG}_plain_$WL.err
   $NCU -k regex:mapf_tile_kernel -s 30 -c 1 -o $REP/${TAG}_fused_$WL $B2 > $OUT/${TAG}_ncu_fused_$WL.log 2>&1
 done
-# the multi-step (mapf_rollout) instantiation at c2: launches 0-2 warm-up, 3.. timed
+# mapf_rollout at c2: the pipelined kernel (launches 0-2 warm-up, 3.. timed), and the tile kernel's in-kernel loop
+# (MAPF_B200_PIPE=0) for comparison
 python profiles/rollout_probe.py c2 > $OUT/${TAG}_rollout_probe_c2.log 2>&1
-$NCU -k regex:mapf_tile_kernel -s 4 -c 1 -o $REP/${TAG}_rollout_c2 python profiles/rollout_probe.py c2 > $OUT/${TAG}_ncu_rollout_c2.log 2>&1
+$NCU -k regex:mapf_pipe_kernel -s 4 -c 1 -o $REP/${TAG}_rollout_c2 python profiles/rollout_probe.py c2 > $OUT/${TAG}_ncu_rollout_c2.log 2>&1
+MAPF_B200_PIPE=0 $NCU -k regex:mapf_tile_kernel -s 4 -c 1 -o $REP/${TAG}_rollout_tile_c2 python profiles/rollout_probe.py c2 > $OUT/${TAG}_ncu_rollout_tile_c2.log 2>&1
 python profiles/summarize_ncu.py $REP/${TAG}_fused_c3.ncu-rep $REP/${TAG}_bfs_c3.ncu-rep > $OUT/${TAG}_ncu_summary_c3.txt
 python profiles/summarize_ncu.py $REP/${TAG}_fused_c4.ncu-rep > $OUT/${TAG}_ncu_summary_c4.txt
-python profiles/summarize_ncu.py $REP/${TAG}_fused_c2.ncu-rep $REP/${TAG}_rollout_c2.ncu-rep > $OUT/${TAG}_ncu_summary_c2.txt
+python profiles/summarize_ncu.py $REP/${TAG}_fused_c2.ncu-rep $REP/${TAG}_rollout_c2.ncu-rep $REP/${TAG}_rollout_tile_c2.ncu-rep > $OUT/${TAG}_ncu_summary_c2.txt
 python - <<PY > $OUT/${TAG}_fused_traffic.json
 import csv, io, json, subprocess
 out = {}
