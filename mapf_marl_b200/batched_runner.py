@@ -70,12 +70,22 @@ class BatchedRunner:
         self.device = env.engine.device
         self.t = 0
         self.t_env = 0
-        self.train_returns, self.test_returns = [], []
+        self._returns = {False: [], True: []}     # per-episode return tensors (device); lists are built on demand
         self.train_stats, self.test_stats = {}, {}
         self.batch = None
 
     def get_env_info(self):
         return self.env_info
+
+    @property
+    def train_returns(self):
+        """Episode returns of the training runs as a Python list (pymarl logs their mean, parallel_runner.py:196-204);
+        kept as device tensors until somebody asks: a million-environment batch must not pay a host list per episode."""
+        return torch.cat(self._returns[False]).tolist() if self._returns[False] else []
+
+    @property
+    def test_returns(self):
+        return torch.cat(self._returns[True]).tolist() if self._returns[True] else []
 
     def new_batch(self):
         return DeviceEpisodeBatch(self.env.rollout_spec(), self.batch_size, self.max_steps + 1,
@@ -160,7 +170,7 @@ class BatchedRunner:
         stats["ep_length"] = n_steps + stats.get("ep_length", 0)
         for k, v in self.env.get_stats().items():
             stats["env_" + k] = v
-        (self.test_returns if test_mode else self.train_returns).extend(st["returns"].tolist())
+        self._returns[bool(test_mode)].append(st["returns"].clone())
         return self.batch
 
 

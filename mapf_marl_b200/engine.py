@@ -351,9 +351,10 @@ class MapfEngine:
         obs = mk("state", (self.E, self.H * self.W), torch.int8)
         return obs, None, I8
 
-    def observe(self, dtype=torch.uint8, want_vec=True):
-        """FOV: (obs [E,N,4,F,F], vec [E,N,3]); full map: (state int8 [E,H*W], None)."""
-        obs, vec, odt = self._obs_buffers(dtype, want_vec)
+    def observe(self, dtype=torch.uint8, want_vec=True, out=None):
+        """FOV: (obs [E,N,4,F,F], vec [E,N,3]); full map: (state int8 [E,H*W], None).  out: optional dict with
+        caller-owned "obs" / "vec" tensors to write into (e.g. time slice 0 of an episode batch)."""
+        obs, vec, odt = self._obs_buffers(dtype, want_vec, out)
         with torch.cuda.device(self.device):
             self._check(self.lib.mapf_observe(self._h, self._ptr(obs), odt, self._ptr(vec), self._stream()),
                         "mapf_observe")

@@ -178,6 +178,7 @@ class MARL_PARTIAL_ENV(MultiAgentEnv):
         obs = self.reset()                                   # engine-owned tensors of the t = 0 observation
         batch.tm["obs"][0].copy_(obs)
         batch.tm["avail_actions"][0].copy_(self.get_avail_actions())
+        self._vstate = batch.tm["state"][0]
 
     def step_into(self, actions, t, batch):
         tm = batch.tm

@@ -88,9 +88,7 @@ class PrimalVecEnv:
     def reset_into(self, batch):
         self.engine.reset(*self._world)
         self._t = 0
-        obs, vec = self.engine.observe()
-        batch.tm["obs"][0].copy_(obs.reshape(self.n_envs, self.n_agents, -1))
-        batch.tm["obs_vec"][0].copy_(vec)
+        self.engine.observe(out={"obs": batch.tm["obs"][0], "vec": batch.tm["obs_vec"][0]})   # straight into the batch
         batch.tm["avail_actions"][0].copy_(self.engine.avail())
 
     def step_into(self, actions, t, batch):
