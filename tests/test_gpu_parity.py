@@ -1528,3 +1528,54 @@ def test_rollout_partial_mode_and_caller_owned_storage():
         so = c.step_observe(acts[t], want=("reward",), dtype=torch.float32, out={"obs": store2[t]})
         assert so["obs"].data_ptr() == store2[t].data_ptr()
     assert torch.equal(store2, store["obs"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [("c2", 4096, 0), ("c3", 1024, 3 * 1024)], ids=["c2_full", "c3_shape_E1024"])
+def test_pipelined_rollout_matches_oracle_at_full_size(cfg):
+    """mapf_rollout through the pipelined kernel (mapf_pipe_kernel) against the CPU oracle, every environment and every
+    one of 16 steps: the oracle is stepped first with actions drawn from ITS action masks on odd steps (uniform on even
+    ones), the recorded action tensor is handed to one mapf_rollout call, and all time-major outputs are compared."""
+    from mapf_marl_b200 import workloads
+    from oracle.oracle import MODE_PRIMAL
+    name, E, lo = cfg
+    wl = workloads.WORKLOADS[name]
+    N, H, W, F, T = wl["N"], wl["H"], wl["W"], wl["F"], 16
+    obst, starts, goals = workloads.make_world(wl, E, lo, distinct=0)
+    orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F)
+    orc.reset(obst, starts, goals)
+    avail = orc.primal_avail()
+    acts = np.zeros((T, E, N), np.uint8)
+    ref = []
+    for t in range(T):
+        acts[t] = workloads.hash_actions_np(321, range(lo, lo + E), t, N, avail=avail if t % 2 else None)
+        out = orc.primal_sweep(acts[t])
+        obs, vec = orc.primal_observe()
+        ref.append((out, obs, vec, orc.positions().copy()))
+        avail = out["avail"]
+    eng = _engine(E, N, H, W, mode="primal", fov=F)
+    eng.reset(obst, starts, goals)
+    want = ("reward", "terminated", "agent_reward", "dones", "status", "valid", "avail")
+    assert eng.rollout_plan(T) == "pipelined"
+    l0 = eng.launch_count()
+    ro = eng.rollout(torch.as_tensor(acts, device="cuda"), want=want)
+    assert eng.launch_count() - l0 == 1
+    for t in range(T):
+        out, obs, vec, pos = ref[t]
+        for k in ("terminated", "dones", "status", "valid", "avail"):
+            assert np.array_equal(_np(ro[k][t]), out[k]), (k, t)
+        assert np.array_equal(_bits(_np(ro["agent_reward"][t])), _bits(out["agent_reward"])), t
+        assert np.array_equal(_bits(_np(ro["reward"][t])), _bits(out["reward"])), t
+        assert np.array_equal(_np(ro["obs"][t]), obs), t
+        assert np.array_equal(_bits(_np(ro["vec"][t])), _bits(vec)), t
+    assert np.array_equal(_np(eng.positions()), ref[-1][3])
+    assert np.array_equal(_np(eng.step_count()), np.full(E, T, np.int32))
+    st = eng.stats()
+    assert st["env_steps"] == E * T and st["agent_steps"] == E * N * T
+    assert st["goal_arrivals"] > 0 and eng.error_flags() == 0
+    # the handle continues from the rollout's final state with single steps
+    a = workloads.hash_actions_np(321, range(lo, lo + E), T, N)
+    so = eng.step_observe(torch.as_tensor(a, device="cuda"), want=want)
+    out = orc.primal_sweep(a)
+    assert np.array_equal(_np(so["status"]), out["status"]) and np.array_equal(_np(so["avail"]), out["avail"])
+    assert np.array_equal(_np(so["obs"]), orc.primal_observe()[0])
