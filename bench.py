@@ -664,6 +664,59 @@ def main():
                 sweep.append({"name": name, "error": repr(exc)})
         eng = None
 
+    # ---- the other two reference semantics on a c3-shaped batch (same worlds): GRID (mapf_gridworld.py: detect-and-
+    #      penalise step + full-map observation) and PARTIAL (marl_partial.py, the env the reference registers: window
+    #      maps + K nearest agents, float64 like the reference and float32 like pymarl's episode batch stores it)
+    modes = None
+    if not args.no_sweep:
+        if eng is not None:
+            eng.close()
+            del eng
+            eng = None
+            torch.cuda.empty_cache()
+        modes = {}
+        c3w = WORKLOADS["c3"]
+        Em = c3w["E"]
+        om, sm, gm = make_world(c3w, Em, rank * Em)
+        pm = None
+        for mname, kw, dts in (("grid", dict(mode="grid", episode_limit=10 ** 6), (None,)),
+                               ("partial", dict(mode="partial", episode_limit=256, obs_window=11, obs_knn_agents=5),
+                                (torch.float64, torch.float32))):
+            try:
+                em = MapfEngine(Em, c3w["N"], c3w["H"], c3w["W"], device=dev, **kw)
+                em.reset(om, sm, gm)
+                if pm is None:
+                    pm = torch.stack([em.random_actions(ACTION_SEED, t, env_offset=rank * Em, dtype=torch.uint8).clone()
+                                      for t in range(16)])
+                for dt in dts:
+                    okw = {} if dt is None else {"dtype": dt}
+                    for t in range(3):
+                        em.step_observe(pm[t], want=WANT, **okw)
+                    n_m = 200 if mname == "grid" else 60
+                    ms_f = float(np.median(timed_passes(lambda: [em.step_observe(pm[t % 16], want=WANT, **okw)
+                                                                 for t in range(n_m)], 3, sync_ranks=False))) / n_m
+                    ms_o = float(np.median(timed_passes(lambda: [em.observe(**okw) for _ in range(n_m)], 3,
+                                                        sync_ranks=False))) / n_m
+                    obs_t = em.observe(**okw)[0]
+                    obs_bytes = obs_t.numel() * obs_t.element_size()
+                    # algorithmic bytes per step: the observation + per agent actions 1, pos r/w 4, goal 2, done r/w 2,
+                    # avail 5 (+ PARTIAL: two distance gathers 4, bookkeeping r/w 18) + per env reward 8, flag 1, step 8
+                    per_agent = 14 + (22 if mname == "partial" else 0)
+                    alg = obs_bytes + Em * c3w["N"] * per_agent + Em * 17
+                    key = mname if dt is None else "%s_%s" % (mname, str(dt).split(".")[-1])
+                    modes[key] = {"envs_per_gpu": Em, "n_agents": c3w["N"], "fused_step_obs_us": ms_f * 1e3,
+                                  "observe_only_us": ms_o * 1e3, "launches_per_step": 1 if mname == "grid" else 2,
+                                  "agent_steps_per_s_per_gpu": Em * c3w["N"] / (ms_f * 1e-3),
+                                  "obs_bytes_per_step": obs_bytes, "algorithmic_bytes_per_step": alg,
+                                  "frac_of_hbm_peak": alg / (ms_f * 1e-3) / 1e9 / peak,
+                                  "observe_only_frac_of_hbm_peak": obs_bytes / (ms_o * 1e-3) / 1e9 / peak}
+                em.close()
+                del em
+                torch.cuda.empty_cache()
+            except Exception as exc:
+                modes[mname] = {"error": repr(exc)}
+        del om, sm, gm
+
     # ---- rollout: the reference-API loop (pymarl ParallelRunner semantics) through BatchedRunner over PrimalVecEnv,
     #      the kernel writing straight into the time-major episode batch; controllers: random over the action mask,
     #      and pymarl's recurrent agent (Linear-GRUCell-Linear, torch) -- the network is a caller, not the path
@@ -769,7 +822,7 @@ def main():
             "stats": dict(zip(sorted(stats), [int(v) for v in svec.tolist()])),
             "stats_rank0_canonical_segment": stats_canonical,
             "device_error_flags": flags,
-            "sweep": sweep, "rollout": rollout, "lifelong": lifelong,
+            "sweep": sweep, "modes": modes, "rollout": rollout, "lifelong": lifelong,
         }
         if not args.lean:
             line["breakdown_ms"] = {

@@ -2629,6 +2629,29 @@ __global__ void mapf_partial_obs_kernel(const MapfDims d, const MapfState S, T* 
   const int k_m1 = min(N, K) - 1;
   constexpr unsigned kSelf = 1u << 22, kNone = 0x7fffffffu;  // kSelf > 2 * 254^2
   constexpr int kMaxPerLane = 8;                             // N <= 255
+  if (N <= 32 && K <= 32) {
+    // at most one candidate per lane and all rows in lanes: no inner loops (the general version below spends half of
+    // its instructions on loop control; the selection was 30 % of this kernel's instructions at N = 32)
+    for (int a = warp; a < N; a += nwarps) {
+      const uchar2 p = spos[a];
+      unsigned key = kNone;
+      if (lane < N) {
+        const uchar2 q = spos[lane];
+        const int dx = (int)p.x - (int)q.x, dy = (int)p.y - (int)q.y;
+        key = (((lane == a) ? kSelf : (unsigned)(dx * dx + dy * dy)) << 8) | (unsigned)lane;
+      }
+      unsigned sel = lane == 0 ? (unsigned)a : kNone;        // row 0: knn_agents.insert(0, agent_id), :352
+      for (int r = 0; r < k_m1; ++r) {
+        const unsigned best = __reduce_min_sync(0xffffffffu, key);
+        if (key == best) key = kNone;                        // keys are unique (the index is part of them)
+        if (lane == r + 1) sel = best;                       // round r's winner stays in lane r + 1
+      }
+      if (lane < K) {
+        knn[a * K + lane] = sel == kNone ? (uint8_t)255 : (uint8_t)(sel & 255u);
+        kkey[a * K + lane] = sel;
+      }
+    }
+  } else
   for (int a = warp; a < N; a += nwarps) {
     const uchar2 p = spos[a];
     unsigned key[kMaxPerLane];
