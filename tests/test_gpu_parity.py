@@ -1579,3 +1579,45 @@ def test_pipelined_rollout_matches_oracle_at_full_size(cfg):
     out = orc.primal_sweep(a)
     assert np.array_equal(_np(so["status"]), out["status"]) and np.array_equal(_np(so["avail"]), out["avail"])
     assert np.array_equal(_np(so["obs"]), orc.primal_observe()[0])
+
+
+@pytest.mark.gpu
+def test_rollout_optional_outputs_single_step_and_long_horizons():
+    """The pipelined kernel with outputs left out (no masks, no goal vector, no per-agent outputs), a one-step rollout,
+    a 150-step rollout (many buffer hand-overs) and a rollout after a masked reset: all equal consecutive fused steps."""
+    from mapf_marl_b200 import maps
+    E, N, H, W, F = 96, 8, 14, 14, 7
+    obst, starts, goals = maps.synthetic_batch(31, E, H, W, 0.15, N, distinct=0)
+    a = _engine(E, N, H, W, mode="primal", fov=F)
+    b = _engine(E, N, H, W, mode="primal", fov=F)
+    a.reset(obst, starts, goals)
+    b.reset(obst, starts, goals)
+    rs = np.random.RandomState(9)
+
+    def compare(T, want, want_vec, dtype):
+        acts = torch.as_tensor(rs.randint(0, 5, (T, E, N)).astype(np.uint8), device="cuda")
+        ro = a.rollout(acts, want=want, dtype=dtype, want_vec=want_vec)
+        ro = {k: v.clone() for k, v in ro.items()}
+        assert ("vec" in ro) == want_vec
+        for t in range(T):
+            so = b.step_observe(acts[t].clone(), want=want, dtype=dtype, want_vec=want_vec)
+            for k in so:
+                assert torch.equal(ro[k][t].reshape(-1).view(torch.uint8), so[k].reshape(-1).view(torch.uint8)), (k, t)
+        assert torch.equal(a.positions(), b.positions()) and torch.equal(a.avail(), b.avail())
+
+    assert a.rollout_plan(4) == "pipelined"
+    compare(4, ("reward",), False, torch.uint8)                     # no masks, no goal vector
+    compare(3, (), True, "bits")                                    # observation + goal vector only
+    compare(1, ("reward", "terminated", "dones", "avail"), True, torch.uint8)      # a single step
+    compare(150, ("terminated", "avail", "status"), True, torch.uint8)             # long horizon
+    mask = (rs.rand(E) < 0.4).astype(np.uint8)
+    a.reset(None, None, None, env_mask=mask)
+    b.reset(None, None, None, env_mask=mask)
+    compare(6, ("reward", "terminated", "dones", "avail", "agent_reward", "valid"), True, torch.float32)
+    assert a.stats() == b.stats() and a.error_flags() == 0
+    # a bad action inside a rollout raises the device flag like a single step does
+    bad = torch.zeros((2, E, N), dtype=torch.uint8, device="cuda")
+    bad[1, 5, 3] = 9
+    a.rollout(bad, want=("reward",))
+    from mapf_marl_b200 import _lib
+    assert a.error_flags() == _lib.FLAG_BAD_ACTION
