@@ -87,6 +87,10 @@ typedef enum mapf_dtype {
 #define MAPF_FLAG_START_ON_WALL 4u
 #define MAPF_FLAG_START_OVERLAP 8u /* PRIMAL only: two agents on one cell (State.scanForAgents, PRIMAL:53-66) */
 #define MAPF_FLAG_GOAL_OVERLAP 16u /* PRIMAL only: two agents share a goal cell (State.goals holds one id per cell) */
+/* Internal consistency check: a guard word between two shared-memory regions of a kernel was overwritten (the kernels
+ * plant canaries around their tile regions and verify them before they exit; compute-sanitizer is not available on every
+ * pool, this check always runs).  Never expected; report it as a bug. */
+#define MAPF_FLAG_INTERNAL 32u
 
 /* Indices into the int64[MAPF_N_STATS] vector returned by mapf_stats. */
 enum {

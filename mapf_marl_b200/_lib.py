@@ -21,6 +21,7 @@ MODE_GRID, MODE_PRIMAL, MODE_PARTIAL = 0, 1, 2
 OBS_FULLMAP, OBS_PRIMAL_FOV, OBS_PARTIAL_WINDOW = 0, 1, 2
 U8, I64, F32, I8, F64, BITS = 0, 1, 2, 3, 4, 5
 FLAG_BAD_ACTION, FLAG_BAD_POSITION, FLAG_START_ON_WALL, FLAG_START_OVERLAP, FLAG_GOAL_OVERLAP = 1, 2, 4, 8, 16
+FLAG_INTERNAL = 32
 N_STATS = 8
 STAT_NAMES = ("env_steps", "agent_steps", "env_collisions", "node_collisions", "edge_collisions",
               "goal_arrivals", "episodes_done", "reserved")

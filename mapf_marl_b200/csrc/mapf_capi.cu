@@ -22,6 +22,7 @@ struct mapf_handle {
   int device;
   int fov_fast;        // a specialised tile kernel exists for cfg.fov
   int64_t* partial_state_out;   // mapf_partial_bind_state_out: get_state() written by every observation launch
+  int debug_corrupt;            // mapf_debug_corrupt_canary: consumed by the next tile / pipe launch
   int64_t launches;
   int mag_lut_len;
   // device staging for the *_host entry points (allocated on first use)
@@ -88,12 +89,15 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L, bool s
   };
   // ---- alive for the whole kernel: maps, occupancy, positions, goals
   L->obst_off = take((d.shared_map ? 1 : epb) * d.bm_words * 4);
+  L->guard_off[0] = take(16);   // canaries (mapf_tile_kernel plants and verifies them: MAPF_FLAG_INTERNAL)
   L->agt_off = take(fov ? epb * d.bm_words * 4 : 16);
   L->grida_off = take(epb * d.grid_bytes);
   // PRIMAL needs the second grid only for the mid-sweep outputs (a copy of the pre-sweep ids)
   L->gridb_off = second_grid ? take(epb * d.grid_bytes) : L->grida_off;
+  L->guard_off[1] = take(16);
   L->posnew_off = take(2 * na);
   L->goal_off = take(2 * na);
+  L->guard_off[2] = take(16);
   // ---- step-phase scratch; dead once the state has been written back, so the observation's bit strings reuse
   //      the same bytes (the kernel puts a barrier between the two uses)
   const int scratch0 = off;
@@ -129,6 +133,7 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L, bool s
   const int str_bytes = fov ? ((na + d.G - 1) / d.G) * d.GW * 4 + 16 : 16;
   L->str_off = scratch0;
   off = align_up(scratch0 + (str_bytes > scratch1 - scratch0 ? str_bytes : scratch1 - scratch0), 16);
+  L->guard_off[3] = take(16);
   L->total_bytes = off;
 }
 
@@ -531,6 +536,8 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
   MapfTileArgs A;
   memset(&A, 0, sizeof(A));
   A.T = n_steps;
+  A.debug_corrupt = h->debug_corrupt;
+  h->debug_corrupt = 0;
   A.actions = actions;
   A.act_dtype = act_dtype;
   A.do_step = actions != nullptr;
@@ -687,6 +694,8 @@ int mapf_rollout(mapf_handle* h, const void* actions_dev, int act_dtype, int n_s
     MapfTileArgs A;
     memset(&A, 0, sizeof(A));
     A.T = n_steps;
+    A.debug_corrupt = h->debug_corrupt;
+    h->debug_corrupt = 0;
     A.actions = actions_dev;
     A.act_dtype = act_dtype;
     A.do_step = 1;
@@ -834,6 +843,14 @@ int mapf_random_actions(mapf_handle* h, const uint8_t* avail_dev, uint32_t seed,
   CK((cudaError_t)mapf_launch_random_actions(h->d, avail_dev, seed, step, (long long)env_offset, actions_dev,
                                              act_dtype == MAPF_I64, stream));
   h->launches++;
+  return MAPF_OK;
+}
+
+// Self-test hook (not part of the public header): the next step / rollout launch of this handle overwrites guard word
+// `which` of its tile on purpose, so that tests can see MAPF_FLAG_INTERNAL being raised by the canary check.
+int mapf_debug_corrupt_canary(mapf_handle* h, int which) {
+  if (!h || which < 0) return MAPF_ERR_INVALID_ARG;
+  h->debug_corrupt = which + 1;
   return MAPF_OK;
 }
 

@@ -65,6 +65,7 @@ struct MapfTileLayout {
   int pastold_off, pastnew_off;   // uchar2 [epb*N]: PRIMAL diagonal mode, State.agents_past before / after the sweep
   int mask16_off, nextmid16_off;  // u16 [epb*N]: 9-wide action masks (diagonal mode)
   int str_off;      // bit strings: ceil(epb*N / G) * GW u32
+  int guard_off[4]; // 16-byte canaries: behind the obstacle rows, behind the occupancy grids, behind the goals, at the end
   int total_bytes;
 };
 
@@ -111,6 +112,7 @@ struct MapfTileArgs {
   int obs_dtype;
   double* vec;             // [E][N][3] or NULL
   int T;                   // steps in this launch (mapf_rollout): actions / outputs / obs / vec are [T][...], T >= 1
+  int debug_corrupt;       // self-test of the canary check: 1 + index of a guard word the kernel overwrites on purpose
 };
 
 #ifdef __cplusplus

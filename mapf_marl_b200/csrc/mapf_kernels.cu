@@ -272,6 +272,7 @@ __device__ __noinline__ double tree_sum_agents(const double* rew, int N, int lo,
 __device__ __forceinline__ int gcell(const MapfDims& d, int r, int c) { return (r + 1) * d.GS + c + 1; }
 
 constexpr uint8_t RES_UNRESOLVED = 0, RES_MOVED = 1, RES_STAYS = 2;
+constexpr uint32_t kCanary = 0xC0FFEE00u;   // guard words between shared-memory regions (MAPF_FLAG_INTERNAL)
 
 // PRIMAL phase A for agent j: State.moveAgent's checks that do not involve other robots (PRIMAL:107-118).
 // mv[j] = padded target cell (0xffffffff: no claim to make); status[j] = pre-status.
@@ -825,6 +826,7 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
   // ---- stage the tile (one exposed global-memory latency): obstacle bitmaps, per-agent records, zeroed grids
   if (tid < MAPF_N_STATS) stat[tid] = 0;
   if (tid == 0) bad_flag = 0;
+  if (tid < 4) *(uint32_t*)(smem_raw + L.guard_off[tid]) = kCanary + tid;   // verified before the kernel exits
   int* envstep = (int*)(smem_raw + L.envstep_off);
   // Every global load of the tile is issued before anything waits on one, and the zero fill runs while they are in
   // flight: ONE exposed memory latency per tile (load -> store -> load -> store chains cost two or three).
@@ -1423,6 +1425,10 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
   sc0 += 1;
   __syncthreads();   // the bit strings alias the step scratch the next staging pass is about to write
   }
+  // nobody wrote outside its region of the tile: the canaries between the regions are intact
+  if (A.debug_corrupt && tid == 0) smem_raw[L.guard_off[(A.debug_corrupt - 1) & 3]] ^= 0xff;   // self-test hook
+  __syncthreads();
+  if (tid < 4 && *(volatile uint32_t*)(smem_raw + L.guard_off[tid]) != kCanary + tid) atomicOr(S.err_flags, MAPF_FLAG_INTERNAL);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1458,6 +1464,7 @@ struct MapfPipeLayout {
   int envcnt_off;               // int [32]
   int str_off;                  // observation bit strings
   int live_bytes;               // bytes of (id grid + agent bit rows) of the tile: what a snapshot copies
+  int guard_off[8];             // 16-byte canaries between the regions (MAPF_FLAG_INTERNAL)
   int total_bytes;
 };
 
@@ -1503,6 +1510,7 @@ __global__ void __launch_bounds__(kThreads, 8) mapf_pipe_kernel(const MapfDims d
     for (int i = tid; i < nvec; i += kThreads) ((uint4*)obst)[i] = __ldg(osrc + i);
   }
   if (tid < na) goal[tid] = ((const uchar2*)S.goal)[a0 + tid];
+  if (tid >= 64 && tid < 70) *(uint32_t*)(smem_raw + L.guard_off[tid - 64]) = kCanary + (tid - 64);
   __syncthreads();
 
   if (tid < 32) {
@@ -1812,6 +1820,10 @@ __global__ void __launch_bounds__(kThreads, 8) mapf_pipe_kernel(const MapfDims d
       // thread reaches after finishing this expansion)
     }
   }
+  // both roles are done: nobody wrote outside its region of the tile (the canaries between the regions are intact)
+  if (A.debug_corrupt && tid == 0) smem_raw[L.guard_off[(A.debug_corrupt - 1) % 6]] ^= 0xff;   // self-test hook
+  __syncthreads();
+  if (tid < 6 && *(volatile uint32_t*)(smem_raw + L.guard_off[tid]) != kCanary + tid) atomicOr(S.err_flags, MAPF_FLAG_INTERNAL);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2965,10 +2977,15 @@ static bool pipe_layout(const MapfDims& d, int epb, MapfPipeLayout* L) {
     return o;
   };
   L->obst_off = take((d.shared_map ? 1 : epb) * d.bm_words * 4);
+  L->guard_off[0] = take(16);
   L->grid_off = take(epb * d.grid_bytes);
   L->agt_off = take(epb * d.bm_words * 4);
   L->live_bytes = off - L->grid_off;
-  for (int b = 0; b < 2; ++b) L->snap_off[b] = take(L->live_bytes);
+  L->guard_off[1] = take(16);
+  L->snap_off[0] = take(L->live_bytes);
+  L->guard_off[2] = take(16);
+  L->snap_off[1] = take(L->live_bytes);
+  L->guard_off[3] = take(16);
   for (int b = 0; b < 2; ++b) L->snappos_off[b] = take(64);
   for (int b = 0; b < 2; ++b) L->snapact_off[b] = take(32);
   L->goal_off = take(64);
@@ -2984,7 +3001,11 @@ static bool pipe_layout(const MapfDims& d, int epb, MapfPipeLayout* L) {
   L->rew_off = take(256);
   L->envrew_off = take(256);
   L->envcnt_off = take(128);
+  L->guard_off[4] = take(16);
   L->str_off = take(((32 + d.G - 1) / d.G) * d.GW * 4 + 16);
+  L->guard_off[5] = take(16);
+  L->guard_off[6] = L->guard_off[5];
+  L->guard_off[7] = L->guard_off[5];
   L->total_bytes = off;
   return off <= 48 * 1024;
 }

@@ -1621,3 +1621,38 @@ def test_rollout_optional_outputs_single_step_and_long_horizons():
     a.rollout(bad, want=("reward",))
     from mapf_marl_b200 import _lib
     assert a.error_flags() == _lib.FLAG_BAD_ACTION
+
+
+@pytest.mark.gpu
+def test_shared_memory_canaries_are_checked():
+    """compute-sanitizer is closed on this pool, so the kernels carry their own bounds evidence: guard words between the
+    shared-memory regions of a tile, verified before the kernel exits (MAPF_FLAG_INTERNAL).  Every other test asserts
+    error_flags() == 0 after stepping; here the self-test hook overwrites one guard on purpose and the flag must appear
+    -- for the step kernel, its in-kernel rollout and the pipelined rollout kernel."""
+    import ctypes
+    from mapf_marl_b200 import _lib, maps
+    E, N, H, W, F = 64, 8, 12, 12, 5
+    obst, starts, goals = maps.synthetic_batch(2, E, H, W, 0.1, N, distinct=0)
+    eng = _engine(E, N, H, W, mode="primal", fov=F)
+    eng.reset(obst, starts, goals)
+    hook = eng.lib.mapf_debug_corrupt_canary
+    hook.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    acts = torch.zeros((4, E, N), dtype=torch.uint8, device="cuda")
+    for which in range(4):
+        eng.step_observe(acts[0])
+        assert eng.error_flags() == 0
+        assert hook(eng._h, which) == 0
+        eng.step_observe(acts[0])
+        assert eng.error_flags() == _lib.FLAG_INTERNAL, which
+        eng.step_observe(acts[0])
+        assert eng.error_flags() == 0                       # the hook is consumed by one launch
+    assert eng.rollout_plan(4) == "pipelined"
+    for which in range(6):
+        assert hook(eng._h, which) == 0
+        eng.rollout(acts)
+        assert eng.error_flags() == _lib.FLAG_INTERNAL, which
+    hook(eng._h, 1)
+    eng.rollout(acts, want=("reward", "done_mid"))          # mid outputs: the step kernel's in-kernel loop
+    assert eng.error_flags() == _lib.FLAG_INTERNAL
+    eng.rollout(acts)
+    assert eng.error_flags() == 0
