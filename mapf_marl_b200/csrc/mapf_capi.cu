@@ -121,6 +121,12 @@ static void compute_layout(const MapfDims& d, int epb, MapfTileLayout* L, bool s
   L->envcnt_off = take(4 * epb);
   L->envcnt2_off = take(4 * epb);
   L->envstep_off = take(4 * epb);
+  if (d.mode != MAPF_MODE_PRIMAL) {   // sum(rewards) of GRID / PARTIAL (py_sum_* in mapf_kernels.cu)
+    L->envff_off = take(4 * epb);
+    L->pre_off = take(8 * na);
+  } else {
+    L->envff_off = L->pre_off = scratch0;
+  }
   if (d.diag) {   // PRIMAL with DIAGONAL_MOVEMENT only: the common layouts stay as they are
     L->pastold_off = take(2 * na);
     L->pastnew_off = take(2 * na);
@@ -330,6 +336,7 @@ int mapf_create(const mapf_cfg* c, mapf_handle** out) {
   d.mode = c->mode;
   d.obs_mode = c->obs_mode;
   d.episode_limit = c->episode_limit;
+  d.inv_limit = 1.0 / (double)c->episode_limit;   // IEEE division on the host == __ddiv_rn(1.0, limit)
   d.sum_mode = c->reward_sum_mode;
   d.step_is_int = c->step_reward_is_int;
   d.collide_is_int = c->collide_reward_is_int;

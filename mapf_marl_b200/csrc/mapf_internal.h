@@ -43,6 +43,7 @@ struct MapfDims {
   int pW, pK, posz;      // obs window, K nearest agents, obs size = 2*W*W + 13*K
   int complete_len;
   double p_move, p_stay, p_stay_goal, p_nc, p_ec, p_envc;
+  double inv_limit;      // 1.0 / episode_limit, correctly rounded (the closer-reward of a unit step, PARTIAL:229-234)
 };
 
 // Byte offsets into the dynamic shared memory of a tile kernel.
@@ -61,6 +62,8 @@ struct MapfTileLayout {
   int envcnt_off;   // int [epb]: per-environment counters (agents on goal / done)
   int envcnt2_off;  // int [epb]: PARTIAL: sum of node flags + edge counts
   int envstep_off;  // int [epb]: step counter before this step
+  int envff_off;    // int [epb]: GRID / PARTIAL: index of the first float item of sum(rewards) (N: none)
+  int pre_off;      // double [epb*N]: GRID / PARTIAL: accumulator before item i, then the compensation term of item i
   int atgoal_off;   // u8 [epb*N]: PARTIAL _agent_at_goals
   int pastold_off, pastnew_off;   // uchar2 [epb*N]: PRIMAL diagonal mode, State.agents_past before / after the sweep
   int mask16_off, nextmid16_off;  // u16 [epb*N]: 9-wide action masks (diagonal mode)

@@ -173,31 +173,63 @@ __device__ __noinline__ void write_mask5(uint8_t* dst, const uint8_t* mask, int 
 //   float, then Neumaier-compensated adds for floats / plain adds for ints, compensation added last.
 // All operations use explicit round-to-nearest intrinsics so that no FMA contraction can occur.
 // ------------------------------------------------------------------------------------------------
+// The loop is branch-free: one thread folds a whole environment while the rest of its warp waits, so what counts is
+// the dependent chain per item.  Every candidate is computed and selected (the compensation term is a chain of its
+// own that trails the accumulator), the loads of four items are issued together: one dependent double add per item
+// instead of three plus two shared-memory round trips and a divergent branch (GRID phase D: 12 400 -> ~2 000 cycles
+// for 32 agents, it was 60 % of the tile's critical path).  Same operations on the same operands in the same order.
 __device__ double py_sum(const double* x, const uint8_t* is_int, int n, int sum_mode) {
   double acc = 0.0;
   if (sum_mode == 0) {
+#pragma unroll 4
     for (int i = 0; i < n; ++i) acc = __dadd_rn(acc, x[i]);
     return acc;
   }
   double c = 0.0;
   bool in_float = false;
+#pragma unroll 4
   for (int i = 0; i < n; ++i) {
     const double xi = x[i];
-    if (!in_float) {
-      acc = __dadd_rn(acc, xi);
-      if (!is_int[i]) in_float = true;
-    } else if (is_int[i]) {
-      acc = __dadd_rn(acc, xi);
-    } else {
-      const double t = __dadd_rn(acc, xi);
-      if (fabs(acc) >= fabs(xi))
-        c = __dadd_rn(c, __dadd_rn(__dsub_rn(acc, t), xi));
-      else
-        c = __dadd_rn(c, __dadd_rn(__dsub_rn(xi, t), acc));
-      acc = t;
-    }
+    const bool flt = is_int[i] == 0;
+    const double t = __dadd_rn(acc, xi);
+    const bool big = fabs(acc) >= fabs(xi);
+    const double hi = big ? acc : xi, lo = big ? xi : acc;
+    const double cn = __dadd_rn(c, __dadd_rn(__dsub_rn(hi, t), lo));
+    c = (in_float && flt) ? cn : c;          // compensated only between floats; the first float is a plain add
+    in_float = in_float || flt;
+    acc = t;
   }
   if (in_float && c != 0.0 && isfinite(c)) acc = __dadd_rn(acc, c);
+  return acc;
+}
+
+// The same sum split over the tile (sum_mode 1), for the thread-per-environment phase D of GRID / PARTIAL, where one
+// warp folds the environments of a tile while every other warp of every resident tile competes for the same issue
+// slots (under load the fold above was 10 000 of a GRID tile's 18 000 cycles).  The accumulator chain needs one add
+// per item; the compensation term of item i is a function of (accumulator before i, item i) alone, so the chain
+// thread only records the accumulators (py_sum_head), every agent's thread computes its own term in parallel
+// (py_sum_term), and the chain thread folds the terms in order (py_sum_tail).  A term that the serial loop would not
+// have added is stored as +0.0: c starts as +0.0 and can never become -0.0, so c + 0.0 leaves c's bits alone.
+__device__ __forceinline__ double py_sum_head(const double* __restrict__ x, double* __restrict__ pre, int n) {
+  double acc = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    pre[i] = acc;
+    acc = __dadd_rn(acc, x[i]);
+  }
+  return acc;
+}
+__device__ __forceinline__ double py_sum_term(double acc, double xi, bool compensated) {
+  if (!compensated) return 0.0;
+  const double t = __dadd_rn(acc, xi);
+  const bool big = fabs(acc) >= fabs(xi);
+  return __dadd_rn(__dsub_rn(big ? acc : xi, t), big ? xi : acc);
+}
+__device__ __forceinline__ double py_sum_tail(double acc, const double* term, int n, bool any_float) {
+  double c = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) c = __dadd_rn(c, term[i]);
+  if (any_float && c != 0.0 && isfinite(c)) acc = __dadd_rn(acc, c);
   return acc;
 }
 
@@ -574,18 +606,26 @@ __device__ __forceinline__ void partial_phase_a(const MapfDims& d, const Smem& s
   const uchar2 p = s.posold[j], g = s.goal[j];
   const bool done_old = s.done[j] != 0;
   const bool at_old = s.atgoal[j] != 0;
+  // the global loads of this phase are issued before anything waits for one: the agent's step counter and the goal
+  // distance of the old cell now, the distance of the new cell as soon as the move is decided (they were three exposed
+  // memory latencies in a row: 12 000 cycles of the tile's critical path)
+  const int16_t* dm = S.goal_dist + gj * d.HW;                       // :229-234
+  const int opd = __ldg(dm + (int)p.x * d.W + p.y);
+  int steps_old = 0;
+  if (!done_old) steps_old = S.agent_steps[gj];
   uchar2 np = p;
   double r = 0.0;
   int flag = 0;
+  const int act = s.act[j];
+  if (!done_old && act < 4) {                                        // __agent_step, :618-643
+    const int t0 = (int)p.x + (act == 0 ? -1 : (act == 1 ? 1 : 0));
+    const int t1 = (int)p.y + (act == 2 ? -1 : (act == 3 ? 1 : 0));
+    if (count_obstacle(d, ob, s.grida + el * d.grid_bytes, t0, t1)) flag = 1;
+    else np = make_uchar2((unsigned char)t0, (unsigned char)t1);
+  }
+  const int npd = (np.x == p.x && np.y == p.y) ? opd : (int)__ldg(dm + (int)np.x * d.W + np.y);
   if (!done_old) {
-    S.agent_steps[gj] += 1;                                          // _agent_step_count, :194
-    const int act = s.act[j];
-    if (act < 4) {                                                   // __agent_step, :618-643
-      const int t0 = (int)p.x + (act == 0 ? -1 : (act == 1 ? 1 : 0));
-      const int t1 = (int)p.y + (act == 2 ? -1 : (act == 3 ? 1 : 0));
-      if (count_obstacle(d, ob, s.grida + el * d.grid_bytes, t0, t1)) flag = 1;
-      else np = make_uchar2((unsigned char)t0, (unsigned char)t1);
-    }
+    S.agent_steps[gj] = steps_old + 1;                               // _agent_step_count, :194
     if (flag) r = __dadd_rn(r, d.p_envc);                            // :203-205
     if (act < 4) r = __dadd_rn(r, d.p_move);                         // :207-208
     else r = __dadd_rn(r, at_old ? d.p_stay_goal : d.p_stay);        // :209-213
@@ -593,9 +633,12 @@ __device__ __forceinline__ void partial_phase_a(const MapfDims& d, const Smem& s
   const bool at_new = (np.x == g.x && np.y == g.y);                  // :217-222
   if (at_new) S.goal_cost[gj] = step_now;
   const bool dn = done_old || (step_now >= d.episode_limit);         // :224-227
-  const int16_t* dm = S.goal_dist + gj * d.HW;                       // :229-234
-  const int opd = dm[(int)p.x * d.W + p.y], npd = dm[(int)np.x * d.W + np.y];
-  r = __dadd_rn(r, __ddiv_rn((double)(opd - npd), (double)d.episode_limit));
+  // (old - new) / episode_limit: a step changes the hop distance by -1, 0 or +1, and IEEE division is sign-symmetric:
+  // +-inv_limit or +0.0 without the division routine; anything else (unreachable-cell sentinels) divides
+  const int diff = opd - npd;
+  double closer = diff == 0 ? 0.0 : (diff == 1 ? d.inv_limit : -d.inv_limit);
+  if (diff < -1 || diff > 1) closer = __ddiv_rn((double)diff, (double)d.episode_limit);
+  r = __dadd_rn(r, closer);
   s.posnew[j] = np;
   s.status[j] = (int8_t)flag;
   s.done[j] = dn ? 1 : 0;
@@ -618,7 +661,9 @@ __device__ __forceinline__ bool grid_phase_c(const MapfDims& d, const Smem& s, i
   const int nc = gcell(d, np.x, np.y);
   const int node = cnew[nc] > 1 ? 1 : 0;
   int edge = 0;
-  if ((p.x != np.x || p.y != np.y) && cold[nc] != 0) {
+  // a swap partner stood on my new cell and stands on my old one now: both count grids must be non-zero there (I
+  // moved, so I am not the one on my old cell).  Without the second test a third of all moves walked the N agents.
+  if ((p.x != np.x || p.y != np.y) && cold[nc] != 0 && cnew[gcell(d, p.x, p.y)] != 0) {
     for (int k = 0; k < N; ++k) {
       if (k == a) continue;
       const uchar2 qo = s.posold[jb + k], qn = s.posnew[jb + k];
@@ -813,6 +858,8 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
   constexpr bool primal = MODE == MAPF_MODE_PRIMAL || diag;
   constexpr bool partial = MODE == MAPF_MODE_PARTIAL;
   int* envcnt2 = (int*)(smem_raw + L.envcnt2_off);
+  int* envff = (int*)(smem_raw + L.envff_off);      // GRID / PARTIAL only (aliases the scratch otherwise: never touched)
+  double* sumpre = (double*)(smem_raw + L.pre_off);
   const bool do_step = A.do_step != 0;
   const bool need_mid = primal && do_step && ((A.out.done_mid_dev != nullptr) || (A.out.next_mid_dev != nullptr));
   // The fused step+observation launch of the 5-action PRIMAL mode does not need a pass of its own for the agent bit map
@@ -921,6 +968,7 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
     envcnt[tid] = 0;
     envcnt2[tid] = 0;
     envstep[tid] = sc0;
+    if (!primal) envff[tid] = N;
   }
   if (tid < na) store_rec(tid, r0);
   if (!SINGLE) {
@@ -928,6 +976,7 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
       envcnt[el] = 0;
       envcnt2[el] = 0;
       envstep[el] = S.step_count[e0 + el];
+      if (!primal) envff[el] = N;
     }
     for (int j = tid + kThreads; j < na; j += kThreads) {
       AgentRec r;
@@ -1047,6 +1096,11 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
       const unsigned peers = __match_any_sync(0xffffffffu, el);
       const unsigned bf = __ballot_sync(0xffffffffu, flag);
       if (active && lane == __ffs(peers) - 1) atomicAdd(&envcnt[el], __popc(bf & peers));
+      if (!primal && d.sum_mode == 1) {
+        // first float item of the environment's sum(rewards): consecutive lanes hold consecutive agents
+        const unsigned fl = __ballot_sync(0xffffffffu, active && s.isint[j] == 0) & peers;
+        if (active && fl != 0 && lane == __ffs(peers) - 1) atomicMin(&envff[el], j - el * N + __ffs(fl) - 1 - lane);
+      }
     }
     if (d.collect_stats && last) {
       c0 = __reduce_add_sync(0xffffffffu, c0);
@@ -1157,19 +1211,37 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
             s.rew[el * N + i] = __dadd_rn(s.rew[el * N + i], bonus);
           }
         }
-        if (A.out.reward_dev)
-          A.out.reward_dev[e0t + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // PARTIAL:310
+        if (A.out.reward_dev) {                                                        // sum(rewards), PARTIAL:310
+          if (d.sum_mode == 1) s.envrew[el] = py_sum_head(s.rew + el * N, sumpre + el * N, N);
+          else A.out.reward_dev[e0t + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);
+        }
         if (A.out.terminated_dev) A.out.terminated_dev[e0t + el] = term ? 1 : 0;
         S.terminated[e0 + el] = term ? 1 : 0;
         S.total_coll[e0 + el] += envcnt2[el] / 2;                                      // PARTIAL:250
         S.step_count[e0 + el] = step_now;
       } else {
-        if (A.out.reward_dev)
-          A.out.reward_dev[e0t + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);   // GRID:141
+        if (A.out.reward_dev) {                                                        // sum(rewards), GRID:141
+          if (d.sum_mode == 1) s.envrew[el] = py_sum_head(s.rew + el * N, sumpre + el * N, N);
+          else A.out.reward_dev[e0t + el] = py_sum(s.rew + el * N, s.isint + el * N, N, d.sum_mode);
+        }
         if (last) S.step_count[e0 + el] = envstep[el] + 1;
       }
       ep_done += all ? 1u : 0u;
       if (d.collect_stats && last && ep_done) atomicAdd(&S.stats[MAPF_STAT_EPISODES_DONE], (unsigned long long)ep_done);
+    }
+    PHASE_MARK(13);
+    if (!primal && d.sum_mode == 1 && A.out.reward_dev != nullptr) {
+      // CPython >= 3.12 sum(rewards): compensation terms by the agents' own threads, folded in order (see py_sum_head)
+      __syncthreads();
+      PHASE_MARK(14);
+      for (int j = tid, it_ = 0; j < na && (!SINGLE || it_ == 0); j += kThreads, ++it_) {
+        const int el = fast_div(j, d.invN), a = j - el * N;
+        sumpre[j] = py_sum_term(sumpre[j], s.rew[j], s.isint[j] == 0 && a > envff[el]);
+      }
+      __syncthreads();
+      PHASE_MARK(15);
+      for (int el = tid, it_ = 0; el < ne && (!SINGLE || it_ == 0); el += kThreads, ++it_)
+        A.out.reward_dev[e0t + el] = py_sum_tail(s.envrew[el], sumpre + el * N, N, envff[el] < N);
     }
     PHASE_MARK(11);
     if (d.collect_stats && last) {   // one global atomic per counter per tile (a rollout: once for all its steps)
@@ -1234,6 +1306,29 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
     // get_obs / get_state, GRID:143-196: -1 on walls, else the number of agents on the cell.
     if (A.obs == nullptr) break;
     int8_t* out = (int8_t*)A.obs + e0t * d.HW;
+    if ((d.W & 15) == 0) {
+      // sixteen cells of a row per thread: one funnel shift for the wall bits, five aligned words of the count grid
+      // shifted into place, one 16-byte store (a quarter of the instructions of the four-cell path below: the
+      // full-map observation was 17 % of the GRID step's instructions)
+      const int q16 = d.HW >> 4, cpr = d.W >> 4;
+      for (int i = tid; i < ne * q16; i += kThreads) {
+        const int el = i / q16, q = i - el * q16;
+        const int r = q / cpr, c = (q - r * cpr) << 4;
+        const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
+        const int g0 = el * d.grid_bytes + gcell(d, r, c);
+        const uint32_t* gw = (const uint32_t*)(gridcur + (g0 & ~3));
+        const int sh = (g0 & 3) << 3;
+        const uint32_t w0 = gw[0], w1 = gw[1], w2 = gw[2], w3 = gw[3], w4 = gw[4];
+        const uint32_t wall = row_field(ob, d.RW, r + d.P, c + d.P, 0xFFFFu);
+        uint4 v;                                                       // `+= 1` on a -1 cell per agent, GRID:299
+        v.x = __vsub4(__funnelshift_r(w0, w1, sh), expand4(wall & 15u));
+        v.y = __vsub4(__funnelshift_r(w1, w2, sh), expand4((wall >> 4) & 15u));
+        v.z = __vsub4(__funnelshift_r(w2, w3, sh), expand4((wall >> 8) & 15u));
+        v.w = __vsub4(__funnelshift_r(w3, w4, sh), expand4(wall >> 12));
+        *(uint4*)(out + (size_t)el * d.HW + ((size_t)q << 4)) = v;
+      }
+      break;
+    }
     if ((d.W & 3) == 0) {
       // four cells of a row per thread: one funnel shift for the wall bits, four count bytes, one packed 32-bit store
       const int q4 = d.HW >> 2;
