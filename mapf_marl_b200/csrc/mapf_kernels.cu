@@ -1310,10 +1310,14 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
       // sixteen cells of a row per thread: one funnel shift for the wall bits, five aligned words of the count grid
       // shifted into place, one 16-byte store (a quarter of the instructions of the four-cell path below: the
       // full-map observation was 17 % of the GRID step's instructions)
-      const int q16 = d.HW >> 4, cpr = d.W >> 4;
-      for (int i = tid; i < ne * q16; i += kThreads) {
-        const int el = i / q16, q = i - el * q16;
-        const int r = q / cpr, c = (q - r * cpr) << 4;
+      const int q16 = d.HW >> 4;
+      int el = 0, q = tid;                                             // chunk q of environment el (no divisions)
+      while (q >= q16) {
+        q -= q16;
+        ++el;
+      }
+      for (; el < ne;) {
+        const int r = fast_div(q << 4, d.invW), c = (q << 4) - r * d.W;
         const uint32_t* ob = s.obst + (d.shared_map ? 0 : el * d.bm_words);
         const int g0 = el * d.grid_bytes + gcell(d, r, c);
         const uint32_t* gw = (const uint32_t*)(gridcur + (g0 & ~3));
@@ -1326,6 +1330,11 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
         v.z = __vsub4(__funnelshift_r(w2, w3, sh), expand4((wall >> 8) & 15u));
         v.w = __vsub4(__funnelshift_r(w3, w4, sh), expand4(wall >> 12));
         *(uint4*)(out + (size_t)el * d.HW + ((size_t)q << 4)) = v;
+        q += kThreads;
+        while (q >= q16) {
+          q -= q16;
+          ++el;
+        }
       }
       break;
     }

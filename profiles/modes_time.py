@@ -36,6 +36,8 @@ def main():
                         (torch.float64, torch.float32))}
     for name in which:
         kw, dts = cfgs[name]
+        if name == "partial" and os.environ.get("MODES_PARTIAL_DTYPE"):
+            dts = (getattr(torch, os.environ["MODES_PARTIAL_DTYPE"]),)
         eng = MapfEngine(E, N, wl["H"], wl["W"], device="cuda:0", **kw)
         eng.reset(obst, starts, goals)
         pool = torch.stack([eng.random_actions(1234, t, dtype=torch.uint8).clone() for t in range(16)])
