@@ -2355,58 +2355,73 @@ __device__ __forceinline__ bool bfs_warp_one(const MapfDims& d, const MapfState&
     for (int p = 0; p < NP; ++p) D[k][p] = 0;
   }
   bool open = true;
-#pragma unroll 4   // bits 3 and 4 of the level become compile-time constants inside the unrolled body (two upper planes less to mask)
-  for (int L0 = 0; L0 < (1 << NP); L0 += 8) {
-    // The kernel is bound by the integer ALU pipe (LOP3 / SHF: one warp instruction per two cycles per scheduler), the
-    // FMA pipe (IMAD) idles.  Every update below whose operands are DISJOINT bit sets is therefore written as an
-    // add / subtract instead of an or / and-not -- a cell is reached exactly once, so the frontier never overlaps the
-    // distance planes or leaves the free-and-not-visited set -- which lets ptxas place it on the FMA pipe (IMAD.IADD).
-    Row fnv0[RPL];
+  // Levels run in GROUPS of 32 (runtime loop) made of four unrolled BATCHES of 8: inside a batch bits 0-2 of the level
+  // are compile-time constants, inside a group bits 3-4 are, and bits 5-7 are constant for the whole group -- the three
+  // upper planes take the union of the group ONCE, when the group ends or the wavefront dies (per batch that was a
+  // mask, an AND and an add for each of them: 12 of a batch's 83 instructions).
+  for (int G0 = 0; G0 < (1 << NP) && open; G0 += 32) {
+    Row fnvG[RPL];
 #pragma unroll
-    for (int k = 0; k < RPL; ++k) fnv0[k] = fnv[k];
+    for (int k = 0; k < RPL; ++k) fnvG[k] = fnv[k];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i > 0 || L0 > 0) {
-        // rows beyond the first / last lane come back as the lane's own row, which is adjacent anyway: harmless
-        const Row from_above = __shfl_up_sync(full, f[RPL - 1], 1);     // last row of the lane above
-        const Row from_below = __shfl_down_sync(full, f[0], 1);         // first row of the lane below
-        Row nw[RPL];
+    for (int b = 0; b < 4; ++b) {
+      // The kernel is bound by the integer ALU pipe (LOP3 / SHF: one warp instruction per two cycles per scheduler),
+      // the FMA pipe (IMAD) idles.  Every update below whose operands are DISJOINT bit sets is therefore written as an
+      // add / subtract instead of an or / and-not -- a cell is reached exactly once, so the frontier never overlaps
+      // the distance planes or leaves the free-and-not-visited set -- which lets ptxas place it on the FMA pipe.
+      Row fnv0[RPL];
 #pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-          Row up = (k > 0) ? f[k - 1] : from_above;
-          Row dn = (k < RPL - 1) ? f[k + 1] : from_below;
-          if (CONN8) {                                                    // diagonal neighbours, PRIMAL:421-437
-            up |= (up << 1) | (up >> 1);
-            dn |= (dn << 1) | (dn >> 1);
+      for (int k = 0; k < RPL; ++k) fnv0[k] = fnv[k];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i > 0 || b > 0 || G0 > 0) {
+          // rows beyond the first / last lane come back as the lane's own row, which is adjacent anyway: harmless
+          const Row from_above = __shfl_up_sync(full, f[RPL - 1], 1);     // last row of the lane above
+          const Row from_below = __shfl_down_sync(full, f[0], 1);         // first row of the lane below
+          Row nw[RPL];
+#pragma unroll
+          for (int k = 0; k < RPL; ++k) {
+            Row up = (k > 0) ? f[k - 1] : from_above;
+            Row dn = (k < RPL - 1) ? f[k + 1] : from_below;
+            if (CONN8) {                                                    // diagonal neighbours, PRIMAL:421-437
+              up |= (up << 1) | (up >> 1);
+              dn |= (dn << 1) | (dn >> 1);
+            }
+            // (the right shift stays a SHF: as IMAD.HI -- __umulhi(f, 1u << 31) -- it measured 5 % slower)
+            nw[k] = ((f[k] + f[k]) | (f[k] >> 1) | up | dn) & fnv[k];
           }
-          // (the right shift stays a SHF: as IMAD.HI -- __umulhi(f, 1u << 31) -- it measured 5 % slower)
-          nw[k] = ((f[k] + f[k]) | (f[k] >> 1) | up | dn) & fnv[k];
+#pragma unroll
+          for (int k = 0; k < RPL; ++k) {
+            f[k] = nw[k];
+            fnv[k] -= nw[k];                 // nw is a subset of fnv
+          }
         }
 #pragma unroll
         for (int k = 0; k < RPL; ++k) {
-          f[k] = nw[k];
-          fnv[k] -= nw[k];                 // nw is a subset of fnv
+          if (i & 1) D[k][0] += f[k];        // disjoint: this cell's distance bits are written once
+          if (i & 2) D[k][1] += f[k];
+          if (i & 4) D[k][2] += f[k];
         }
       }
+      bool any = false;
 #pragma unroll
       for (int k = 0; k < RPL; ++k) {
-        if (i & 1) D[k][0] += f[k];        // disjoint: this cell's distance bits are written once
-        if (i & 2) D[k][1] += f[k];
-        if (i & 4) D[k][2] += f[k];
+        const Row U = fnv0[k] - fnv[k];      // everything reached in this batch (level 0 has all planes zero anyway)
+        if (b & 1) D[k][3] += U;
+        if (b & 2) D[k][4] += U;
+        any |= f[k] != 0;
+      }
+      if (!__any_sync(full, any)) {
+        open = false;
+        break;
       }
     }
-    bool any = false;
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
-      const Row U = fnv0[k] - fnv[k];      // everything reached in this batch (level 0 has all planes zero anyway)
+      const Row UG = fnvG[k] - fnv[k];       // everything reached in this group
 #pragma unroll
-      for (int p = 3; p < NP; ++p)
-        if ((L0 >> p) & 1) D[k][p] += U;
-      any |= f[k] != 0;
-    }
-    if (!__any_sync(full, any)) {
-      open = false;
-      break;
+      for (int p = 5; p < NP; ++p)
+        if ((G0 >> p) & 1) D[k][p] += UG;
     }
   }
   if (open) return false;                  // deeper than 255 levels: the caller hands the map to the generic kernel
