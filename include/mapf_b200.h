@@ -248,6 +248,22 @@ int mapf_set_goals(mapf_handle* h, const int16_t* goals_dev, const uint8_t* dirt
 int mapf_pop_goals(mapf_handle* h, const int16_t* queue_dev, int32_t* head_dev, int queue_len, uint8_t* dirty_dev,
                    void* stream);
 
+/* The same hand-out fused into the step: binds the queues to the handle, and from then on every full-range PRIMAL step
+ * launch (mapf_step, mapf_step_observe, mapf_step_observe_host, the launches of mapf_rollout) pops the queue of every
+ * agent that ENDS the step on its goal, in the step kernel's own write-back -- bit for bit the state that
+ * mapf_step* followed by mapf_pop_goals leaves (the step's outputs and observation still show the old goal), without
+ * the extra launch and without the dirty mask: the re-assigned (env, agent) pairs are collected in a list that
+ * mapf_bfs_popped hands to the BFS.  queue_dev / head_dev as in mapf_pop_goals, owned by the caller and read at every
+ * step; queue_dev == NULL unbinds.  PRIMAL mode only; multi-step single-launch rollouts fall back to one launch per
+ * step while queues are bound. */
+int mapf_lifelong_bind(mapf_handle* h, const int16_t* queue_dev, int32_t* head_dev, int queue_len);
+
+/* Goal-distance maps (mapf_bfs) of the agents whose goals the MOST RECENT step launch re-assigned (queues bound with
+ * mapf_lifelong_bind).  dist_dev as in mapf_bfs (NULL: the handle's own maps).  May run on another stream than the
+ * step, concurrently with the NEXT step: the handle keeps two lists and alternates between them, so the caller only
+ * has to order this call behind the step it belongs to and ahead of the step after the next one. */
+int mapf_bfs_popped(mapf_handle* h, int16_t* dist_dev, void* stream);
+
 /* Replaces MAPF_GRID.step (GRID:85-141) or one full sweep `for id in 1..N: MAPFEnv._step((id, a[id]))`
  * (PRIMAL:549-637).  actions_dev: [E,N] of act_dtype (MAPF_U8 or MAPF_I64). */
 int mapf_step(mapf_handle* h, const void* actions_dev, int act_dtype, const mapf_step_out* out, void* stream);

@@ -77,6 +77,8 @@ PROTOTYPES = {
     "mapf_reset": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_set_goals": (_i, [_vp, _vp, _vp, _vp]),
     "mapf_pop_goals": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "mapf_lifelong_bind": (_i, [_vp, _vp, _vp, _i]),
+    "mapf_bfs_popped": (_i, [_vp, _vp, _vp]),
     "mapf_step": (_i, [_vp, _vp, _i, ctypes.POINTER(MapfStepOut), _vp]),
     "mapf_step_agents": (_i, [_vp, _vp, _i, _i, _i, ctypes.POINTER(MapfStepOut), _vp]),
     "mapf_observe": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -25,6 +25,14 @@ struct mapf_handle {
   int debug_corrupt;            // mapf_debug_corrupt_canary: consumed by the next tile / pipe launch
   int64_t launches;
   int mag_lut_len;
+  // mapf_lifelong_bind: goal queues popped by the step kernel itself
+  const int16_t* life_queue;
+  int32_t* life_head;
+  int life_Q;
+  int32_t* life_lists;   // device [2][E*N]: re-assigned (env, agent) pairs of the last two step launches
+  int32_t* life_cnts;    // device [2][2]: list length, overflow counter of the BFS
+  int life_slot;         // the list the next step launch appends to
+  int life_last;         // the list of the most recent step launch (-1: none yet)
   // device staging for the *_host entry points (allocated on first use)
   uint8_t* hs_actions;
   double* hs_reward;
@@ -227,6 +235,8 @@ int mapf_destroy(mapf_handle* h) {
   cudaFree((void*)h->S.vec_lut);
   cudaFree(h->S.stats);
   cudaFree(h->S.bfs_list);
+  cudaFree(h->life_lists);
+  cudaFree(h->life_cnts);
   cudaFree(h->S.err_flags);
   cudaFree(h->S.pos_prev);
   cudaFree(h->S.past);
@@ -532,6 +542,49 @@ int mapf_pop_goals(mapf_handle* h, const int16_t* queue_dev, int32_t* head_dev, 
   return MAPF_OK;
 }
 
+int mapf_lifelong_bind(mapf_handle* h, const int16_t* queue_dev, int32_t* head_dev, int queue_len) {
+  if (!h) return MAPF_ERR_INVALID_ARG;
+  if (!queue_dev) {
+    h->life_queue = nullptr;
+    h->life_head = nullptr;
+    h->life_last = -1;
+    return MAPF_OK;
+  }
+  if (!head_dev) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_lifelong_bind: head_dev is NULL");
+  if (queue_len < 1) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_lifelong_bind: queue_len must be >= 1");
+  if (h->d.mode != MAPF_MODE_PRIMAL)
+    return fail(h, MAPF_ERR_UNSUPPORTED, "mapf_lifelong_bind: PRIMAL mode only (use mapf_pop_goals)");
+  const size_t EN = (size_t)h->d.E * h->d.N;
+  if (!h->life_lists) {
+    CK(cudaMalloc((void**)&h->life_lists, 2 * EN * 4));
+    CK(cudaMalloc((void**)&h->life_cnts, 4 * 4));
+  }
+  CK(cudaMemset(h->life_cnts, 0, 4 * 4));
+  h->life_queue = queue_dev;
+  h->life_head = head_dev;
+  h->life_Q = queue_len;
+  h->life_slot = 0;
+  h->life_last = -1;
+  return MAPF_OK;
+}
+
+int mapf_bfs_popped(mapf_handle* h, int16_t* dist_dev, void* stream) {
+  if (!h) return MAPF_ERR_INVALID_ARG;
+  if (!h->life_queue) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_bfs_popped: no queues bound (mapf_lifelong_bind)");
+  int16_t* dist = dist_dev ? dist_dev : h->S.goal_dist;
+  if (!dist) return fail(h, MAPF_ERR_INVALID_ARG, "mapf_bfs_popped: no output (dist_dev NULL and cfg.goal_dist == 0)");
+  int rc;
+  if ((rc = check_aligned(h, dist, "dist_dev")) != MAPF_OK) return rc;
+  if (h->life_last < 0) return MAPF_OK;   // no step since the queues were bound
+  const size_t EN = (size_t)h->d.E * h->d.N;
+  int n = 0;
+  CK((cudaError_t)mapf_launch_bfs(h->d, h->S, nullptr, nullptr, dist, 0, stream, &n, h->life_lists + h->life_last * EN,
+                                  h->life_cnts + 2 * h->life_last));
+  h->launches += n;
+  h->life_last = -1;                      // consumed
+  return MAPF_OK;
+}
+
 // MAPF_BITS output: a specialised field-of-view kernel, and every tile holds whole observation groups (tile strings
 // start on word boundaries).
 static bool bits_supported(const mapf_handle* h) {
@@ -590,10 +643,22 @@ static int run_tile(mapf_handle* h, const void* actions, int act_dtype, int lo, 
     A.out.status_dev = h->S.last_status;
     A.out.agent_reward_dev = h->S.last_reward;
   }
+  const bool life = h->life_queue && A.do_step && n_steps == 1 && lo == 0 && hi == h->d.N;
+  if (life) {   // the write-back of this launch pops the goal queues (mapf_lifelong_bind)
+    A.life_queue = h->life_queue;
+    A.life_head = h->life_head;
+    A.life_Q = h->life_Q;
+    A.life_list = h->life_lists + (size_t)h->life_slot * h->d.E * h->d.N;
+    A.life_cnt = h->life_cnts + 2 * h->life_slot;
+  }
   if (any_out) {
     const bool need_mid = A.out.done_mid_dev || A.out.next_mid_dev;
     CK((cudaError_t)mapf_launch_tile(d, need_mid ? h->L : h->L_lite, h->S, A, stream));
     h->launches++;
+    if (life) {
+      h->life_last = h->life_slot;
+      h->life_slot ^= 1;
+    }
   }
   if (blocking) {   // PRIMAL:579-585: stay-on-goal rewards get the blocking term
     int n = 0;
@@ -648,6 +713,7 @@ int mapf_step_observe(mapf_handle* h, const void* actions_dev, int act_dtype, co
 static bool rollout_in_kernel(const mapf_handle* h, const void* obs, int obs_dtype, const double* vec) {
   const MapfDims& d = h->d;
   if (!mapf_tile_has_rollout(d.mode) || d.diag || d.blocking) return false;
+  if (h->life_queue) return false;                                          // the queues are popped once per launch
   if (d.epb * d.N > MAPF_TILE_THREADS) return false;                       // one thread per agent of the tile
   const bool fov = d.obs_mode == MAPF_OBS_PRIMAL_FOV;
   if (fov && !h->fov_fast && (obs || vec)) return false;                    // generic-F observation kernel

@@ -116,6 +116,13 @@ struct MapfTileArgs {
   double* vec;             // [E][N][3] or NULL
   int T;                   // steps in this launch (mapf_rollout): actions / outputs / obs / vec are [T][...], T >= 1
   int debug_corrupt;       // self-test of the canary check: 1 + index of a guard word the kernel overwrites on purpose
+  // lifelong goal queues bound to the handle (mapf_lifelong_bind): the step's write-back pops the queue of every agent
+  // that ends the step on its goal -- what mapf_pop_goals does as a launch of its own behind the step
+  const int16_t* life_queue;   // [E][N][Q][2] or NULL
+  int32_t* life_head;          // [E][N]
+  int life_Q;
+  int32_t* life_list;          // (env, agent) indices popped by this launch ...
+  int32_t* life_cnt;           // ... and their number ([0]; [1] is the overflow counter of the BFS that follows)
 };
 
 #ifdef __cplusplus
@@ -135,7 +142,8 @@ int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, const int16_t* 
 int mapf_launch_pop_goals(const MapfDims& d, const MapfState& S, const int16_t* queue, int32_t* head, int queue_len,
                           uint8_t* dirty, void* stream);
 int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, const uint8_t* env_mask, int16_t* dist,
-                    int primal_costs, void* stream, int* n_launches);   // 8-connected when primal_costs && d.diag
+                    int primal_costs, void* stream, int* n_launches,   // 8-connected when primal_costs && d.diag
+                    int32_t* ext_list = nullptr, int32_t* ext_cnt = nullptr);   // a list some kernel already compacted
 int mapf_launch_blocking(const MapfDims& d, const MapfState& S, int agent_lo, int agent_hi, const mapf_step_out& out,
                          void* stream, int* n_launches);
 int mapf_launch_partial_obs(const MapfDims& d, const MapfState& S, void* obs, int f32, long long* state_out,

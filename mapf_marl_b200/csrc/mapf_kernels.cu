@@ -1286,6 +1286,31 @@ mapf_tile_kernel(const MapfDims d, const MapfTileLayout L, const MapfState S, co
       if (A.out.valid_dev) A.out.valid_dev[gt] = primal ? ((s.flag[j] >> 1) & 1) : 1;
       if (primal && A.out.done_mid_dev) A.out.done_mid_dev[gt] = (s.flag[j] >> 2) & 1;
     }
+    if (primal && A.life_queue != nullptr) {
+      // Lifelong hand-out (MAPF-490-main/Global.cpp:85-94), exactly mapf_pop_goals_kernel behind this step: an agent that
+      // ends the step on its goal takes the front of its queue.  This step's outputs and observation keep the old
+      // goal (they read the tile's copy); the handle's goal, its on-goal flag and the list of re-assigned
+      // (env, agent) pairs for the BFS that follows change here.  A loop of its own, behind a uniform branch: inside
+      // the write-back loop it cost the plain step 3 % (registers kept live across the stores).
+      for (int j = tid; j < na; j += kThreads) {
+        const size_t gj = a0 + j;
+        const uchar2 pn = s.posnew[j], g = s.goal[j];
+        if (pn.x != g.x || pn.y != g.y) continue;
+        const int hd = A.life_head[gj];
+        if (hd >= A.life_Q) continue;
+        const short2 q = ((const short2*)A.life_queue)[gj * (size_t)A.life_Q + hd];
+        int g0 = q.x, g1 = q.y;
+        if (g0 < 0 || g0 >= d.H || g1 < 0 || g1 >= d.W) {
+          atomicOr(S.err_flags, MAPF_FLAG_BAD_POSITION);
+          g0 = min(max(g0, 0), d.H - 1);
+          g1 = min(max(g1, 0), d.W - 1);
+        }
+        A.life_head[gj] = hd + 1;
+        ((uchar2*)S.goal)[gj] = make_uchar2((unsigned char)g0, (unsigned char)g1);
+        S.done[gj] = (uint8_t)(pn.x == g0 && pn.y == g1);
+        A.life_list[atomicAdd(A.life_cnt, 1)] = (int32_t)gj;
+      }
+    }
     if constexpr (diag) {
       if (A.out.next_mid_dev) write_mask_n(A.out.next_mid_dev + 9 * a0t, s.nextmid16, na, 9, tid);
     } else {
@@ -3261,7 +3286,8 @@ extern "C" int mapf_launch_export16(const MapfDims& d, const uint8_t* src, int16
 }
 
 extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint8_t* dirty, const uint8_t* env_mask,
-                               int16_t* dist, int primal_costs, void* stream, int* n_launches) {
+                               int16_t* dist, int primal_costs, void* stream, int* n_launches, int32_t* ext_list,
+                               int32_t* ext_cnt) {
   cudaStream_t st = (cudaStream_t)stream;
   const int RWB = (d.W + 31) / 32;
   const size_t bm_bytes = (size_t)4 * d.H * RWB * 4;
@@ -3281,17 +3307,19 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
   const long long maps = (long long)d.E * d.N;
   const int conn8 = (primal_costs && d.diag) ? 1 : 0;   // getAstarCosts with DIAGONAL_MOVEMENT, PRIMAL:421-437
   // S.bfs_list: [0] number of flagged maps, [1] number of overflowed maps, then the two lists (maps entries each)
-  int32_t* cnt = S.bfs_list;
+  int32_t* cnt = ext_cnt ? ext_cnt : S.bfs_list;
   int32_t* flagged = S.bfs_list + 2;
   int32_t* overflow = flagged + maps;
-  {
+  if (!ext_cnt) {
     cudaError_t e = cudaMemsetAsync(cnt, 0, 8, st);
     if (e != cudaSuccess) return (int)e;
   }
   // masked launch: compact the flagged maps, then a resident grid walks the list
   const int32_t* list = nullptr;
   int extra = 0;
-  if (dirty || env_mask) {
+  if (ext_list) {   // the list was written by the step kernel (lifelong hand-out): nothing to compact
+    list = ext_list;
+  } else if (dirty || env_mask) {
     mapf_bfs_compact_kernel<<<grid_for(maps, 256), 256, 0, st>>>(d, dirty, env_mask, S.bfs_list);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -3333,6 +3361,7 @@ extern "C" int mapf_launch_bfs(const MapfDims& d, const MapfState& S, const uint
   }
   cudaError_t err = cudaGetLastError();
   *n_launches = 1 + extra;
+  if (err == cudaSuccess && ext_cnt) err = cudaMemsetAsync(ext_cnt, 0, 8, st);   // the list is consumed
   if (err == cudaSuccess && primal_costs) {
     mapf_primal_costs_agents_kernel<<<grid_for(maps * d.N, 256), 256, 0, st>>>(d, S, dirty, dist);
     mapf_primal_costs_free_kernel<<<grid_for(maps * d.HW, 256), 256, 0, st>>>(d, dirty, dist);

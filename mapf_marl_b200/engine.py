@@ -248,6 +248,28 @@ class MapfEngine:
                                                 self._ptr(dirty_out), self._stream()), "mapf_pop_goals")
         return dirty_out
 
+    def lifelong_bind(self, queue, head):
+        """Fuses the lifelong hand-out into the step: from now on every full-range step launch pops the queue of every
+        agent that ends the step on its goal (exactly pop_goals() behind the step, without the launch).  queue int16
+        [E,N,Q,2], head int32 [E,N], both kept alive and read by every step; queue=None unbinds."""
+        if queue is None:
+            self._life = None
+            self._check(self.lib.mapf_lifelong_bind(self._h, None, None, 0), "mapf_lifelong_bind")
+            return
+        assert queue.dtype == torch.int16 and queue.is_cuda and queue.is_contiguous()
+        assert head.dtype == torch.int32 and head.is_cuda and head.is_contiguous()
+        assert tuple(queue.shape[:2]) == (self.E, self.N) and queue.shape[3] == 2 and tuple(head.shape) == (self.E, self.N)
+        self._life = (queue, head)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_lifelong_bind(self._h, self._ptr(queue), self._ptr(head), int(queue.shape[2])),
+                        "mapf_lifelong_bind")
+
+    def bfs_popped(self, out=None):
+        """Goal-distance maps of the agents whose goals the most recent step re-assigned (lifelong_bind), into `out`
+        (int16 [E,N,H,W]) or the handle's own maps."""
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_bfs_popped(self._h, self._ptr(out), self._stream()), "mapf_bfs_popped")
+
     def set_prev_actions(self, prev):
         p = self._to_dev(prev, torch.uint8, (self.E, self.N))
         self._keep = [p]

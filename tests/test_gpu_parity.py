@@ -642,7 +642,7 @@ def test_full_size_every_env_every_step_matches_oracle(cfg):
         queue = workloads.make_goal_queue(wl, obst, goals, E, lo, depth=Q, distinct=distinct)
         dist = torch.full((E, N, H, W), -9, dtype=torch.int16, device="cuda")
         eng.goal_dist(out=dist)
-        life = LifelongGoals(eng, queue, dist_out=dist, overlap=True)
+        life = LifelongGoals(eng, queue, dist_out=dist, overlap=True, fused=True)   # queues popped by the step kernel
         head = np.zeros((E, N), np.int64)
         cur_goals = goals.copy()
         ref_dist = orc.goal_dist()
@@ -671,10 +671,9 @@ def test_full_size_every_env_every_step_matches_oracle(cfg):
         avail = out["avail"]
         arrivals += int(ref["dones"].sum())
         if life is not None:                                  # lifelong: arrived agents take the next queued goal
-            dirty = _np(life.reassign(out["dones"]))
+            life.reassign(out["dones"])
             life.sync()
             ref_dirty = ((ref["dones"] != 0) & (head < Q)).astype(np.uint8)
-            assert np.array_equal(dirty, ref_dirty), t
             new_goals = np.take_along_axis(queue, np.minimum(head, Q - 1)[..., None, None].repeat(2, -1), 2)[:, :, 0, :]
             head += ref_dirty
             orc.set_goals(new_goals, ref_dirty)
@@ -683,6 +682,7 @@ def test_full_size_every_env_every_step_matches_oracle(cfg):
                 assert np.array_equal(_np(dist), ref_dist), t
             cur_goals[ref_dirty != 0] = new_goals[ref_dirty != 0]
             assert np.array_equal(_np(eng.goals()), cur_goals), t
+            assert np.array_equal(_np(life.head), head), t
     assert arrivals > 0 and eng.error_flags() == 0
     if life is not None:
         assert int(head.sum()) > 0
@@ -950,11 +950,14 @@ def test_marl_partial_dropin_class(tmp_path):
     assert env3.reset().shape == (3, env3.get_obs_size())
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("overlap", [False, True])
-def test_c4_shape_lifelong_goal_reassignment_matches_oracle(overlap):
+def test_c4_shape_lifelong_goal_reassignment_matches_oracle(overlap, fused):
     """BASELINE config c4: 64x64 warehouse layout, 128 agents, goals popped from a per-agent queue on arrival
     (mapf_pop_goals), distance maps recomputed only for the reassigned goals (mapf_bfs with the dirty mask: compacted
-    list + resident warps), optionally on a side stream overlapped with the next step."""
+    list + resident warps), optionally on a side stream overlapped with the next step.  fused: the queues are bound to
+    the handle (mapf_lifelong_bind), the step kernel pops them in its write-back and mapf_bfs_popped takes the list the
+    kernel collected -- same goals, heads, distance maps and observations, no pop launch."""
     from mapf_marl_b200 import maps
     from mapf_marl_b200.lifelong import LifelongGoals
     from oracle.oracle import MODE_PRIMAL
@@ -981,7 +984,7 @@ def test_c4_shape_lifelong_goal_reassignment_matches_oracle(overlap):
     orc.reset(obst, starts, goals)
     dist = torch.full((E, N, H, W), -9, dtype=torch.int16, device="cuda")
     eng.goal_dist(out=dist)
-    life = LifelongGoals(eng, queue, dist_out=dist, overlap=overlap)
+    life = LifelongGoals(eng, queue, dist_out=dist, overlap=overlap, fused=fused)
     ref_dist = orc.goal_dist()
     head = np.zeros((E, N), np.int64)
     cur_goals = goals.copy()
@@ -990,10 +993,14 @@ def test_c4_shape_lifelong_goal_reassignment_matches_oracle(overlap):
         out = eng.step_observe(torch.as_tensor(a, device="cuda"), want=("dones", "status", "avail", "terminated"))
         ref = orc.primal_sweep(a)
         assert np.array_equal(_np(out["status"]), ref["status"]) and np.array_equal(_np(out["dones"]), ref["dones"])
-        dirty = _np(life.reassign(out["dones"]))
+        l0 = eng.launch_count()
+        dirty = life.reassign(out["dones"])
         life.sync()
         ref_dirty = ((ref["dones"] != 0) & (head < Q)).astype(np.uint8)
-        assert np.array_equal(dirty, ref_dirty)
+        if fused:
+            assert dirty is None and eng.launch_count() - l0 <= 2      # the BFS over the kernel's list (+ overflow pass)
+        else:
+            assert np.array_equal(_np(dirty), ref_dirty)
         new_goals = np.take_along_axis(queue, np.minimum(head, Q - 1)[..., None, None].repeat(2, -1), 2)[:, :, 0, :]
         head += ref_dirty
         orc.set_goals(new_goals, ref_dirty)
@@ -1001,6 +1008,7 @@ def test_c4_shape_lifelong_goal_reassignment_matches_oracle(overlap):
         assert np.array_equal(_np(dist), ref_dist), t
         cur_goals[ref_dirty != 0] = new_goals[ref_dirty != 0]
         assert np.array_equal(_np(eng.goals()), cur_goals), t
+        assert np.array_equal(_np(life.head), head), t
         obs, vec = eng.observe()
         robs, rvec = orc.primal_observe()
         assert np.array_equal(_np(obs), robs) and np.array_equal(_bits(_np(vec)), _bits(rvec)), t
