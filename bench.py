@@ -791,7 +791,8 @@ def main():
                     # launches of this library in one eager episode: 4 at reset (obstacle rows, reset, observe, masks),
                     # then per environment step the fused step+obs kernel (+ the random policy's own kernel)
                     n_mac = T if mac_name == "random_mac" else 0
-                    env_launches_per_step = (env.engine.launch_count() - l0 - 4 - n_mac) / float(T)
+                    n_book = 2 * T if runner.fused_bookkeeping else 0   # mapf_runner_mask_actions + mapf_runner_account
+                    env_launches_per_step = (env.engine.launch_count() - l0 - 4 - n_mac - n_book) / float(T)
                     runner.run()                                       # captures the CUDA graphs, replays them
                     ms = []
                     for _ in range(3):
@@ -807,6 +808,7 @@ def main():
                     ent[mac_name] = {"value": world * Ex * c3w["N"] * T / (ms * 1e-3), "unit": UNIT,
                                      "ms_per_env_step": ms / T, "engine_launches_per_env_step": env_launches_per_step,
                                      "policy_launches_per_env_step": n_mac / float(T),
+                                     "bookkeeping_launches_per_env_step": n_book / float(T),
                                      "loop": "one episode = reset + CUDA graphs of 8 environment steps each (controller + "
                                              "masking + fused engine launch + bookkeeping), one host check per graph; "
                                              "launch counts are those of the eager warm-up episode",

@@ -377,6 +377,21 @@ int mapf_partial_state(mapf_handle* h, int64_t* state_dev, uint8_t* at_goal_dev,
 int mapf_random_actions(mapf_handle* h, const uint8_t* avail_dev, uint32_t seed, uint32_t step, int64_t env_offset,
                         void* actions_dev, int act_dtype, void* stream);
 
+/* The bookkeeping of a rollout loop around one vector-env step, replacing what pymarl's ParallelRunner.run does on the
+ * host per environment (MARL-curve-main/src/runners/parallel_runner.py:123-175: actions only to running envs;
+ * episode_returns / episode_lengths / terminated bookkeeping; the `filled` mask of EpisodeBatch.update,
+ * components/episode_buffer.py:100-134).
+ * mapf_runner_mask_actions: actions_dev [E,N] (act_dtype MAPF_U8 or MAPF_I64) -> actions_u8_dev uint8[E,N] (the step's
+ *   input) and, when not NULL, actions_i64_dev int64[E,N] (the episode batch's storage); environments with
+ *   alive_dev[e] == 0 (uint8[E]) get stay_action.
+ * mapf_runner_account: for every environment with alive != 0: returns += reward (float64[E], round-to-nearest add),
+ *   lengths += 1 (int64[E]); filled_next_dev[e] = alive (uint8[E]: the NEXT time slot holds data); then
+ *   alive &= (terminated == 0). */
+int mapf_runner_mask_actions(mapf_handle* h, const void* actions_dev, int act_dtype, const uint8_t* alive_dev,
+                             int stay_action, uint8_t* actions_u8_dev, int64_t* actions_i64_dev, void* stream);
+int mapf_runner_account(mapf_handle* h, const double* reward_dev, const uint8_t* terminated_dev, uint8_t* alive_dev,
+                        double* returns_dev, int64_t* lengths_dev, uint8_t* filled_next_dev, void* stream);
+
 /* MAPF_MODE_PARTIAL: from now on every observation launch of this handle (mapf_observe, mapf_step_observe,
  * mapf_rollout) also writes get_state() (PARTIAL:384-393) to state_dev int64[E,3] -- the state rides along with the
  * observation kernel instead of costing a launch of its own per environment step.  NULL unbinds.  The pointer is

@@ -102,6 +102,8 @@ PROTOTYPES = {
     "mapf_partial_state": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_random_actions": (_i, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _i64, _vp, _i, _vp]),
     "mapf_partial_bind_state_out": (_i, [_vp, _vp]),
+    "mapf_runner_mask_actions": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "mapf_runner_account": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mapf_stats": (_i, [_vp, _vp, _vp]),
     "mapf_error_flags": (_i, [_vp, _vp, _vp]),
     "mapf_launch_count": (_i64, [_vp]),

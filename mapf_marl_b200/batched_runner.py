@@ -58,8 +58,9 @@ class DeviceEpisodeBatch:
 
 
 class BatchedRunner:
-    def __init__(self, env, mac, check_every=8, max_steps=None, cuda_graph=False):
+    def __init__(self, env, mac, check_every=8, max_steps=None, cuda_graph=False, fused_bookkeeping=True):
         self.env, self.mac = env, mac
+        self.fused_bookkeeping = bool(fused_bookkeeping)
         self.cuda_graph = bool(cuda_graph)
         self._graphs = None
         self.batch_size = env.n_envs
@@ -106,6 +107,19 @@ class BatchedRunner:
         alive = st["alive"]
         actions = self.mac.select_actions(batch, t_ep=t, t_env=self.t_env, bs=slice(None), test_mode=test_mode)
         actions = actions.reshape(B, -1)
+        eng = getattr(self.env, "engine", None)
+        if (self.fused_bookkeeping and eng is not None and actions.dtype in (torch.uint8, torch.int64)
+                and batch.tm["reward"].dtype == torch.float64 and batch.tm["terminated"].dtype == torch.uint8):
+            # the same bookkeeping as below in two library kernels instead of a dozen element-wise launches
+            # (36 us of a 89 us environment step at c3)
+            if "act_u8" not in st:
+                st["act_u8"] = torch.empty((B, actions.shape[1]), dtype=torch.uint8, device=self.device)
+            eng.runner_mask_actions(actions.contiguous(), alive, self.env.stay_action, st["act_u8"],
+                                    batch.tm["actions"][t])
+            self.env.step_into(st["act_u8"], t, batch)
+            eng.runner_account(batch.tm["reward"][t], batch.tm["terminated"][t], alive, st["returns"], st["lengths"],
+                               batch.tm["filled"][t + 1])
+            return
         # finished environments idle; their entries stay masked (filled == 0)
         actions = torch.where(alive.unsqueeze(1), actions, torch.full_like(actions, self.env.stay_action))
         batch.tm["actions"][t] = actions.unsqueeze(-1)

@@ -919,6 +919,27 @@ int mapf_random_actions(mapf_handle* h, const uint8_t* avail_dev, uint32_t seed,
   return MAPF_OK;
 }
 
+int mapf_runner_mask_actions(mapf_handle* h, const void* actions_dev, int act_dtype, const uint8_t* alive_dev,
+                             int stay_action, uint8_t* actions_u8_dev, int64_t* actions_i64_dev, void* stream) {
+  if (!h || !actions_dev || !alive_dev || !actions_u8_dev)
+    return fail(h, MAPF_ERR_INVALID_ARG, "mapf_runner_mask_actions: NULL argument");
+  if (act_dtype != MAPF_U8 && act_dtype != MAPF_I64) return fail(h, MAPF_ERR_INVALID_ARG, "actions must be MAPF_U8 or MAPF_I64");
+  CK((cudaError_t)mapf_launch_runner_mask_actions(h->d, actions_dev, act_dtype == MAPF_I64, alive_dev, stay_action,
+                                                  actions_u8_dev, (long long*)actions_i64_dev, stream));
+  h->launches++;
+  return MAPF_OK;
+}
+
+int mapf_runner_account(mapf_handle* h, const double* reward_dev, const uint8_t* terminated_dev, uint8_t* alive_dev,
+                        double* returns_dev, int64_t* lengths_dev, uint8_t* filled_next_dev, void* stream) {
+  if (!h || !reward_dev || !terminated_dev || !alive_dev || !returns_dev || !lengths_dev || !filled_next_dev)
+    return fail(h, MAPF_ERR_INVALID_ARG, "mapf_runner_account: NULL argument");
+  CK((cudaError_t)mapf_launch_runner_account(h->d, reward_dev, terminated_dev, alive_dev, returns_dev,
+                                             (long long*)lengths_dev, filled_next_dev, stream));
+  h->launches++;
+  return MAPF_OK;
+}
+
 // Self-test hook (not part of the public header): the next step / rollout launch of this handle overwrites guard word
 // `which` of its tile on purpose, so that tests can see MAPF_FLAG_INTERNAL being raised by the canary check.
 int mapf_debug_corrupt_canary(mapf_handle* h, int which) {

@@ -152,6 +152,10 @@ int mapf_launch_partial_state(const MapfDims& d, const MapfState& S, long long* 
 int mapf_launch_export16(const MapfDims& d, const uint8_t* src_u8x2, int16_t* dst, void* stream);
 int mapf_launch_random_actions(const MapfDims& d, const uint8_t* avail, uint32_t seed, uint32_t step,
                                long long env_offset, void* out, int i64, void* stream);
+int mapf_launch_runner_mask_actions(const MapfDims& d, const void* actions, int i64, const uint8_t* alive, int stay,
+                                    uint8_t* out8, long long* out64, void* stream);
+int mapf_launch_runner_account(const MapfDims& d, const double* reward, const uint8_t* term, uint8_t* alive,
+                               double* returns, long long* lengths, uint8_t* filled_next, void* stream);
 int mapf_tile_has_fov(int F);
 int mapf_tile_has_rollout(int mode);
 int mapf_pipe_supported(const MapfDims& d);

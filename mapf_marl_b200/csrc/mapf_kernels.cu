@@ -3215,6 +3215,53 @@ extern "C" int mapf_launch_set_goals(const MapfDims& d, const MapfState& S, cons
   return (int)cudaGetLastError();
 }
 
+// Bookkeeping of a rollout loop around one vector-env step (pymarl ParallelRunner.run, parallel_runner.py:123-175), two
+// kernels instead of a dozen element-wise launches.  (1) actions of finished environments become the STAY action;
+// the result goes to the engine's uint8 input and, optionally, to the episode batch's int64 storage.
+__global__ void mapf_runner_mask_actions_kernel(const MapfDims d, const void* __restrict__ actions, int i64,
+                                                const uint8_t* __restrict__ alive, int stay, uint8_t* __restrict__ out8,
+                                                long long* __restrict__ out64) {
+  const long long total = (long long)d.E * d.N;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total;
+       j += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)((unsigned long long)j / (unsigned)d.N);
+    long long a = i64 ? ((const long long*)actions)[j] : (long long)((const uint8_t*)actions)[j];
+    if (!alive[e]) a = stay;
+    out8[j] = (uint8_t)a;          // out-of-range values still trip the step kernel's action check (low byte kept)
+    if (i64 && (a < 0 || a > 255)) out8[j] = 255;
+    if (out64) out64[j] = a;
+  }
+}
+// (2) returns / lengths / filled / alive after the step: an environment that was running accumulates the reward and a
+// step, its next time slot is marked filled, and it stops running when the step terminated it.
+__global__ void mapf_runner_account_kernel(int E, const double* __restrict__ reward, const uint8_t* __restrict__ term,
+                                           uint8_t* __restrict__ alive, double* __restrict__ returns,
+                                           long long* __restrict__ lengths, uint8_t* __restrict__ filled_next) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    const uint8_t al = alive[e];
+    if (al) {
+      returns[e] = __dadd_rn(returns[e], reward[e]);
+      lengths[e] += 1;
+    }
+    filled_next[e] = al;
+    alive[e] = (uint8_t)(al && term[e] == 0);
+  }
+}
+
+extern "C" int mapf_launch_runner_mask_actions(const MapfDims& d, const void* actions, int i64, const uint8_t* alive,
+                                               int stay, uint8_t* out8, long long* out64, void* stream) {
+  mapf_runner_mask_actions_kernel<<<grid_for((long long)d.E * d.N, 256), 256, 0, (cudaStream_t)stream>>>(
+      d, actions, i64, alive, stay, out8, out64);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mapf_launch_runner_account(const MapfDims& d, const double* reward, const uint8_t* term, uint8_t* alive,
+                                          double* returns, long long* lengths, uint8_t* filled_next, void* stream) {
+  mapf_runner_account_kernel<<<grid_for(d.E, 256), 256, 0, (cudaStream_t)stream>>>(d.E, reward, term, alive, returns,
+                                                                                    lengths, filled_next);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int mapf_launch_pop_goals(const MapfDims& d, const MapfState& S, const int16_t* queue, int32_t* head,
                                      int queue_len, uint8_t* dirty, void* stream) {
   mapf_pop_goals_kernel<<<grid_for((long long)d.E * d.N, 256), 256, 0, (cudaStream_t)stream>>>(d, S, queue, head,

@@ -444,6 +444,33 @@ class MapfEngine:
                         "mapf_random_actions")
         return out
 
+    def runner_mask_actions(self, actions, alive, stay_action, out_u8, out_i64=None):
+        """Rollout bookkeeping (mapf_runner_mask_actions): actions [E,N] uint8 / int64 -> out_u8 (the step's input) and
+        out_i64 (the episode batch's int64 [E,N] slice), finished environments (alive bool/uint8 [E] == 0) STAY."""
+        assert actions.is_cuda and actions.is_contiguous() and actions.dtype in (torch.uint8, torch.int64)
+        assert alive.is_contiguous() and alive.dtype in (torch.bool, torch.uint8) and alive.numel() == self.E
+        assert out_u8.dtype == torch.uint8 and out_u8.is_contiguous() and out_u8.numel() == self.E * self.N
+        if out_i64 is not None:
+            assert out_i64.dtype == torch.int64 and out_i64.is_contiguous() and out_i64.numel() == self.E * self.N
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_runner_mask_actions(self._h, self._ptr(actions),
+                                                          U8 if actions.dtype == torch.uint8 else I64, self._ptr(alive),
+                                                          int(stay_action), self._ptr(out_u8), self._ptr(out_i64),
+                                                          self._stream()), "mapf_runner_mask_actions")
+        return out_u8
+
+    def runner_account(self, reward, terminated, alive, returns, lengths, filled_next):
+        """Rollout bookkeeping after a step (mapf_runner_account): returns / lengths of running environments, the
+        `filled` flag of the next time slot, alive &= not terminated; all [E], in place."""
+        for t, dt in ((reward, torch.float64), (returns, torch.float64), (lengths, torch.int64)):
+            assert t.dtype == dt and t.is_contiguous() and t.numel() == self.E
+        for t in (terminated, alive, filled_next):
+            assert t.dtype in (torch.uint8, torch.bool) and t.is_contiguous() and t.numel() == self.E
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mapf_runner_account(self._h, self._ptr(reward), self._ptr(terminated), self._ptr(alive),
+                                                     self._ptr(returns), self._ptr(lengths), self._ptr(filled_next),
+                                                     self._stream()), "mapf_runner_account")
+
     def rollout_in_one_launch(self, dtype=torch.uint8):
         odt = BITS if dtype == "bits" else (F32 if dtype == torch.float32 else U8)
         return bool(self.lib.mapf_rollout_in_one_launch(self._h, odt))

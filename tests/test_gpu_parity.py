@@ -1040,7 +1040,8 @@ def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path
     bn = lambda k: _cache.setdefault(k, _np(batch[k]))       # noqa: E731
     # two launches per environment step (tile kernel + PARTIAL observation kernel carrying get_state)
     n_reset = 3 + 2                                          # reset: reset + BFS (+overflow) ; observe + avail
-    assert env.engine.launch_count() - l0 <= 2 * T + T + n_reset + 2      # + the random policy: one kernel per step
+    # + the random policy: one kernel per step; + the runner's two bookkeeping kernels per step
+    assert env.engine.launch_count() - l0 <= 2 * T + T + 2 * T + n_reset + 2
     odt = np.float32 if obs_float32 else np.float64
     assert bn("obs").dtype == odt
     H, W = g["obst"].shape
@@ -1107,9 +1108,10 @@ def test_batched_runner_primal_vec_env_one_launch_per_step_and_grid_env(tmp_path
             assert runner._graphs is not None and len(runner._graphs) == 3
         _cache = {}
         bn = lambda k, _c=_cache, _b=batch: _c.setdefault(k, _np(_b[k]))   # noqa: E731
-        # reset (2 kernels) + observe + avail at t = 0, then ONE launch per environment step (+ the random policy's)
+        # reset (2 kernels) + observe + avail at t = 0, then ONE launch per environment step (+ the random policy's, +
+        # the runner's two bookkeeping kernels: mapf_runner_mask_actions, mapf_runner_account)
         if not graph:
-            assert env.engine.launch_count() - l0 == 4 + T + n_mac
+            assert env.engine.launch_count() - l0 == 4 + T + n_mac + 2 * T
         orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F)
         orc.reset(obst, starts, goals)
         robs, rvec = orc.primal_observe()
