@@ -1015,6 +1015,50 @@ def test_c4_shape_lifelong_goal_reassignment_matches_oracle(overlap, fused):
     assert int(head.sum()) > E * N // 4          # several hundred reassignments happened
 
 
+def test_lifelong_bind_rollout_falls_back_to_one_launch_per_step_and_rejects_other_modes():
+    """While goal queues are bound, a T-step mapf_rollout runs as T launches (every launch pops the queues once) and
+    equals T single steps + mapf_pop_goals; binding is PRIMAL-only; unbinding restores the single launch."""
+    from mapf_marl_b200 import maps
+    E, N, H, W, F, Q, T = 32, 8, 20, 20, 11, 3, 6
+    obst, starts, goals = maps.synthetic_batch(77, E, H, W, 0.2, N, distinct=0)
+    goals = goals.copy()
+    goals[:, ::2] = starts[:, ::2]                     # every other agent starts on its goal: pops from step 1 on
+    rs = np.random.RandomState(5)
+    free = [np.argwhere(obst[e] == 0) for e in range(E)]
+    queue = np.stack([np.stack([free[e][rs.permutation(len(free[e]))[:Q]] for _ in range(N)]) for e in range(E)])
+    queue = queue.astype(np.int16)
+    acts = torch.as_tensor(rs.randint(0, 5, (T, E, N)).astype(np.uint8), device="cuda")
+    a = _engine(E, N, H, W, mode="primal", fov=F)
+    b = _engine(E, N, H, W, mode="primal", fov=F)
+    qd = torch.as_tensor(queue, device="cuda").contiguous()
+    head_a = torch.zeros((E, N), dtype=torch.int32, device="cuda")
+    head_b = torch.zeros((E, N), dtype=torch.int32, device="cuda")
+    a.reset(obst, starts, goals)
+    b.reset(obst, starts, goals)
+    assert b.rollout_in_one_launch()
+    b.lifelong_bind(qd, head_b)
+    assert not b.rollout_in_one_launch()
+    l0 = b.launch_count()
+    ob = b.rollout(acts, want=("reward", "dones", "avail"))
+    assert b.launch_count() - l0 == T
+    ob = {k: v.clone() for k, v in ob.items()}
+    for t in range(T):
+        oa = a.step_observe(acts[t], want=("reward", "dones", "avail"))
+        for k in ("obs", "vec", "reward", "dones", "avail"):
+            assert torch.equal(oa[k].view(torch.uint8), ob[k][t].view(torch.uint8)), (k, t)
+        a.pop_goals(qd, head_a)
+    assert torch.equal(head_a, head_b) and int(head_a.sum()) > E
+    assert torch.equal(a.goals(), b.goals()) and torch.equal(a.positions(), b.positions())
+    # (an agent moved onto its start may share that cell with somebody's goal: reset flags the overlap, nothing else)
+    assert a.error_flags() == b.error_flags() and (a.error_flags() & ~16) == 0
+    b.lifelong_bind(None, None)
+    assert b.rollout_in_one_launch()
+    g = _engine(4, 4, 10, 10, mode="grid")
+    with pytest.raises(Exception):
+        g.lifelong_bind(torch.zeros((4, 4, 2, 2), dtype=torch.int16, device="cuda"),
+                        torch.zeros((4, 4), dtype=torch.int32, device="cuda"))
+
+
 @pytest.mark.parametrize("obs_float32", [False, True])
 @pytest.mark.parametrize("check_every", [1, 5])
 def test_batched_runner_fills_an_episode_batch_like_the_parallel_runner(tmp_path, obs_float32, check_every):
@@ -1094,9 +1138,11 @@ def test_batched_runner_primal_vec_env_one_launch_per_step_and_grid_env(tmp_path
     E, N, H, W, F, T = 48, 8, 20, 20, 11, 10
     obst, starts, goals = maps.synthetic_batch(21, E, H, W, 0.2, N, distinct=0)
     env = PrimalVecEnv(obst, starts, goals, fov=F, episode_limit=T)
-    for mac, graph in ((RandomMAC(env.engine, seed=3), False), (RNNAgentMAC(4 * F * F, 5, "cuda", extra_dim=3), False),
-                       (RandomMAC(env.engine, seed=4), True)):
-        runner = BatchedRunner(env, mac, check_every=4, cuda_graph=graph)
+    for mac, graph, fusedbk in ((RandomMAC(env.engine, seed=3), False, True),
+                                (RNNAgentMAC(4 * F * F, 5, "cuda", extra_dim=3), False, True),
+                                (RandomMAC(env.engine, seed=4), True, True),
+                                (RandomMAC(env.engine, seed=5), False, False)):   # bookkeeping in torch
+        runner = BatchedRunner(env, mac, check_every=4, cuda_graph=graph, fused_bookkeeping=fusedbk)
         n_mac = T if isinstance(mac, RandomMAC) else 0          # the random policy is one engine kernel per step
         if graph:
             runner.run()                                         # eager warm-up episode; the next run captures + replays
@@ -1111,7 +1157,7 @@ def test_batched_runner_primal_vec_env_one_launch_per_step_and_grid_env(tmp_path
         # reset (2 kernels) + observe + avail at t = 0, then ONE launch per environment step (+ the random policy's, +
         # the runner's two bookkeeping kernels: mapf_runner_mask_actions, mapf_runner_account)
         if not graph:
-            assert env.engine.launch_count() - l0 == 4 + T + n_mac + 2 * T
+            assert env.engine.launch_count() - l0 == 4 + T + n_mac + (2 * T if fusedbk else 0)
         orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F)
         orc.reset(obst, starts, goals)
         robs, rvec = orc.primal_observe()
