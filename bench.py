@@ -787,12 +787,13 @@ def main():
                                       ("rnn_mac", RNNAgentMAC(4 * c3w["F"] ** 2, 5, dev, extra_dim=3))):
                     runner = BatchedRunner(env, mac, check_every=8, cuda_graph=True)
                     l0 = env.engine.launch_count()
+                    n_rst = 3 if env._maps_loaded else 4               # obstacle rows are built by the first reset only
                     runner.run()                                       # eager warm-up episode (allocates the batch)
-                    # launches of this library in one eager episode: 4 at reset (obstacle rows, reset, observe, masks),
+                    # launches of this library in one eager episode: 3-4 at reset (obstacle rows, reset, observe, masks),
                     # then per environment step the fused step+obs kernel (+ the random policy's own kernel)
                     n_mac = T if mac_name == "random_mac" else 0
                     n_book = 2 * T if runner.fused_bookkeeping else 0   # mapf_runner_mask_actions + mapf_runner_account
-                    env_launches_per_step = (env.engine.launch_count() - l0 - 4 - n_mac - n_book) / float(T)
+                    env_launches_per_step = (env.engine.launch_count() - l0 - n_rst - n_mac - n_book) / float(T)
                     runner.run()                                       # captures the CUDA graphs, replays them
                     ms = []
                     for _ in range(3):

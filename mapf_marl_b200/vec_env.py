@@ -38,6 +38,12 @@ class PrimalVecEnv:
                        torch.as_tensor(np.asarray(goals), device=dev).to(torch.int16).contiguous())
         self._last = None
         self._t = 0
+        self._maps_loaded = False        # the obstacle rows are built by the first reset only (the world is constant)
+
+    def _engine_reset(self):
+        obst, starts, goals = self._world
+        self.engine.reset(None if self._maps_loaded else obst, starts, goals)
+        self._maps_loaded = True
 
     # ------------------------------------------------------------------ MultiAgentEnv-style surface (vector)
     def get_env_info(self):
@@ -45,7 +51,7 @@ class PrimalVecEnv:
                 "n_agents": self.n_agents, "episode_limit": self.episode_limit}
 
     def reset(self):
-        self.engine.reset(*self._world)
+        self._engine_reset()
         self._t = 0
         obs, vec = self.engine.observe()
         self._last = {"obs": obs, "vec": vec, "avail": self.engine.avail()}
@@ -86,7 +92,7 @@ class PrimalVecEnv:
                 "_views": {"state": lambda tm: tm["obs_vec"].reshape(tm["obs_vec"].shape[0], self.n_envs, 3 * N)}}
 
     def reset_into(self, batch):
-        self.engine.reset(*self._world)
+        self._engine_reset()
         self._t = 0
         self.engine.observe(out={"obs": batch.tm["obs"][0], "vec": batch.tm["obs_vec"][0]})   # straight into the batch
         batch.tm["avail_actions"][0].copy_(self.engine.avail())

@@ -1148,16 +1148,17 @@ def test_batched_runner_primal_vec_env_one_launch_per_step_and_grid_env(tmp_path
             runner.run()                                         # eager warm-up episode; the next run captures + replays
             mac.episode = -1                                     # same draws as the warm-up: (seed, episode 0, step)
         l0 = env.engine.launch_count()
+        n_reset = 3 if env._maps_loaded else 4                   # the obstacle rows are built by the first reset only
         batch = runner.run()
         assert runner.t == T
         if graph:
             assert runner._graphs is not None and len(runner._graphs) == 3
         _cache = {}
         bn = lambda k, _c=_cache, _b=batch: _c.setdefault(k, _np(_b[k]))   # noqa: E731
-        # reset (2 kernels) + observe + avail at t = 0, then ONE launch per environment step (+ the random policy's, +
+        # reset (2 kernels the first time, then 1) + observe + avail at t = 0, then ONE launch per environment step (+ the random policy's, +
         # the runner's two bookkeeping kernels: mapf_runner_mask_actions, mapf_runner_account)
         if not graph:
-            assert env.engine.launch_count() - l0 == 4 + T + n_mac + (2 * T if fusedbk else 0)
+            assert env.engine.launch_count() - l0 == n_reset + T + n_mac + (2 * T if fusedbk else 0)
         orc = _oracle(E, N, H, W, MODE_PRIMAL, fov=F)
         orc.reset(obst, starts, goals)
         robs, rvec = orc.primal_observe()
