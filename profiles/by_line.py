@@ -18,10 +18,11 @@ def main():
     print("   %s" % rows[1][1][:150])
     hdr = rows[2]
     isamp, iinst = hdr.index("# Samples"), hdr.index("Instructions Executed")
-    iw, iex = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Excessive")
+    iw = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
+    iex = hdr.index("L1 Wavefronts Shared Excessive") if "L1 Wavefronts Shared Excessive" in hdr else None
     stall = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     agg = [r for r in rows[3:] if len(r) > isamp and r[2] == "-"]          # the per-source-line rows
-    num = lambda r, i: int(r[i] or 0)   # noqa: E731
+    num = lambda r, i: 0 if i is None else int(r[i] or 0)   # noqa: E731
     ti, ts, tw = (max(sum(num(r, i) for r in agg), 1) for i in (iinst, isamp, iw))
     print("   warp instructions %d, samples %d, shared-memory wavefronts %d" % (ti, ts, tw))
     print("%6s %7s %7s %7s %9s  %-34s %s" % ("line", "inst%", "samp%", "wavef%", "excess", "top stalls", "source"))
