@@ -63,6 +63,7 @@ class BatchedRunner:
         self.fused_bookkeeping = bool(fused_bookkeeping)
         self.cuda_graph = bool(cuda_graph)
         self._graphs = None
+        self._reset_graph = None
         self.batch_size = env.n_envs
         self.env_info = env.get_env_info()
         self.episode_limit = self.env_info["episode_limit"]
@@ -70,10 +71,52 @@ class BatchedRunner:
         self.check_every = max(int(check_every), 1)
         self.device = env.engine.device
         self.t = 0
-        self.t_env = 0
+        self._t_env = 0
         self._returns = {False: [], True: []}     # per-episode return tensors (device); lists are built on demand
-        self.train_stats, self.test_stats = {}, {}
+        self._stats = {False: {}, True: {}}
+        self._pending = []                        # (test_mode, device scalar: env steps of a finished run()), unresolved
+        self._env_stats_stale = {False: False, True: False}
         self.batch = None
+
+    # What run() learns about an episode only on the device -- how many environment steps it took, the engine's
+    # counters -- is resolved when somebody reads it, not at the end of run(): two host synchronisations per episode
+    # kept the GPU idle while the next episode's launches were still being issued (14 % of a 16-step c3 episode).
+    def _resolve(self):
+        if self._pending:
+            for test_mode, steps in self._pending:
+                n = int(steps.item())
+                if not test_mode:
+                    self._t_env += n
+                st = self._stats[test_mode]
+                st["ep_length"] = n + st.get("ep_length", 0)
+            self._pending = []
+
+    @property
+    def t_env(self):
+        self._resolve()
+        return self._t_env
+
+    @t_env.setter
+    def t_env(self, v):
+        self._resolve()
+        self._t_env = int(v)
+
+    def _stats_view(self, test_mode):
+        self._resolve()
+        st = self._stats[test_mode]
+        if self._env_stats_stale[test_mode]:
+            for k, v in self.env.get_stats().items():
+                st["env_" + k] = v
+            self._env_stats_stale[test_mode] = False
+        return st
+
+    @property
+    def train_stats(self):
+        return self._stats_view(False)
+
+    @property
+    def test_stats(self):
+        return self._stats_view(True)
 
     def get_env_info(self):
         return self.env_info
@@ -105,7 +148,7 @@ class BatchedRunner:
         """Environment step t of the episode; every tensor it touches is persistent (graph-capturable)."""
         B, batch = self.batch_size, self.batch
         alive = st["alive"]
-        actions = self.mac.select_actions(batch, t_ep=t, t_env=self.t_env, bs=slice(None), test_mode=test_mode)
+        actions = self.mac.select_actions(batch, t_ep=t, t_env=self._t_env, bs=slice(None), test_mode=test_mode)
         actions = actions.reshape(B, -1)
         eng = getattr(self.env, "engine", None)
         if (self.fused_bookkeeping and eng is not None and actions.dtype in (torch.uint8, torch.int64)
@@ -135,7 +178,13 @@ class BatchedRunner:
     def run(self, test_mode=False, reuse_batch=False):
         """One episode in every environment; returns the filled batch (parallel_runner.py:91-206)."""
         reuse_batch = reuse_batch or self.cuda_graph         # captured graphs hold the batch's addresses
-        self.reset(reuse_batch)
+        if self._graphs is None:
+            self._resolve()                                  # eager steps (and a capture) read t_env on the host
+        if self._graphs is not None and self._reset_graph is not None:
+            self._reset_graph.replay()                       # the same launches as reset(True), without the host side
+            self.t = 0
+        else:
+            self.reset(reuse_batch)
         B, dev = self.batch_size, self.device
         if getattr(self, "_st", None) is None:
             self._st = {"returns": torch.zeros(B, dtype=torch.float64, device=dev),
@@ -154,6 +203,12 @@ class BatchedRunner:
             self._graphs = []
             pool = None
             torch.cuda.synchronize()
+            if getattr(self.env, "graph_safe_reset", False):
+                # the episode reset as a graph of its own (envs whose reset_into touches nothing but device tensors)
+                g0 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g0):
+                    self.reset(True)
+                self._reset_graph, pool = g0, g0.pool()
             for blk in blocks:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):
@@ -176,15 +231,12 @@ class BatchedRunner:
             if self.t < T and not bool(st["alive"].any()):
                 break                                        # the only host synchronisation of the loop
         self._warm = True
-        n_steps = int(st["lengths"].sum().item())
-        if not test_mode:
-            self.t_env += n_steps
-        stats = self.test_stats if test_mode else self.train_stats
+        test_mode = bool(test_mode)
+        self._pending.append((test_mode, st["lengths"].sum()))        # a device scalar: resolved when somebody asks
+        stats = self._stats[test_mode]
         stats["n_episodes"] = B + stats.get("n_episodes", 0)
-        stats["ep_length"] = n_steps + stats.get("ep_length", 0)
-        for k, v in self.env.get_stats().items():
-            stats["env_" + k] = v
-        self._returns[bool(test_mode)].append(st["returns"].clone())
+        self._env_stats_stale[test_mode] = True
+        self._returns[test_mode].append(st["returns"].clone())
         return self.batch
 
 

@@ -22,6 +22,7 @@ from .engine import MapfEngine
 
 class PrimalVecEnv:
     stay_action = 0                      # dirDict[0] = (0, 0), mapf_primal.py:28
+    graph_safe_reset = True              # reset_into() launches kernels on device tensors only (BatchedRunner)
 
     def __init__(self, obst, starts, goals, fov=11, episode_limit=256, device=None, shared_map=False, **engine_kwargs):
         starts = np.asarray(starts)

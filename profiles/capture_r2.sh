@@ -46,6 +46,7 @@ for wl in ("c2", "c3", "c4"):
     out[wl] = int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
 print(json.dumps(out))
 PY
-python profiles/sass_by_line.py $REP/${TAG}_fused_c3.ncu-rep > $OUT/${TAG}_sass_by_line_fused_c3.txt 2>/dev/null || true
+python profiles/by_line.py $REP/${TAG}_fused_c3.ncu-rep 40 > $OUT/${TAG}_by_line_fused_c3.txt 2>/dev/null || true
+python profiles/by_line.py $REP/${TAG}_fused_c4.ncu-rep 40 > $OUT/${TAG}_by_line_fused_c4.txt 2>/dev/null || true
 cp $REP/${TAG}_fused_c3.ncu-rep $OUT/ || true
 ls -la $OUT | grep ${TAG}_
