@@ -362,3 +362,68 @@ def test_reference_staging_archive_roundtrip(tmp_path):
     # no reference source is tracked by git: the staging directory is ignored
     ign = open(os.path.join(os.path.dirname(stage_ref.HERE), ".gitignore")).read()
     assert "oracle/_ref/" in ign
+
+
+def test_split_sum_of_rewards_equals_the_interpreters_sum():
+    """The tile kernel evaluates CPython >= 3.12's `sum(rewards)` (GRID:141, PARTIAL:310) in three pieces
+    (mapf_kernels.cu: py_sum_head / py_sum_term / py_sum_tail): the accumulator chain, every item's compensation
+    term computed independently from (accumulator before the item, item), and the chain that folds the terms -- a
+    skipped term is stored as +0.0.  The same decomposition in Python doubles must reproduce the interpreter's builtin
+    bit for bit, for int / float mixes, signed zeros, huge and tiny magnitudes, infinities."""
+    if sys.version_info < (3, 12):
+        pytest.skip("the compensated builtin sum exists from CPython 3.12 on")
+    import struct
+
+    def bits(x):
+        return struct.pack("<d", float(x))
+
+    def split_sum(items):
+        acc, pre, first_float = 0.0, [], len(items)
+        for i, x in enumerate(items):                      # head: one add per item
+            pre.append(acc)
+            acc = acc + float(x)
+            if isinstance(x, float) and first_float == len(items):
+                first_float = i
+        terms = []
+        for i, x in enumerate(items):                      # terms: independent of each other
+            if isinstance(x, float) and i > first_float:
+                a, xi = pre[i], float(x)
+                t = a + xi
+                big = abs(a) >= abs(xi)
+                terms.append(((a if big else xi) - t) + (xi if big else a))
+            else:
+                terms.append(0.0)
+        c = 0.0
+        for t in terms:                                    # tail: folded in order
+            c = c + t
+        if first_float < len(items) and c != 0.0 and np.isfinite(c):
+            acc = acc + c
+        return acc
+
+    rs = np.random.RandomState(11)
+    pool_f = [-0.01, -10.0, -0.3, -2.0, 0.5, 1e16, -1e16, 1e-300, 3.3333333333333335, -0.0, 0.0, 1e308, -1e308]
+    pool_i = [0, -1, -10, 3, 20, 10 ** 9]
+    for trial in range(4000):
+        n = int(rs.randint(1, 40))
+        p_int = rs.rand()
+        items = [pool_i[rs.randint(len(pool_i))] if rs.rand() < p_int else
+                 (pool_f[rs.randint(len(pool_f))] if rs.rand() < 0.7 else float(rs.randn() * 10.0 ** rs.randint(-8, 9)))
+                 for _ in range(n)]
+        want = sum(items)
+        got = split_sum(items)
+        assert bits(want) == bits(got) or (np.isnan(float(want)) and np.isnan(got)), (items, want, got)
+    assert bits(split_sum([-0.0, -0.0])) == bits(sum([-0.0, -0.0]))
+    assert bits(split_sum([float("inf"), 1.0, -5.0])) == bits(sum([float("inf"), 1.0, -5.0]))
+
+
+def test_unit_step_closer_reward_needs_no_division():
+    """PARTIAL's shaping term (dist[old] - dist[new]) / episode_limit (marl_partial.py:229-234): the kernel replaces the
+    division by +-(1.0 / limit) or +0.0 when the hop distance changed by -1, 0 or +1 (partial_phase_a).  IEEE division is
+    sign-symmetric and 0 / L is +0.0, so the substitution is exact for every limit."""
+    lim = np.arange(1, 200001, dtype=np.float64)
+    inv = 1.0 / lim
+    assert np.array_equal((np.float64(-1.0) / lim).view(np.uint64), (-inv).view(np.uint64))
+    assert np.array_equal((np.float64(1.0) / lim).view(np.uint64), inv.view(np.uint64))
+    assert np.array_equal((np.float64(0.0) / lim).view(np.uint64), np.zeros_like(lim).view(np.uint64))
+    for L in (1, 3, 7, 256, 10 ** 6, 2 ** 31 - 1):          # Python's float division is the same IEEE operation
+        assert (-1) / L == -(1.0 / L) and (1 / L) == 1.0 / float(L) and str(0 / L) == "0.0"
